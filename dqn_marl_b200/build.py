@@ -1,0 +1,85 @@
+"""In-tree build of libmarl_b200.so (nvcc, sm_100a only).
+
+    python -m dqn_marl_b200.build [--force] [--verbose]
+
+Every translation unit is compiled with
+    -gencode arch=compute_100a,code=sm_100a -lineinfo
+The env kernels additionally get -fmad=false: the reference's scores and rewards are sequences of
+separately rounded float64 operations (people.py:287-291, evacuation_env.py:174-288) and a fused
+multiply-add would change their bits.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "csrc", "_obj")
+OUT = os.path.join(HERE, "libmarl_b200.so")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
+          "-I", os.path.join(HERE, "..", "include")]
+# per-file extra flags
+EXTRA = {
+    "env.cu": ["-fmad=false", "-Xptxas", "-v"],
+    "replay.cu": ["-Xptxas", "-v"],
+    "qnet.cu": ["-Xptxas", "-v"],
+}
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libmarl_b200.so cannot be built (there is no CPU fallback)")
+
+
+def sources():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp")))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cpp", ".h", ".cuh"))]
+    deps.append(os.path.join(HERE, "..", "include", "marl_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return OUT
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+    objs = []
+    logs = []
+    for src in sources():
+        obj = os.path.join(OBJ, src + ".o")
+        cmd = [nvcc, *ARCH, *COMMON, *EXTRA.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        p = subprocess.run(cmd, capture_output=True, text=True)
+        logs.append(f"== {src}\n{p.stdout}{p.stderr}")
+        if p.returncode != 0:
+            sys.stderr.write(logs[-1])
+            raise RuntimeError(f"nvcc failed on {src}")
+        if verbose:
+            print(p.stdout + p.stderr)
+        objs.append(obj)
+    cmd = [nvcc, *ARCH, "-shared", "-o", OUT, *objs]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout + p.stderr)
+        raise RuntimeError("nvcc link failed")
+    with open(os.path.join(OBJ, "build.log"), "w") as f:
+        f.write("\n".join(logs))
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,764 @@
+// Batched Louvre_Evacuation environment — fused reset / step kernels (sm_100a).
+//
+// One CTA steps one env instance: EvacuationEnv.step of the reference
+// (Louvre_Evacuation/envs/evacuation_env.py:122-172) = move_robot (map.py:160-202) + People.run
+// (people.py:196-253) + fire update (fire_model.py:63-67) + _calculate_reward (:174-288) + done (:155-157)
+// + _get_state (:84-120) in ONE launch.  The occupancy map of the env (People.rmap, 1 bit per cell) is
+// staged in shared memory for the whole step; person state streams through registers, SoA across envs
+// in HBM.  Everything that is fp64 in the reference stays fp64 and is evaluated with the reference's
+// operation order (compiled with -fmad=false), so rewards/health/accumulators are bit-identical.
+//
+// Sequential semantics reproduced in parallel (DESIGN.md "Conflict resolution"):
+//   * proposals only read rmap as it was before phase 4 (people.py:211-230) -> embarrassingly parallel;
+//   * move_plan is a dict keyed by target cell in first-proposer order (people.py:228-230): the key of a
+//     target is min(list index of its proposers) (shared-memory hash table + atomicMin);
+//   * random.shuffle picks the mover (people.py:239): keyed priority, atomicMin on (prio<<32 | index);
+//   * rmap is a FLAG map written in key order (people.py:301-302,312-314): the final bit of a cell is the
+//     write with the largest key, i.e. SET (or CLEAR when the cell evacuates) iff key(cell) > max key of
+//     the winners that left it; a left cell that is nobody's target is simply cleared.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <new>
+#include "common.h"
+#include "philox.cuh"
+
+namespace mq {
+
+constexpr int MAXR = MQ_MAX_ROBOTS;
+constexpr uint32_t HEMPTY = 0xFFFFFFFFu;
+
+struct DevLayout {
+    int L, W, stride, G, wpr, rmap_words;
+    int n_fire_steps;
+    int ctr_box[4], int_box[4];
+    int robot_range[2];
+    int robot_start[MAXR][2];
+    int reset_center[2];
+    int obs_exit[2];
+    const double* dp5;
+    const uint8_t* cellinfo;
+    const double* danger_ctr;
+    const double* danger_int;
+};
+
+struct DevCfg {
+    int n_envs, N, n_pad, R;
+    unsigned long long seed;
+    int env_id_base, max_steps, reset_robots, reset_fire, auto_reset;
+    int hash_cap, hash_shift, n_leaf_max;
+    double evac_reward, death_penalty, death_acc_penalty, alive_bonus;
+};
+
+struct DevState {
+    uint32_t* pos; double* health; double* acc; uint8_t* flags; uint32_t* rmap; int* robots; int* scalars;
+};
+
+// -20.0 / (sqrt(d2) + 0.1) for d2 = 0..24: People.ROBOT_REPEL_K / (dist + 0.1), dist < ROBOT_REPEL_RANGE
+// (people.py:94-95,282-284).  dist = sqrt of an exact integer, so the table is exact.
+__constant__ double c_repel[25];
+__constant__ int c_dx[8] = {1, 0, -1, 0, 1, -1, -1, 1};    // map.py:11-19 MoveTO
+__constant__ int c_dy[8] = {0, -1, 0, 1, -1, -1, 1, 1};
+
+struct Smem {
+    unsigned long long* hbest;
+    double* health; double* dist; double* leaf_sum;
+    uint32_t* bm; uint32_t* hkey; uint32_t* hmin; uint32_t* hleave; uint32_t* pos; uint32_t* mv;
+    int* leaf_off; int* leaf_len;
+    uint8_t* fl;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline size_t carve(Smem& s, unsigned char* base, int N, int cap, int words, int nleaf) {
+    size_t o = 0;
+    s.hbest = (unsigned long long*)(base + o); o += sizeof(unsigned long long) * cap;
+    s.health = (double*)(base + o); o += sizeof(double) * N;
+    s.dist = (double*)(base + o); o += sizeof(double) * N;
+    s.leaf_sum = (double*)(base + o); o += sizeof(double) * nleaf;
+    o = align_up(o, 16);
+    s.bm = (uint32_t*)(base + o); o += sizeof(uint32_t) * align_up(words, 4);
+    s.hkey = (uint32_t*)(base + o); o += sizeof(uint32_t) * cap;
+    s.hmin = (uint32_t*)(base + o); o += sizeof(uint32_t) * cap;
+    s.hleave = (uint32_t*)(base + o); o += sizeof(uint32_t) * cap;
+    s.pos = (uint32_t*)(base + o); o += sizeof(uint32_t) * N;
+    s.mv = (uint32_t*)(base + o); o += sizeof(uint32_t) * N;
+    s.leaf_off = (int*)(base + o); o += sizeof(int) * nleaf;
+    s.leaf_len = (int*)(base + o); o += sizeof(int) * nleaf;
+    s.fl = (uint8_t*)(base + o); o += align_up(N, 16);
+    return o;
+}
+
+__device__ __forceinline__ uint32_t bm_get(const uint32_t* bm, int wpr, int x, int y) {
+    return (bm[x * wpr + (y >> 5)] >> (y & 31)) & 1u;
+}
+__device__ __forceinline__ void bm_set(uint32_t* bm, int wpr, int x, int y) {
+    atomicOr(&bm[x * wpr + (y >> 5)], 1u << (y & 31));
+}
+__device__ __forceinline__ void bm_clear(uint32_t* bm, int wpr, int x, int y) {
+    atomicAnd(&bm[x * wpr + (y >> 5)], ~(1u << (y & 31)));
+}
+__device__ __forceinline__ uint32_t hash_cell(uint32_t c, int shift) { return (c * 0x9E3779B1u) >> shift; }
+
+__device__ __forceinline__ double box_lookup(const int* box, const double* tab, int step, int x, int y) {
+    int rx = x - box[0], ry = y - box[1];
+    if (rx < 0 || ry < 0 || rx >= box[2] || ry >= box[3]) return 0.0;
+    return __ldg(tab + ((size_t)step * box[2] + rx) * box[3] + ry);
+}
+
+// ---------------------------------------------------------------------------------------------
+// _get_state (evacuation_env.py:84-120) for every robot of the env + occupancy write-back.
+// centre of robot 0 = Map.robot_position (cx0, cy0); robots r >= 1 use Map.robot_positions[r]
+// (evacuation_env_multi.py:44-53).
+// ---------------------------------------------------------------------------------------------
+__device__ void gather_obs(const DevLayout& lay, const DevCfg& cfg, const Smem& sm, const int (*rob)[2], int cx0,
+                           int cy0, int fire_step, float* obs, double* obs64, int env) {
+    const int total = cfg.R * MQ_OBS_SIZE;
+    const int fs = min(fire_step, lay.n_fire_steps - 1);
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        int r = idx / MQ_OBS_SIZE, e = idx - r * MQ_OBS_SIZE;
+        int cell = e / MQ_OBS_CH, c = e - cell * MQ_OBS_CH;
+        int i = cell / MQ_OBS_WIN, j = cell - i * MQ_OBS_WIN;
+        int cx = r == 0 ? cx0 : rob[r][0], cy = r == 0 ? cy0 : rob[r][1];
+        int mx = cx + i - 5, my = cy + j - 5;
+        bool in_grid = mx >= 0 && mx <= lay.L + 1 && my >= 0 && my <= lay.W + 1;
+        uint32_t ci = in_grid ? (uint32_t)__ldg(lay.cellinfo + mx * lay.stride + my) : 2u;   // off-grid: blocked
+        double v;
+        switch (c) {
+            case 0: v = 0.0; break;                                                   // space/inf (quirk Q1)
+            case 1: v = (ci & 1u) ? (double)bm_get(sm.bm, lay.wpr, mx, my) : 0.0; break;
+            case 2: v = box_lookup(lay.int_box, lay.danger_int, fs, mx, my); break;
+            case 3: v = (ci & 2u) ? 1.0 : 0.0; break;
+            case 4: v = (ci & 4u) ? 1.0 : 0.0; break;
+            default: v = (i == 5 && j == 5) ? 1.0 : 0.0; break;
+        }
+        size_t o = (size_t)env * total + idx;
+        if (obs) obs[o] = (float)v;           // = state.astype(np.float32) at dqn_agent.py:109
+        if (obs64) obs64[o] = v;
+    }
+}
+
+__device__ void store_bitmap(const DevLayout& lay, const Smem& sm, uint32_t* g_rmap, int env) {
+    uint4* dst = reinterpret_cast<uint4*>(g_rmap + (size_t)env * lay.rmap_words);
+    const uint4* src = reinterpret_cast<const uint4*>(sm.bm);
+    for (int w = threadIdx.x; w < lay.rmap_words / 4; w += blockDim.x) dst[w] = src[w];
+}
+
+// ---------------------------------------------------------------------------------------------
+// EvacuationEnv.reset (evacuation_env.py:61-82) + People.__init__ spawn (people.py:185-194), CTA-wide.
+// sc = shared copy of the env scalars, rob = shared copy of robot_positions.
+// ---------------------------------------------------------------------------------------------
+__device__ void reset_env(const DevLayout& lay, const DevCfg& cfg, const DevState& st, const Smem& sm, int* sc,
+                          int (*rob)[2], const int16_t* inject, float* obs, double* obs64, int env) {
+    const int N = cfg.N, T = blockDim.x, tid = threadIdx.x;
+    for (int w = tid; w < (int)align_up(lay.rmap_words, 4); w += T) sm.bm[w] = 0u;
+    __syncthreads();
+    const uint32_t env_id = (uint32_t)(cfg.env_id_base + env);
+    const uint32_t episode = (uint32_t)sc[MQ_S_EPISODE];
+    const size_t base = (size_t)env * cfg.n_pad;
+    for (int i = tid; i < N; i += T) {
+        int x, y;
+        if (inject) {
+            x = inject[((size_t)env * N + i) * 2];
+            y = inject[((size_t)env * N + i) * 2 + 1];
+        } else {
+            for (uint32_t attempt = 0;; ++attempt) {   // randint(1, L-2), randint(1, W-2) until Check_Valid
+                uint4 w = philox4x32(env_id, episode, (uint32_t)i, STREAM_SPAWN + (attempt >> 1), cfg.seed);
+                uint32_t wx = (attempt & 1) ? w.z : w.x, wy = (attempt & 1) ? w.w : w.y;
+                x = 1 + (int)__umulhi(wx, (uint32_t)(lay.L - 2));
+                y = 1 + (int)__umulhi(wy, (uint32_t)(lay.W - 2));
+                if (__ldg(lay.cellinfo + x * lay.stride + y) & 1u) break;
+            }
+        }
+        st.pos[base + i] = (uint32_t)x | ((uint32_t)y << 16);
+        st.health[base + i] = 100.0;      // people.py:19
+        st.acc[base + i] = 0.0;           // people.py:22
+        st.flags[base + i] = 0;
+        bm_set(sm.bm, lay.wpr, x, y);     // rmap[x][y] = 1, duplicates allowed (quirk Q2)
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (cfg.reset_robots) {           // evacuation_env_multi.py:35-36
+            for (int r = 0; r < cfg.R; ++r) { rob[r][0] = lay.robot_start[r][0]; rob[r][1] = lay.robot_start[r][1]; }
+            sc[MQ_S_ROBOT_POS_X] = rob[0][0]; sc[MQ_S_ROBOT_POS_Y] = rob[0][1];
+        } else {                          // evacuation_env.py:64 — robot_positions untouched (quirk Q7)
+            sc[MQ_S_ROBOT_POS_X] = lay.reset_center[0]; sc[MQ_S_ROBOT_POS_Y] = lay.reset_center[1];
+        }
+        if (cfg.reset_fire) sc[MQ_S_FIRE_STEP] = 0;
+        sc[MQ_S_CUR_STEP] = 0; sc[MQ_S_PREV_EVAC] = 0; sc[MQ_S_PREV_DEAD] = 0;
+        sc[MQ_S_EVAC] = 0; sc[MQ_S_DEAD] = 0;
+        sc[MQ_S_EPISODE] = (int)(episode + 1);
+    }
+    __syncthreads();
+    if (tid < MQ_ENV_SCALARS) st.scalars[(size_t)env * MQ_ENV_SCALARS + tid] = sc[tid];
+    if (tid < MAXR * 2) st.robots[(size_t)env * MAXR * 2 + tid] = rob[tid >> 1][tid & 1];
+    store_bitmap(lay, sm, st.rmap, env);
+    gather_obs(lay, cfg, sm, rob, sc[MQ_S_ROBOT_POS_X], sc[MQ_S_ROBOT_POS_Y], sc[MQ_S_FIRE_STEP], obs, obs64, env);
+}
+
+__global__ void __launch_bounds__(256)
+env_reset_kernel(DevLayout lay, DevCfg cfg, DevState st, const uint8_t* env_mask, const int16_t* inject, float* obs,
+                 double* obs64) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int env = blockIdx.x;
+    if (env_mask && !env_mask[env]) return;
+    Smem sm;
+    carve(sm, smem_raw, cfg.N, cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
+    __shared__ int sc[MQ_ENV_SCALARS];
+    __shared__ int rob[MAXR][2];
+    if (threadIdx.x < MQ_ENV_SCALARS) sc[threadIdx.x] = st.scalars[(size_t)env * MQ_ENV_SCALARS + threadIdx.x];
+    if (threadIdx.x < MAXR * 2) rob[threadIdx.x >> 1][threadIdx.x & 1] = st.robots[(size_t)env * MAXR * 2 + threadIdx.x];
+    __syncthreads();
+    reset_env(lay, cfg, st, sm, sc, rob, inject, obs, obs64, env);
+}
+
+// numpy pairwise summation tree (np.mean at evacuation_env.py:228): leaves are blocks of <= 128 elements
+// summed with 8 interleaved accumulators, inner nodes split at n/2 rounded down to a multiple of 8.
+__device__ int enumerate_leaves(int n, int* off, int* len) {
+    int so[24], sn[24], sp = 0, nl = 0;
+    so[0] = 0; sn[0] = n; sp = 1;
+    while (sp) {
+        --sp;
+        int o = so[sp], m = sn[sp];
+        if (m <= 128) { off[nl] = o; len[nl] = m; ++nl; }
+        else {
+            int n2 = m / 2; n2 -= n2 % 8;
+            so[sp] = o + n2; sn[sp] = m - n2; ++sp;     // right, popped after
+            so[sp] = o; sn[sp] = n2; ++sp;              // left, popped first
+        }
+    }
+    return nl;
+}
+__device__ double combine_leaves(int n, const double* leaf_sum) {
+    int sn[40]; signed char sk[40]; double val[24];
+    int sp = 0, vp = 0, next = 0;
+    sn[0] = n; sk[0] = 0; sp = 1;
+    while (sp) {
+        --sp;
+        int m = sn[sp];
+        if (sk[sp]) { double b = val[--vp]; double a = val[--vp]; val[vp++] = a + b; }
+        else if (m <= 128) val[vp++] = leaf_sum[next++];
+        else {
+            int n2 = m / 2; n2 -= n2 % 8;
+            sk[sp] = 1; ++sp;
+            sn[sp] = m - n2; sk[sp] = 0; ++sp;
+            sn[sp] = n2; sk[sp] = 0; ++sp;
+        }
+    }
+    return val[0];
+}
+// one leaf by a group of 8 lanes (lane g = accumulator r[g]); result valid in group lane 0
+__device__ double leaf_sum8(const double* a, int n, int g, uint32_t gmask) {
+    if (n < 8) {
+        double res = 0.;
+        if (g == 0) for (int i = 0; i < n; ++i) res += a[i];
+        return res;
+    }
+    double r = a[g];
+    int main_end = n - (n % 8);
+    for (int i = 8; i < main_end; i += 8) r += a[i + g];
+    double r1 = r + __shfl_down_sync(gmask, r, 1, 8);       // lanes 0,2,4,6: r[g]+r[g+1]
+    double r2 = r1 + __shfl_down_sync(gmask, r1, 2, 8);     // lanes 0,4: (r0+r1)+(r2+r3), (r4+r5)+(r6+r7)
+    double res = r2 + __shfl_down_sync(gmask, r2, 4, 8);    // lane 0
+    if (g == 0) for (int i = main_end; i < n; ++i) res += a[i];
+    return res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The fused step.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ actions, float* obs, double* obs64,
+                double* reward_out, uint8_t* done_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem sm;
+    carve(sm, smem_raw, cfg.N, cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
+    __shared__ int sc[MQ_ENV_SCALARS];
+    __shared__ int rob[MAXR][2];
+    __shared__ int s_cnt[4];            // evacuated, dead, guidance in halves, remaining (live)
+    __shared__ int s_wtot[8];
+    __shared__ double s_dist_sum, s_total_health;
+    __shared__ int s_reset;
+
+    const int env = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int N = cfg.N, stride = lay.stride, wpr = lay.wpr;
+    const size_t base = (size_t)env * cfg.n_pad;
+    const uint32_t hmask = (uint32_t)cfg.hash_cap - 1u;
+
+    // ---- stage: scalars, robots, occupancy bitmap; clear the proposal table ------------------------
+    if (tid < MQ_ENV_SCALARS) sc[tid] = st.scalars[(size_t)env * MQ_ENV_SCALARS + tid];
+    if (tid < MAXR * 2) rob[tid >> 1][tid & 1] = st.robots[(size_t)env * MAXR * 2 + tid];
+    if (tid < 4) s_cnt[tid] = 0;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(st.rmap + (size_t)env * lay.rmap_words);
+        uint4* dst = reinterpret_cast<uint4*>(sm.bm);
+        for (int w = tid; w < lay.rmap_words / 4; w += T) dst[w] = src[w];
+    }
+    for (int h = tid; h < cfg.hash_cap; h += T) {
+        sm.hkey[h] = HEMPTY; sm.hmin[h] = 0xFFFFFFFFu; sm.hleave[h] = 0u; sm.hbest[h] = ~0ull;
+    }
+    __syncthreads();
+
+    // ---- Map.move_robot for every robot, in robot order (map.py:160-202; evacuation_env_multi.py:60-63) ----
+    if (tid == 0) {
+        for (int r = 0; r < cfg.R; ++r) {
+            int a = actions[(size_t)env * cfg.R + r];
+            if (a < 0 || a > 4) continue;                       // map.py:180-181 (returns before the re-alias)
+            int x = rob[r][0], y = rob[r][1], nx = x, ny = y;
+            if (a == 0) nx = x + 1; else if (a == 1) ny = y - 1; else if (a == 2) nx = x - 1; else if (a == 3) ny = y + 1;
+            bool ok = lay.robot_range[0] <= nx && nx <= lay.robot_range[1] && 0 <= ny && ny <= lay.W;
+            // Check_Valid (map.py:85-92): inside 1..L x 1..W and finite potential
+            ok = ok && nx >= 1 && nx <= lay.L && ny >= 1 && ny <= lay.W && (__ldg(lay.cellinfo + nx * stride + ny) & 1u);
+            if (ok) { rob[r][0] = nx; rob[r][1] = ny; }
+            if (r == 0) { sc[MQ_S_ROBOT_POS_X] = rob[0][0]; sc[MQ_S_ROBOT_POS_Y] = rob[0][1]; }   // map.py:200-201
+        }
+    }
+    __syncthreads();
+
+    const uint32_t env_id = (uint32_t)(cfg.env_id_base + env);
+    const uint32_t tick = (uint32_t)sc[MQ_S_TICK];
+    const int fire_step = min(sc[MQ_S_FIRE_STEP], lay.n_fire_steps - 1);
+    int rbx[MAXR], rby[MAXR];
+#pragma unroll
+    for (int r = 0; r < MAXR; ++r) { rbx[r] = rob[r < cfg.R ? r : 0][0]; rby[r] = rob[r < cfg.R ? r : 0][1]; }
+
+    // ---- phase 1 + 2 (people.py:203-230): health, speed, accumulator, proposal ---------------------
+    for (int i = tid; i < N; i += T) {
+        uint32_t p = st.pos[base + i];
+        uint32_t fl = st.flags[base + i];
+        double h = st.health[base + i];
+        uint32_t mv = 0;
+        if (!(fl & 3u)) {
+            const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
+            double a = st.acc[base + i];
+            const double danger = box_lookup(lay.ctr_box, lay.danger_ctr, fire_step, x, y);
+            uint4 w4 = make_uint4(0, 0, 0, 0);
+            bool have4 = false;
+            if (danger > 0.0) {                                   // Person.update_health (people.py:61-88)
+                w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
+                have4 = true;
+                const double u = u53(w4.x, w4.y);
+                double loss;
+                if (danger >= 0.8) loss = danger * 50.0 + (1.0 + (3.0 - 1.0) * u);
+                else if (danger >= 0.5) loss = danger * 40.0 + (0.8 + (2.0 - 0.8) * u);
+                else if (danger >= 0.2) loss = danger * 30.0 + (0.5 + (1.5 - 0.5) * u);
+                else loss = danger * 20.0 + (0.2 + (1.0 - 0.2) * u);
+                if (h < 50.0) loss *= 1.2;
+                h -= loss;
+                if (h <= 0.0) { h = 0.0; fl |= 2u; } else if (h <= 8.0) fl |= 2u;
+                h = fmax(0.0, fmin(h, 100.0));
+                st.health[base + i] = h;
+                if (fl & 2u) st.flags[base + i] = (uint8_t)fl;
+            }
+            if (!(fl & 2u)) {
+                // Person.update_state speed (people.py:38-44), then accumulator (people.py:216-220)
+                const double speed = (h < 20.0) ? 0.4 : 1.0 * (0.3 + 0.7 * (h / 100.0));
+                a += speed * 0.5;
+                if (a >= 1.0) {
+                    a -= 1.0;
+                    // People.find_best_direction (people.py:255-297)
+                    const double2* dp = reinterpret_cast<const double2*>(lay.dp5 + (size_t)(x * stride + y) * 8);
+                    int best = -1;
+                    double max_score = -INFINITY;
+#pragma unroll
+                    for (int pc = 0; pc < 4; ++pc) {
+                        const double2 d2v = __ldg(dp + pc);
+                        const double dpv[2] = {d2v.x, d2v.y};
+                        bool adm[2];
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const int d = pc * 2 + k;
+                            adm[k] = (dpv[k] > -INFINITY) && !bm_get(sm.bm, wpr, x + c_dx[d], y + c_dy[d]);
+                        }
+                        if (adm[0] || adm[1]) {
+                            const uint4 w = philox4x32(env_id, tick, (uint32_t)i, (uint32_t)pc, cfg.seed);
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                if (!adm[k]) continue;
+                                const int d = pc * 2 + k;
+                                const int nx = x + c_dx[d], ny = y + c_dy[d];
+                                int d2 = 0x7FFFFFFF;
+                                for (int r = 0; r < cfg.R; ++r) {
+                                    int ddx = nx - rbx[r], ddy = ny - rby[r];
+                                    // robots may sit far off-map (evaluate_strategies.py:83 sets [1000,1000])
+                                    int q = (abs(ddx) > 30000 || abs(ddy) > 30000) ? 0x7FFFFFFF : ddx * ddx + ddy * ddy;
+                                    d2 = min(d2, q);
+                                }
+                                const double eff = d2 < 25 ? c_repel[d2] : 0.0;
+                                const double u = k ? u53(w.z, w.w) : u53(w.x, w.y);
+                                const double noise = -0.1 + (0.1 - -0.1) * u;        // random.uniform(-0.1, 0.1)
+                                const double score = (dpv[k] + eff) + noise;           // people.py:287-291
+                                if (score > max_score) { max_score = score; best = d; }
+                            }
+                        }
+                    }
+                    if (best >= 0) {
+                        if (!have4) w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
+                        const uint32_t t = (uint32_t)((x + c_dx[best]) * stride + (y + c_dy[best]));
+                        uint32_t hh = hash_cell(t, cfg.hash_shift);
+                        for (;;) {                                 // move_plan[(new_x,new_y)] (people.py:228-230)
+                            uint32_t prev = atomicCAS(&sm.hkey[hh], HEMPTY, t);
+                            if (prev == HEMPTY || prev == t) break;
+                            hh = (hh + 1) & hmask;
+                        }
+                        atomicMin(&sm.hmin[hh], (uint32_t)i);
+                        atomicMin(&sm.hbest[hh], ((unsigned long long)w4.z << 32) | (unsigned long long)i);
+                        mv = (hh + 1u) | ((uint32_t)best << 24);
+                    }
+                }
+                st.acc[base + i] = a;
+            }
+        }
+        sm.pos[i] = p;
+        sm.fl[i] = (uint8_t)fl;
+        sm.mv[i] = mv;
+        sm.health[i] = (fl & 2u) ? 0.0 : h;          // summand of evacuation_env.py:245 (dead -> +0.0)
+    }
+    __syncthreads();
+
+    // ---- phase 4a: winners leave their old cell (people.py:239-246,301) ---------------------------------
+    for (int i = tid; i < N; i += T) {
+        uint32_t mv = sm.mv[i];
+        if (!mv) continue;
+        const uint32_t slot = (mv & 0xFFFFFFu) - 1u;
+        if ((uint32_t)sm.hbest[slot] != (uint32_t)i) continue;      // lost the shuffle: stays (people.py:248-249)
+        sm.mv[i] = mv | 0x80000000u;
+        const uint32_t key = sm.hmin[slot];
+        const uint32_t p = sm.pos[i];
+        const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
+        const uint32_t c_old = (uint32_t)(x * stride + y);
+        uint32_t hh = hash_cell(c_old, cfg.hash_shift);
+        bool found = false;
+        for (;;) {
+            uint32_t k = sm.hkey[hh];
+            if (k == HEMPTY) break;
+            if (k == c_old) { found = true; break; }
+            hh = (hh + 1) & hmask;
+        }
+        if (found) atomicMax(&sm.hleave[hh], key + 1u);     // old cell is somebody's target: order decides
+        else bm_clear(sm.bm, wpr, x, y);                    // rmap[old] = 0
+    }
+    __syncthreads();
+
+    // ---- phase 4b: winners enter their target (people.py:302-314) --------------------------------------
+    for (int i = tid; i < N; i += T) {
+        const uint32_t mv = sm.mv[i];
+        if (!(mv & 0x80000000u)) continue;
+        const uint32_t slot = (mv & 0xFFFFFFu) - 1u;
+        const int dir = (int)((mv >> 24) & 7u);
+        const uint32_t p = sm.pos[i];
+        const int nx = (int)(p & 0xFFFFu) + c_dx[dir], ny = (int)(p >> 16) + c_dy[dir];
+        const bool evac = (__ldg(lay.cellinfo + nx * stride + ny) & 8u) != 0;      // Map.checkSavefy (map.py:93-113)
+        if (sm.hmin[slot] + 1u > sm.hleave[slot] && !evac) bm_set(sm.bm, wpr, nx, ny);
+        else bm_clear(sm.bm, wpr, nx, ny);
+        const uint32_t np = (uint32_t)nx | ((uint32_t)ny << 16);
+        sm.pos[i] = np;
+        st.pos[base + i] = np;
+        if (evac) { uint8_t f = sm.fl[i] | 1u; sm.fl[i] = f; st.flags[base + i] = f; }
+    }
+    __syncthreads();
+
+    // ---- reward inputs (evacuation_env.py:174-233): counts, guidance, ordered list of distances --------
+    const int rpx = sc[MQ_S_ROBOT_POS_X], rpy = sc[MQ_S_ROBOT_POS_Y];
+    {
+        const int P = (N + T - 1) / T;
+        const int i0 = min(tid * P, N), i1 = min(i0 + P, N);
+        int live = 0, evac = 0, dead = 0, guid = 0;
+        for (int i = i0; i < i1; ++i) {
+            const uint32_t f = sm.fl[i];
+            evac += f & 1u; dead += (f >> 1) & 1u;
+            if (!(f & 3u)) ++live;
+        }
+        // exclusive block scan of `live`
+        int incl = live;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) s_wtot[warp] = incl;
+        __syncthreads();
+        int off = incl - live;
+        for (int w = 0; w < warp; ++w) off += s_wtot[w];
+        for (int i = i0; i < i1; ++i) {
+            const uint32_t f = sm.fl[i];
+            if (f & 3u) continue;
+            const uint32_t p = sm.pos[i];
+            const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
+            // 2*(x+.5-rx) is an odd integer: compare squared distances exactly (sqrt is monotone, thresholds exact)
+            const long long X = 2LL * x + 1 - 2LL * rpx, Y = 2LL * y + 1 - 2LL * rpy;
+            const long long q4 = X * X + Y * Y;                             // 4 * dist^2
+            if (q4 <= 100) {                                                // dist_to_robot <= 5 (:202)
+                const long long EX = 2LL * x + 1 - 2LL * lay.obs_exit[0], EY = 2LL * y + 1 - 2LL * lay.obs_exit[1];
+                const long long e4 = EX * EX + EY * EY;
+                guid += e4 > 1600 ? 4 : (e4 > 400 ? 3 : 2);                 // 2.0 / 1.5 / 1.0 (:207-212)
+                if (sm.health[i] < 80.0) guid += 2;                         // +1.0 (:215-216)
+            }
+            const double dx = ((double)x + 0.5) - (double)rpx, dy = ((double)y + 0.5) - (double)rpy;
+            sm.dist[off++] = sqrt(dx * dx + dy * dy);                       // np.linalg.norm (:228)
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            evac += __shfl_xor_sync(0xFFFFFFFFu, evac, o);
+            dead += __shfl_xor_sync(0xFFFFFFFFu, dead, o);
+            guid += __shfl_xor_sync(0xFFFFFFFFu, guid, o);
+            live += __shfl_xor_sync(0xFFFFFFFFu, live, o);
+        }
+        if (lane == 0) { atomicAdd(&s_cnt[0], evac); atomicAdd(&s_cnt[1], dead); atomicAdd(&s_cnt[2], guid); atomicAdd(&s_cnt[3], live); }
+    }
+    __syncthreads();
+
+    // fire models step (evacuation_env.py:138-142; fire_model.py:63-67) — observation uses the new step
+    const int new_fire = min(sc[MQ_S_FIRE_STEP] + 1, lay.n_fire_steps - 1);
+
+    // ---- order-dependent fp64 sums: warp 0 = np.mean tree, warp 1 lane 0 = sum() chain; rest: outputs ----
+    if (warp == 0) {
+        const int n = s_cnt[3];
+        int nl = 0;
+        if (lane == 0) nl = enumerate_leaves(n, sm.leaf_off, sm.leaf_len);
+        nl = __shfl_sync(0xFFFFFFFFu, nl, 0);
+        __syncwarp();
+        const int g = lane & 7, grp = lane >> 3;
+        const uint32_t gmask = 0xFFu << (grp * 8);
+        for (int l0 = 0; l0 < nl; l0 += 4) {
+            const int l = l0 + grp;
+            if (l < nl) {
+                double s = leaf_sum8(sm.dist + sm.leaf_off[l], sm.leaf_len[l], g, gmask);
+                if (g == 0) sm.leaf_sum[l] = s;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) s_dist_sum = combine_leaves(n, sm.leaf_sum);
+    } else if (warp == 1 && lane == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < N; ++i) tot += sm.health[i];       // left-to-right, dead contribute +0.0
+        s_total_health = tot;
+    }
+    store_bitmap(lay, sm, st.rmap, env);
+    gather_obs(lay, cfg, sm, rob, rpx, rpy, new_fire, obs, obs64, env);
+    __syncthreads();
+
+    // ---- _calculate_reward (evacuation_env.py:174-288), done (:150-157), scalars -----------------------
+    if (tid == 0) {
+        const int cur_evac = s_cnt[0], cur_dead = s_cnt[1], n_rem = s_cnt[3];
+        const int cur_step = sc[MQ_S_CUR_STEP];
+        const int remaining = N - cur_evac - cur_dead;
+        double reward = 0.0;
+        reward += (double)(cur_evac - sc[MQ_S_PREV_EVAC]) * cfg.evac_reward;
+        reward += (double)s_cnt[2] * 0.5;
+        if (remaining > 0 && n_rem > 0) {
+            const double avg = s_dist_sum / (double)n_rem;
+            double dr = 2.0 - fabs(avg - 8.0) * 0.2;
+            if (!(dr > 0.0)) dr = 0.0;
+            reward += dr;
+        }
+        if (remaining > 0) {
+            const double urgency = (double)remaining / (double)N;
+            const double time_penalty = -0.05 - (urgency * 0.1);
+            reward += time_penalty;
+        } else {
+            reward -= 0.02;
+        }
+        if (N - cur_dead > 0) {
+            const double avg_health = s_total_health / (double)(N - cur_dead);
+            reward += (avg_health - 90.0) * 0.05;
+        }
+        if (cur_evac == N) {
+            const int rem_steps = max(0, 300 - cur_step);
+            const double time_bonus = (double)rem_steps * 0.2;
+            const double final_avg = s_total_health / (double)N;      // nobody is dead here: same chain
+            const double health_bonus = (final_avg - 80.0) * 1.0;
+            reward += (100.0 + time_bonus) + health_bonus;
+        }
+        reward -= (double)(cur_dead - sc[MQ_S_PREV_DEAD]) * cfg.death_penalty;
+        reward -= (double)cur_dead * cfg.death_acc_penalty;
+        reward += (double)(N - cur_dead) * cfg.alive_bonus;
+        if (cur_step > 0) {
+            const double eff = (double)cur_evac / (double)cur_step;
+            if (eff > 0.1) reward += eff * 5.0;
+        }
+        const int done = (cur_evac + cur_dead == N) || (cur_step + 1 >= cfg.max_steps);
+        reward_out[env] = reward;
+        done_out[env] = (uint8_t)done;
+        sc[MQ_S_FIRE_STEP] = new_fire;
+        sc[MQ_S_CUR_STEP] = cur_step + 1;
+        sc[MQ_S_PREV_EVAC] = cur_evac; sc[MQ_S_PREV_DEAD] = cur_dead;
+        sc[MQ_S_EVAC] = cur_evac; sc[MQ_S_DEAD] = cur_dead;
+        sc[MQ_S_TICK] = (int)(tick + 1u);
+        s_reset = done && cfg.auto_reset;
+    }
+    __syncthreads();
+    if (s_reset) {
+        reset_env(lay, cfg, st, sm, sc, rob, nullptr, obs, obs64, env);
+    } else {
+        if (tid < MQ_ENV_SCALARS) st.scalars[(size_t)env * MQ_ENV_SCALARS + tid] = sc[tid];
+        if (tid < MAXR * 2) st.robots[(size_t)env * MAXR * 2 + tid] = rob[tid >> 1][tid & 1];
+    }
+}
+
+__global__ void unpack_rmap_kernel(DevLayout lay, const uint32_t* __restrict__ rmap, uint8_t* __restrict__ out,
+                                   long long total) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    long long env = idx / lay.G;
+    int c = (int)(idx - env * lay.G);
+    int x = c / lay.stride, y = c - x * lay.stride;
+    out[idx] = (uint8_t)((rmap[env * lay.rmap_words + x * lay.wpr + (y >> 5)] >> (y & 31)) & 1u);
+}
+
+}  // namespace mq
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+struct mq_env {
+    mq::DevLayout lay;
+    mq::DevCfg cfg;
+    mq::DevState st;
+    void* d_dp5 = nullptr; void* d_cellinfo = nullptr; void* d_ctr = nullptr; void* d_int = nullptr;
+    int threads = 256;
+    size_t smem = 0;
+    int64_t launches = 0;
+};
+
+static int round_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+extern "C" int mq_env_state_sizes(const mq_env_cfg* cfg, const mq_layout* layout, int64_t* n_pad, int64_t* rmap_words) {
+    MQ_REQUIRE(cfg && layout, "mq_env_state_sizes: null argument");
+    if (n_pad) *n_pad = (cfg->n_people + 15) / 16 * 16;
+    if (rmap_words) {
+        int64_t wpr = (layout->W + 2 + 31) / 32;
+        *rmap_words = ((int64_t)(layout->L + 2) * wpr + 3) / 4 * 4;
+    }
+    return MQ_OK;
+}
+
+extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layout* layout, const mq_env_state* state) {
+    MQ_REQUIRE(out && cfg && layout && state, "mq_env_create: null argument");
+    MQ_REQUIRE(cfg->n_envs > 0 && cfg->n_people > 0, "mq_env_create: n_envs and n_people must be positive");
+    MQ_REQUIRE(cfg->n_robots >= 1 && cfg->n_robots <= MQ_MAX_ROBOTS, "mq_env_create: n_robots must be in 1..%d", MQ_MAX_ROBOTS);
+    MQ_REQUIRE(layout->L >= 3 && layout->W >= 3 && layout->L <= 32000 && layout->W <= 32000, "mq_env_create: bad grid size");
+    MQ_REQUIRE(layout->dp5 && layout->cellinfo && layout->danger_ctr && layout->danger_int, "mq_env_create: layout tables missing");
+    MQ_REQUIRE(state->pos && state->health && state->acc && state->flags && state->rmap && state->robots && state->scalars,
+               "mq_env_create: state buffers missing");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return mq::fail(MQ_ERR_CUDA, "mq_env_create: no CUDA device (this build has no CPU fallback)");
+    MQ_CUDA(cudaSetDevice(cfg->device));
+
+    mq_env* e = new (std::nothrow) mq_env();
+    if (!e) return mq::fail(MQ_ERR_ALLOC, "mq_env_create: out of host memory");
+    mq::DevLayout& l = e->lay;
+    l.L = layout->L; l.W = layout->W; l.stride = layout->W + 2; l.G = (layout->L + 2) * (layout->W + 2);
+    l.wpr = (layout->W + 2 + 31) / 32;
+    l.rmap_words = ((layout->L + 2) * l.wpr + 3) / 4 * 4;
+    l.n_fire_steps = layout->n_fire_steps;
+    memcpy(l.ctr_box, layout->ctr_box, sizeof(l.ctr_box));
+    memcpy(l.int_box, layout->int_box, sizeof(l.int_box));
+    memcpy(l.robot_range, layout->robot_range, sizeof(l.robot_range));
+    memcpy(l.robot_start, layout->robot_start, sizeof(l.robot_start));
+    memcpy(l.reset_center, layout->reset_obs_center, sizeof(l.reset_center));
+    memcpy(l.obs_exit, layout->obs_exit, sizeof(l.obs_exit));
+
+    const size_t n_dp5 = (size_t)l.G * 8 * sizeof(double);
+    const size_t n_ctr = (size_t)l.n_fire_steps * l.ctr_box[2] * l.ctr_box[3] * sizeof(double);
+    const size_t n_int = (size_t)l.n_fire_steps * l.int_box[2] * l.int_box[3] * sizeof(double);
+    cudaError_t ce = cudaSuccess;
+    if ((ce = cudaMalloc(&e->d_dp5, n_dp5)) == cudaSuccess && (ce = cudaMalloc(&e->d_cellinfo, l.G)) == cudaSuccess &&
+        (ce = cudaMalloc(&e->d_ctr, n_ctr)) == cudaSuccess && (ce = cudaMalloc(&e->d_int, n_int)) == cudaSuccess &&
+        (ce = cudaMemcpy(e->d_dp5, layout->dp5, n_dp5, cudaMemcpyHostToDevice)) == cudaSuccess &&
+        (ce = cudaMemcpy(e->d_cellinfo, layout->cellinfo, l.G, cudaMemcpyHostToDevice)) == cudaSuccess &&
+        (ce = cudaMemcpy(e->d_ctr, layout->danger_ctr, n_ctr, cudaMemcpyHostToDevice)) == cudaSuccess &&
+        (ce = cudaMemcpy(e->d_int, layout->danger_int, n_int, cudaMemcpyHostToDevice)) == cudaSuccess) {
+    }
+    if (ce != cudaSuccess) {
+        mq_env_destroy(e);
+        return mq::fail(MQ_ERR_CUDA, "mq_env_create: uploading layout tables failed: %s", cudaGetErrorString(ce));
+    }
+    l.dp5 = (const double*)e->d_dp5; l.cellinfo = (const uint8_t*)e->d_cellinfo;
+    l.danger_ctr = (const double*)e->d_ctr; l.danger_int = (const double*)e->d_int;
+
+    double repel[25];
+    for (int d2 = 0; d2 < 25; ++d2) repel[d2] = -20.0 / (std::sqrt((double)d2) + 0.1);    // people.py:94,284
+    ce = cudaMemcpyToSymbol(mq::c_repel, repel, sizeof(repel));
+    if (ce != cudaSuccess) { mq_env_destroy(e); return mq::fail(MQ_ERR_CUDA, "mq_env_create: c_repel upload: %s", cudaGetErrorString(ce)); }
+
+    mq::DevCfg& c = e->cfg;
+    c.n_envs = cfg->n_envs; c.N = cfg->n_people; c.n_pad = (cfg->n_people + 15) / 16 * 16; c.R = cfg->n_robots;
+    c.seed = cfg->seed; c.env_id_base = cfg->env_id_base; c.max_steps = cfg->max_steps;
+    c.reset_robots = cfg->reset_robots; c.reset_fire = cfg->reset_fire; c.auto_reset = cfg->auto_reset;
+    c.hash_cap = round_pow2(2 * c.N < 64 ? 64 : 2 * c.N);
+    int lg = 0; while ((1 << lg) < c.hash_cap) ++lg;
+    c.hash_shift = 32 - lg;
+    c.n_leaf_max = c.N / 64 + 4;
+    c.evac_reward = cfg->evac_reward; c.death_penalty = cfg->death_penalty;
+    c.death_acc_penalty = cfg->death_acc_penalty; c.alive_bonus = cfg->alive_bonus;
+    e->st = {state->pos, state->health, state->acc, state->flags, state->rmap, state->robots, state->scalars};
+
+    e->threads = (c.N + 31) / 32 * 32;
+    if (e->threads < 64) e->threads = 64;
+    if (e->threads > 256) e->threads = 256;
+    mq::Smem tmp;
+    e->smem = mq::carve(tmp, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max);
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+    if ((int)e->smem + 1024 > max_smem) {
+        size_t need = e->smem;
+        mq_env_destroy(e);
+        return mq::fail(MQ_ERR_UNSUPPORTED,
+                        "mq_env_create: env of %d people on a %dx%d grid needs %zu B of shared memory per CTA (limit %d); "
+                        "the tiled large-env kernel is not built yet", cfg->n_people, layout->L, layout->W, need, max_smem);
+    }
+    if ((ce = cudaFuncSetAttribute(mq::env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem)) != cudaSuccess ||
+        (ce = cudaFuncSetAttribute(mq::env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem)) != cudaSuccess) {
+        mq_env_destroy(e);
+        return mq::fail(MQ_ERR_CUDA, "mq_env_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+    }
+    *out = e;
+    return MQ_OK;
+}
+
+extern "C" int mq_env_destroy(mq_env* e) {
+    if (!e) return MQ_OK;
+    cudaFree(e->d_dp5); cudaFree(e->d_cellinfo); cudaFree(e->d_ctr); cudaFree(e->d_int);
+    delete e;
+    return MQ_OK;
+}
+
+extern "C" int mq_env_set_reward_coefs(mq_env* e, double evac_reward, double death_penalty, double death_acc_penalty,
+                                       double alive_bonus) {
+    MQ_REQUIRE(e, "mq_env_set_reward_coefs: null handle");
+    e->cfg.evac_reward = evac_reward; e->cfg.death_penalty = death_penalty;
+    e->cfg.death_acc_penalty = death_acc_penalty; e->cfg.alive_bonus = alive_bonus;
+    return MQ_OK;
+}
+
+extern "C" int mq_env_reset(mq_env* e, const uint8_t* env_mask, const int16_t* inject_spawn, float* obs_out,
+                            double* obs64_out, void* stream) {
+    MQ_REQUIRE(e, "mq_env_reset: null handle");
+    mq::env_reset_kernel<<<e->cfg.n_envs, e->threads, e->smem, (cudaStream_t)stream>>>(e->lay, e->cfg, e->st, env_mask,
+                                                                                       inject_spawn, obs_out, obs64_out);
+    MQ_CUDA(cudaGetLastError());
+    e->launches += 1;
+    return MQ_OK;
+}
+
+extern "C" int mq_env_step(mq_env* e, const int32_t* actions, float* obs_out, double* obs64_out, double* reward_out,
+                           uint8_t* done_out, void* stream) {
+    MQ_REQUIRE(e && actions && reward_out && done_out, "mq_env_step: null argument");
+    mq::env_step_kernel<<<e->cfg.n_envs, e->threads, e->smem, (cudaStream_t)stream>>>(e->lay, e->cfg, e->st, actions, obs_out,
+                                                                                      obs64_out, reward_out, done_out);
+    MQ_CUDA(cudaGetLastError());
+    e->launches += 1;
+    return MQ_OK;
+}
+
+extern "C" int mq_env_unpack_rmap(mq_env* e, uint8_t* rmap_out, void* stream) {
+    MQ_REQUIRE(e && rmap_out, "mq_env_unpack_rmap: null argument");
+    long long total = (long long)e->cfg.n_envs * e->lay.G;
+    int blocks = (int)((total + 255) / 256);
+    mq::unpack_rmap_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(e->lay, e->st.rmap, rmap_out, total);
+    MQ_CUDA(cudaGetLastError());
+    e->launches += 1;
+    return MQ_OK;
+}
+
+extern "C" int64_t mq_env_launch_count(const mq_env* e) { return e ? e->launches : 0; }

@@ -1,0 +1,174 @@
+"""VecEvacuationEnv — n_envs independent Louvre_Evacuation instances stepped by one fused CUDA launch.
+
+Host-side mirror of the reference's env surface (reference Louvre_Evacuation/envs/evacuation_env.py:
+``reset()`` :61, ``step()`` :122; evacuation_env_multi.py for n_robots = 2), batched: actions in,
+(obs, reward, done) out as device tensors.  All arithmetic happens in libmarl_b200.so
+(csrc/env.cu); this file only owns the tensors and the handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..layout import MAX_ROBOTS, Layout
+
+# scalars layout (include/marl_b200.h)
+S_FIRE_STEP, S_CUR_STEP, S_PREV_EVAC, S_PREV_DEAD, S_EPISODE, S_TICK, S_EVAC, S_DEAD, S_RPX, S_RPY = range(10)
+
+
+def _require_cuda(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda" or not torch.cuda.is_available():
+        raise RuntimeError("dqn_marl_b200 runs on CUDA devices only (sm_100a); there is no CPU fallback. "
+                           f"Requested device: {device!r}, torch.cuda.is_available()={torch.cuda.is_available()}")
+    return dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device())
+
+
+class VecEvacuationEnv:
+    """Batch of environments sharing one ``Layout``.
+
+    strict_reference=True keeps the reference's reset quirks (fire step survives reset — Q6; the
+    single-robot env keeps its robot cell and only centres the reset observation at (15,15) — Q7).
+    strict_reference=False restarts fire and robots at every reset (what a fresh training run wants).
+    """
+
+    def __init__(self, layout: Layout, n_envs: int, num_people: int = 150, device="cuda", seed: int = 0,
+                 env_id_base: int = 0, strict_reference: bool = True, auto_reset: bool = True,
+                 max_steps: int = 1200, reward_coefs=(50.0, 200.0, 0.5, 1.0)):
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        self.layout = layout
+        self.n_envs, self.num_people, self.n_robots = int(n_envs), int(num_people), layout.n_robots
+        self.seed = int(seed)
+        self.strict_reference = bool(strict_reference)
+        L, W = layout.L, layout.W
+
+        lay = _lib.MqLayout()
+        lay.L, lay.W, lay.n_fire_steps = L, W, layout.danger_ctr.shape[0]
+        lay.ctr_box[:] = layout.ctr_box
+        lay.int_box[:] = layout.int_box
+        lay.robot_range[:] = layout.robot_range
+        for r in range(MAX_ROBOTS):
+            s = layout.robot_starts[min(r, len(layout.robot_starts) - 1)]
+            lay.robot_start[r][0], lay.robot_start[r][1] = int(s[0]), int(s[1])
+        lay.reset_obs_center[:] = layout.reset_obs_center
+        lay.obs_exit[:] = layout.obs_exit
+        self._keep = [np.ascontiguousarray(layout.dp5, dtype=np.float64),
+                      np.ascontiguousarray(layout.cellinfo, dtype=np.uint8),
+                      np.ascontiguousarray(layout.danger_ctr, dtype=np.float64),
+                      np.ascontiguousarray(layout.danger_int, dtype=np.float64)]
+        lay.dp5, lay.cellinfo, lay.danger_ctr, lay.danger_int = [a.ctypes.data for a in self._keep]
+
+        cfg = _lib.MqEnvCfg()
+        cfg.n_envs, cfg.n_people, cfg.n_robots = self.n_envs, self.num_people, self.n_robots
+        cfg.device = self.device.index
+        cfg.seed, cfg.env_id_base, cfg.max_steps = self.seed, int(env_id_base), int(max_steps)
+        if strict_reference:
+            cfg.reset_robots = 0 if self.n_robots == 1 else 1     # evacuation_env.py:64 vs evacuation_env_multi.py:35
+            cfg.reset_fire = 0
+        else:
+            cfg.reset_robots, cfg.reset_fire = 1, 1
+        cfg.auto_reset = int(auto_reset)
+        cfg.evac_reward, cfg.death_penalty, cfg.death_acc_penalty, cfg.alive_bonus = [float(v) for v in reward_coefs]
+
+        n_pad, words = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.mq_env_state_sizes(C.byref(cfg), C.byref(lay), C.byref(n_pad), C.byref(words)), "mq_env_state_sizes")
+        self.n_pad, self.rmap_words = n_pad.value, words.value
+        E, dev = self.n_envs, self.device
+        with torch.cuda.device(dev):
+            self.pos = torch.zeros((E, self.n_pad), dtype=torch.int32, device=dev)
+            self.health = torch.zeros((E, self.n_pad), dtype=torch.float64, device=dev)
+            self.acc = torch.zeros((E, self.n_pad), dtype=torch.float64, device=dev)
+            self.flags = torch.zeros((E, self.n_pad), dtype=torch.uint8, device=dev)
+            self.rmap = torch.zeros((E, self.rmap_words), dtype=torch.int32, device=dev)
+            self.robots = torch.zeros((E, MAX_ROBOTS, 2), dtype=torch.int32, device=dev)
+            self.scalars = torch.zeros((E, _lib.MQ_ENV_SCALARS), dtype=torch.int32, device=dev)
+            starts = torch.tensor([[int(v) for v in layout.robot_starts[min(r, self.n_robots - 1)]] for r in range(MAX_ROBOTS)],
+                                  dtype=torch.int32, device=dev)
+            self.robots[:] = starts                                   # map.py:76-78
+            self.scalars[:, S_RPX] = int(layout.robot_starts[0][0])
+            self.scalars[:, S_RPY] = int(layout.robot_starts[0][1])
+            self.obs = torch.zeros((E, self.n_robots, 11, 11, 6), dtype=torch.float32, device=dev)
+            self.reward = torch.zeros((E,), dtype=torch.float64, device=dev)
+            self.done = torch.zeros((E,), dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize(dev)
+        st = _lib.MqEnvState(*[_lib.ptr(t) for t in (self.pos, self.health, self.acc, self.flags, self.rmap,
+                                                    self.robots, self.scalars)])
+        h = C.c_void_p()
+        _lib.check(self.lib.mq_env_create(C.byref(h), C.byref(cfg), C.byref(lay), C.byref(st)), "mq_env_create")
+        self._h = h
+
+    # ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mq_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_reward_coefs(self, evac_reward, death_penalty, death_acc_penalty, alive_bonus):
+        """EvacuationEnv.EVAC_REWARD etc. are class attributes mutated at runtime (overnight_experiments.py:69-70)."""
+        _lib.check(self.lib.mq_env_set_reward_coefs(self._h, evac_reward, death_penalty, death_acc_penalty, alive_bonus),
+                   "mq_env_set_reward_coefs")
+
+    def reset(self, env_mask: Optional[torch.Tensor] = None, inject_spawn: Optional[torch.Tensor] = None,
+              obs64: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """EvacuationEnv.reset (evacuation_env.py:61-82) for all (or masked) envs -> obs (E, R, 11, 11, 6) f32."""
+        if env_mask is not None:
+            env_mask = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        if inject_spawn is not None:
+            inject_spawn = inject_spawn.to(device=self.device, dtype=torch.int16).contiguous()
+            assert inject_spawn.shape == (self.n_envs, self.num_people, 2)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mq_env_reset(self._h, _lib.ptr(env_mask), _lib.ptr(inject_spawn), _lib.ptr(self.obs),
+                                             _lib.ptr(obs64), self._stream()), "mq_env_reset")
+        return self.obs
+
+    def step(self, actions: torch.Tensor, obs64: Optional[torch.Tensor] = None):
+        """EvacuationEnv.step (evacuation_env.py:122-172) for every env.  actions: int (E, R) or (E,) on device.
+        Returns (obs f32 (E,R,11,11,6), reward f64 (E,), done u8 (E,)) — views of internal buffers that the next
+        call overwrites."""
+        a = actions.to(device=self.device, dtype=torch.int32).reshape(self.n_envs, self.n_robots).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mq_env_step(self._h, _lib.ptr(a), _lib.ptr(self.obs), _lib.ptr(obs64), _lib.ptr(self.reward),
+                                            _lib.ptr(self.done), self._stream()), "mq_env_step")
+        return self.obs, self.reward, self.done
+
+    def step_into(self, actions_i32: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor):
+        """Zero-overhead variant for benchmarks / trainers: caller-owned, correctly typed device tensors."""
+        _lib.check(self.lib.mq_env_step(self._h, _lib.ptr(actions_i32), _lib.ptr(obs), None, _lib.ptr(reward), _lib.ptr(done),
+                                        self._stream()), "mq_env_step")
+
+    def rmap_bytes(self) -> torch.Tensor:
+        """People.rmap of every env as uint8 (E, L+2, W+2)."""
+        out = torch.empty((self.n_envs, self.layout.L + 2, self.layout.W + 2), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mq_env_unpack_rmap(self._h, _lib.ptr(out), self._stream()), "mq_env_unpack_rmap")
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mq_env_launch_count(self._h))
+
+    # ------------------------------------------------------------------
+    def snapshot(self, env: int = 0) -> dict:
+        """Host copy of one env's state in the layout of the golden frames (tests / single-env facade)."""
+        N = self.num_people
+        pos = self.pos[env, :N].cpu().numpy().view(np.uint32)
+        sc = self.scalars[env].cpu().numpy()
+        return dict(px=(pos & 0xFFFF).astype(np.int16), py=(pos >> 16).astype(np.int16),
+                    health=self.health[env, :N].cpu().numpy(), acc=self.acc[env, :N].cpu().numpy(),
+                    flags=self.flags[env, :N].cpu().numpy(), rmap=self.rmap_bytes()[env].cpu().numpy(),
+                    robots=self.robots[env, :self.n_robots].cpu().numpy().astype(np.int16),
+                    fire_step=np.int32(sc[S_FIRE_STEP]), cur_step=np.int32(sc[S_CUR_STEP]), scalars=sc)

@@ -1,0 +1,248 @@
+/* marl_b200.h — C-ABI of libmarl_b200.so
+ *
+ * Drop-in boundary of the B200-native DQN-MARL hot path.  The reference
+ * (LX-530/DQN-MARL) is pure Python and has no FFI of its own: the boundary its
+ * runners use is the Python class surface
+ *     EvacuationEnv.reset()/step()           Louvre_Evacuation/envs/evacuation_env.py:61,122
+ *     EvacuationEnvMulti.reset()/step()      Louvre_Evacuation/envs/evacuation_env_multi.py:31,55
+ *     DQNAgent.act()/remember()/learn()      Louvre_Evacuation/agents/dqn_agent.py:97,101,126
+ *     DQNAgent.update_target_network()       Louvre_Evacuation/agents/dqn_agent.py:170
+ * The Python mirror of those classes lives in dqn_marl_b200/{envs,agents}; every
+ * entry point below is what that mirror binds (ctypes) and cites the reference
+ * code it replaces.  INTEGRATION.md shows the binding stub.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked `dev` is a CUDA device pointer
+ *     owned by the CALLER (PyTorch tensors), `host` pointers are host memory;
+ *   - all GPU work is enqueued on the caller's stream (`stream` is a
+ *     cudaStream_t passed as void*), the library never synchronises on its own
+ *     unless the function is documented as host-returning;
+ *   - return 0 on success, negative mq_status on failure; mq_last_error() gives
+ *     a thread-local message;
+ *   - no CPU fallback: every compute entry point fails with MQ_ERR_CUDA when no
+ *     device is usable.
+ */
+#ifndef MARL_B200_H
+#define MARL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MQ_ABI_VERSION 1
+#define MQ_MAX_ROBOTS 4
+#define MQ_OBS_WIN 11                          /* evacuation_env.py:56  state_size = (11, 11, 6) */
+#define MQ_OBS_CH 6
+#define MQ_OBS_SIZE (MQ_OBS_WIN * MQ_OBS_WIN * MQ_OBS_CH)   /* 726 */
+#define MQ_N_ACTIONS 5                         /* evacuation_env.py:57 */
+
+typedef enum mq_status {
+    MQ_OK = 0,
+    MQ_ERR_ARG = -1,
+    MQ_ERR_CUDA = -2,
+    MQ_ERR_ALLOC = -3,
+    MQ_ERR_UNSUPPORTED = -4
+} mq_status;
+
+const char* mq_last_error(void);
+int mq_abi_version(void);
+
+/* ------------------------------------------------------------------------
+ * Static floor field (host, init time).  Replaces Map.Init_Potential
+ * (map.py:127-148): 8-connected Dijkstra from the exits, step cost 1.0 / 1.4,
+ * start value 1, then += add_term (200*danger^2 at fire step 0) on reached cells.
+ *   wall      host u8  [(L+2)*(W+2)]  1 = inf before the search (map.py:44-57,66-71)
+ *   exits     host i32 [n_exits][2]
+ *   add_term  host f64 [(L+2)*(W+2)]
+ *   space_out host f64 [(L+2)*(W+2)]  inf where unreached
+ * ---------------------------------------------------------------------- */
+int mq_floor_field(int32_t L, int32_t W, const uint8_t* wall, const int32_t* exits, int32_t n_exits,
+                   const double* add_term, double* space_out);
+
+/* ------------------------------------------------------------------------
+ * Layout tables (host pointers; copied to the device by mq_env_create).
+ * Cell index = x*(W+2)+y, the reference indexes space[x][y] (map.py:44).
+ * ---------------------------------------------------------------------- */
+typedef struct mq_layout {
+    int32_t L, W;                       /* Map.Length / Map.Width (map.py:39-40) */
+    int32_t n_fire_steps;               /* FireSpreadModel max_steps + 1 = 181 (fire_model.py:213) */
+    int32_t ctr_box[4];                 /* x0, y0, w, h of danger_ctr */
+    int32_t int_box[4];                 /* x0, y0, w, h of danger_int (x0/y0 may be negative) */
+    int32_t robot_range[2];             /* map.py:75 */
+    int32_t robot_start[MQ_MAX_ROBOTS][2];   /* map.py:76 / evacuation_env_multi.py:27 */
+    int32_t reset_obs_center[2];        /* evacuation_env.py:64 */
+    int32_t obs_exit[2];                /* evacuation_env.py:194 exit_location used by the reward */
+    const double*  dp5;                 /* [G][8]  (space[c]-space[n])*5.0, -inf if n invalid (people.py:270,288) */
+    const uint8_t* cellinfo;            /* [G] bit0 Check_Valid(map.py:85) bit1 obs ch3 bit2 obs ch4 bit3 checkSavefy(map.py:93) */
+    const double*  danger_ctr;          /* [n_fire_steps][w][h]  get_max_danger at cell centres (people.py:205) */
+    const double*  danger_int;          /* [n_fire_steps][w][h]  get_max_danger at integer coords (evacuation_env.py:106) */
+} mq_layout;
+
+/* ------------------------------------------------------------------------
+ * Batched environment.  One handle = n_envs independent instances of
+ * EvacuationEnv (n_robots = 1) / EvacuationEnvMulti (n_robots = 2) on one GPU.
+ * ---------------------------------------------------------------------- */
+typedef struct mq_env_cfg {
+    int32_t  n_envs;
+    int32_t  n_people;                  /* evacuation_env.py:24 */
+    int32_t  n_robots;                  /* 1..MQ_MAX_ROBOTS */
+    int32_t  device;                    /* CUDA ordinal */
+    uint64_t seed;                      /* Philox key */
+    int32_t  env_id_base;               /* global id of env 0 (rank offset) -> Philox counter word 0 */
+    int32_t  max_steps;                 /* evacuation_env.py:27-30: 600 s / 0.5 s = 1200 */
+    int32_t  reset_robots;              /* 0: keep robot cells across reset, obs from reset_obs_center (quirk Q7,
+                                              EvacuationEnv); 1: robots return to robot_start (EvacuationEnvMulti) */
+    int32_t  reset_fire;                /* 0: fire step survives reset (quirk Q6, reference); 1: restart at 0 */
+    int32_t  auto_reset;                /* 1: an env that reports done is re-spawned inside the same step call and
+                                              obs_out holds the first observation of the new episode */
+    int32_t  reserved;
+    double   evac_reward;               /* evacuation_env.py:16-19 class attributes */
+    double   death_penalty;
+    double   death_acc_penalty;
+    double   alive_bonus;
+} mq_env_cfg;
+
+/* Device-resident state, allocated by the caller, SoA across envs.
+ * n_pad = n_people rounded up to 16; rmap_words = (L+2) * ceil((W+2)/32). */
+typedef struct mq_env_state {
+    uint32_t* pos;        /* dev [n_envs][n_pad]  cell x | y<<16  (Person.pos is always a cell centre, people.py:303) */
+    double*   health;     /* dev [n_envs][n_pad]  Person.health (people.py:19) */
+    double*   acc;        /* dev [n_envs][n_pad]  Person.move_accumulator (people.py:22) */
+    uint8_t*  flags;      /* dev [n_envs][n_pad]  bit0 savety, bit1 dead (people.py:18,20) */
+    uint32_t* rmap;       /* dev [n_envs][rmap_words]  People.rmap as 1 bit/cell, row x, bit y (people.py:162) */
+    int32_t*  robots;     /* dev [n_envs][MQ_MAX_ROBOTS][2]  Map.robot_positions (map.py:78) */
+    int32_t*  scalars;    /* dev [n_envs][MQ_ENV_SCALARS]  see enum below */
+} mq_env_state;
+
+enum {
+    MQ_S_FIRE_STEP = 0,   /* progressive_model.current_step (fire_model.py:63-67), never reset in the reference */
+    MQ_S_CUR_STEP = 1,    /* EvacuationEnv.current_step (evacuation_env.py:71,148) */
+    MQ_S_PREV_EVAC = 2,   /* evacuation_env.py:72,285 */
+    MQ_S_PREV_DEAD = 3,   /* evacuation_env.py:73,286 */
+    MQ_S_EPISODE = 4,     /* number of resets so far -> spawn draw key */
+    MQ_S_TICK = 5,        /* number of steps since creation -> step draw key */
+    MQ_S_EVAC = 6,        /* current evacuated count (info / get_performance_metrics) */
+    MQ_S_DEAD = 7,        /* current dead count */
+    MQ_S_ROBOT_POS_X = 8, /* Map.robot_position (map.py:76,200-201): aliases robots[0] except between a reset() */
+    MQ_S_ROBOT_POS_Y = 9, /*   and the next valid move_robot call (evacuation_env.py:64, quirk Q7) */
+    MQ_ENV_SCALARS = 16   /* 64 B per env; 10..15 reserved */
+};
+
+typedef struct mq_env mq_env;
+
+int mq_env_state_sizes(const mq_env_cfg* cfg, const mq_layout* layout, int64_t* n_pad, int64_t* rmap_words);
+int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layout* layout, const mq_env_state* state);
+int mq_env_destroy(mq_env* env);
+/* EvacuationEnv.EVAC_REWARD etc. are mutated at runtime by overnight_experiments.py:69-70 */
+int mq_env_set_reward_coefs(mq_env* env, double evac_reward, double death_penalty, double death_acc_penalty,
+                            double alive_bonus);
+
+/* EvacuationEnv.reset (evacuation_env.py:61-82) + People.__init__ spawn (people.py:185-194).
+ *   env_mask      dev u8 [n_envs] or NULL (= all): which envs to reset
+ *   inject_spawn  dev i16 [n_envs][n_people][2] or NULL: cells to use instead of keyed draws (test mode)
+ *   obs_out       dev f32 [n_envs][n_robots][11][11][6] or NULL
+ *   obs64_out     dev f64 same shape or NULL (single-env facade returns float64 like the reference) */
+int mq_env_reset(mq_env* env, const uint8_t* env_mask, const int16_t* inject_spawn, float* obs_out,
+                 double* obs64_out, void* stream);
+
+/* EvacuationEnv.step (evacuation_env.py:122-172): move_robot (map.py:160-202), People.run
+ * (people.py:196-253), fire update, _calculate_reward (:174-288), done (:155-157), _get_state (:84-120).
+ *   actions     dev i32 [n_envs][n_robots]; values outside 0..4 are ignored (map.py:180-181)
+ *   reward_out  dev f64 [n_envs]
+ *   done_out    dev u8  [n_envs] */
+int mq_env_step(mq_env* env, const int32_t* actions, float* obs_out, double* obs64_out, double* reward_out,
+                uint8_t* done_out, void* stream);
+
+/* People.rmap as bytes: dev u8 [n_envs][(L+2)*(W+2)] */
+int mq_env_unpack_rmap(mq_env* env, uint8_t* rmap_out, void* stream);
+/* number of kernels this handle has launched so far (bench.py gpu_launches) */
+int64_t mq_env_launch_count(const mq_env* env);
+
+#if 0 /* MQ_PENDING: declared for review, enabled when replay.cu / qnet.cu land */
+/* ------------------------------------------------------------------------
+ * Replay ring (device resident).  Replaces DQNAgent.memory = deque(maxlen)
+ * (dqn_agent.py:88-89), remember() (:97-99) and random.sample + stacking in
+ * learn() (:132-140).  Storage is caller-owned fp32 SoA.
+ * ---------------------------------------------------------------------- */
+typedef struct mq_replay_store {
+    float*   state;       /* dev [capacity][726] */
+    float*   next_state;  /* dev [capacity][726] */
+    int32_t* action;      /* dev [capacity] */
+    float*   reward;      /* dev [capacity] */
+    uint8_t* done;        /* dev [capacity] */
+} mq_replay_store;
+
+typedef struct mq_replay mq_replay;
+
+int mq_replay_create(mq_replay** out, int64_t capacity, int32_t device, const mq_replay_store* store);
+int mq_replay_destroy(mq_replay* rb);
+int64_t mq_replay_size(const mq_replay* rb);      /* len(agent.memory) */
+int64_t mq_replay_cursor(const mq_replay* rb);
+/* n transitions appended FIFO (oldest overwritten once full).  reward is the env's f64 reward,
+ * cast to f32 exactly as torch.FloatTensor(rewards) does at dqn_agent.py:138. */
+int mq_replay_push(mq_replay* rb, const float* state, const int32_t* action, const double* reward,
+                   const float* next_state, const uint8_t* done, int64_t n, void* stream);
+/* B transitions sampled uniformly WITHOUT replacement from the current contents.
+ *   inject_idx  dev i64 [B] logical indices (0 = oldest) or NULL -> keyed permutation (seed, draw_id) */
+int mq_replay_sample(mq_replay* rb, int64_t B, uint64_t seed, uint64_t draw_id, const int64_t* inject_idx,
+                     float* state, int64_t* action, float* reward, float* next_state, uint8_t* done,
+                     int64_t* idx_out, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Q-network (DQNNetwork, dqn_agent.py:15-61) and learner (DQNAgent.act/learn, :101-172).
+ * Parameters live in 12 caller-owned fp32 tensors in state_dict order:
+ * conv1.weight(32,6,3,3) conv1.bias conv2.weight(64,32,3,3) conv2.bias conv3.weight(128,64,3,3)
+ * conv3.bias fc1.weight(512,15488) fc1.bias fc2.weight(256,512) fc2.bias fc3.weight(5,256) fc3.bias
+ * ---------------------------------------------------------------------- */
+#define MQ_QNET_TENSORS 12
+#define MQ_QNET_PARAMS 8157093
+
+typedef struct mq_qnet_bind {
+    float* online[MQ_QNET_TENSORS];   /* dev */
+    float* target[MQ_QNET_TENSORS];   /* dev */
+    float* grad[MQ_QNET_TENSORS];     /* dev */
+    float* adam_m[MQ_QNET_TENSORS];   /* dev */
+    float* adam_v[MQ_QNET_TENSORS];   /* dev */
+} mq_qnet_bind;
+
+typedef struct mq_hparams {
+    float gamma;          /* dqn_agent.py:73 */
+    float lr;             /* :77 */
+    float beta1, beta2;   /* torch.optim.Adam defaults (:85) */
+    float adam_eps;
+    float clip_norm;      /* :158 */
+    int32_t huber;        /* 0 = MSE (:151, reference), 1 = Huber(delta=1) option of north_star */
+    int32_t adam_step;    /* t (1-based) of this update */
+} mq_hparams;
+
+typedef struct mq_qnet mq_qnet;
+
+int mq_qnet_create(mq_qnet** out, int32_t device, int64_t max_batch, const mq_qnet_bind* bind);
+int mq_qnet_destroy(mq_qnet* net);
+/* which: 0 online, 1 target.  obs dev f32 [B][11][11][6] (NHWC as the env writes it; the permute of
+ * dqn_agent.py:37-45 is folded into the conv1 loader).  drop_mask dev u8 [B][512] or NULL (= eval mode). */
+int mq_qnet_forward(mq_qnet* net, int32_t which, const float* obs, int64_t B, const uint8_t* drop_mask,
+                    float* q_out, void* stream);
+/* epsilon-greedy (dqn_agent.py:101-124) fused on top of the online forward: action = keyed random if
+ * u <= eps else first argmax.  q_out may be NULL. */
+int mq_qnet_act(mq_qnet* net, const float* obs, int64_t B, float eps, uint64_t seed, uint32_t env_id_base,
+                uint32_t tick, int32_t n_robots, int32_t* action_out, float* q_out, void* stream);
+/* One DQNAgent.learn() update (dqn_agent.py:143-160) on a sampled batch: TD target, loss, backward,
+ * (optional all-reduce hook between backward and clip), global-norm clip, Adam.  loss_out dev f32 [1]. */
+int mq_qnet_backward(mq_qnet* net, const float* state, const int64_t* action, const float* reward,
+                     const float* next_state, const uint8_t* done, int64_t B, const mq_hparams* hp,
+                     float* loss_out, void* stream);
+int mq_qnet_clip_adam(mq_qnet* net, const mq_hparams* hp, float grad_scale, float* gnorm_out, void* stream);
+/* update_target_network (dqn_agent.py:170-172): tau = 1 hard copy (reference); tau < 1 Polyak option */
+int mq_qnet_sync_target(mq_qnet* net, float tau, void* stream);
+int64_t mq_qnet_launch_count(const mq_qnet* net);
+
+#endif /* MQ_PENDING */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARL_B200_H */

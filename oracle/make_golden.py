@@ -1,0 +1,103 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):  python oracle/make_golden.py
+Each trajectory file holds F frames; frame 0 is the state right after the env constructor (which
+spawns episode 0, evacuation_env.py:59), every later frame the state after one op:
+    op = 0  step(actions[f])     (evacuation_env.py:122)
+    op = 1  reset()              (evacuation_env.py:61)
+Pin: numpy / torch / python versions of this container are recorded in each file's ``meta``.
+"""
+from __future__ import annotations
+
+import json
+import os
+import platform
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from keyed_draws import philox4x32  # noqa: E402
+from ref_harness import RefEnv  # noqa: E402
+
+OUT = os.path.join(HERE, "..", "tests", "golden")
+OP_STEP, OP_RESET = 0, 1
+
+
+def meta(**kw):
+    import torch
+    d = dict(numpy=np.__version__, torch=torch.__version__, python=platform.python_version(),
+             machine=platform.processor() or platform.machine(), reference="LX-530/DQN-MARL @ /root/reference")
+    d.update(kw)
+    return np.array(json.dumps(d))
+
+
+def actions_for(seed, t, R, n_act=6):
+    """Keyed test actions in 0..5 (5 is invalid on purpose: map.py:180-181 ignores it)."""
+    w = philox4x32(0, t, 0, 99, seed)
+    return [int((w[r] * n_act) >> 32) for r in range(R)]
+
+
+def record(kind, W, H, exit_loc, N, seed, n_steps, name, extra_resets=()):
+    R = 2 if kind == "multi" else 1
+    ref = RefEnv(kind, W, H, exit_loc, N, seed=seed)
+    frames = []
+
+    def grab(op, act, obs, reward, done):
+        s = ref.snapshot()
+        s.update(op=np.int8(op), actions=np.array(act, dtype=np.int32), obs=obs, reward=np.float64(reward),
+                 done=np.uint8(done), rmap=np.packbits(s["rmap"], axis=None))
+        frames.append(s)
+
+    grab(OP_RESET, [0] * R, ref.observe(), 0.0, 0)
+    t = 0
+    while t < n_steps:
+        act = actions_for(seed, t, R)
+        obs, rew, done, _ = ref.step(act if kind == "multi" else act[0])
+        grab(OP_STEP, act, obs, rew, done)
+        t += 1
+        if done or t in extra_resets:
+            obs = ref.reset()
+            grab(OP_RESET, [0] * R, obs, 0.0, 0)
+    out = {k: np.stack([f[k] for f in frames]) for k in frames[0]}
+    out["meta"] = meta(kind=kind, width=W, height=H, exit=list(exit_loc) if exit_loc else [36, 15], n_people=N,
+                       seed=seed, n_robots=R)
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **out)
+    print(name, "frames", len(frames), "resets", int((out["op"][1:] == OP_RESET).sum()),
+          "kB", os.path.getsize(path) // 1024)
+    return ref
+
+
+def layout_file(ref, name, steps, box=None):
+    t = ref.layout_tables(steps=steps, box=box)
+    probe_in = -np.linspace(0.0, 4.0, 64)
+    t["exp_probe_in"] = probe_in
+    t["exp_probe_out"] = np.exp(probe_in)       # lets a test tell whether this machine's np.exp matches
+    t["meta"] = meta(L=ref.L, W=ref.W)
+    if box is not None:
+        # large grid: keep only the evaluated box of the danger tables
+        pad = int(t["pad"])
+        x0, y0, x1, y1 = box
+        t["danger_ctr"] = t["danger_ctr"][:, max(0, x0):x1, max(0, y0):y1]
+        t["danger_int"] = t["danger_int"][:, x0 + pad:x1 + pad, y0 + pad:y1 + pad]
+        t["box"] = np.array(box, dtype=np.int32)
+    path = os.path.join(OUT, name)
+    np.savez_compressed(path, **t)
+    print(name, "kB", os.path.getsize(path) // 1024)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = record("single", 36, 30, None, 150, 1234, 260, "traj_room_single.npz", extra_resets=(7,))
+    layout_file(ref, "layout_room.npz", steps=range(0, 181))
+    record("multi", 36, 30, None, 150, 99, 120, "traj_room_multi.npz")
+    record("single", 36, 30, [36, 15], 20, 5, 200, "traj_room_small.npz")
+    record("single", 40, 24, [1, 12], 60, 77, 120, "traj_room_westexit.npz")
+    ref = record("single", 256, 256, [256, 128], 1000, 2024, 24, "traj_big256.npz")
+    layout_file(ref, "layout_big256.npz", steps=[0, 5, 24, 90, 180], box=(-6, -6, 50, 46))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,55 @@
+"""The oracle (oracle/env_oracle.c) pinned against trajectories recorded from the UNMODIFIED Python
+reference (oracle/make_golden.py).  Bit-exact: positions, health, accumulators, flags, rmap, robots,
+observations (float64), rewards (float64 bits), dones."""
+import numpy as np
+import pytest
+
+from util import OP_RESET, OP_STEP, assert_frame_equal, layout_for, load_golden
+
+TRAJS = ["traj_room_single.npz", "traj_room_multi.npz", "traj_room_small.npz", "traj_room_westexit.npz",
+         "traj_big256.npz"]
+
+
+@pytest.mark.parametrize("name", TRAJS)
+def test_oracle_replays_reference(name):
+    from oracle import LayoutTables, OracleEnv
+    g = load_golden(name)
+    m = g["meta"]
+    lay = layout_for(m)
+    env = OracleEnv(LayoutTables.from_layout(lay), m["n_people"], m["n_robots"], seed=m["seed"])
+    F = len(g["op"])
+    obs = env.reset()
+    assert_frame_equal(g, 0, env.snapshot(), obs, None, None, lay.L, lay.W, name)
+    for f in range(1, F):
+        if g["op"][f] == OP_STEP:
+            obs, r, d = env.step(g["actions"][f])
+            assert_frame_equal(g, f, env.snapshot(), obs, r, d, lay.L, lay.W, name)
+        else:
+            obs = env.reset()
+            assert_frame_equal(g, f, env.snapshot(), obs, None, None, lay.L, lay.W, name)
+
+
+def test_pairwise_sum_matches_numpy():
+    """np.mean at evacuation_env.py:228 is numpy's pairwise add.reduce (third party, numpy 2.3.x)."""
+    from oracle import pairwise_sum
+    rng = np.random.default_rng(0)
+    for n in list(range(0, 40)) + [127, 128, 129, 150, 255, 256, 257, 999, 1000, 1001, 4097, 20000, 30001]:
+        a = rng.uniform(0, 300, size=n)
+        assert pairwise_sum(a) == np.add.reduce(a), n
+        if n:
+            assert pairwise_sum(a) / n == np.mean(a), n
+
+
+def test_keyed_draws_known_answer():
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors)."""
+    from keyed_draws import philox4x32, philox4x32_np, sample_indices
+    assert philox4x32(0, 0, 0, 0, 0) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    ones = 0xffffffff
+    assert philox4x32(ones, ones, ones, ones, (ones << 32) | ones) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert philox4x32(0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, (0x299f31d0 << 32) | 0xa4093822) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+    w = philox4x32_np([1, 2, 3], 7, [4, 5, 6], 0, 0xABCDEF0123)
+    for k in range(3):
+        assert tuple(int(x) for x in w[:, k]) == philox4x32(k + 1, 7, k + 4, 0, 0xABCDEF0123)
+    idx = sample_indices(3, 11, 5000, 512)
+    assert len(set(idx.tolist())) == 512 and idx.min() >= 0 and idx.max() < 5000
