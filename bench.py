@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the DQN-MARL hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+
+Metric (BASELINE.json): env agent-steps/s.  Workload at N=1 = BASELINE.json configs[1] ("CA-dqn1
+single-room cellular-automaton evacuation, 4096 batched envs, env-step-only throughput on 1 B200"):
+36x30 room, 150 people per env, 4096 envs, uniform random robot actions, auto-reset.  One "step" = one
+fused env-step launch over the whole batch = 4096*150 agent-steps (every person counted every step,
+SURVEY.md §8d).
+
+  value     device-resident throughput: K back-to-back steps, inputs already in HBM, CUDA events.
+            The whole state of one batch (27 MB) would sit in the 126 MB L2, so the timed loop ROTATES over
+            enough independent batches that the state touched between two visits of the same batch exceeds
+            L2 (config.l2 says how many) — every step reads its state from HBM.
+  e2e       same metric through the host-facing call: actions from pinned host memory (H2D), step, and
+            obs/reward/done read back to pinned host memory (D2H) inside the timed region, every step.
+  roofline  env_step_kernel: algorithmic bytes (2*N*24 + 2*G + R*2904 + 9 per env-step)
+            / measured launch duration vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the oracle port (oracle/env_oracle.c, the reference's algorithm restated in C) on the
+            host cores, bounded sample.  `--impl reference` times the same port on all host threads as
+            its own arm (the reference is pure Python; there is no compiled reference to build).
+
+N > 1 (torchrun): every rank owns its own env batches (weak scaling, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (L, W, people, envs, synthetic layout?)
+    "c2": dict(L=36, W=30, people=150, envs=4096, synthetic=False,
+               desc="CA-dqn1 single room 36x30, 150 people/env, 4096 envs, env-step only (BASELINE.json configs[1])"),
+    "c3": dict(L=256, W=256, people=1000, envs=16384, synthetic=True,
+               desc="synthetic Louvre layout 256x256, 1000 people/env, 16384 envs, env-step only (BASELINE.json configs[2] env part)"),
+}
+L2_BYTES = 126e6
+
+
+def algorithmic_bytes_per_env_step(L, W, N, R=1):
+    """person SoA read+write padded to 24 B, uint8 occupancy read+write, fp32 obs, reward+done."""
+    G = (L + 2) * (W + 2)
+    return 2 * N * 24 + 2 * G + R * 2904 + 9
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(workload):
+    """dram bytes per launch from the committed ncu capture of this kernel, if any (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "env_step_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = []
+        with open(self.f.name) as f:
+            for line in f:
+                c = [x.strip() for x in line.split(",")]
+                if len(c) >= 7:
+                    try:
+                        rows.append((float(c[0]), float(c[1]), float(c[2]), c[3:7]))
+                    except ValueError:
+                        pass
+        os.unlink(self.f.name)
+        if rows:
+            busy = [r for r in rows if r[2] > 250.0] or rows
+            sm = sorted(r[0] for r in busy)
+            out["sm_mhz"] = sm[len(sm) // 2]
+            out["sm_max_mhz"] = rows[0][1]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            out["reasons"] = sorted({names[k] for r in rows for k in range(4) if r[3][k].lower().startswith("active")})
+            out["samples"] = len(rows)
+        return out
+
+
+def make_layout(wl):
+    from dqn_marl_b200.layout import Layout
+    if wl["synthetic"]:
+        return Layout.synthetic(wl["L"], wl["W"], n_exits=1, seed=2024)
+    return Layout.reference_room(wl["L"], wl["W"])
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_throughput(layout, wl, n_envs, steps, warm, threads, seed=2026):
+    """agent-steps/s of the oracle port on `threads` host threads (same layout, people, reset policy)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    from oracle import LayoutTables, OracleBatch
+    tabs = LayoutTables.from_layout(layout)
+    batch = OracleBatch(tabs, n_envs, wl["people"], 1, seed=seed, threads=threads, reset_robots=1, reset_fire=1)
+    batch.reset()
+    rng = np.random.default_rng(seed)
+    acts = rng.integers(0, 5, size=(steps + warm, n_envs, 1)).astype(np.int32)
+    for t in range(warm):
+        batch.step(acts[t])
+    t0 = time.perf_counter()
+    for t in range(warm, warm + steps):
+        batch.step(acts[t])
+    dt = time.perf_counter() - t0
+    return n_envs * wl["people"] * steps / dt, dt
+
+
+def run_reference(args, wl):
+    """`--impl reference`: the reference's CPU implementation of the path = the oracle port on all host threads
+    (the reference itself is pure Python and cannot travel to the GPU box; BASELINE.md quotes it at
+    ~1.9e4 agent-steps/s/core).  Each step = one pass over the whole batch of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    layout = make_layout(wl)
+    threads = os.cpu_count() or 1
+    # bounded sample: size one step so that K+W steps take about a minute at ~2e6 agent-steps/s/thread
+    budget_agent_steps = 60.0 * 2.0e6 * threads
+    n_envs = int(budget_agent_steps / max(1, args.steps + args.warmup) / wl["people"])
+    n_envs = max(threads * 4, min(wl["envs"], n_envs))
+    value, dt = cpu_port_throughput(layout, wl, n_envs, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": "env agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl["desc"], "envs_per_step": n_envs, "people": wl["people"]},
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_envs} envs x {wl['people']} people x {args.steps} steps, oracle/env_oracle.c, {threads} threads"},
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from dqn_marl_b200.envs import VecEvacuationEnv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    layout = make_layout(wl)
+    E, N = wl["envs"], wl["people"]
+    state_bytes = E * (160 * 0 + ((N + 15) // 16 * 16) * 21 + ((layout.L + 2) * ((layout.W + 2 + 31) // 32) + 3) // 4 * 16 + 96 + 2904 + 13)
+    n_rot = max(2, int(L2_BYTES * 1.5 / state_bytes) + 1)
+    envs = [VecEvacuationEnv(layout, E, N, device=dev, seed=2026, env_id_base=(rank * n_rot + b) * E,
+                             strict_reference=False, auto_reset=True) for b in range(n_rot)]
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    n_act = 64
+    actions = torch.randint(0, 5, (n_act, E, 1), generator=g, device=dev, dtype=torch.int32)
+    obs = [torch.empty((E, 1, 11, 11, 6), dtype=torch.float32, device=dev) for _ in range(n_rot)]
+    rew = [torch.empty((E,), dtype=torch.float64, device=dev) for _ in range(n_rot)]
+    don = [torch.empty((E,), dtype=torch.uint8, device=dev) for _ in range(n_rot)]
+
+    for b, env in enumerate(envs):
+        env.reset()
+    # prime: bring every batch to a desynchronised mid-episode mix (untimed)
+    for t in range(args.prime):
+        for b, env in enumerate(envs):
+            env.step_into(actions[t % n_act], obs[b], rew[b], don[b])
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    step_no = 0
+
+    def one_step():
+        nonlocal step_no
+        b = step_no % n_rot
+        envs[b].step_into(actions[step_no % n_act], obs[b], rew[b], don[b])
+        step_no += 1
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = sum(e.launch_count for e in envs)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize(dev)
+    ev0.record()
+    for _ in range(args.steps):
+        one_step()
+    ev1.record()
+    torch.cuda.synchronize(dev); barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = sum(e.launch_count for e in envs) - launches0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    value = world * E * N * args.steps / (elapsed_ms * 1e-3)
+
+    # L2-resident variant (what a production loop that steps ONE batch sees) — reported, not the headline
+    torch.cuda.synchronize(dev)
+    ev0.record()
+    for k in range(args.steps):
+        envs[0].step_into(actions[k % n_act], obs[0], rew[0], don[0])
+    ev1.record(); torch.cuda.synchronize(dev)
+    warm_ms = ev0.elapsed_time(ev1)
+
+    # ---- e2e: host buffers, H2D actions + D2H (obs, reward, done) every step, synchronous like a host caller ----
+    h_act = torch.randint(0, 5, (n_act, E, 1), dtype=torch.int32).pin_memory()
+    h_obs = torch.empty((E, 1, 11, 11, 6), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty((E,), dtype=torch.float64).pin_memory()
+    h_don = torch.empty((E,), dtype=torch.uint8).pin_memory()
+    d_act = torch.empty((E, 1), dtype=torch.int32, device=dev)
+    e2e_steps = max(10, min(args.steps, 300))
+
+    def e2e_step(k):
+        b = k % n_rot
+        d_act.copy_(h_act[k % n_act], non_blocking=True)
+        envs[b].step_into(d_act, obs[b], rew[b], don[b])
+        h_obs.copy_(obs[b], non_blocking=True); h_rew.copy_(rew[b], non_blocking=True); h_don.copy_(don[b], non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    for k in range(3):
+        e2e_step(k)
+    barrier(); torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * N * e2e_steps / float(t.item())
+    h2d = h_act[0].numel() * 4
+    d2h = h_obs.numel() * 4 + h_rew.numel() * 8 + h_don.numel()
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        alg = algorithmic_bytes_per_env_step(layout.L, layout.W, N) * E
+        kernel_ms = elapsed_ms / args.steps
+        achieved = alg / (kernel_ms * 1e-3) / 1e9
+        traffic = load_traffic(args.workload)
+        line = {
+            "metric": "env agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "envs_per_gpu": E, "people": N, "grid": [layout.L, layout.W],
+                       "l2": f"inputs larger than L2: timed loop rotates over {n_rot} independent batches "
+                             f"({n_rot * state_bytes / 1e6:.0f} MB of state > 126 MB L2)",
+                       "reset_policy": "auto-reset, fresh fire per episode (strict_reference=False)",
+                       "prime_steps": args.prime},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "note": "pinned host actions in, obs+reward+done out, synchronous per step"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                         "note": "canonical bytes of SURVEY.md §8d (uint8 occupancy, 24 B/person); this build packs "
+                                 "occupancy to 1 bit/cell and rewrites only changed person fields, so it moves fewer bytes"},
+            "value_l2_resident": E * N * args.steps / (warm_ms * 1e-3),
+        }
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            n_cpu_envs = min(E, 512)
+            cpu_steps = 40
+            v, dt = cpu_port_throughput(layout, wl, n_cpu_envs, cpu_steps, 5, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                                    "sample": f"{n_cpu_envs} envs x {N} people x {cpu_steps} steps of the same workload, "
+                                              f"oracle/env_oracle.c on {threads} threads ({dt:.1f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--prime", type=int, default=150, help="untimed steps per batch before warm-up")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()
