@@ -73,6 +73,13 @@ SIGNATURES = {
     "mq_env_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mq_env_unpack_rmap": (C.c_int, [_vp, _vp, _vp]),
     "mq_env_launch_count": (_i64, [_vp]),
+    "mq_replay_create": (C.c_int, [C.POINTER(_vp), _i64, _i32, C.POINTER(MqReplayStore)]),
+    "mq_replay_destroy": (C.c_int, [_vp]),
+    "mq_replay_size": (_i64, [_vp]),
+    "mq_replay_cursor": (_i64, [_vp]),
+    "mq_replay_launch_count": (_i64, [_vp]),
+    "mq_replay_push": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "mq_replay_sample": (C.c_int, [_vp, _i64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

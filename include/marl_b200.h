@@ -161,7 +161,6 @@ int mq_env_unpack_rmap(mq_env* env, uint8_t* rmap_out, void* stream);
 /* number of kernels this handle has launched so far (bench.py gpu_launches) */
 int64_t mq_env_launch_count(const mq_env* env);
 
-#if 0 /* MQ_PENDING: declared for review, enabled when replay.cu / qnet.cu land */
 /* ------------------------------------------------------------------------
  * Replay ring (device resident).  Replaces DQNAgent.memory = deque(maxlen)
  * (dqn_agent.py:88-89), remember() (:97-99) and random.sample + stacking in
@@ -181,6 +180,7 @@ int mq_replay_create(mq_replay** out, int64_t capacity, int32_t device, const mq
 int mq_replay_destroy(mq_replay* rb);
 int64_t mq_replay_size(const mq_replay* rb);      /* len(agent.memory) */
 int64_t mq_replay_cursor(const mq_replay* rb);
+int64_t mq_replay_launch_count(const mq_replay* rb);
 /* n transitions appended FIFO (oldest overwritten once full).  reward is the env's f64 reward,
  * cast to f32 exactly as torch.FloatTensor(rewards) does at dqn_agent.py:138. */
 int mq_replay_push(mq_replay* rb, const float* state, const int32_t* action, const double* reward,
@@ -191,6 +191,7 @@ int mq_replay_sample(mq_replay* rb, int64_t B, uint64_t seed, uint64_t draw_id, 
                      float* state, int64_t* action, float* reward, float* next_state, uint8_t* done,
                      int64_t* idx_out, void* stream);
 
+#if 0 /* MQ_PENDING: declared for review, enabled when qnet.cu lands */
 /* ------------------------------------------------------------------------
  * Q-network (DQNNetwork, dqn_agent.py:15-61) and learner (DQNAgent.act/learn, :101-172).
  * Parameters live in 12 caller-owned fp32 tensors in state_dict order:

@@ -204,3 +204,36 @@ def test_full_size_c2_properties():
     assert ((env.flags[:, :N] & 1).sum(1) == sc[:, 6]).all() and (((env.flags[:, :N] >> 1) & 1).sum(1) == sc[:, 7]).all()
     _, r2 = run()
     assert torch.equal(r1, r2)
+
+
+@pytest.mark.parametrize("name", ["traj_room_single.npz", "traj_room_multi.npz"])
+def test_reference_facade_replays_golden(name):
+    """The drop-in classes (same ctor / reset / step / info surface as evacuation_env.py) on the goldens."""
+    from dqn_marl_b200.envs.evacuation_env import EvacuationEnv, EvacuationEnvMulti
+    g = load_golden(name)
+    m = g["meta"]
+    cls = EvacuationEnvMulti if m["kind"] == "multi" else EvacuationEnv
+    env = cls(m["width"], m["height"], None, m["exit"], m["n_people"], device="cuda:0", seed=m["seed"])
+    assert env.state_size == (11, 11, 6) and env.action_size == 5 and env.max_steps == 1200
+    F = min(len(g["op"]), 80)
+    for f in range(1, F):
+        if g["op"][f] == OP_STEP:
+            a = g["actions"][f]
+            state, reward, done, info = env.step([int(x) for x in a] if m["kind"] == "multi" else int(a[0]))
+            assert isinstance(reward, float) and isinstance(done, bool)
+            assert reward == g["reward"][f] and done == bool(g["done"][f])
+            assert info["current_step"] == int(g["cur_step"][f]) and info["simulation_time"] == 0.5 * int(g["cur_step"][f])
+            if m["kind"] == "single":
+                assert info["robot_position"] == tuple(int(v) for v in g["robot_obs"][f])
+                assert len(info["people_positions"]) == m["n_people"] and "health_values" in info
+        else:
+            state = env.reset()
+        st = np.stack(state) if m["kind"] == "multi" else state[None]
+        assert st.dtype == np.float64 and np.array_equal(st, g["obs"][f]), f"{name} frame {f}"
+        p = env.people.list
+        assert [int(q.pos[0]) for q in p] == g["px"][f].tolist() and [q.health for q in p] == g["health"][f].tolist()
+        assert [q.savety for q in p] == [(b & 1) == 1 for b in g["flags"][f]]
+    pm = env.get_performance_metrics()
+    assert pm["evacuated"] + pm["dead"] + pm["remaining"] == m["n_people"]
+    assert np.array_equal(env.people.rmap != 0, np.unpackbits(g["rmap"][F - 1])[:(m["width"] + 2) * (m["height"] + 2)].reshape(m["width"] + 2, -1) != 0)
+    assert env.map.Check_Valid(5, 5) and not env.map.Check_Valid(19, 15) and not env.map.Check_Valid(0, 3)
