@@ -1,0 +1,294 @@
+"""DQNAgent — drop-in for the reference's agent (reference Louvre_Evacuation/agents/dqn_agent.py:64-191), and
+VecDQNAgent, its batched form for thousands of envs per step.
+
+Same constructor / attributes / methods as the reference (``act``, ``remember``, ``learn``,
+``update_target_network``, ``save``, ``load``; ``memory``, ``batch_size``, ``epsilon``, ``steps``, ``q_network``,
+``target_network``, ``optimizer``), but every tensor lives on the GPU and all arithmetic runs in
+libmarl_b200.so: replay ring (csrc/replay.cu) and Q-network / learner kernels (csrc/qnet.cu).
+
+Randomness: epsilon-greedy, replay sampling and dropout use keyed Philox draws; the key comes from
+``random.getrandbits(63)`` at construction (so ``random.seed`` makes runs reproducible) unless ``config['seed']``
+is given.  ``config['dropout']``: "train" (default — the reference never calls .eval(), so Dropout(0.2) is active in
+act() and in both networks during learn(), dqn_agent.py:33,57) or "eval".
+"""
+from __future__ import annotations
+
+import random
+from collections import OrderedDict
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import _lib
+from ..replay import ReplayRing
+from . import qnet_params as qp
+from .qnet import QNet
+
+
+class _NetworkView:
+    """`agent.q_network` / `agent.target_network`: callable on a (B,11,11,6) tensor, state_dict()/load_state_dict()/
+    parameters() like the reference's nn.Module (used by train_dqn.py:75, train_qmix.py:92-100).  Forward only: it
+    does not record an autograd graph (the QMIX mixer of train_qmix.py is a later row of SURVEY.md §8f)."""
+
+    def __init__(self, agent: "DQNAgent", which: str):
+        self._a, self._which = agent, which
+        self.training = True
+
+    def __call__(self, x):
+        a = self._a
+        if x.dim() == 3:
+            x = x.unsqueeze(0)
+        mask = a._mask(x.shape[0]) if (self.training and a.dropout_mode == "train") else None
+        return a.net.forward(x, self._which, mask)
+
+    forward = __call__
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def train(self, mode: bool = True):
+        self.training = mode
+        return self
+
+    def state_dict(self):
+        return self._a.net.state_dict(self._which)
+
+    def load_state_dict(self, sd):
+        self._a.net.load_state_dict(sd, self._which)
+
+    def parameters(self):
+        flat = self._a.net.flat_p if self._which == "online" else self._a.net.flat_t
+        return [flat[qp.OFFSETS[k]:qp.OFFSETS[k] + qp.NUMEL[k]] for k in range(len(qp.NAMES))]
+
+    def to(self, *_a, **_k):
+        return self
+
+
+class _OptimizerView:
+    """`agent.optimizer` with torch.optim.Adam's state_dict format (dqn_agent.py:85,179,189)."""
+
+    def __init__(self, agent: "DQNAgent"):
+        self._a = agent
+
+    def zero_grad(self, set_to_none: bool = False):
+        self._a.net.flat_g.zero_()
+
+    def step(self):
+        a = self._a
+        a._adam_t += 1
+        hp = a._hparams(clip=float("inf"))
+        a.net.clip_adam(hp)
+
+    def state_dict(self):
+        a = self._a
+        state = {}
+        if a._adam_t > 0:
+            m, v = qp.unpack(a.net.flat_m), qp.unpack(a.net.flat_v)
+            for k, name in enumerate(qp.NAMES):
+                state[k] = {"step": torch.tensor(float(a._adam_t)), "exp_avg": m[name].cpu(), "exp_avg_sq": v[name].cpu()}
+        group = {"lr": a.learning_rate, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                 "foreach": None, "capturable": False, "differentiable": False, "fused": None, "decoupled_weight_decay": False,
+                 "params": list(range(len(qp.NAMES)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        a = self._a
+        st = sd.get("state", {})
+        if st:
+            m = OrderedDict((name, st[k]["exp_avg"]) for k, name in enumerate(qp.NAMES))
+            v = OrderedDict((name, st[k]["exp_avg_sq"]) for k, name in enumerate(qp.NAMES))
+            qp.pack(m, a.net.flat_m)
+            qp.pack(v, a.net.flat_v)
+            a._adam_t = int(float(st[0]["step"]))
+        else:
+            a.net.flat_m.zero_(); a.net.flat_v.zero_(); a._adam_t = 0
+        groups = sd.get("param_groups")
+        if groups:
+            a.learning_rate = float(groups[0].get("lr", a.learning_rate))
+
+
+class DQNAgent:
+    def __init__(self, state_size, action_size, device, config, max_batch: Optional[int] = None):
+        self.state_size, self.action_size = state_size, action_size
+        assert tuple(state_size) == (11, 11, 6) and action_size == 5, "the CUDA Q-network is the reference's 11x11x6 -> 5 net"
+        dev = torch.device(device) if not isinstance(device, torch.device) else device
+        if dev.type != "cuda":
+            raise RuntimeError(f"dqn_marl_b200.DQNAgent needs a CUDA device (got {device!r}); there is no CPU fallback")
+        self.device = dev
+        # dqn_agent.py:73-80 (note the default warmup_steps = 1000 when the key is absent)
+        self.gamma = config.get("gamma", 0.99)
+        self.epsilon = config.get("epsilon", 1.0)
+        self.epsilon_min = config.get("epsilon_min", 0.02)
+        self.epsilon_decay = config.get("epsilon_decay", 0.9995)
+        self.learning_rate = config.get("learning_rate", 0.0001)
+        self.batch_size = config.get("batch_size", 32)
+        self.target_update_freq = config.get("target_update_freq", 200)     # stored, never used (quirk Q13)
+        self.warmup_steps = config.get("warmup_steps", 1000)
+        self.huber = bool(config.get("huber", False))
+        self.dropout_mode = config.get("dropout", "train")
+        self.seed = int(config["seed"]) if "seed" in config else random.getrandbits(63)
+        memory_size = config.get("memory_size", 50000)
+
+        self.net = QNet(dev, max_batch=max_batch or max(self.batch_size, 64), trainable=True)
+        # PyTorch default init, same RNG consumption order as the reference (q_network, then target_network)
+        online, _target = qp.TorchDQN(), qp.TorchDQN()
+        self.net.load_state_dict(online.state_dict(), "online")
+        self.q_network = _NetworkView(self, "online")
+        self.target_network = _NetworkView(self, "target")
+        self.optimizer = _OptimizerView(self)
+        self.memory = ReplayRing(memory_size, device=self.net.device, seed=self.seed)
+        self.steps = 0
+        self._adam_t = 0
+        self._act_calls = 0
+        self._mask_calls = 0
+        self.update_target_network()
+        d = self.net.device
+        self._s1 = torch.zeros((1, 726), dtype=torch.float32, device=d)
+
+    # ------------------------------------------------------------------
+    def _hparams(self, clip: float = 1.0) -> "_lib.MqHparams":
+        hp = _lib.MqHparams()
+        hp.gamma, hp.lr, hp.beta1, hp.beta2, hp.adam_eps = self.gamma, self.learning_rate, 0.9, 0.999, 1e-8
+        hp.clip_norm = clip if np.isfinite(clip) else 3.0e38
+        hp.huber, hp.adam_step = int(self.huber), max(self._adam_t, 1)
+        return hp
+
+    def _mask(self, B: int):
+        self._mask_calls += 1
+        return self.net.dropout_mask(B, self.seed, self._mask_calls)
+
+    def _to_dev(self, state) -> torch.Tensor:
+        if isinstance(state, np.ndarray):
+            state = torch.from_numpy(state.astype(np.float32))      # dqn_agent.py:109
+        return state.to(device=self.net.device, dtype=torch.float32)
+
+    # ------------------------------------------------------------------
+    def remember(self, state, action, reward, next_state, done):
+        """dqn_agent.py:97-99"""
+        d = self.net.device
+        self.memory.push(self._to_dev(state).reshape(1, 726).contiguous(), torch.tensor([int(action)], dtype=torch.int32, device=d),
+                         torch.tensor([float(reward)], dtype=torch.float64, device=d),
+                         self._to_dev(next_state).reshape(1, 726).contiguous(), torch.tensor([1 if done else 0], dtype=torch.uint8, device=d))
+
+    def act(self, state, training=False):
+        """dqn_agent.py:101-124 — epsilon-greedy on top of the online forward, one fused launch sequence."""
+        x = self._to_dev(state)
+        if x.dim() == 3:
+            x = x.unsqueeze(0)
+        x = x.contiguous()
+        B = x.shape[0]
+        mask = self._mask(B) if self.dropout_mode == "train" else None
+        self._act_calls += 1
+        a = self.net.act(x, self.epsilon if training else 0.0, self.seed, 0, self._act_calls, 1, mask)
+        return int(a[0].item()) if B == 1 else a
+
+    def learn(self):
+        """dqn_agent.py:126-168"""
+        if len(self.memory) < self.batch_size or self.steps < self.warmup_steps:
+            return None
+        B = self.batch_size
+        batch = self.memory.sample(B)
+        train = self.dropout_mode == "train"
+        self._adam_t += 1
+        hp = self._hparams()
+        loss = self.net.td_backward(batch, hp, self._mask(B) if train else None, self._mask(B) if train else None)
+        self._allreduce_grads()
+        self.net.clip_adam(hp, self._grad_scale())
+        if self.epsilon > self.epsilon_min:
+            self.epsilon *= self.epsilon_decay
+        self.steps += 1
+        return loss.item()
+
+    # hooks for the data-parallel learner (VecDQNAgent overrides)
+    def _allreduce_grads(self):
+        pass
+
+    def _grad_scale(self) -> float:
+        return 1.0
+
+    def update_target_network(self):
+        """dqn_agent.py:170-172 — hard copy"""
+        self.net.sync_target(1.0)
+
+    def save(self, filepath):
+        """dqn_agent.py:174-182 — same dict keys and state_dict layouts as the reference's checkpoints"""
+        torch.save({
+            "q_network": OrderedDict((k, v.cpu()) for k, v in self.q_network.state_dict().items()),
+            "target_network": OrderedDict((k, v.cpu()) for k, v in self.target_network.state_dict().items()),
+            "optimizer": self.optimizer.state_dict(),
+            "epsilon": self.epsilon,
+            "steps": self.steps,
+        }, filepath)
+
+    def load(self, filepath):
+        """dqn_agent.py:184-191"""
+        ck = torch.load(filepath, map_location="cpu", weights_only=False)
+        self.q_network.load_state_dict(ck["q_network"])
+        self.target_network.load_state_dict(ck["target_network"])
+        self.optimizer.load_state_dict(ck["optimizer"])
+        self.epsilon = ck.get("epsilon", self.epsilon_min)
+        self.steps = ck.get("steps", 0)
+
+
+class VecDQNAgent(DQNAgent):
+    """Batched agent for VecEvacuationEnv: act on (E*R) observations at once, push E*R transitions per env step,
+    learn on large batches; data-parallel over ranks with ONE collective — the all-reduce of the flat gradient."""
+
+    def __init__(self, device, config, n_envs: int, n_robots: int = 1, env_id_base: int = 0, process_group=None):
+        cfg = dict(config)
+        cfg.setdefault("warmup_steps", 0)
+        super().__init__((11, 11, 6), 5, device, cfg, max_batch=max(cfg.get("batch_size", 32), n_envs * n_robots))
+        self.n_envs, self.n_robots, self.env_id_base = n_envs, n_robots, env_id_base
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        if self.world > 1:       # identical replicas: rank 0's initial weights everywhere
+            torch.distributed.broadcast(self.net.flat_p, src=torch.distributed.get_global_rank(self.pg, 0) if self.pg else 0,
+                                        group=self.pg)
+            self.update_target_network()
+        self._actions = torch.zeros((n_envs * n_robots,), dtype=torch.int32, device=self.net.device)
+        self._tick = 0
+
+    def act_batch(self, obs: torch.Tensor, training: bool = True) -> torch.Tensor:
+        """obs (E, R, 11, 11, 6) f32 on device -> actions (E, R) i32 on device (no host sync)."""
+        B = self.n_envs * self.n_robots
+        x = obs.reshape(B, 726)
+        mask = self._mask(B) if self.dropout_mode == "train" else None
+        self.net.act(x, self.epsilon if training else 0.0, self.seed, self.env_id_base, self._tick, self.n_robots, mask, out=self._actions)
+        self._tick += 1
+        return self._actions.view(self.n_envs, self.n_robots)
+
+    def remember_batch(self, obs, actions, reward, next_obs, done):
+        """Push E*R transitions (all device tensors).  The shared env reward/done is repeated per robot
+        (train_double_dqn.py:52-56 gives both agents the same scalar reward)."""
+        R = self.n_robots
+        if R > 1:
+            reward = reward.repeat_interleave(R)
+            done = done.repeat_interleave(R)
+        self.memory.push(obs.reshape(-1, 726), actions.reshape(-1), reward, next_obs.reshape(-1, 726), done)
+
+    def _allreduce_grads(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.net.flat_g, group=self.pg)      # the one exchange step
+
+    def _grad_scale(self) -> float:
+        return 1.0 / self.world
+
+    def learn_device(self) -> torch.Tensor:
+        """learn() without the host sync of loss.item(): returns the device loss tensor."""
+        B = self.batch_size
+        batch = self.memory.sample(B, out=getattr(self, "_batch", None))
+        self._batch = batch
+        train = self.dropout_mode == "train"
+        self._adam_t += 1
+        hp = self._hparams()
+        loss = self.net.td_backward(batch, hp, self._mask(B) if train else None, self._mask(B) if train else None)
+        self._allreduce_grads()
+        self.net.clip_adam(hp, self._grad_scale())
+        if self.epsilon > self.epsilon_min:
+            self.epsilon *= self.epsilon_decay
+        self.steps += 1
+        return loss

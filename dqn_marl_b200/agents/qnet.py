@@ -1,0 +1,108 @@
+"""QNet — device buffers + handle of the CUDA Q-network / learner (csrc/qnet.cu)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from .. import _lib
+from ..envs.vec_env import _require_cuda
+from . import qnet_params as qp
+
+
+class QNet:
+    def __init__(self, device="cuda", max_batch: int = 4096, trainable: bool = True):
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        self.max_batch = int(max_batch)
+        dev = self.device
+        self.flat_p = torch.zeros(qp.TOTAL, dtype=torch.float32, device=dev)     # online parameters
+        self.flat_t = torch.zeros(qp.TOTAL, dtype=torch.float32, device=dev)     # target parameters
+        self.trainable = trainable
+        if trainable:
+            self.flat_g = torch.zeros(qp.TOTAL, dtype=torch.float32, device=dev)
+            self.flat_m = torch.zeros(qp.TOTAL, dtype=torch.float32, device=dev)
+            self.flat_v = torch.zeros(qp.TOTAL, dtype=torch.float32, device=dev)
+        bind = _lib.MqQnetBind()
+        for k in range(_lib.MQ_QNET_TENSORS):
+            off = qp.OFFSETS[k] * 4
+            bind.online[k] = self.flat_p.data_ptr() + off
+            bind.target[k] = self.flat_t.data_ptr() + off
+            if trainable:
+                bind.grad[k] = self.flat_g.data_ptr() + off
+                bind.adam_m[k] = self.flat_m.data_ptr() + off
+                bind.adam_v[k] = self.flat_v.data_ptr() + off
+        h = C.c_void_p()
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.mq_qnet_create(C.byref(h), dev.index, self.max_batch, C.byref(bind)), "mq_qnet_create")
+        self._h = h
+        self._loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.mq_qnet_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mq_qnet_launch_count(self._h))
+
+    # -- parameters ------------------------------------------------------------------------------------
+    def load_state_dict(self, sd, which="online"):
+        qp.pack(sd, self.flat_p if which == "online" else self.flat_t)
+
+    def state_dict(self, which="online"):
+        return qp.unpack(self.flat_p if which == "online" else self.flat_t)
+
+    # -- compute ---------------------------------------------------------------------------------------
+    def forward(self, obs: torch.Tensor, which: str = "online", drop_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """DQNNetwork.forward (dqn_agent.py:35-61): obs (B,11,11,6) f32 on device -> Q (B,5) f32."""
+        B = obs.shape[0]
+        obs = obs.to(device=self.device, dtype=torch.float32).contiguous()
+        q = torch.empty((B, 5), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mq_qnet_forward(self._h, 0 if which == "online" else 1, _lib.ptr(obs), B, _lib.ptr(drop_mask),
+                                                _lib.ptr(q), self._stream()), "mq_qnet_forward")
+        return q
+
+    def act(self, obs: torch.Tensor, eps: float, seed: int, env_id_base: int, tick: int, n_robots: int = 1,
+            drop_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, q_out: Optional[torch.Tensor] = None):
+        B = obs.shape[0]
+        if out is None:
+            out = torch.empty((B,), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.mq_qnet_act(self._h, _lib.ptr(obs), B, float(eps), int(seed), int(env_id_base), int(tick) & 0xFFFFFFFF,
+                                        int(n_robots), _lib.ptr(drop_mask), _lib.ptr(out), _lib.ptr(q_out), self._stream()), "mq_qnet_act")
+        return out
+
+    def td_backward(self, batch: dict, hp: "_lib.MqHparams", drop_online=None, drop_target=None) -> torch.Tensor:
+        B = batch["actions"].shape[0]
+        _lib.check(self.lib.mq_qnet_td_backward(self._h, _lib.ptr(batch["states"]), _lib.ptr(batch["actions"]), _lib.ptr(batch["rewards"]),
+                                                _lib.ptr(batch["next_states"]), _lib.ptr(batch["dones"]), B, C.byref(hp),
+                                                _lib.ptr(drop_online), _lib.ptr(drop_target), _lib.ptr(self._loss), self._stream()),
+                   "mq_qnet_td_backward")
+        return self._loss
+
+    def clip_adam(self, hp: "_lib.MqHparams", grad_scale: float = 1.0) -> torch.Tensor:
+        _lib.check(self.lib.mq_qnet_clip_adam(self._h, C.byref(hp), float(grad_scale), _lib.ptr(self._gnorm), self._stream()),
+                   "mq_qnet_clip_adam")
+        return self._gnorm
+
+    def sync_target(self, tau: float = 1.0):
+        _lib.check(self.lib.mq_qnet_sync_target(self._h, float(tau), self._stream()), "mq_qnet_sync_target")
+
+    def dropout_mask(self, B: int, seed: int, counter: int, p: float = 0.2) -> torch.Tensor:
+        m = torch.empty((B, 512), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.mq_qnet_dropout_mask(_lib.ptr(m), B * 512, float(p), int(seed), int(counter), self._stream()),
+                   "mq_qnet_dropout_mask")
+        return m

@@ -1,0 +1,217 @@
+// fp32 CUDA-core GEMM with implicit-convolution operand loaders — the parity path of the Q-network.
+//
+// The reference's DQNNetwork (Louvre_Evacuation/agents/dqn_agent.py:15-61) is evaluated by PyTorch in fp32
+// and north_star asks for Q-values / losses within 1e-5 relative of it, which rules out TF32/bf16 tensor
+// cores for THIS path: every contraction here is plain FFMA with fp32 accumulation.  One templated kernel
+// covers all twelve contractions of a learn step (3 convs + 2 fcs forward, their dgrad and wgrad) through
+// operand-loader modes, so the 3x3/pad-1 convolutions never materialise an im2col buffer in HBM.
+//
+// Tiling: CTA tile 128 x BN x 16 (BN = 128/64/32), 256 threads, 8 x (BN/16) register micro-tile, operands
+// staged k-major in shared memory and double-buffered through registers.  Split-K over gridDim.z for the
+// skinny shapes (fc1 at small batch, every wgrad), partials reduced by `splitk_epilogue_kernel`.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace mq {
+
+enum AMode { A_ROW = 0, A_COL = 1, A_IM2COL = 2, A_IM2COL_T = 3, A_IM2COL_FLIP = 4 };
+enum BMode { B_ROW = 0, B_COL = 1, B_CONVW_T = 2 };
+
+struct GemmParams {
+    int M, N, K;
+    const float* A; const float* B; float* C;
+    int lda, ldb, ldc;
+    int batch;                   // conv: number of images (M or K = batch * 121)
+    // epilogue: C = f(acc + bias[n]) with optional relu, * (mask_act[m][n] > 0), * drop[m][n] * drop_scale
+    const float* bias;
+    int relu;
+    const float* mask_act;       // same shape / ld as C
+    const uint8_t* drop;         // [M][N] u8 keep-mask or null
+    float drop_scale;
+    // split-K
+    float* partial;              // [splits][M][N] when splits > 1
+    int splits, k_chunk;
+};
+
+constexpr int GEMM_BM = 128, GEMM_BK = 16, GEMM_THREADS = 256;
+constexpr int OBS_HW = 11, OBS_PIX = 121;
+
+// ---- operand loaders (element-wise; divisors are compile-time constants) -------------------------------
+// A_IM2COL:      X NHWC [batch][11][11][C]; m = (b, i, j); k = (tap, c) -> X[b][i+di-1][j+dj-1][c]
+// A_IM2COL_T:    transposed view of the same matrix: m = (tap, c); k = (b, i, j)           (conv wgrad)
+// A_IM2COL_FLIP: dY NHWC [batch][11][11][C]; m = (b, i, j); k = (tap, n) -> dY[b][i-(di-1)][j-(dj-1)][n]  (conv dgrad)
+template <int AMODE, int CDIM>
+__device__ __forceinline__ float load_a(const GemmParams& p, int m, int k) {
+    if (m >= p.M || k >= p.K) return 0.f;
+    if (AMODE == A_ROW) return __ldg(p.A + (size_t)m * p.lda + k);
+    if (AMODE == A_COL) return __ldg(p.A + (size_t)k * p.lda + m);
+    int pix, tc;
+    if (AMODE == A_IM2COL_T) { pix = k; tc = m; } else { pix = m; tc = k; }
+    const int b = pix / OBS_PIX, q = pix - b * OBS_PIX;
+    const int i = q / OBS_HW, j = q - i * OBS_HW;
+    const int tap = tc / CDIM, c = tc - tap * CDIM;
+    const int di = tap / 3 - 1, dj = tap - (tap / 3) * 3 - 1;
+    const int ii = (AMODE == A_IM2COL_FLIP) ? i - di : i + di;
+    const int jj = (AMODE == A_IM2COL_FLIP) ? j - dj : j + dj;
+    if ((unsigned)ii >= (unsigned)OBS_HW || (unsigned)jj >= (unsigned)OBS_HW) return 0.f;
+    return __ldg(p.A + ((size_t)(b * OBS_PIX + ii * OBS_HW + jj)) * CDIM + c);
+}
+// B_ROW:     B[k][n] (row-major, n contiguous)
+// B_COL:     B[n][k] (PyTorch Linear weight)
+// B_CONVW_T: conv weight Wc[(tap*Cin + c)][Cout] read as (k = (tap, n), col = c); CDIM = Cout, N = Cin  (conv dgrad)
+template <int BMODE, int CDIM>
+__device__ __forceinline__ float load_b(const GemmParams& p, int k, int n) {
+    if (k >= p.K || n >= p.N) return 0.f;
+    if (BMODE == B_ROW) return __ldg(p.B + (size_t)k * p.ldb + n);
+    if (BMODE == B_COL) return __ldg(p.B + (size_t)n * p.ldb + k);
+    const int tap = k / CDIM, co = k - tap * CDIM;
+    return __ldg(p.B + ((size_t)(tap * p.N + n)) * CDIM + co);
+}
+
+__device__ __forceinline__ float epilogue_value(const GemmParams& p, float v, int m, int n) {
+    if (p.bias) v += __ldg(p.bias + n);
+    if (p.relu) v = fmaxf(v, 0.f);
+    if (p.mask_act) v = (__ldg(p.mask_act + (size_t)m * p.ldc + n) > 0.f) ? v : 0.f;
+    if (p.drop) v = __ldg(p.drop + (size_t)m * p.N + n) ? v * p.drop_scale : 0.f;
+    return v;
+}
+
+template <int AMODE, int BMODE, int BN, int CDIM>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_f32_kernel(GemmParams p) {
+    constexpr int TN = BN / 16;                       // micro-tile columns per thread
+    constexpr int B_PER_THREAD = GEMM_BK * BN / GEMM_THREADS;   // 8 / 4 / 2
+    __shared__ __align__(16) float As[2][GEMM_BK][GEMM_BM + 4];
+    __shared__ __align__(16) float Bs[2][GEMM_BK][BN + 4];
+
+    const int t = threadIdx.x;
+    const int m0 = blockIdx.y * GEMM_BM, n0 = blockIdx.x * BN;
+    const int k_begin = blockIdx.z * p.k_chunk;
+    const int k_end = min(p.K, k_begin + p.k_chunk);
+    const int tx = t & 15, ty = t >> 4;
+
+    // global -> register staging assignment
+    const int a_m = t & 127, a_k0 = (t >> 7) * 8;
+    const int b_n = t % BN, b_k0 = (t / BN) * B_PER_THREAD;
+    // micro-tile column j of thread tx: two interleaved groups of 4 for BN = 128 (conflict-free float4 reads)
+    auto col_of = [&](int j) { return TN == 8 ? (j >> 2) * 64 + tx * 4 + (j & 3) : tx * TN + j; };
+    float ra[8], rb[B_PER_THREAD];
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ra[q] = (k0 + a_k0 + q < k_end) ? load_a<AMODE, CDIM>(p, m0 + a_m, k0 + a_k0 + q) : 0.f;
+#pragma unroll
+        for (int q = 0; q < B_PER_THREAD; ++q)
+            rb[q] = (k0 + b_k0 + q < k_end) ? load_b<BMODE, CDIM>(p, k0 + b_k0 + q, n0 + b_n) : 0.f;
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) As[buf][a_k0 + q][a_m] = ra[q];
+#pragma unroll
+        for (int q = 0; q < B_PER_THREAD; ++q) Bs[buf][b_k0 + q][b_n] = rb[q];
+    };
+
+    int buf = 0;
+    if (k_begin < k_end) { fetch(k_begin); stash(0); }
+    __syncthreads();
+    for (int k0 = k_begin; k0 < k_end; k0 += GEMM_BK) {
+        const bool more = k0 + GEMM_BK < k_end;
+        if (more) fetch(k0 + GEMM_BK);
+#pragma unroll
+        for (int kk = 0; kk < GEMM_BK; ++kk) {
+            float a[8], b[TN];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 8 + 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            if (TN >= 4) {
+#pragma unroll
+                for (int j = 0; j < TN; j += 4) {
+                    const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][kk][col_of(j)]);
+                    b[j] = bv.x; b[j + 1] = bv.y; b[j + 2] = bv.z; b[j + 3] = bv.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) b[j] = Bs[buf][kk][tx * TN + j];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (more) { stash(buf ^ 1); }
+        __syncthreads();
+        buf ^= 1;
+    }
+
+    if (p.splits > 1) {
+        float* dst = p.partial + (size_t)blockIdx.z * p.M * p.N;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + ty * 8 + i;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = n0 + col_of(j);
+                if (n < p.N) dst[(size_t)m * p.N + n] = acc[i][j];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + ty * 8 + i;
+            if (m >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int n = n0 + col_of(j);
+                if (n < p.N) p.C[(size_t)m * p.ldc + n] = epilogue_value(p, acc[i][j], m, n);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) splitk_epilogue_kernel(GemmParams p) {
+    const size_t total = (size_t)p.M * p.N;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int m = (int)(idx / p.N), n = (int)(idx - (size_t)m * p.N);
+        float v = 0.f;
+        for (int s = 0; s < p.splits; ++s) v += p.partial[(size_t)s * total + idx];     // fixed order: deterministic
+        p.C[(size_t)m * p.ldc + n] = epilogue_value(p, v, m, n);
+    }
+}
+
+// Launch helper.  `partial_cap` = floats available in p.partial.  Returns the number of kernels launched.
+template <int AMODE, int BMODE, int BN, int CDIM>
+inline int launch_gemm(GemmParams p, size_t partial_cap, int n_sms, cudaStream_t stream) {
+    const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM, tiles_n = (p.N + BN - 1) / BN;
+    const int tiles = tiles_m * tiles_n;
+    const int k_tiles = (p.K + GEMM_BK - 1) / GEMM_BK;
+    int splits = 1;
+    if (tiles < n_sms && k_tiles >= 8) {
+        splits = (2 * n_sms + tiles - 1) / tiles;
+        if (splits > k_tiles / 4) splits = k_tiles / 4;
+        while (splits > 1 && (size_t)splits * p.M * p.N > partial_cap) --splits;
+        if (splits < 1) splits = 1;
+    }
+    int chunk_tiles = (k_tiles + splits - 1) / splits;
+    splits = (k_tiles + chunk_tiles - 1) / chunk_tiles;
+    p.splits = splits;
+    p.k_chunk = chunk_tiles * GEMM_BK;
+    dim3 grid(tiles_n, tiles_m, splits);
+    gemm_f32_kernel<AMODE, BMODE, BN, CDIM><<<grid, GEMM_THREADS, 0, stream>>>(p);
+    if (splits > 1) {
+        size_t total = (size_t)p.M * p.N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 4 * n_sms) blocks = 4 * n_sms;
+        splitk_epilogue_kernel<<<blocks, 256, 0, stream>>>(p);
+        return 2;
+    }
+    return 1;
+}
+
+}  // namespace mq

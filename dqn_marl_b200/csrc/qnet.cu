@@ -1,0 +1,493 @@
+// Q-network act / learn — DQNNetwork.forward, DQNAgent.act and DQNAgent.learn of the reference
+// (Louvre_Evacuation/agents/dqn_agent.py:15-61, :101-124, :126-168) as hand-written CUDA.
+//
+//   forward : conv1(6->32) conv2(32->64) conv3(64->128), 3x3 pad 1, ReLU; fc1(15488->512) ReLU Dropout(0.2);
+//             fc2(512->256) ReLU; fc3(256->5).  The NHWC->NCHW permute of dqn_agent.py:37-45 never happens:
+//             activations stay NHWC and the loaders of gemm_f32.cuh index them directly.
+//   act     : fc3 + first-max argmax + epsilon-greedy keyed draw in one kernel (dqn_agent.py:103-104,124).
+//   learn   : target forward -> max_a' Q^-(s',a');  online forward (activations kept);  fused TD target + loss +
+//             dL/dq (dqn_agent.py:143-151);  hand-written backward;  global-norm clip folded into a fused
+//             multi-tensor Adam (dqn_agent.py:158-160);  hard / Polyak target sync (:170-172).
+//
+// INTERNAL PARAMETER LAYOUTS (the 12 bound tensors; the Python side permutes at the state_dict boundary):
+//   convK.weight  [(kh*3+kw)*Cin + c][Cout]      (PyTorch: [Cout][Cin][kh][kw])
+//   fc1.weight    [512][p*128 + c], p = i*11+j   (PyTorch: [512][c*121 + p])
+//   fc2.weight / fc3.weight / all biases: PyTorch layout.
+// Gradients and Adam moments use the same layouts, so clip/Adam are layout-agnostic elementwise passes.
+#include <cmath>
+#include <cstdint>
+#include <new>
+#include "common.h"
+#include "gemm_f32.cuh"
+#include "philox.cuh"
+
+namespace mq {
+
+constexpr int C1 = 32, C2 = 64, C3 = 128, CIN = 6, PIX = 121, FLAT = PIX * C3, H1 = 512, H2 = 256, NA = MQ_N_ACTIONS;
+
+enum { P_C1W, P_C1B, P_C2W, P_C2B, P_C3W, P_C3B, P_F1W, P_F1B, P_F2W, P_F2B, P_F3W, P_F3B };
+static const long long kParamCount[MQ_QNET_TENSORS] = {
+    9LL * CIN * C1, C1, 9LL * C1 * C2, C2, 9LL * C2 * C3, C3, (long long)H1 * FLAT, H1, (long long)H2 * H1, H2, (long long)NA * H2, NA};
+
+// ---- fc3 head ------------------------------------------------------------------------------------------
+// one warp per sample: q[a] = h2 . W3[a] + b3[a]
+// mode 0: write q.  mode 1 (act): epsilon-greedy -> action_out.  mode 2: q_sel[b] = q[action[b]].  mode 3: q_sel[b] = max_a q.
+__global__ void __launch_bounds__(256)
+qhead_kernel(const float* __restrict__ h2, const float* __restrict__ w3, const float* __restrict__ b3, long long B, int mode,
+             float* __restrict__ q_out, const long long* __restrict__ action_in, float* __restrict__ q_sel,
+             int* __restrict__ action_out, float eps, unsigned long long seed, unsigned env_id_base, unsigned tick, int n_robots) {
+    const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float q[NA];
+#pragma unroll
+    for (int a = 0; a < NA; ++a) q[a] = 0.f;
+    const float* h = h2 + b * H2;
+    for (int k = lane; k < H2; k += 32) {
+        const float hv = h[k];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) q[a] = fmaf(hv, __ldg(w3 + a * H2 + k), q[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) q[a] += __shfl_xor_sync(0xFFFFFFFFu, q[a], o);
+        q[a] += __ldg(b3 + a);
+    }
+    if (lane != 0) return;
+    if (q_out) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a) q_out[b * NA + a] = q[a];
+    }
+    int best = 0;
+#pragma unroll
+    for (int a = 1; a < NA; ++a) if (q[a] > q[best]) best = a;          // np.argmax: first maximum (dqn_agent.py:124)
+    if (mode == 1) {
+        // training and np.random.random() <= epsilon -> random.randrange(5) (dqn_agent.py:103-104), keyed draws
+        const unsigned env = env_id_base + (unsigned)(b / n_robots), robot = (unsigned)(b % n_robots);
+        const uint4 w = philox4x32(env, tick, robot, STREAM_AGENT, seed);
+        const double u = u53(w.x, w.y);
+        action_out[b] = (eps > 0.f && u <= (double)eps) ? (int)__umulhi(w.z, (unsigned)NA) : best;
+    } else if (mode == 2) {
+        q_sel[b] = q[(int)action_in[b]];
+    } else if (mode == 3) {
+        q_sel[b] = q[best];
+    }
+}
+
+// ---- TD target + loss + dL/dq (dqn_agent.py:146-151), single CTA: deterministic reduction -------------------
+__global__ void __launch_bounds__(1024)
+td_loss_kernel(const float* __restrict__ q_sa, const float* __restrict__ maxq_next, const float* __restrict__ reward,
+               const uint8_t* __restrict__ done, const long long* __restrict__ action, long long B, float gamma, int huber,
+               float* __restrict__ dq, float* __restrict__ loss_out) {
+    __shared__ float red[32];
+    float local = 0.f;
+    const float invB = 1.f / (float)B;
+    for (long long b = threadIdx.x; b < B; b += blockDim.x) {
+        // target = rewards + (gamma * next_q * ~dones)
+        const float y = reward[b] + (gamma * maxq_next[b]) * (done[b] ? 0.f : 1.f);
+        const float diff = q_sa[b] - y;
+        float l, g;
+        if (huber) { const float ad = fabsf(diff); l = ad <= 1.f ? 0.5f * diff * diff : ad - 0.5f; g = ad <= 1.f ? diff : copysignf(1.f, diff); }
+        else { l = diff * diff; g = 2.f * diff; }                    // F.mse_loss, reduction='mean'
+        local += l;
+        const int a = (int)action[b];
+#pragma unroll
+        for (int k = 0; k < NA; ++k) dq[b * NA + k] = (k == a) ? g * invB : 0.f;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xFFFFFFFFu, local, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (threadIdx.x == 0) *loss_out = v * invB;
+    }
+}
+
+// ---- fc3 backward: dW3[a][k] = sum_b dq[b][a] h2[b][k];  db3[a] = sum_b dq[b][a];  dh2 = (dq W3) * (h2 > 0) --------
+__global__ void __launch_bounds__(256)
+fc3_wgrad_kernel(const float* __restrict__ dq, const float* __restrict__ h2, long long B, float* __restrict__ dw3,
+                 float* __restrict__ db3) {
+    // grid = NA blocks; thread k owns dW3[a][k]; fixed b order: deterministic
+    const int a = blockIdx.x, k = threadIdx.x;
+    float acc = 0.f, accb = 0.f;
+    for (long long b = 0; b < B; ++b) {
+        const float g = __ldg(dq + b * NA + a);
+        if (g != 0.f) { acc = fmaf(g, __ldg(h2 + b * H2 + k), acc); accb += g; }
+    }
+    dw3[a * H2 + k] = acc;
+    if (k == 0) db3[a] = accb;
+}
+__global__ void __launch_bounds__(256)
+fc3_dgrad_kernel(const float* __restrict__ dq, const float* __restrict__ w3, const float* __restrict__ h2, long long B,
+                 float* __restrict__ dh2) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * H2) return;
+    const long long b = idx / H2;
+    const int k = (int)(idx - b * H2);
+    float v = 0.f;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) v = fmaf(__ldg(dq + b * NA + a), __ldg(w3 + a * H2 + k), v);
+    dh2[idx] = h2[idx] > 0.f ? v : 0.f;
+}
+
+// ---- bias gradients: out[n] = sum_m X[m][n], two deterministic stages ---------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ X, long long M, int N, int rows_per_block, float* __restrict__ partial) {
+    const long long m0 = (long long)blockIdx.x * rows_per_block;
+    const long long m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+        float acc = 0.f;
+        for (long long m = m0; m < m1; ++m) acc += __ldg(X + m * N + n);
+        partial[(size_t)blockIdx.x * N + n] = acc;
+    }
+}
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int blocks, int N, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float acc = 0.f;
+    for (int b = 0; b < blocks; ++b) acc += partial[(size_t)b * N + n];
+    out[n] = acc;
+}
+
+// ---- global grad norm (clip_grad_norm_, dqn_agent.py:158) + Adam (:85,160), multi-tensor ---------------------
+struct TensorList {
+    float* p[MQ_QNET_TENSORS]; float* g[MQ_QNET_TENSORS]; float* m[MQ_QNET_TENSORS]; float* v[MQ_QNET_TENSORS];
+    float* t[MQ_QNET_TENSORS];
+    long long n[MQ_QNET_TENSORS];
+    long long chunk_start[MQ_QNET_TENSORS + 1];     // in units of CHUNK elements
+};
+constexpr int CHUNK = 4096;
+
+__device__ __forceinline__ int find_tensor(const TensorList& tl, long long chunk) {
+    int k = 0;
+#pragma unroll
+    for (int i = 1; i < MQ_QNET_TENSORS; ++i) if (chunk >= tl.chunk_start[i]) k = i;
+    return k;
+}
+
+__global__ void __launch_bounds__(256)
+sqnorm_partial_kernel(TensorList tl, float grad_scale, float* __restrict__ partial) {
+    __shared__ float red[8];
+    const long long chunk = blockIdx.x;
+    const int k = find_tensor(tl, chunk);
+    const long long base = (chunk - tl.chunk_start[k]) * CHUNK;
+    const long long end = base + CHUNK < tl.n[k] ? base + CHUNK : tl.n[k];
+    float acc = 0.f;
+    for (long long i = base + threadIdx.x; i < end; i += blockDim.x) { const float g = tl.g[k][i] * grad_scale; acc = fmaf(g, g, acc); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; partial[chunk] = s; }
+}
+__global__ void __launch_bounds__(1024)
+sqnorm_final_kernel(const float* __restrict__ partial, int n, float* __restrict__ gnorm_out) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = red[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (threadIdx.x == 0) *gnorm_out = sqrtf(v);
+    }
+}
+// PyTorch Adam (single-tensor formulation): m.lerp_(g, 1-b1); v = v*b2 + (1-b2) g*g;
+// denom = sqrt(v)/sqrt(bc2) + eps;  p += -(lr/bc1) * m/denom.   g is first scaled by grad_scale (1/world after the
+// all-reduce) and by clip_coef = min(1, clip/(norm + 1e-6)).
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(TensorList tl, const float* __restrict__ gnorm, float grad_scale, float clip_norm, float beta1, float beta2,
+                 float eps, float step_size, float bc2_sqrt) {
+    const long long chunk = blockIdx.x;
+    const int k = find_tensor(tl, chunk);
+    const long long base = (chunk - tl.chunk_start[k]) * CHUNK;
+    const long long end = base + CHUNK < tl.n[k] ? base + CHUNK : tl.n[k];
+    float coef = clip_norm / (*gnorm + 1e-6f);
+    coef = coef > 1.f ? 1.f : coef;
+    const float gs = grad_scale * coef;
+    float* __restrict__ P = tl.p[k]; float* __restrict__ M = tl.m[k]; float* __restrict__ V = tl.v[k];
+    const float* __restrict__ G = tl.g[k];
+    for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
+        const float g = G[i] * gs;
+        float m = M[i], v = V[i];
+        m = m + (g - m) * (1.f - beta1);
+        v = v * beta2 + (1.f - beta2) * g * g;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        P[i] = P[i] - step_size * (m / denom);
+        M[i] = m; V[i] = v;
+    }
+}
+__global__ void __launch_bounds__(256)
+sync_target_kernel(TensorList tl, float tau) {
+    const long long chunk = blockIdx.x;
+    const int k = find_tensor(tl, chunk);
+    const long long base = (chunk - tl.chunk_start[k]) * CHUNK;
+    const long long end = base + CHUNK < tl.n[k] ? base + CHUNK : tl.n[k];
+    for (long long i = base + threadIdx.x; i < end; i += blockDim.x)
+        tl.t[k][i] = tau >= 1.f ? tl.p[k][i] : tau * tl.p[k][i] + (1.f - tau) * tl.t[k][i];
+}
+
+// nn.Dropout(0.2) keep-mask (dqn_agent.py:33,57 — active in act() and learn() because the reference never
+// calls .eval()): 16 keyed Bernoulli(1-p) bytes per Philox call.
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(uint8_t* __restrict__ mask, long long n, unsigned threshold, unsigned long long seed, unsigned long long counter) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // group of 4 bytes... 4 words -> 4 bytes
+    const long long base = g * 4;
+    if (base >= n) return;
+    const uint4 w = philox4x32((unsigned)g, (unsigned)(g >> 32), (unsigned)counter, 64u + (unsigned)(counter >> 32), seed);
+    const unsigned ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (base + k < n) mask[base + k] = ws[k] >= threshold ? 1 : 0;   // keep with prob 1-p
+}
+
+}  // namespace mq
+
+// =================================================================================================
+struct mq_qnet {
+    int device = 0, n_sms = 148;
+    long long max_batch = 0;
+    mq::TensorList tl;
+    long long total_chunks = 0;
+    // workspaces (device)
+    float *a1 = nullptr, *a2 = nullptr, *a3 = nullptr, *h1 = nullptr, *h2 = nullptr;      // activations
+    float *da1 = nullptr, *da2 = nullptr, *da3 = nullptr, *dh1 = nullptr, *dh2 = nullptr; // activation grads
+    float *q = nullptr, *dq = nullptr, *q_sa = nullptr, *maxq = nullptr;
+    float *partial = nullptr; size_t partial_cap = 0;
+    float *norm_partial = nullptr, *gnorm = nullptr;
+    int64_t launches = 0;
+};
+
+namespace mq {
+
+static void free_ws(mq_qnet* n) {
+    float* ptrs[] = {n->a1, n->a2, n->a3, n->h1, n->h2, n->da1, n->da2, n->da3, n->dh1, n->dh2, n->q, n->dq, n->q_sa, n->maxq,
+                     n->partial, n->norm_partial, n->gnorm};
+    for (float* p : ptrs) cudaFree(p);
+}
+
+// forward of one network over B samples; activations land in the handle's workspace
+static int forward_net(mq_qnet* n, float* const* W, const float* obs, long long B, const uint8_t* drop_mask, cudaStream_t s) {
+    const int M = (int)(B * PIX);
+    GemmParams p{};
+    p.batch = (int)B; p.partial = n->partial;
+    // conv1: [M][54] x [54][32]
+    p.M = M; p.N = C1; p.K = 9 * CIN; p.A = obs; p.B = W[P_C1W]; p.ldb = C1; p.C = n->a1; p.ldc = C1; p.bias = W[P_C1B]; p.relu = 1;
+    n->launches += launch_gemm<A_IM2COL, B_ROW, 32, CIN>(p, n->partial_cap, n->n_sms, s);
+    // conv2: [M][288] x [288][64]
+    p.N = C2; p.K = 9 * C1; p.A = n->a1; p.B = W[P_C2W]; p.ldb = C2; p.C = n->a2; p.ldc = C2; p.bias = W[P_C2B];
+    n->launches += launch_gemm<A_IM2COL, B_ROW, 64, C1>(p, n->partial_cap, n->n_sms, s);
+    // conv3: [M][576] x [576][128]
+    p.N = C3; p.K = 9 * C2; p.A = n->a2; p.B = W[P_C3W]; p.ldb = C3; p.C = n->a3; p.ldc = C3; p.bias = W[P_C3B];
+    n->launches += launch_gemm<A_IM2COL, B_ROW, 128, C2>(p, n->partial_cap, n->n_sms, s);
+    // fc1: [B][15488] x W1^T, ReLU, Dropout(0.2) (dqn_agent.py:56-57)
+    p.M = (int)B; p.N = H1; p.K = FLAT; p.A = n->a3; p.lda = FLAT; p.B = W[P_F1W]; p.ldb = FLAT; p.C = n->h1; p.ldc = H1;
+    p.bias = W[P_F1B]; p.drop = drop_mask; p.drop_scale = 1.f / (1.f - 0.2f);
+    n->launches += launch_gemm<A_ROW, B_COL, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    // fc2
+    p.N = H2; p.K = H1; p.A = n->h1; p.lda = H1; p.B = W[P_F2W]; p.ldb = H1; p.C = n->h2; p.ldc = H2; p.bias = W[P_F2B]; p.drop = nullptr;
+    n->launches += launch_gemm<A_ROW, B_COL, 64, 1>(p, n->partial_cap, n->n_sms, s);
+    return 0;
+}
+
+static void launch_colsum(mq_qnet* n, const float* X, long long M, int N, float* out, cudaStream_t s) {
+    int rows = 256;
+    int blocks = (int)((M + rows - 1) / rows);
+    while ((size_t)blocks * N > n->partial_cap) { rows *= 2; blocks = (int)((M + rows - 1) / rows); }
+    colsum_partial_kernel<<<blocks, 256, 0, s>>>(X, M, N, rows, n->partial);
+    colsum_final_kernel<<<(N + 255) / 256, 256, 0, s>>>(n->partial, blocks, N, out);
+    n->launches += 2;
+}
+
+}  // namespace mq
+
+extern "C" int mq_qnet_create(mq_qnet** out, int32_t device, int64_t max_batch, const mq_qnet_bind* bind) {
+    MQ_REQUIRE(out && bind && max_batch > 0, "mq_qnet_create: bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return mq::fail(MQ_ERR_CUDA, "mq_qnet_create: no CUDA device (this build has no CPU fallback)");
+    MQ_CUDA(cudaSetDevice(device));
+    mq_qnet* n = new (std::nothrow) mq_qnet();
+    if (!n) return mq::fail(MQ_ERR_ALLOC, "mq_qnet_create: out of host memory");
+    n->device = device; n->max_batch = max_batch;
+    cudaDeviceGetAttribute(&n->n_sms, cudaDevAttrMultiProcessorCount, device);
+    long long chunk = 0;
+    for (int k = 0; k < MQ_QNET_TENSORS; ++k) {
+        MQ_REQUIRE(bind->online[k] && bind->target[k], "mq_qnet_create: parameter tensor %d missing", k);
+        n->tl.p[k] = bind->online[k]; n->tl.t[k] = bind->target[k]; n->tl.g[k] = bind->grad[k];
+        n->tl.m[k] = bind->adam_m[k]; n->tl.v[k] = bind->adam_v[k];
+        n->tl.n[k] = mq::kParamCount[k];
+        n->tl.chunk_start[k] = chunk;
+        chunk += (mq::kParamCount[k] + mq::CHUNK - 1) / mq::CHUNK;
+    }
+    n->tl.chunk_start[MQ_QNET_TENSORS] = chunk;
+    n->total_chunks = chunk;
+    const size_t B = (size_t)max_batch, f = sizeof(float);
+    n->partial_cap = (size_t)16 << 20;     // 16 Mi floats = 64 MB of split-K / column-sum partials
+    cudaError_t ce = cudaSuccess;
+    auto alloc = [&](float** p, size_t count) { if (ce == cudaSuccess) ce = cudaMalloc((void**)p, count * f); };
+    alloc(&n->a1, B * mq::PIX * mq::C1); alloc(&n->a2, B * mq::PIX * mq::C2); alloc(&n->a3, B * mq::FLAT);
+    alloc(&n->h1, B * mq::H1); alloc(&n->h2, B * mq::H2);
+    if (bind->grad[0]) {
+        alloc(&n->da1, B * mq::PIX * mq::C1); alloc(&n->da2, B * mq::PIX * mq::C2); alloc(&n->da3, B * mq::FLAT);
+        alloc(&n->dh1, B * mq::H1); alloc(&n->dh2, B * mq::H2);
+    }
+    alloc(&n->q, B * mq::NA); alloc(&n->dq, B * mq::NA); alloc(&n->q_sa, B); alloc(&n->maxq, B);
+    alloc(&n->partial, n->partial_cap); alloc(&n->norm_partial, (size_t)chunk + 1); alloc(&n->gnorm, 1);
+    if (ce != cudaSuccess) {
+        mq::free_ws(n); delete n;
+        return mq::fail(MQ_ERR_ALLOC, "mq_qnet_create: workspace allocation for max_batch=%lld failed: %s", (long long)max_batch,
+                        cudaGetErrorString(ce));
+    }
+    *out = n;
+    return MQ_OK;
+}
+
+extern "C" int mq_qnet_destroy(mq_qnet* n) {
+    if (!n) return MQ_OK;
+    mq::free_ws(n);
+    delete n;
+    return MQ_OK;
+}
+extern "C" int64_t mq_qnet_launch_count(const mq_qnet* n) { return n ? n->launches : 0; }
+
+extern "C" int mq_qnet_forward(mq_qnet* n, int32_t which, const float* obs, int64_t B, const uint8_t* drop_mask, float* q_out,
+                               void* stream) {
+    MQ_REQUIRE(n && obs && q_out, "mq_qnet_forward: null argument");
+    MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_forward: batch %lld outside 1..%lld", (long long)B, n->max_batch);
+    cudaStream_t s = (cudaStream_t)stream;
+    float* const* W = which ? n->tl.t : n->tl.p;
+    mq::forward_net(n, W, obs, B, drop_mask, s);
+    const int blocks = (int)((B * 32 + 255) / 256);
+    mq::qhead_kernel<<<blocks, 256, 0, s>>>(n->h2, W[mq::P_F3W], W[mq::P_F3B], B, 0, q_out, nullptr, nullptr, nullptr, 0.f, 0, 0, 0, 1);
+    n->launches += 1;
+    MQ_CUDA(cudaGetLastError());
+    return MQ_OK;
+}
+
+extern "C" int mq_qnet_act(mq_qnet* n, const float* obs, int64_t B, float eps, uint64_t seed, uint32_t env_id_base, uint32_t tick,
+                           int32_t n_robots, const uint8_t* drop_mask, int32_t* action_out, float* q_out, void* stream) {
+    MQ_REQUIRE(n && obs && action_out && n_robots >= 1, "mq_qnet_act: bad argument");
+    MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_act: batch %lld outside 1..%lld", (long long)B, n->max_batch);
+    cudaStream_t s = (cudaStream_t)stream;
+    mq::forward_net(n, n->tl.p, obs, B, drop_mask, s);
+    const int blocks = (int)((B * 32 + 255) / 256);
+    mq::qhead_kernel<<<blocks, 256, 0, s>>>(n->h2, n->tl.p[mq::P_F3W], n->tl.p[mq::P_F3B], B, 1, q_out, nullptr, nullptr, action_out, eps,
+                                            seed, env_id_base, tick, n_robots);
+    n->launches += 1;
+    MQ_CUDA(cudaGetLastError());
+    return MQ_OK;
+}
+
+extern "C" int mq_qnet_td_backward(mq_qnet* n, const float* state, const int64_t* action, const float* reward, const float* next_state,
+                                   const uint8_t* done, int64_t B, const mq_hparams* hp, const uint8_t* drop_online,
+                                   const uint8_t* drop_target, float* loss_out, void* stream) {
+    using namespace mq;
+    MQ_REQUIRE(n && state && action && reward && next_state && done && hp && loss_out, "mq_qnet_td_backward: null argument");
+    MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_td_backward: batch %lld outside 1..%lld", (long long)B, n->max_batch);
+    MQ_REQUIRE(n->tl.g[0] && n->da3, "mq_qnet_td_backward: handle was created without gradient buffers");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int hb = (int)((B * 32 + 255) / 256);
+    // next_q = target_network(next_states).max(1)[0]   (dqn_agent.py:146-147)
+    forward_net(n, n->tl.t, next_state, B, drop_target, s);
+    qhead_kernel<<<hb, 256, 0, s>>>(n->h2, n->tl.t[P_F3W], n->tl.t[P_F3B], B, 3, nullptr, nullptr, n->maxq, nullptr, 0.f, 0, 0, 0, 1);
+    // current_q = q_network(states).gather(1, actions)   (dqn_agent.py:143)
+    forward_net(n, n->tl.p, state, B, drop_online, s);
+    qhead_kernel<<<hb, 256, 0, s>>>(n->h2, n->tl.p[P_F3W], n->tl.p[P_F3B], B, 2, nullptr, (const long long*)action, n->q_sa, nullptr, 0.f,
+                                    0, 0, 0, 1);
+    td_loss_kernel<<<1, 1024, 0, s>>>(n->q_sa, n->maxq, reward, done, (const long long*)action, B, hp->gamma, hp->huber, n->dq, loss_out);
+    n->launches += 3;
+
+    // ---- backward (loss.backward(), dqn_agent.py:154-155) ----
+    float* const* W = n->tl.p; float* const* G = n->tl.g;
+    fc3_wgrad_kernel<<<NA, H2, 0, s>>>(n->dq, n->h2, B, G[P_F3W], G[P_F3B]);
+    fc3_dgrad_kernel<<<(int)((B * H2 + 255) / 256), 256, 0, s>>>(n->dq, W[P_F3W], n->h2, B, n->dh2);
+    n->launches += 2;
+    GemmParams p{};
+    p.batch = (int)B; p.partial = n->partial;
+    // fc2: dW2[256][512] = dh2^T h1 ; db2 ; dh1 = dh2 W2, masked by relu(fc1) > 0 and the dropout mask
+    p.M = H2; p.N = H1; p.K = (int)B; p.A = n->dh2; p.lda = H2; p.B = n->h1; p.ldb = H1; p.C = G[P_F2W]; p.ldc = H1;
+    n->launches += launch_gemm<A_COL, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    launch_colsum(n, n->dh2, B, H2, G[P_F2B], s);
+    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
+    p.M = (int)B; p.N = H1; p.K = H2; p.A = n->dh2; p.lda = H2; p.B = W[P_F2W]; p.ldb = H1; p.C = n->dh1; p.ldc = H1;
+    p.mask_act = n->h1; p.drop = drop_online; p.drop_scale = 1.f / (1.f - 0.2f);
+    n->launches += launch_gemm<A_ROW, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    // fc1: dW1[512][15488] = dh1^T a3 ; db1 ; da3 = dh1 W1 masked by a3 > 0
+    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
+    p.M = H1; p.N = FLAT; p.K = (int)B; p.A = n->dh1; p.lda = H1; p.B = n->a3; p.ldb = FLAT; p.C = G[P_F1W]; p.ldc = FLAT;
+    n->launches += launch_gemm<A_COL, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    launch_colsum(n, n->dh1, B, H1, G[P_F1B], s);
+    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
+    p.M = (int)B; p.N = FLAT; p.K = H1; p.A = n->dh1; p.lda = H1; p.B = W[P_F1W]; p.ldb = FLAT; p.C = n->da3; p.ldc = FLAT; p.mask_act = n->a3;
+    n->launches += launch_gemm<A_ROW, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    // conv3: dWc3[(tap,c)][n] = im2col(a2)^T da3 ; db ; da2 = dgrad masked by a2 > 0
+    const int M = (int)(B * PIX);
+    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
+    p.M = 9 * C2; p.N = C3; p.K = M; p.A = n->a2; p.B = n->da3; p.ldb = C3; p.C = G[P_C3W]; p.ldc = C3;
+    n->launches += launch_gemm<A_IM2COL_T, B_ROW, 128, C2>(p, n->partial_cap, n->n_sms, s);
+    launch_colsum(n, n->da3, M, C3, G[P_C3B], s);
+    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
+    p.M = M; p.N = C2; p.K = 9 * C3; p.A = n->da3; p.B = W[P_C3W]; p.C = n->da2; p.ldc = C2; p.mask_act = n->a2;
+    n->launches += launch_gemm<A_IM2COL_FLIP, B_CONVW_T, 64, C3>(p, n->partial_cap, n->n_sms, s);
+    // conv2
+    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
+    p.M = 9 * C1; p.N = C2; p.K = M; p.A = n->a1; p.B = n->da2; p.ldb = C2; p.C = G[P_C2W]; p.ldc = C2;
+    n->launches += launch_gemm<A_IM2COL_T, B_ROW, 64, C1>(p, n->partial_cap, n->n_sms, s);
+    launch_colsum(n, n->da2, M, C2, G[P_C2B], s);
+    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
+    p.M = M; p.N = C1; p.K = 9 * C2; p.A = n->da2; p.B = W[P_C2W]; p.C = n->da1; p.ldc = C1; p.mask_act = n->a1;
+    n->launches += launch_gemm<A_IM2COL_FLIP, B_CONVW_T, 32, C2>(p, n->partial_cap, n->n_sms, s);
+    // conv1 (no dgrad: the observation needs no gradient)
+    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
+    p.M = 9 * CIN; p.N = C1; p.K = M; p.A = state; p.B = n->da1; p.ldb = C1; p.C = G[P_C1W]; p.ldc = C1;
+    n->launches += launch_gemm<A_IM2COL_T, B_ROW, 32, CIN>(p, n->partial_cap, n->n_sms, s);
+    launch_colsum(n, n->da1, M, C1, G[P_C1B], s);
+    MQ_CUDA(cudaGetLastError());
+    return MQ_OK;
+}
+
+extern "C" int mq_qnet_clip_adam(mq_qnet* n, const mq_hparams* hp, float grad_scale, float* gnorm_out, void* stream) {
+    using namespace mq;
+    MQ_REQUIRE(n && hp && hp->adam_step >= 1, "mq_qnet_clip_adam: bad argument");
+    MQ_REQUIRE(n->tl.g[0] && n->tl.m[0] && n->tl.v[0], "mq_qnet_clip_adam: gradient / Adam buffers not bound");
+    cudaStream_t s = (cudaStream_t)stream;
+    sqnorm_partial_kernel<<<(int)n->total_chunks, 256, 0, s>>>(n->tl, grad_scale, n->norm_partial);
+    sqnorm_final_kernel<<<1, 1024, 0, s>>>(n->norm_partial, (int)n->total_chunks, n->gnorm);
+    // scalars as torch.optim.Adam computes them (Python floats = double), then cast to fp32
+    const double bc1 = 1.0 - std::pow((double)hp->beta1, (double)hp->adam_step);
+    const double bc2 = 1.0 - std::pow((double)hp->beta2, (double)hp->adam_step);
+    const float step_size = (float)((double)hp->lr / bc1);
+    const float bc2_sqrt = (float)std::sqrt(bc2);
+    clip_adam_kernel<<<(int)n->total_chunks, 256, 0, s>>>(n->tl, n->gnorm, grad_scale, hp->clip_norm, hp->beta1, hp->beta2, hp->adam_eps,
+                                                          step_size, bc2_sqrt);
+    if (gnorm_out) MQ_CUDA(cudaMemcpyAsync(gnorm_out, n->gnorm, sizeof(float), cudaMemcpyDeviceToDevice, s));
+    n->launches += 3;
+    MQ_CUDA(cudaGetLastError());
+    return MQ_OK;
+}
+
+extern "C" int mq_qnet_sync_target(mq_qnet* n, float tau, void* stream) {
+    MQ_REQUIRE(n, "mq_qnet_sync_target: null handle");
+    mq::sync_target_kernel<<<(int)n->total_chunks, 256, 0, (cudaStream_t)stream>>>(n->tl, tau);
+    n->launches += 1;
+    MQ_CUDA(cudaGetLastError());
+    return MQ_OK;
+}
+
+extern "C" int mq_qnet_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t counter, void* stream) {
+    MQ_REQUIRE(mask && n > 0 && p >= 0.f && p < 1.f, "mq_qnet_dropout_mask: bad argument");
+    const unsigned threshold = (unsigned)((double)p * 4294967296.0);
+    const long long groups = (n + 3) / 4;
+    mq::dropout_mask_kernel<<<(int)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mask, n, threshold, seed, counter);
+    MQ_CUDA(cudaGetLastError());
+    return MQ_OK;
+}

@@ -191,12 +191,13 @@ int mq_replay_sample(mq_replay* rb, int64_t B, uint64_t seed, uint64_t draw_id, 
                      float* state, int64_t* action, float* reward, float* next_state, uint8_t* done,
                      int64_t* idx_out, void* stream);
 
-#if 0 /* MQ_PENDING: declared for review, enabled when qnet.cu lands */
 /* ------------------------------------------------------------------------
  * Q-network (DQNNetwork, dqn_agent.py:15-61) and learner (DQNAgent.act/learn, :101-172).
- * Parameters live in 12 caller-owned fp32 tensors in state_dict order:
- * conv1.weight(32,6,3,3) conv1.bias conv2.weight(64,32,3,3) conv2.bias conv3.weight(128,64,3,3)
- * conv3.bias fc1.weight(512,15488) fc1.bias fc2.weight(256,512) fc2.bias fc3.weight(5,256) fc3.bias
+ * Parameters live in 12 caller-owned fp32 tensors in state_dict order (conv1.weight conv1.bias conv2.weight
+ * conv2.bias conv3.weight conv3.bias fc1.weight fc1.bias fc2.weight fc2.bias fc3.weight fc3.bias) in the library's
+ * kernel layouts: convK.weight as [(kh*3+kw)*Cin + c][Cout] (PyTorch [Cout][Cin][kh][kw]); fc1.weight as
+ * [512][p*128 + c] with p = i*11+j (PyTorch [512][c*121 + p]); everything else as in PyTorch.  The Python mirror
+ * permutes at the state_dict / checkpoint boundary (dqn_marl_b200/agents/qnet_params.py).
  * ---------------------------------------------------------------------- */
 #define MQ_QNET_TENSORS 12
 #define MQ_QNET_PARAMS 8157093
@@ -227,21 +228,27 @@ int mq_qnet_destroy(mq_qnet* net);
  * dqn_agent.py:37-45 is folded into the conv1 loader).  drop_mask dev u8 [B][512] or NULL (= eval mode). */
 int mq_qnet_forward(mq_qnet* net, int32_t which, const float* obs, int64_t B, const uint8_t* drop_mask,
                     float* q_out, void* stream);
-/* epsilon-greedy (dqn_agent.py:101-124) fused on top of the online forward: action = keyed random if
- * u <= eps else first argmax.  q_out may be NULL. */
+/* epsilon-greedy (dqn_agent.py:101-124) fused on top of the online forward: action = keyed random action if
+ * u <= eps else first argmax.  Sample b belongs to env env_id_base + b / n_robots, robot b % n_robots.
+ * eps = 0 is `training=False`.  q_out may be NULL. */
 int mq_qnet_act(mq_qnet* net, const float* obs, int64_t B, float eps, uint64_t seed, uint32_t env_id_base,
-                uint32_t tick, int32_t n_robots, int32_t* action_out, float* q_out, void* stream);
-/* One DQNAgent.learn() update (dqn_agent.py:143-160) on a sampled batch: TD target, loss, backward,
- * (optional all-reduce hook between backward and clip), global-norm clip, Adam.  loss_out dev f32 [1]. */
-int mq_qnet_backward(mq_qnet* net, const float* state, const int64_t* action, const float* reward,
-                     const float* next_state, const uint8_t* done, int64_t B, const mq_hparams* hp,
-                     float* loss_out, void* stream);
+                uint32_t tick, int32_t n_robots, const uint8_t* drop_mask, int32_t* action_out, float* q_out,
+                void* stream);
+/* The differentiable half of DQNAgent.learn() (dqn_agent.py:143-155) on a sampled batch: target forward, online
+ * forward, TD target, loss, full backward into the bound gradient tensors.  drop_online / drop_target: u8 [B][512]
+ * keep-masks of the two forward passes or NULL (= .eval()).  loss_out dev f32 [1].  The caller may all-reduce the
+ * gradients between this call and mq_qnet_clip_adam. */
+int mq_qnet_td_backward(mq_qnet* net, const float* state, const int64_t* action, const float* reward,
+                        const float* next_state, const uint8_t* done, int64_t B, const mq_hparams* hp,
+                        const uint8_t* drop_online, const uint8_t* drop_target, float* loss_out, void* stream);
+/* clip_grad_norm_(params, clip_norm) + optimizer.step() (dqn_agent.py:158-160).  Gradients are multiplied by
+ * grad_scale first (1/world_size after a summing all-reduce).  gnorm_out dev f32 [1] or NULL. */
 int mq_qnet_clip_adam(mq_qnet* net, const mq_hparams* hp, float grad_scale, float* gnorm_out, void* stream);
 /* update_target_network (dqn_agent.py:170-172): tau = 1 hard copy (reference); tau < 1 Polyak option */
 int mq_qnet_sync_target(mq_qnet* net, float tau, void* stream);
+/* nn.Dropout(0.2) keep-mask from keyed draws: mask dev u8 [n], keep probability 1-p (dqn_agent.py:33,57) */
+int mq_qnet_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t counter, void* stream);
 int64_t mq_qnet_launch_count(const mq_qnet* net);
-
-#endif /* MQ_PENDING */
 
 #ifdef __cplusplus
 }
