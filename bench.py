@@ -276,6 +276,12 @@ def run_ours(args, wl):
     h2d = h_act[0].numel() * 4
     d2h = h_obs.numel() * 4 + h_rew.numel() * 8 + h_don.numel()
 
+    learner = None
+    if args.loop_steps > 0:
+        del envs, obs, rew, don
+        torch.cuda.empty_cache()
+        learner = run_learner_loop(args, wl, layout, dev, rank, world)
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         alg = algorithmic_bytes_per_env_step(layout.L, layout.W, N) * E
@@ -302,10 +308,13 @@ def run_ours(args, wl):
                                  "occupancy to 1 bit/cell and rewrites only changed person fields, so it moves fewer bytes"},
             "value_l2_resident": E * N * args.steps / (warm_ms * 1e-3),
         }
+        if args.loop_steps > 0:
+            line["learner"] = learner
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
-            n_cpu_envs = min(E, 512)
-            cpu_steps = 40
+            n_cpu_envs = min(E, 1024)
+            v0, _ = cpu_port_throughput(layout, wl, n_cpu_envs, 5, 2, threads)
+            cpu_steps = int(max(20, min(5000, 12.0 * v0 / (n_cpu_envs * N))))        # ~12 s of CPU work
             v, dt = cpu_port_throughput(layout, wl, n_cpu_envs, cpu_steps, 5, threads)
             line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
                                     "sample": f"{n_cpu_envs} envs x {N} people x {cpu_steps} steps of the same workload, "
@@ -313,6 +322,64 @@ def run_ours(args, wl):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_learner_loop(args, wl, layout, dev, rank, world):
+    """Secondary metric of BASELINE.json: learner transitions/s in the full act -> step -> push -> learn loop
+    (train_dqn.py:98-125 batched), fp32 parity path of the Q-network, gradient all-reduce over NCCL when N > 1."""
+    import torch
+    import torch.distributed as dist
+    from dqn_marl_b200.runners.train_dqn_vec import VecTrainer
+    E, N, B = wl["envs"], wl["people"], args.learner_batch
+    torch.manual_seed(0)
+    tr = VecTrainer(layout, E, N, dev, dict(batch_size=B, learning_rate=1e-4, gamma=0.99, epsilon=1.0, epsilon_min=0.02,
+                                             epsilon_decay=0.9995, dropout="train"),
+                    env_id_base=rank * E, seed=2026, replay_capacity=max(1 << 17, 4 * E))
+    for _ in range(3):
+        tr.step()
+    torch.cuda.synchronize(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    seg = [0.0, 0.0, 0.0, 0.0]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    l0 = tr.env.launch_count + tr.agent.net.launch_count + tr.agent.memory.launch_count
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.loop_steps):
+        a, e = tr.agent, tr.env
+        o, o2 = tr.obs[tr.cur], tr.obs[tr.cur ^ 1]
+        ev[0].record()
+        actions = a.act_batch(o, training=True)
+        ev[1].record()
+        e.step_into(actions, o2, tr.reward, tr.done)
+        ev[2].record()
+        a.remember_batch(o, actions, tr.reward, o2, tr.done)
+        ev[3].record()
+        a.learn_device()
+        ev[4].record()
+        tr.cur ^= 1
+        torch.cuda.synchronize(dev)
+        for k in range(4):
+            seg[k] += ev[k].elapsed_time(ev[k + 1])
+    t1.record(); torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    total_ms = t0.elapsed_time(t1)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    K = args.loop_steps
+    launches = tr.env.launch_count + tr.agent.net.launch_count + tr.agent.memory.launch_count - l0
+    learn_ms = seg[3] / K
+    return {"metric": "learner transitions/s (full act->step->push->learn loop)", "value": world * B * K / (total_ms * 1e-3),
+            "unit": "transitions/s", "batch_per_gpu": B, "loop_steps": K, "ms_per_loop_step": total_ms / K,
+            "env_agent_steps_per_s_in_loop": world * E * N * K / (total_ms * 1e-3),
+            "segments_ms": {"act": seg[0] / K, "env_step": seg[1] / K, "replay_push": seg[2] / K, "sample+learn": learn_ms},
+            "qnet_dtype": "f32 (parity path, CUDA-core FFMA)", "learn_tflops": 155.4e6 * B / (learn_ms * 1e-3) / 1e12,
+            "act_tflops": 38.85e6 * E / (seg[0] / K * 1e-3) / 1e12, "gpu_launches": int(launches),
+            "allreduce": "nccl all-reduce of the flat 8,157,093-float gradient per learn step" if world > 1 else None}
 
 
 def main():
@@ -324,6 +391,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--prime", type=int, default=150, help="untimed steps per batch before warm-up")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--loop-steps", type=int, default=8, help="steps of the full act/step/push/learn loop (0 = skip)")
+    ap.add_argument("--learner-batch", type=int, default=4096)
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -1,0 +1,98 @@
+"""Batched DQN training loop: the reference's `runners/train_dqn.py` episode loop (act -> env.step -> remember ->
+learn every step once len(memory) > batch_size, train_dqn.py:98-125) over thousands of envs per GPU, with every
+tensor resident on the device and no host synchronisation inside the loop.
+
+    python -m dqn_marl_b200.runners.train_dqn_vec --envs 4096 --people 150 --steps 200 --batch 1024
+    torchrun --nproc-per-node 8 -m dqn_marl_b200.runners.train_dqn_vec ...      (env shards + gradient all-reduce)
+"""
+from __future__ import annotations
+
+import argparse
+import os
+from dataclasses import dataclass
+
+import torch
+
+from ..agents.dqn_agent import VecDQNAgent
+from ..envs.vec_env import VecEvacuationEnv
+from ..layout import Layout
+from ..parallel import env_shard, rank_world
+
+
+@dataclass
+class LoopStats:
+    env_steps: int = 0
+    learn_steps: int = 0
+    last_loss: float = float("nan")
+
+
+class VecTrainer:
+    """One rank's share of the loop.  target_sync_every counts learn steps (the reference syncs every 50 episodes,
+    train_dqn.py:124-125; with thousands of asynchronous episodes per step a step count is the batched analogue)."""
+
+    def __init__(self, layout: Layout, n_envs: int, people: int, device, agent_cfg: dict, env_id_base: int = 0, seed: int = 0,
+                 replay_capacity: int = 1 << 18, target_sync_every: int = 200, strict_reference: bool = False, process_group=None):
+        cfg = dict(agent_cfg)
+        cfg.setdefault("memory_size", replay_capacity)
+        cfg.setdefault("seed", seed)
+        self.env = VecEvacuationEnv(layout, n_envs, people, device=device, seed=seed, env_id_base=env_id_base,
+                                    strict_reference=strict_reference, auto_reset=True)
+        self.agent = VecDQNAgent(self.env.device, cfg, n_envs, layout.n_robots, env_id_base, process_group)
+        dev, E, R = self.env.device, n_envs, layout.n_robots
+        self.obs = [torch.zeros((E, R, 11, 11, 6), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.reward = torch.zeros((E,), dtype=torch.float64, device=dev)
+        self.done = torch.zeros((E,), dtype=torch.uint8, device=dev)
+        self.cur = 0
+        self.target_sync_every = target_sync_every
+        self.stats = LoopStats()
+        self.obs[0].copy_(self.env.reset())
+
+    def step(self, learn: bool = True):
+        a, e = self.agent, self.env
+        o, o2 = self.obs[self.cur], self.obs[self.cur ^ 1]
+        actions = a.act_batch(o, training=True)                                   # dqn_agent.py:101
+        e.step_into(actions, o2, self.reward, self.done)                          # evacuation_env.py:122
+        a.remember_batch(o, actions, self.reward, o2, self.done)                  # dqn_agent.py:97
+        self.cur ^= 1
+        self.stats.env_steps += 1
+        loss = None
+        if learn and len(a.memory) > a.batch_size:                                # train_dqn.py:117-118
+            loss = a.learn_device()
+            self.stats.learn_steps += 1
+            if self.stats.learn_steps % self.target_sync_every == 0:
+                a.update_target_network()
+        return loss
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--envs", type=int, default=4096, help="global number of envs (sharded over ranks)")
+    ap.add_argument("--people", type=int, default=150)
+    ap.add_argument("--grid", type=int, nargs=2, default=[36, 30])
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    rank, world, local = rank_world()
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    first, count = env_shard(rank, world, args.envs)
+    L, W = args.grid
+    layout = Layout.reference_room(L, W) if (L, W) == (36, 30) else Layout.synthetic(L, W, seed=2024)
+    torch.manual_seed(args.seed)
+    tr = VecTrainer(layout, count, args.people, torch.device("cuda", local),
+                    dict(batch_size=args.batch, learning_rate=1e-4, gamma=0.99, epsilon=1.0, epsilon_min=0.02, epsilon_decay=0.9995),
+                    env_id_base=first, seed=args.seed)
+    for t in range(args.steps):
+        loss = tr.step()
+        if rank == 0 and loss is not None and (t % 20 == 0 or t == args.steps - 1):
+            sc = tr.env.scalars
+            print(f"step {t:5d}  loss {loss.item():12.4f}  eps {tr.agent.epsilon:.4f}  evac/env {sc[:, 6].float().mean().item():.2f}"
+                  f"  dead/env {sc[:, 7].float().mean().item():.2f}", flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
