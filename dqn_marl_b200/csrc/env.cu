@@ -1,15 +1,19 @@
 // Batched Louvre_Evacuation environment — fused reset / step kernels (sm_100a).
 //
-// One CTA steps one env instance: EvacuationEnv.step of the reference
+// A GROUP of WPE warps steps one env instance: EvacuationEnv.step of the reference
 // (Louvre_Evacuation/envs/evacuation_env.py:122-172) = move_robot (map.py:160-202) + People.run
 // (people.py:196-253) + fire update (fire_model.py:63-67) + _calculate_reward (:174-288) + done (:155-157)
-// + _get_state (:84-120) in ONE launch.  The occupancy map of the env (People.rmap, 1 bit per cell) is
-// staged in shared memory for the whole step; person state streams through registers, SoA across envs
-// in HBM.  Everything that is fp64 in the reference stays fp64 and is evaluated with the reference's
-// operation order (compiled with -fmad=false), so rewards/health/accumulators are bit-identical.
+// + _get_state (:84-120) in ONE launch.  WPE = 1 (one warp per env, 8 envs per CTA, only __syncwarp between
+// phases) for small envs such as the 150-people room; WPE = 8 (one CTA per env) for the 1000-people grids.
+// The occupancy map of the env (People.rmap, 1 bit per cell) is staged in shared memory for the whole step;
+// person state streams through registers, SoA across envs in HBM.  Everything that is fp64 in the reference
+// stays fp64 and is evaluated in the reference's operation order (compiled with -fmad=false), so
+// rewards / health / accumulators are bit-identical.
 //
-// Sequential semantics reproduced in parallel (DESIGN.md "Conflict resolution"):
-//   * proposals only read rmap as it was before phase 4 (people.py:211-230) -> embarrassingly parallel;
+// Sequential semantics reproduced in parallel:
+//   * proposals only read rmap as it was before phase 4 (people.py:211-230) -> embarrassingly parallel; movers
+//     are compacted and the 8 directions of a mover are scored by 4 lanes (2 directions each), reduced with the
+//     reference's "first strictly greater wins" rule;
 //   * move_plan is a dict keyed by target cell in first-proposer order (people.py:228-230): the key of a
 //     target is min(list index of its proposers) (shared-memory hash table + atomicMin);
 //   * random.shuffle picks the mover (people.py:239): keyed priority, atomicMin on (prio<<32 | index);
@@ -27,6 +31,8 @@ namespace mq {
 
 constexpr int MAXR = MQ_MAX_ROBOTS;
 constexpr uint32_t HEMPTY = 0xFFFFFFFFu;
+constexpr int CTA_THREADS = 256;
+constexpr int CTA_WARPS = CTA_THREADS / 32;
 
 struct DevLayout {
     int L, W, stride, G, wpr, rmap_words;
@@ -47,6 +53,7 @@ struct DevCfg {
     unsigned long long seed;
     int env_id_base, max_steps, reset_robots, reset_fire, auto_reset;
     int hash_cap, hash_shift, n_leaf_max;
+    int smem_per_env;
     double evac_reward, death_penalty, death_acc_penalty, alive_bonus;
 };
 
@@ -60,11 +67,13 @@ __constant__ double c_repel[25];
 __constant__ int c_dx[8] = {1, 0, -1, 0, 1, -1, -1, 1};    // map.py:11-19 MoveTO
 __constant__ int c_dy[8] = {0, -1, 0, 1, -1, -1, 1, 1};
 
+// per-env shared memory (dist aliases the proposal table, which is dead once the moves are applied)
 struct Smem {
     unsigned long long* hbest;
     double* health; double* dist; double* leaf_sum;
     uint32_t* bm; uint32_t* hkey; uint32_t* hmin; uint32_t* hleave; uint32_t* pos; uint32_t* mv;
     int* leaf_off; int* leaf_len;
+    uint16_t* mov;
     uint8_t* fl;
 };
 
@@ -72,22 +81,38 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 
 __host__ __device__ inline size_t carve(Smem& s, unsigned char* base, int N, int cap, int words, int nleaf) {
     size_t o = 0;
-    s.hbest = (unsigned long long*)(base + o); o += sizeof(unsigned long long) * cap;
+    const size_t table = align_up((size_t)cap * 20, 8);                 // hbest u64 + hkey/hmin/hleave u32
+    const size_t distb = sizeof(double) * (size_t)N;
+    s.hbest = (unsigned long long*)(base + o);
+    s.hkey = (uint32_t*)(base + o + (size_t)cap * 8);
+    s.hmin = s.hkey + cap; s.hleave = s.hmin + cap;
+    s.dist = (double*)(base + o);
+    o += table > distb ? table : distb;
     s.health = (double*)(base + o); o += sizeof(double) * N;
-    s.dist = (double*)(base + o); o += sizeof(double) * N;
     s.leaf_sum = (double*)(base + o); o += sizeof(double) * nleaf;
     o = align_up(o, 16);
     s.bm = (uint32_t*)(base + o); o += sizeof(uint32_t) * align_up(words, 4);
-    s.hkey = (uint32_t*)(base + o); o += sizeof(uint32_t) * cap;
-    s.hmin = (uint32_t*)(base + o); o += sizeof(uint32_t) * cap;
-    s.hleave = (uint32_t*)(base + o); o += sizeof(uint32_t) * cap;
     s.pos = (uint32_t*)(base + o); o += sizeof(uint32_t) * N;
     s.mv = (uint32_t*)(base + o); o += sizeof(uint32_t) * N;
     s.leaf_off = (int*)(base + o); o += sizeof(int) * nleaf;
     s.leaf_len = (int*)(base + o); o += sizeof(int) * nleaf;
+    s.mov = (uint16_t*)(base + o); o += sizeof(uint16_t) * align_up(N, 2);
     s.fl = (uint8_t*)(base + o); o += align_up(N, 16);
-    return o;
+    return align_up(o, 16);
 }
+
+// group = the WPE warps that own one env
+template <int WPE>
+struct Group {
+    static constexpr int SIZE = 32 * WPE;
+    int gtid, gid;
+    __device__ __forceinline__ Group() : gtid(threadIdx.x % SIZE), gid(threadIdx.x / SIZE) {}
+    __device__ __forceinline__ void sync() const {
+        if (WPE == 1) __syncwarp();
+        else if (WPE == CTA_WARPS) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(SIZE) : "memory");
+    }
+};
 
 __device__ __forceinline__ uint32_t bm_get(const uint32_t* bm, int wpr, int x, int y) {
     return (bm[x * wpr + (y >> 5)] >> (y & 31)) & 1u;
@@ -107,52 +132,59 @@ __device__ __forceinline__ double box_lookup(const int* box, const double* tab, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// _get_state (evacuation_env.py:84-120) for every robot of the env + occupancy write-back.
-// centre of robot 0 = Map.robot_position (cx0, cy0); robots r >= 1 use Map.robot_positions[r]
-// (evacuation_env_multi.py:44-53).
+// _get_state (evacuation_env.py:84-120) for every robot of the env: one lane per window CELL, six channels
+// written as three 8-byte stores.  Centre of robot 0 = Map.robot_position (cx0, cy0); robots r >= 1 use
+// Map.robot_positions[r] (evacuation_env_multi.py:44-53).
 // ---------------------------------------------------------------------------------------------
-__device__ void gather_obs(const DevLayout& lay, const DevCfg& cfg, const Smem& sm, const int (*rob)[2], int cx0,
-                           int cy0, int fire_step, float* obs, double* obs64, int env) {
-    const int total = cfg.R * MQ_OBS_SIZE;
+template <int WPE>
+__device__ __forceinline__ void gather_obs(const Group<WPE>& g, const DevLayout& lay, const DevCfg& cfg, const Smem& sm,
+                                           const int (*rob)[2], int cx0, int cy0, int fire_step, float* obs, double* obs64,
+                                           int env) {
+    const int cells = cfg.R * MQ_OBS_WIN * MQ_OBS_WIN;
     const int fs = min(fire_step, lay.n_fire_steps - 1);
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        int r = idx / MQ_OBS_SIZE, e = idx - r * MQ_OBS_SIZE;
-        int cell = e / MQ_OBS_CH, c = e - cell * MQ_OBS_CH;
-        int i = cell / MQ_OBS_WIN, j = cell - i * MQ_OBS_WIN;
-        int cx = r == 0 ? cx0 : rob[r][0], cy = r == 0 ? cy0 : rob[r][1];
-        int mx = cx + i - 5, my = cy + j - 5;
-        bool in_grid = mx >= 0 && mx <= lay.L + 1 && my >= 0 && my <= lay.W + 1;
-        uint32_t ci = in_grid ? (uint32_t)__ldg(lay.cellinfo + mx * lay.stride + my) : 2u;   // off-grid: blocked
-        double v;
-        switch (c) {
-            case 0: v = 0.0; break;                                                   // space/inf (quirk Q1)
-            case 1: v = (ci & 1u) ? (double)bm_get(sm.bm, lay.wpr, mx, my) : 0.0; break;
-            case 2: v = box_lookup(lay.int_box, lay.danger_int, fs, mx, my); break;
-            case 3: v = (ci & 2u) ? 1.0 : 0.0; break;
-            case 4: v = (ci & 4u) ? 1.0 : 0.0; break;
-            default: v = (i == 5 && j == 5) ? 1.0 : 0.0; break;
+    for (int idx = g.gtid; idx < cells; idx += Group<WPE>::SIZE) {
+        const int r = idx / (MQ_OBS_WIN * MQ_OBS_WIN), cell = idx - r * (MQ_OBS_WIN * MQ_OBS_WIN);
+        const int i = cell / MQ_OBS_WIN, j = cell - i * MQ_OBS_WIN;
+        const int cx = r == 0 ? cx0 : rob[r][0], cy = r == 0 ? cy0 : rob[r][1];
+        const int mx = cx + i - 5, my = cy + j - 5;
+        const bool in_grid = mx >= 0 && mx <= lay.L + 1 && my >= 0 && my <= lay.W + 1;
+        const uint32_t ci = in_grid ? (uint32_t)__ldg(lay.cellinfo + mx * lay.stride + my) : 2u;   // off-grid: blocked
+        const double v1 = (ci & 1u) ? (double)bm_get(sm.bm, lay.wpr, mx, my) : 0.0;      // rmap if Check_Valid
+        const double v2 = box_lookup(lay.int_box, lay.danger_int, fs, mx, my);           // danger at integer coords
+        const double v3 = (ci & 2u) ? 1.0 : 0.0, v4 = (ci & 4u) ? 1.0 : 0.0;
+        const double v5 = (i == 5 && j == 5) ? 1.0 : 0.0;
+        const size_t o = ((size_t)env * cfg.R + r) * MQ_OBS_SIZE + (size_t)cell * MQ_OBS_CH;
+        if (obs) {                                    // = state.astype(np.float32) at dqn_agent.py:109
+            float2* dst = reinterpret_cast<float2*>(obs + o);
+            dst[0] = make_float2(0.f, (float)v1);     // channel 0 is space/inf == 0 (quirk Q1)
+            dst[1] = make_float2((float)v2, (float)v3);
+            dst[2] = make_float2((float)v4, (float)v5);
         }
-        size_t o = (size_t)env * total + idx;
-        if (obs) obs[o] = (float)v;           // = state.astype(np.float32) at dqn_agent.py:109
-        if (obs64) obs64[o] = v;
+        if (obs64) {
+            double* d = obs64 + o;
+            d[0] = 0.0; d[1] = v1; d[2] = v2; d[3] = v3; d[4] = v4; d[5] = v5;
+        }
     }
 }
 
-__device__ void store_bitmap(const DevLayout& lay, const Smem& sm, uint32_t* g_rmap, int env) {
+template <int WPE>
+__device__ __forceinline__ void store_bitmap(const Group<WPE>& g, const DevLayout& lay, const Smem& sm, uint32_t* g_rmap, int env) {
     uint4* dst = reinterpret_cast<uint4*>(g_rmap + (size_t)env * lay.rmap_words);
     const uint4* src = reinterpret_cast<const uint4*>(sm.bm);
-    for (int w = threadIdx.x; w < lay.rmap_words / 4; w += blockDim.x) dst[w] = src[w];
+    for (int w = g.gtid; w < lay.rmap_words / 4; w += Group<WPE>::SIZE) dst[w] = src[w];
 }
 
 // ---------------------------------------------------------------------------------------------
-// EvacuationEnv.reset (evacuation_env.py:61-82) + People.__init__ spawn (people.py:185-194), CTA-wide.
+// EvacuationEnv.reset (evacuation_env.py:61-82) + People.__init__ spawn (people.py:185-194), group-wide.
 // sc = shared copy of the env scalars, rob = shared copy of robot_positions.
 // ---------------------------------------------------------------------------------------------
-__device__ void reset_env(const DevLayout& lay, const DevCfg& cfg, const DevState& st, const Smem& sm, int* sc,
-                          int (*rob)[2], const int16_t* inject, float* obs, double* obs64, int env) {
-    const int N = cfg.N, T = blockDim.x, tid = threadIdx.x;
-    for (int w = tid; w < (int)align_up(lay.rmap_words, 4); w += T) sm.bm[w] = 0u;
-    __syncthreads();
+template <int WPE>
+__device__ void reset_env(const Group<WPE>& g, const DevLayout& lay, const DevCfg& cfg, const DevState& st, const Smem& sm,
+                          int* sc, int (*rob)[2], const int16_t* inject, float* obs, double* obs64, int env) {
+    constexpr int T = Group<WPE>::SIZE;
+    const int N = cfg.N, tid = g.gtid;
+    for (int w = tid; w < lay.rmap_words; w += T) sm.bm[w] = 0u;
+    g.sync();
     const uint32_t env_id = (uint32_t)(cfg.env_id_base + env);
     const uint32_t episode = (uint32_t)sc[MQ_S_EPISODE];
     const size_t base = (size_t)env * cfg.n_pad;
@@ -176,7 +208,7 @@ __device__ void reset_env(const DevLayout& lay, const DevCfg& cfg, const DevStat
         st.flags[base + i] = 0;
         bm_set(sm.bm, lay.wpr, x, y);     // rmap[x][y] = 1, duplicates allowed (quirk Q2)
     }
-    __syncthreads();
+    g.sync();
     if (tid == 0) {
         if (cfg.reset_robots) {           // evacuation_env_multi.py:35-36
             for (int r = 0; r < cfg.R; ++r) { rob[r][0] = lay.robot_start[r][0]; rob[r][1] = lay.robot_start[r][1]; }
@@ -189,32 +221,39 @@ __device__ void reset_env(const DevLayout& lay, const DevCfg& cfg, const DevStat
         sc[MQ_S_EVAC] = 0; sc[MQ_S_DEAD] = 0;
         sc[MQ_S_EPISODE] = (int)(episode + 1);
     }
-    __syncthreads();
+    g.sync();
     if (tid < MQ_ENV_SCALARS) st.scalars[(size_t)env * MQ_ENV_SCALARS + tid] = sc[tid];
     if (tid < MAXR * 2) st.robots[(size_t)env * MAXR * 2 + tid] = rob[tid >> 1][tid & 1];
-    store_bitmap(lay, sm, st.rmap, env);
-    gather_obs(lay, cfg, sm, rob, sc[MQ_S_ROBOT_POS_X], sc[MQ_S_ROBOT_POS_Y], sc[MQ_S_FIRE_STEP], obs, obs64, env);
+    store_bitmap<WPE>(g, lay, sm, st.rmap, env);
+    gather_obs<WPE>(g, lay, cfg, sm, rob, sc[MQ_S_ROBOT_POS_X], sc[MQ_S_ROBOT_POS_Y], sc[MQ_S_FIRE_STEP], obs, obs64, env);
 }
 
-__global__ void __launch_bounds__(256)
+template <int WPE>
+__global__ void __launch_bounds__(CTA_THREADS)
 env_reset_kernel(DevLayout lay, DevCfg cfg, DevState st, const uint8_t* env_mask, const int16_t* inject, float* obs,
                  double* obs64) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int env = blockIdx.x;
+    constexpr int GROUPS = CTA_WARPS / WPE;
+    __shared__ int s_sc[GROUPS][MQ_ENV_SCALARS];
+    __shared__ int s_rob[GROUPS][MAXR][2];
+    const Group<WPE> g;
+    const int env = blockIdx.x * GROUPS + g.gid;
+    if (env >= cfg.n_envs) return;
     if (env_mask && !env_mask[env]) return;
     Smem sm;
-    carve(sm, smem_raw, cfg.N, cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
-    __shared__ int sc[MQ_ENV_SCALARS];
-    __shared__ int rob[MAXR][2];
-    if (threadIdx.x < MQ_ENV_SCALARS) sc[threadIdx.x] = st.scalars[(size_t)env * MQ_ENV_SCALARS + threadIdx.x];
-    if (threadIdx.x < MAXR * 2) rob[threadIdx.x >> 1][threadIdx.x & 1] = st.robots[(size_t)env * MAXR * 2 + threadIdx.x];
-    __syncthreads();
-    reset_env(lay, cfg, st, sm, sc, rob, inject, obs, obs64, env);
+    carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, cfg.N, cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
+    int* sc = s_sc[g.gid];
+    int(*rob)[2] = s_rob[g.gid];
+    if (g.gtid < MQ_ENV_SCALARS) sc[g.gtid] = st.scalars[(size_t)env * MQ_ENV_SCALARS + g.gtid];
+    if (g.gtid < MAXR * 2) rob[g.gtid >> 1][g.gtid & 1] = st.robots[(size_t)env * MAXR * 2 + g.gtid];
+    g.sync();
+    reset_env<WPE>(g, lay, cfg, st, sm, sc, rob, inject, obs, obs64, env);
 }
 
 // numpy pairwise summation tree (np.mean at evacuation_env.py:228): leaves are blocks of <= 128 elements
 // summed with 8 interleaved accumulators, inner nodes split at n/2 rounded down to a multiple of 8.
 __device__ int enumerate_leaves(int n, int* off, int* len) {
+    if (n <= 128) { off[0] = 0; len[0] = n; return 1; }
     int so[24], sn[24], sp = 0, nl = 0;
     so[0] = 0; sn[0] = n; sp = 1;
     while (sp) {
@@ -230,6 +269,7 @@ __device__ int enumerate_leaves(int n, int* off, int* len) {
     return nl;
 }
 __device__ double combine_leaves(int n, const double* leaf_sum) {
+    if (n <= 128) return leaf_sum[0];
     int sn[40]; signed char sk[40]; double val[24];
     int sp = 0, vp = 0, next = 0;
     sn[0] = n; sk[0] = 0; sp = 1;
@@ -248,7 +288,7 @@ __device__ double combine_leaves(int n, const double* leaf_sum) {
     return val[0];
 }
 // one leaf by a group of 8 lanes (lane g = accumulator r[g]); result valid in group lane 0
-__device__ double leaf_sum8(const double* a, int n, int g, uint32_t gmask) {
+__device__ __forceinline__ double leaf_sum8(const double* a, int n, int g, uint32_t gmask) {
     if (n < 8) {
         double res = 0.;
         if (g == 0) for (int i = 0; i < n; ++i) res += a[i];
@@ -267,20 +307,31 @@ __device__ double leaf_sum8(const double* a, int n, int g, uint32_t gmask) {
 // ---------------------------------------------------------------------------------------------
 // The fused step.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+template <int WPE>
+__global__ void __launch_bounds__(CTA_THREADS)
 env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ actions, float* obs, double* obs64,
                 double* reward_out, uint8_t* done_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem sm;
-    carve(sm, smem_raw, cfg.N, cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
-    __shared__ int sc[MQ_ENV_SCALARS];
-    __shared__ int rob[MAXR][2];
-    __shared__ int s_cnt[4];            // evacuated, dead, guidance in halves, remaining (live)
-    __shared__ int s_wtot[8];
-    __shared__ double s_dist_sum, s_total_health;
-    __shared__ int s_reset;
+    constexpr int GROUPS = CTA_WARPS / WPE;
+    constexpr int T = Group<WPE>::SIZE;
+    __shared__ int s_sc[GROUPS][MQ_ENV_SCALARS];
+    __shared__ int s_rob[GROUPS][MAXR][2];
+    __shared__ int s_cnt_all[GROUPS][6];        // evacuated, dead, guidance in halves, live, movers, reset flag
+    __shared__ int s_wtot_all[GROUPS][WPE];
+    __shared__ double s_sum_all[GROUPS][2];     // sum of distances, total health
 
-    const int env = blockIdx.x, tid = threadIdx.x, T = blockDim.x;
+    const Group<WPE> g;
+    const int env = blockIdx.x * GROUPS + g.gid;
+    if (env >= cfg.n_envs) return;              // whole group leaves together (GROUPS == 1 when WPE == CTA_WARPS)
+    Smem sm;
+    carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, cfg.N, cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
+    int* sc = s_sc[g.gid];
+    int(*rob)[2] = s_rob[g.gid];
+    int* s_cnt = s_cnt_all[g.gid];
+    int* s_wtot = s_wtot_all[g.gid];
+    double* s_sum = s_sum_all[g.gid];
+
+    const int tid = g.gtid;
     const int lane = tid & 31, warp = tid >> 5;
     const int N = cfg.N, stride = lay.stride, wpr = lay.wpr;
     const size_t base = (size_t)env * cfg.n_pad;
@@ -289,7 +340,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     // ---- stage: scalars, robots, occupancy bitmap; clear the proposal table ------------------------
     if (tid < MQ_ENV_SCALARS) sc[tid] = st.scalars[(size_t)env * MQ_ENV_SCALARS + tid];
     if (tid < MAXR * 2) rob[tid >> 1][tid & 1] = st.robots[(size_t)env * MAXR * 2 + tid];
-    if (tid < 4) s_cnt[tid] = 0;
+    if (tid < 6) s_cnt[tid] = 0;
     {
         const uint4* src = reinterpret_cast<const uint4*>(st.rmap + (size_t)env * lay.rmap_words);
         uint4* dst = reinterpret_cast<uint4*>(sm.bm);
@@ -298,7 +349,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     for (int h = tid; h < cfg.hash_cap; h += T) {
         sm.hkey[h] = HEMPTY; sm.hmin[h] = 0xFFFFFFFFu; sm.hleave[h] = 0u; sm.hbest[h] = ~0ull;
     }
-    __syncthreads();
+    g.sync();
 
     // ---- Map.move_robot for every robot, in robot order (map.py:160-202; evacuation_env_multi.py:60-63) ----
     if (tid == 0) {
@@ -314,112 +365,138 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
             if (r == 0) { sc[MQ_S_ROBOT_POS_X] = rob[0][0]; sc[MQ_S_ROBOT_POS_Y] = rob[0][1]; }   // map.py:200-201
         }
     }
-    __syncthreads();
+    g.sync();
 
     const uint32_t env_id = (uint32_t)(cfg.env_id_base + env);
     const uint32_t tick = (uint32_t)sc[MQ_S_TICK];
     const int fire_step = min(sc[MQ_S_FIRE_STEP], lay.n_fire_steps - 1);
-    int rbx[MAXR], rby[MAXR];
-#pragma unroll
-    for (int r = 0; r < MAXR; ++r) { rbx[r] = rob[r < cfg.R ? r : 0][0]; rby[r] = rob[r < cfg.R ? r : 0][1]; }
 
-    // ---- phase 1 + 2 (people.py:203-230): health, speed, accumulator, proposal ---------------------
-    for (int i = tid; i < N; i += T) {
-        uint32_t p = st.pos[base + i];
-        uint32_t fl = st.flags[base + i];
-        double h = st.health[base + i];
-        uint32_t mv = 0;
-        if (!(fl & 3u)) {
-            const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
-            double a = st.acc[base + i];
-            const double danger = box_lookup(lay.ctr_box, lay.danger_ctr, fire_step, x, y);
-            uint4 w4 = make_uint4(0, 0, 0, 0);
-            bool have4 = false;
-            if (danger > 0.0) {                                   // Person.update_health (people.py:61-88)
-                w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
-                have4 = true;
-                const double u = u53(w4.x, w4.y);
-                double loss;
-                if (danger >= 0.8) loss = danger * 50.0 + (1.0 + (3.0 - 1.0) * u);
-                else if (danger >= 0.5) loss = danger * 40.0 + (0.8 + (2.0 - 0.8) * u);
-                else if (danger >= 0.2) loss = danger * 30.0 + (0.5 + (1.5 - 0.5) * u);
-                else loss = danger * 20.0 + (0.2 + (1.0 - 0.2) * u);
-                if (h < 50.0) loss *= 1.2;
-                h -= loss;
-                if (h <= 0.0) { h = 0.0; fl |= 2u; } else if (h <= 8.0) fl |= 2u;
-                h = fmax(0.0, fmin(h, 100.0));
-                st.health[base + i] = h;
-                if (fl & 2u) st.flags[base + i] = (uint8_t)fl;
+    // ---- phase 1 (people.py:203-220): health, speed, accumulator; movers are compacted ------------------
+    for (int i0 = 0; i0 < N; i0 += T) {
+        const int i = i0 + tid;
+        bool mover = false;
+        if (i < N) {
+            const uint32_t p = st.pos[base + i];
+            uint32_t fl = st.flags[base + i];
+            double h = st.health[base + i];
+            if (!(fl & 3u)) {
+                const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
+                double a = st.acc[base + i];
+                const double danger = box_lookup(lay.ctr_box, lay.danger_ctr, fire_step, x, y);
+                if (danger > 0.0) {                                   // Person.update_health (people.py:61-88)
+                    const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
+                    const double u = u53(w4.x, w4.y);
+                    double loss;
+                    if (danger >= 0.8) loss = danger * 50.0 + (1.0 + (3.0 - 1.0) * u);
+                    else if (danger >= 0.5) loss = danger * 40.0 + (0.8 + (2.0 - 0.8) * u);
+                    else if (danger >= 0.2) loss = danger * 30.0 + (0.5 + (1.5 - 0.5) * u);
+                    else loss = danger * 20.0 + (0.2 + (1.0 - 0.2) * u);
+                    if (h < 50.0) loss *= 1.2;
+                    h -= loss;
+                    if (h <= 0.0) { h = 0.0; fl |= 2u; } else if (h <= 8.0) fl |= 2u;
+                    h = fmax(0.0, fmin(h, 100.0));
+                    st.health[base + i] = h;
+                    if (fl & 2u) st.flags[base + i] = (uint8_t)fl;
+                }
+                if (!(fl & 2u)) {
+                    // Person.update_state speed (people.py:38-44), then accumulator (people.py:216-220)
+                    const double speed = (h < 20.0) ? 0.4 : 1.0 * (0.3 + 0.7 * (h / 100.0));
+                    a += speed * 0.5;
+                    if (a >= 1.0) { a -= 1.0; mover = true; }
+                    st.acc[base + i] = a;
+                }
             }
-            if (!(fl & 2u)) {
-                // Person.update_state speed (people.py:38-44), then accumulator (people.py:216-220)
-                const double speed = (h < 20.0) ? 0.4 : 1.0 * (0.3 + 0.7 * (h / 100.0));
-                a += speed * 0.5;
-                if (a >= 1.0) {
-                    a -= 1.0;
-                    // People.find_best_direction (people.py:255-297)
-                    const double2* dp = reinterpret_cast<const double2*>(lay.dp5 + (size_t)(x * stride + y) * 8);
-                    int best = -1;
-                    double max_score = -INFINITY;
+            sm.pos[i] = p;
+            sm.fl[i] = (uint8_t)fl;
+            sm.mv[i] = 0u;
+            sm.health[i] = (fl & 2u) ? 0.0 : h;          // summand of evacuation_env.py:245 (dead -> +0.0)
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mover);
+        if (bal) {
+            int wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&s_cnt[4], __popc(bal));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+            if (mover) sm.mov[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
+        }
+    }
+    g.sync();
+    const int n_mov = s_cnt[4];
+
+    // ---- phase 2 (people.py:221-230, 255-297): 4 lanes score the 8 directions of one mover ----------------
+    {
+        int rbx[MAXR], rby[MAXR];
 #pragma unroll
-                    for (int pc = 0; pc < 4; ++pc) {
-                        const double2 d2v = __ldg(dp + pc);
-                        const double dpv[2] = {d2v.x, d2v.y};
-                        bool adm[2];
+        for (int r = 0; r < MAXR; ++r) { rbx[r] = rob[r < cfg.R ? r : 0][0]; rby[r] = rob[r < cfg.R ? r : 0][1]; }
+        const int q = lane & 3;
+        const int n_items = (n_mov * 4 + 31) & ~31;          // whole warps take part in the shuffles
+        for (int it = tid; it < n_items; it += T) {
+            const int mi = it >> 2;
+            const bool act = mi < n_mov;
+            int i = 0, x = 0, y = 0;
+            double best_score = -INFINITY;
+            int best_dir = 8;
+            if (act) {
+                i = sm.mov[mi];
+                const uint32_t p = sm.pos[i];
+                x = (int)(p & 0xFFFFu); y = (int)(p >> 16);
+                const double2 dpv2 = __ldg(reinterpret_cast<const double2*>(lay.dp5 + (size_t)(x * stride + y) * 8) + q);
+                const double dpv[2] = {dpv2.x, dpv2.y};
+                bool adm[2];
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const int d = pc * 2 + k;
-                            adm[k] = (dpv[k] > -INFINITY) && !bm_get(sm.bm, wpr, x + c_dx[d], y + c_dy[d]);
-                        }
-                        if (adm[0] || adm[1]) {
-                            const uint4 w = philox4x32(env_id, tick, (uint32_t)i, (uint32_t)pc, cfg.seed);
+                for (int k = 0; k < 2; ++k) {
+                    const int d = q * 2 + k;
+                    adm[k] = (dpv[k] > -INFINITY) && !bm_get(sm.bm, wpr, x + c_dx[d], y + c_dy[d]);
+                }
+                if (adm[0] || adm[1]) {
+                    const uint4 w = philox4x32(env_id, tick, (uint32_t)i, (uint32_t)q, cfg.seed);
 #pragma unroll
-                            for (int k = 0; k < 2; ++k) {
-                                if (!adm[k]) continue;
-                                const int d = pc * 2 + k;
-                                const int nx = x + c_dx[d], ny = y + c_dy[d];
-                                int d2 = 0x7FFFFFFF;
-                                for (int r = 0; r < cfg.R; ++r) {
-                                    int ddx = nx - rbx[r], ddy = ny - rby[r];
-                                    // robots may sit far off-map (evaluate_strategies.py:83 sets [1000,1000])
-                                    int q = (abs(ddx) > 30000 || abs(ddy) > 30000) ? 0x7FFFFFFF : ddx * ddx + ddy * ddy;
-                                    d2 = min(d2, q);
-                                }
-                                const double eff = d2 < 25 ? c_repel[d2] : 0.0;
-                                const double u = k ? u53(w.z, w.w) : u53(w.x, w.y);
-                                const double noise = -0.1 + (0.1 - -0.1) * u;        // random.uniform(-0.1, 0.1)
-                                const double score = (dpv[k] + eff) + noise;           // people.py:287-291
-                                if (score > max_score) { max_score = score; best = d; }
-                            }
+                    for (int k = 0; k < 2; ++k) {
+                        if (!adm[k]) continue;
+                        const int d = q * 2 + k;
+                        const int nx = x + c_dx[d], ny = y + c_dy[d];
+                        int d2 = 0x7FFFFFFF;
+                        for (int r = 0; r < cfg.R; ++r) {
+                            const int ddx = nx - rbx[r], ddy = ny - rby[r];
+                            // robots may sit far off-map (evaluate_strategies.py:83 sets [1000,1000])
+                            const int qq = (abs(ddx) > 30000 || abs(ddy) > 30000) ? 0x7FFFFFFF : ddx * ddx + ddy * ddy;
+                            d2 = min(d2, qq);
                         }
-                    }
-                    if (best >= 0) {
-                        if (!have4) w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
-                        const uint32_t t = (uint32_t)((x + c_dx[best]) * stride + (y + c_dy[best]));
-                        uint32_t hh = hash_cell(t, cfg.hash_shift);
-                        for (;;) {                                 // move_plan[(new_x,new_y)] (people.py:228-230)
-                            uint32_t prev = atomicCAS(&sm.hkey[hh], HEMPTY, t);
-                            if (prev == HEMPTY || prev == t) break;
-                            hh = (hh + 1) & hmask;
-                        }
-                        atomicMin(&sm.hmin[hh], (uint32_t)i);
-                        atomicMin(&sm.hbest[hh], ((unsigned long long)w4.z << 32) | (unsigned long long)i);
-                        mv = (hh + 1u) | ((uint32_t)best << 24);
+                        const double eff = d2 < 25 ? c_repel[d2] : 0.0;
+                        const double u = k ? u53(w.z, w.w) : u53(w.x, w.y);
+                        const double noise = -0.1 + (0.1 - -0.1) * u;        // random.uniform(-0.1, 0.1)
+                        const double score = (dpv[k] + eff) + noise;           // people.py:287-291
+                        if (score > best_score) { best_score = score; best_dir = d; }
                     }
                 }
-                st.acc[base + i] = a;
+            }
+            // strict '>' in direction order (people.py:293): larger score wins, ties go to the lower direction
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score, o);
+                const int od = __shfl_xor_sync(0xFFFFFFFFu, best_dir, o);
+                if (os > best_score || (os == best_score && od < best_dir)) { best_score = os; best_dir = od; }
+            }
+            if (act && q == 0 && best_dir < 8) {
+                const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
+                const uint32_t t = (uint32_t)((x + c_dx[best_dir]) * stride + (y + c_dy[best_dir]));
+                uint32_t hh = hash_cell(t, cfg.hash_shift);
+                for (;;) {                                 // move_plan[(new_x,new_y)] (people.py:228-230)
+                    const uint32_t prev = atomicCAS(&sm.hkey[hh], HEMPTY, t);
+                    if (prev == HEMPTY || prev == t) break;
+                    hh = (hh + 1) & hmask;
+                }
+                atomicMin(&sm.hmin[hh], (uint32_t)i);
+                atomicMin(&sm.hbest[hh], ((unsigned long long)w4.z << 32) | (unsigned long long)i);
+                sm.mv[i] = (hh + 1u) | ((uint32_t)best_dir << 24);
             }
         }
-        sm.pos[i] = p;
-        sm.fl[i] = (uint8_t)fl;
-        sm.mv[i] = mv;
-        sm.health[i] = (fl & 2u) ? 0.0 : h;          // summand of evacuation_env.py:245 (dead -> +0.0)
     }
-    __syncthreads();
+    g.sync();
 
     // ---- phase 4a: winners leave their old cell (people.py:239-246,301) ---------------------------------
-    for (int i = tid; i < N; i += T) {
-        uint32_t mv = sm.mv[i];
+    for (int mi = tid; mi < n_mov; mi += T) {
+        const int i = sm.mov[mi];
+        const uint32_t mv = sm.mv[i];
         if (!mv) continue;
         const uint32_t slot = (mv & 0xFFFFFFu) - 1u;
         if ((uint32_t)sm.hbest[slot] != (uint32_t)i) continue;      // lost the shuffle: stays (people.py:248-249)
@@ -431,7 +508,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         uint32_t hh = hash_cell(c_old, cfg.hash_shift);
         bool found = false;
         for (;;) {
-            uint32_t k = sm.hkey[hh];
+            const uint32_t k = sm.hkey[hh];
             if (k == HEMPTY) break;
             if (k == c_old) { found = true; break; }
             hh = (hh + 1) & hmask;
@@ -439,10 +516,11 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         if (found) atomicMax(&sm.hleave[hh], key + 1u);     // old cell is somebody's target: order decides
         else bm_clear(sm.bm, wpr, x, y);                    // rmap[old] = 0
     }
-    __syncthreads();
+    g.sync();
 
     // ---- phase 4b: winners enter their target (people.py:302-314) --------------------------------------
-    for (int i = tid; i < N; i += T) {
+    for (int mi = tid; mi < n_mov; mi += T) {
+        const int i = sm.mov[mi];
         const uint32_t mv = sm.mv[i];
         if (!(mv & 0x80000000u)) continue;
         const uint32_t slot = (mv & 0xFFFFFFu) - 1u;
@@ -455,9 +533,9 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         const uint32_t np = (uint32_t)nx | ((uint32_t)ny << 16);
         sm.pos[i] = np;
         st.pos[base + i] = np;
-        if (evac) { uint8_t f = sm.fl[i] | 1u; sm.fl[i] = f; st.flags[base + i] = f; }
+        if (evac) { const uint8_t f = sm.fl[i] | 1u; sm.fl[i] = f; st.flags[base + i] = f; }
     }
-    __syncthreads();
+    g.sync();      // the proposal table is dead from here on: sm.dist may overwrite it
 
     // ---- reward inputs (evacuation_env.py:174-233): counts, guidance, ordered list of distances --------
     const int rpx = sc[MQ_S_ROBOT_POS_X], rpy = sc[MQ_S_ROBOT_POS_Y];
@@ -470,14 +548,16 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
             evac += f & 1u; dead += (f >> 1) & 1u;
             if (!(f & 3u)) ++live;
         }
-        // exclusive block scan of `live`
+        // exclusive scan of `live` over the group
         int incl = live;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
-        if (lane == 31) s_wtot[warp] = incl;
-        __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
         int off = incl - live;
-        for (int w = 0; w < warp; ++w) off += s_wtot[w];
+        if (WPE > 1) {
+            if (lane == 31) s_wtot[warp] = incl;
+            g.sync();
+            for (int w = 0; w < warp; ++w) off += s_wtot[w];
+        }
         for (int i = i0; i < i1; ++i) {
             const uint32_t f = sm.fl[i];
             if (f & 3u) continue;
@@ -502,50 +582,58 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
             guid += __shfl_xor_sync(0xFFFFFFFFu, guid, o);
             live += __shfl_xor_sync(0xFFFFFFFFu, live, o);
         }
-        if (lane == 0) { atomicAdd(&s_cnt[0], evac); atomicAdd(&s_cnt[1], dead); atomicAdd(&s_cnt[2], guid); atomicAdd(&s_cnt[3], live); }
+        if (lane == 0) {
+            if (WPE == 1) { s_cnt[0] = evac; s_cnt[1] = dead; s_cnt[2] = guid; s_cnt[3] = live; }
+            else { atomicAdd(&s_cnt[0], evac); atomicAdd(&s_cnt[1], dead); atomicAdd(&s_cnt[2], guid); atomicAdd(&s_cnt[3], live); }
+        }
     }
-    __syncthreads();
+    g.sync();
 
     // fire models step (evacuation_env.py:138-142; fire_model.py:63-67) — observation uses the new step
     const int new_fire = min(sc[MQ_S_FIRE_STEP] + 1, lay.n_fire_steps - 1);
 
-    // ---- order-dependent fp64 sums: warp 0 = np.mean tree, warp 1 lane 0 = sum() chain; rest: outputs ----
+    // ---- order-dependent fp64 sums: np.mean tree (warp 0) and the left-to-right sum() chain -----------------
+    // WPE > 1: warp 0 does the tree, lane 0 of warp 1 the chain, the other warps start on the outputs.
+    // WPE == 1: lane 31 runs the chain while lanes 0..7 of the same warp... no: a warp executes one path at a time,
+    // so the chain (lane 0) simply follows the tree.
     if (warp == 0) {
         const int n = s_cnt[3];
         int nl = 0;
         if (lane == 0) nl = enumerate_leaves(n, sm.leaf_off, sm.leaf_len);
         nl = __shfl_sync(0xFFFFFFFFu, nl, 0);
         __syncwarp();
-        const int g = lane & 7, grp = lane >> 3;
+        const int gl = lane & 7, grp = lane >> 3;
         const uint32_t gmask = 0xFFu << (grp * 8);
         for (int l0 = 0; l0 < nl; l0 += 4) {
             const int l = l0 + grp;
             if (l < nl) {
-                double s = leaf_sum8(sm.dist + sm.leaf_off[l], sm.leaf_len[l], g, gmask);
-                if (g == 0) sm.leaf_sum[l] = s;
+                const double s = leaf_sum8(sm.dist + sm.leaf_off[l], sm.leaf_len[l], gl, gmask);
+                if (gl == 0) sm.leaf_sum[l] = s;
             }
         }
         __syncwarp();
-        if (lane == 0) s_dist_sum = combine_leaves(n, sm.leaf_sum);
-    } else if (warp == 1 && lane == 0) {
+        if (lane == 0) s_sum[0] = combine_leaves(n, sm.leaf_sum);
+    }
+    if ((WPE == 1 && lane == 0) || (WPE > 1 && warp == 1 && lane == 0)) {
         double tot = 0.0;
         for (int i = 0; i < N; ++i) tot += sm.health[i];       // left-to-right, dead contribute +0.0
-        s_total_health = tot;
+        s_sum[1] = tot;
     }
-    store_bitmap(lay, sm, st.rmap, env);
-    gather_obs(lay, cfg, sm, rob, rpx, rpy, new_fire, obs, obs64, env);
-    __syncthreads();
+    store_bitmap<WPE>(g, lay, sm, st.rmap, env);
+    gather_obs<WPE>(g, lay, cfg, sm, rob, rpx, rpy, new_fire, obs, obs64, env);
+    g.sync();
 
     // ---- _calculate_reward (evacuation_env.py:174-288), done (:150-157), scalars -----------------------
     if (tid == 0) {
         const int cur_evac = s_cnt[0], cur_dead = s_cnt[1], n_rem = s_cnt[3];
         const int cur_step = sc[MQ_S_CUR_STEP];
         const int remaining = N - cur_evac - cur_dead;
+        const double total_health = s_sum[1];
         double reward = 0.0;
         reward += (double)(cur_evac - sc[MQ_S_PREV_EVAC]) * cfg.evac_reward;
         reward += (double)s_cnt[2] * 0.5;
         if (remaining > 0 && n_rem > 0) {
-            const double avg = s_dist_sum / (double)n_rem;
+            const double avg = s_sum[0] / (double)n_rem;
             double dr = 2.0 - fabs(avg - 8.0) * 0.2;
             if (!(dr > 0.0)) dr = 0.0;
             reward += dr;
@@ -558,13 +646,13 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
             reward -= 0.02;
         }
         if (N - cur_dead > 0) {
-            const double avg_health = s_total_health / (double)(N - cur_dead);
+            const double avg_health = total_health / (double)(N - cur_dead);
             reward += (avg_health - 90.0) * 0.05;
         }
         if (cur_evac == N) {
             const int rem_steps = max(0, 300 - cur_step);
             const double time_bonus = (double)rem_steps * 0.2;
-            const double final_avg = s_total_health / (double)N;      // nobody is dead here: same chain
+            const double final_avg = total_health / (double)N;      // nobody is dead here: same chain
             const double health_bonus = (final_avg - 80.0) * 1.0;
             reward += (100.0 + time_bonus) + health_bonus;
         }
@@ -583,11 +671,11 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         sc[MQ_S_PREV_EVAC] = cur_evac; sc[MQ_S_PREV_DEAD] = cur_dead;
         sc[MQ_S_EVAC] = cur_evac; sc[MQ_S_DEAD] = cur_dead;
         sc[MQ_S_TICK] = (int)(tick + 1u);
-        s_reset = done && cfg.auto_reset;
+        s_cnt[5] = done && cfg.auto_reset;
     }
-    __syncthreads();
-    if (s_reset) {
-        reset_env(lay, cfg, st, sm, sc, rob, nullptr, obs, obs64, env);
+    g.sync();
+    if (s_cnt[5]) {
+        reset_env<WPE>(g, lay, cfg, st, sm, sc, rob, nullptr, obs, obs64, env);
     } else {
         if (tid < MQ_ENV_SCALARS) st.scalars[(size_t)env * MQ_ENV_SCALARS + tid] = sc[tid];
         if (tid < MAXR * 2) st.robots[(size_t)env * MAXR * 2 + tid] = rob[tid >> 1][tid & 1];
@@ -614,8 +702,9 @@ struct mq_env {
     mq::DevCfg cfg;
     mq::DevState st;
     void* d_dp5 = nullptr; void* d_cellinfo = nullptr; void* d_ctr = nullptr; void* d_int = nullptr;
-    int threads = 256;
-    size_t smem = 0;
+    int wpe = 8;            // warps per env
+    int blocks = 0;
+    size_t smem = 0;        // dynamic shared memory per CTA
     int64_t launches = 0;
 };
 
@@ -631,9 +720,17 @@ extern "C" int mq_env_state_sizes(const mq_env_cfg* cfg, const mq_layout* layout
     return MQ_OK;
 }
 
+template <int WPE>
+static cudaError_t set_smem_attr(int bytes) {
+    cudaError_t e = cudaFuncSetAttribute(mq::env_step_kernel<WPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(mq::env_reset_kernel<WPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layout* layout, const mq_env_state* state) {
     MQ_REQUIRE(out && cfg && layout && state, "mq_env_create: null argument");
     MQ_REQUIRE(cfg->n_envs > 0 && cfg->n_people > 0, "mq_env_create: n_envs and n_people must be positive");
+    MQ_REQUIRE(cfg->n_people < 65536, "mq_env_create: at most 65535 people per env");
     MQ_REQUIRE(cfg->n_robots >= 1 && cfg->n_robots <= MQ_MAX_ROBOTS, "mq_env_create: n_robots must be in 1..%d", MQ_MAX_ROBOTS);
     MQ_REQUIRE(layout->L >= 3 && layout->W >= 3 && layout->L <= 32000 && layout->W <= 32000, "mq_env_create: bad grid size");
     MQ_REQUIRE(layout->dp5 && layout->cellinfo && layout->danger_ctr && layout->danger_int, "mq_env_create: layout tables missing");
@@ -685,7 +782,8 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     c.n_envs = cfg->n_envs; c.N = cfg->n_people; c.n_pad = (cfg->n_people + 15) / 16 * 16; c.R = cfg->n_robots;
     c.seed = cfg->seed; c.env_id_base = cfg->env_id_base; c.max_steps = cfg->max_steps;
     c.reset_robots = cfg->reset_robots; c.reset_fire = cfg->reset_fire; c.auto_reset = cfg->auto_reset;
-    c.hash_cap = round_pow2(2 * c.N < 64 ? 64 : 2 * c.N);
+    int want = c.N + c.N / 3 + 8;                      // load factor <= 0.75 even if everybody proposes a distinct cell
+    c.hash_cap = round_pow2(want < 64 ? 64 : want);
     int lg = 0; while ((1 << lg) < c.hash_cap) ++lg;
     c.hash_shift = 32 - lg;
     c.n_leaf_max = c.N / 64 + 4;
@@ -693,22 +791,26 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     c.death_acc_penalty = cfg->death_acc_penalty; c.alive_bonus = cfg->alive_bonus;
     e->st = {state->pos, state->health, state->acc, state->flags, state->rmap, state->robots, state->scalars};
 
-    e->threads = (c.N + 31) / 32 * 32;
-    if (e->threads < 64) e->threads = 64;
-    if (e->threads > 256) e->threads = 256;
     mq::Smem tmp;
-    e->smem = mq::carve(tmp, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max);
+    c.smem_per_env = (int)mq::carve(tmp, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
-    if ((int)e->smem + 1024 > max_smem) {
+    // warps per env: one warp for small envs (no CTA barriers), the whole CTA for big ones
+    e->wpe = c.N <= 256 ? 1 : (c.N <= 512 ? 2 : 8);
+    while (e->wpe < 8 && (size_t)c.smem_per_env * (mq::CTA_WARPS / e->wpe) + 2048 > (size_t)max_smem) e->wpe *= 2;
+    if (e->wpe == 4) e->wpe = 8;
+    const int groups = mq::CTA_WARPS / e->wpe;
+    e->smem = (size_t)c.smem_per_env * groups;
+    if ((int)e->smem + 2048 > max_smem) {
         size_t need = e->smem;
         mq_env_destroy(e);
         return mq::fail(MQ_ERR_UNSUPPORTED,
                         "mq_env_create: env of %d people on a %dx%d grid needs %zu B of shared memory per CTA (limit %d); "
                         "the tiled large-env kernel is not built yet", cfg->n_people, layout->L, layout->W, need, max_smem);
     }
-    if ((ce = cudaFuncSetAttribute(mq::env_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem)) != cudaSuccess ||
-        (ce = cudaFuncSetAttribute(mq::env_reset_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem)) != cudaSuccess) {
+    e->blocks = (c.n_envs + groups - 1) / groups;
+    ce = e->wpe == 1 ? set_smem_attr<1>((int)e->smem) : (e->wpe == 2 ? set_smem_attr<2>((int)e->smem) : set_smem_attr<8>((int)e->smem));
+    if (ce != cudaSuccess) {
         mq_env_destroy(e);
         return mq::fail(MQ_ERR_CUDA, "mq_env_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
     }
@@ -734,8 +836,10 @@ extern "C" int mq_env_set_reward_coefs(mq_env* e, double evac_reward, double dea
 extern "C" int mq_env_reset(mq_env* e, const uint8_t* env_mask, const int16_t* inject_spawn, float* obs_out,
                             double* obs64_out, void* stream) {
     MQ_REQUIRE(e, "mq_env_reset: null handle");
-    mq::env_reset_kernel<<<e->cfg.n_envs, e->threads, e->smem, (cudaStream_t)stream>>>(e->lay, e->cfg, e->st, env_mask,
-                                                                                       inject_spawn, obs_out, obs64_out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (e->wpe == 1) mq::env_reset_kernel<1><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
+    else if (e->wpe == 2) mq::env_reset_kernel<2><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
+    else mq::env_reset_kernel<8><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
     MQ_CUDA(cudaGetLastError());
     e->launches += 1;
     return MQ_OK;
@@ -744,8 +848,10 @@ extern "C" int mq_env_reset(mq_env* e, const uint8_t* env_mask, const int16_t* i
 extern "C" int mq_env_step(mq_env* e, const int32_t* actions, float* obs_out, double* obs64_out, double* reward_out,
                            uint8_t* done_out, void* stream) {
     MQ_REQUIRE(e && actions && reward_out && done_out, "mq_env_step: null argument");
-    mq::env_step_kernel<<<e->cfg.n_envs, e->threads, e->smem, (cudaStream_t)stream>>>(e->lay, e->cfg, e->st, actions, obs_out,
-                                                                                      obs64_out, reward_out, done_out);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (e->wpe == 1) mq::env_step_kernel<1><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
+    else if (e->wpe == 2) mq::env_step_kernel<2><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
+    else mq::env_step_kernel<8><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
     MQ_CUDA(cudaGetLastError());
     e->launches += 1;
     return MQ_OK;
