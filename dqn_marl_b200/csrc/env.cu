@@ -31,8 +31,7 @@ namespace mq {
 
 constexpr int MAXR = MQ_MAX_ROBOTS;
 constexpr uint32_t HEMPTY = 0xFFFFFFFFu;
-constexpr int CTA_THREADS = 256;
-constexpr int CTA_WARPS = CTA_THREADS / 32;
+constexpr int MAX_CTA_THREADS = 256;
 
 struct DevLayout {
     int L, W, stride, G, wpr, rmap_words;
@@ -64,16 +63,21 @@ struct DevState {
 // -20.0 / (sqrt(d2) + 0.1) for d2 = 0..24: People.ROBOT_REPEL_K / (dist + 0.1), dist < ROBOT_REPEL_RANGE
 // (people.py:94-95,282-284).  dist = sqrt of an exact integer, so the table is exact.
 __constant__ double c_repel[25];
-__constant__ int c_dx[8] = {1, 0, -1, 0, 1, -1, -1, 1};    // map.py:11-19 MoveTO
-__constant__ int c_dy[8] = {0, -1, 0, 1, -1, -1, 1, 1};
+// map.py:11-19 MoveTO = (1,0) (0,-1) (-1,0) (0,1) (1,-1) (-1,-1) (-1,1) (1,1), packed 2 bits per direction (+1)
+__device__ __forceinline__ int move_dx(int d) { return (int)((0x8246u >> (2 * d)) & 3u) - 1; }
+__device__ __forceinline__ int move_dy(int d) { return (int)((0xA091u >> (2 * d)) & 3u) - 1; }
+
+// proposal-table slot (16 B): best = (priority << 32 | proposer index) min; key = target cell;
+// ml = (min proposer index) | (max key+1 of the winners that left this cell) << 16
+struct __align__(16) Slot { unsigned long long best; uint32_t key; uint32_t ml; };
 
 // per-env shared memory (dist aliases the proposal table, which is dead once the moves are applied)
 struct Smem {
-    unsigned long long* hbest;
+    Slot* tab;
     double* health; double* dist; double* leaf_sum;
-    uint32_t* bm; uint32_t* hkey; uint32_t* hmin; uint32_t* hleave; uint32_t* pos; uint32_t* mv;
+    uint32_t* bm; uint32_t* pos;
     int* leaf_off; int* leaf_len;
-    uint16_t* mov;
+    uint16_t* mov; uint16_t* mv;
     uint8_t* fl;
 };
 
@@ -81,37 +85,42 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 
 __host__ __device__ inline size_t carve(Smem& s, unsigned char* base, int N, int cap, int words, int nleaf) {
     size_t o = 0;
-    const size_t table = align_up((size_t)cap * 20, 8);                 // hbest u64 + hkey/hmin/hleave u32
+    const size_t table = (size_t)cap * sizeof(Slot);
     const size_t distb = sizeof(double) * (size_t)N;
-    s.hbest = (unsigned long long*)(base + o);
-    s.hkey = (uint32_t*)(base + o + (size_t)cap * 8);
-    s.hmin = s.hkey + cap; s.hleave = s.hmin + cap;
+    s.tab = (Slot*)(base + o);
     s.dist = (double*)(base + o);
-    o += table > distb ? table : distb;
+    o += align_up(table > distb ? table : distb, 16);
     s.health = (double*)(base + o); o += sizeof(double) * N;
     s.leaf_sum = (double*)(base + o); o += sizeof(double) * nleaf;
     o = align_up(o, 16);
     s.bm = (uint32_t*)(base + o); o += sizeof(uint32_t) * align_up(words, 4);
     s.pos = (uint32_t*)(base + o); o += sizeof(uint32_t) * N;
-    s.mv = (uint32_t*)(base + o); o += sizeof(uint32_t) * N;
     s.leaf_off = (int*)(base + o); o += sizeof(int) * nleaf;
     s.leaf_len = (int*)(base + o); o += sizeof(int) * nleaf;
     s.mov = (uint16_t*)(base + o); o += sizeof(uint16_t) * align_up(N, 2);
+    s.mv = (uint16_t*)(base + o); o += sizeof(uint16_t) * align_up(N, 2);
     s.fl = (uint8_t*)(base + o); o += align_up(N, 16);
     return align_up(o, 16);
 }
 
-// group = the WPE warps that own one env
-template <int WPE>
+// group = the WPE warps that own one env; CW = warps per CTA.  With WPE == 8 the last warp is the "chain warp": it
+// takes part in the load phases, then runs the sequential health sum while the 7 worker warps do everything else.
+template <int WPE, int CW>
 struct Group {
     static constexpr int SIZE = 32 * WPE;
+    static constexpr int WORKERS = WPE == 1 ? 32 : SIZE - 32;
     int gtid, gid;
     __device__ __forceinline__ Group() : gtid(threadIdx.x % SIZE), gid(threadIdx.x / SIZE) {}
-    __device__ __forceinline__ void sync() const {
+    __device__ __forceinline__ void sync() const {          // all threads of the group
         if (WPE == 1) __syncwarp();
-        else if (WPE == CTA_WARPS) __syncthreads();
-        else asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "r"(SIZE) : "memory");
+        else if (WPE == CW) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(2 * gid + 1), "r"(SIZE) : "memory");
     }
+    __device__ __forceinline__ void wsync() const {         // worker threads only
+        if (WPE == 1) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(2 * gid + 2), "r"(WORKERS) : "memory");
+    }
+    __device__ __forceinline__ bool worker() const { return WPE == 1 || gtid < WORKERS; }
 };
 
 __device__ __forceinline__ uint32_t bm_get(const uint32_t* bm, int wpr, int x, int y) {
@@ -134,15 +143,14 @@ __device__ __forceinline__ double box_lookup(const int* box, const double* tab, 
 // ---------------------------------------------------------------------------------------------
 // _get_state (evacuation_env.py:84-120) for every robot of the env: one lane per window CELL, six channels
 // written as three 8-byte stores.  Centre of robot 0 = Map.robot_position (cx0, cy0); robots r >= 1 use
-// Map.robot_positions[r] (evacuation_env_multi.py:44-53).
+// Map.robot_positions[r] (evacuation_env_multi.py:44-53).  Executed by `nthr` threads with ids `tid`.
 // ---------------------------------------------------------------------------------------------
-template <int WPE>
-__device__ __forceinline__ void gather_obs(const Group<WPE>& g, const DevLayout& lay, const DevCfg& cfg, const Smem& sm,
+__device__ __forceinline__ void gather_obs(int tid, int nthr, const DevLayout& lay, const DevCfg& cfg, const Smem& sm,
                                            const int (*rob)[2], int cx0, int cy0, int fire_step, float* obs, double* obs64,
                                            int env) {
     const int cells = cfg.R * MQ_OBS_WIN * MQ_OBS_WIN;
     const int fs = min(fire_step, lay.n_fire_steps - 1);
-    for (int idx = g.gtid; idx < cells; idx += Group<WPE>::SIZE) {
+    for (int idx = tid; idx < cells; idx += nthr) {
         const int r = idx / (MQ_OBS_WIN * MQ_OBS_WIN), cell = idx - r * (MQ_OBS_WIN * MQ_OBS_WIN);
         const int i = cell / MQ_OBS_WIN, j = cell - i * MQ_OBS_WIN;
         const int cx = r == 0 ? cx0 : rob[r][0], cy = r == 0 ? cy0 : rob[r][1];
@@ -167,21 +175,20 @@ __device__ __forceinline__ void gather_obs(const Group<WPE>& g, const DevLayout&
     }
 }
 
-template <int WPE>
-__device__ __forceinline__ void store_bitmap(const Group<WPE>& g, const DevLayout& lay, const Smem& sm, uint32_t* g_rmap, int env) {
+__device__ __forceinline__ void store_bitmap(int tid, int nthr, const DevLayout& lay, const Smem& sm, uint32_t* g_rmap, int env) {
     uint4* dst = reinterpret_cast<uint4*>(g_rmap + (size_t)env * lay.rmap_words);
     const uint4* src = reinterpret_cast<const uint4*>(sm.bm);
-    for (int w = g.gtid; w < lay.rmap_words / 4; w += Group<WPE>::SIZE) dst[w] = src[w];
+    for (int w = tid; w < lay.rmap_words / 4; w += nthr) dst[w] = src[w];
 }
 
 // ---------------------------------------------------------------------------------------------
 // EvacuationEnv.reset (evacuation_env.py:61-82) + People.__init__ spawn (people.py:185-194), group-wide.
 // sc = shared copy of the env scalars, rob = shared copy of robot_positions.
 // ---------------------------------------------------------------------------------------------
-template <int WPE>
-__device__ void reset_env(const Group<WPE>& g, const DevLayout& lay, const DevCfg& cfg, const DevState& st, const Smem& sm,
+template <int WPE, int CW>
+__device__ void reset_env(const Group<WPE, CW>& g, const DevLayout& lay, const DevCfg& cfg, const DevState& st, const Smem& sm,
                           int* sc, int (*rob)[2], const int16_t* inject, float* obs, double* obs64, int env) {
-    constexpr int T = Group<WPE>::SIZE;
+    constexpr int T = Group<WPE, CW>::SIZE;
     const int N = cfg.N, tid = g.gtid;
     for (int w = tid; w < lay.rmap_words; w += T) sm.bm[w] = 0u;
     g.sync();
@@ -224,19 +231,19 @@ __device__ void reset_env(const Group<WPE>& g, const DevLayout& lay, const DevCf
     g.sync();
     if (tid < MQ_ENV_SCALARS) st.scalars[(size_t)env * MQ_ENV_SCALARS + tid] = sc[tid];
     if (tid < MAXR * 2) st.robots[(size_t)env * MAXR * 2 + tid] = rob[tid >> 1][tid & 1];
-    store_bitmap<WPE>(g, lay, sm, st.rmap, env);
-    gather_obs<WPE>(g, lay, cfg, sm, rob, sc[MQ_S_ROBOT_POS_X], sc[MQ_S_ROBOT_POS_Y], sc[MQ_S_FIRE_STEP], obs, obs64, env);
+    store_bitmap(tid, T, lay, sm, st.rmap, env);
+    gather_obs(tid, T, lay, cfg, sm, rob, sc[MQ_S_ROBOT_POS_X], sc[MQ_S_ROBOT_POS_Y], sc[MQ_S_FIRE_STEP], obs, obs64, env);
 }
 
-template <int WPE>
-__global__ void __launch_bounds__(CTA_THREADS)
+template <int WPE, int CW>
+__global__ void __launch_bounds__(32 * CW)
 env_reset_kernel(DevLayout lay, DevCfg cfg, DevState st, const uint8_t* env_mask, const int16_t* inject, float* obs,
                  double* obs64) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int GROUPS = CTA_WARPS / WPE;
+    constexpr int GROUPS = CW / WPE;
     __shared__ int s_sc[GROUPS][MQ_ENV_SCALARS];
     __shared__ int s_rob[GROUPS][MAXR][2];
-    const Group<WPE> g;
+    const Group<WPE, CW> g;
     const int env = blockIdx.x * GROUPS + g.gid;
     if (env >= cfg.n_envs) return;
     if (env_mask && !env_mask[env]) return;
@@ -247,7 +254,7 @@ env_reset_kernel(DevLayout lay, DevCfg cfg, DevState st, const uint8_t* env_mask
     if (g.gtid < MQ_ENV_SCALARS) sc[g.gtid] = st.scalars[(size_t)env * MQ_ENV_SCALARS + g.gtid];
     if (g.gtid < MAXR * 2) rob[g.gtid >> 1][g.gtid & 1] = st.robots[(size_t)env * MAXR * 2 + g.gtid];
     g.sync();
-    reset_env<WPE>(g, lay, cfg, st, sm, sc, rob, inject, obs, obs64, env);
+    reset_env<WPE, CW>(g, lay, cfg, st, sm, sc, rob, inject, obs, obs64, env);
 }
 
 // numpy pairwise summation tree (np.mean at evacuation_env.py:228): leaves are blocks of <= 128 elements
@@ -303,26 +310,42 @@ __device__ __forceinline__ double leaf_sum8(const double* a, int n, int g, uint3
     if (g == 0) for (int i = main_end; i < n; ++i) res += a[i];
     return res;
 }
+// sum(p.health for p in list if not p.dead) (evacuation_env.py:245): strictly left to right; dead entries hold +0.0
+__device__ __forceinline__ double health_chain(const double* h, int N) {
+    double tot = 0.0;
+    int i = 0;
+    for (; i + 4 <= N; i += 4) {
+        const double2 a = *reinterpret_cast<const double2*>(h + i);
+        const double2 b = *reinterpret_cast<const double2*>(h + i + 2);
+        tot += a.x; tot += a.y; tot += b.x; tot += b.y;
+    }
+    for (; i < N; ++i) tot += h[i];
+    return tot;
+}
 
 // ---------------------------------------------------------------------------------------------
 // The fused step.
 // ---------------------------------------------------------------------------------------------
-template <int WPE>
-__global__ void __launch_bounds__(CTA_THREADS)
+constexpr int PF = 4;     // persons per thread whose state is fetched before any of them is processed
+
+template <int WPE, int CW>
+__global__ void __launch_bounds__(32 * CW, WPE == 1 ? 7 : 3)      // 28 env-warps / 3 env-CTAs resident per SM
 env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ actions, float* obs, double* obs64,
                 double* reward_out, uint8_t* done_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int GROUPS = CTA_WARPS / WPE;
-    constexpr int T = Group<WPE>::SIZE;
+    using G = Group<WPE, CW>;
+    constexpr int GROUPS = CW / WPE;
+    constexpr int T = G::SIZE;          // threads of the group
+    constexpr int TW = G::WORKERS;      // threads that do the parallel phases after phase 1
     __shared__ int s_sc[GROUPS][MQ_ENV_SCALARS];
     __shared__ int s_rob[GROUPS][MAXR][2];
     __shared__ int s_cnt_all[GROUPS][6];        // evacuated, dead, guidance in halves, live, movers, reset flag
     __shared__ int s_wtot_all[GROUPS][WPE];
     __shared__ double s_sum_all[GROUPS][2];     // sum of distances, total health
 
-    const Group<WPE> g;
+    const G g;
     const int env = blockIdx.x * GROUPS + g.gid;
-    if (env >= cfg.n_envs) return;              // whole group leaves together (GROUPS == 1 when WPE == CTA_WARPS)
+    if (env >= cfg.n_envs) return;              // whole group leaves together (GROUPS == 1 when WPE == CW)
     Smem sm;
     carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, cfg.N, cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
     int* sc = s_sc[g.gid];
@@ -345,13 +368,18 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         const uint4* src = reinterpret_cast<const uint4*>(st.rmap + (size_t)env * lay.rmap_words);
         uint4* dst = reinterpret_cast<uint4*>(sm.bm);
         for (int w = tid; w < lay.rmap_words / 4; w += T) dst[w] = src[w];
-    }
-    for (int h = tid; h < cfg.hash_cap; h += T) {
-        sm.hkey[h] = HEMPTY; sm.hmin[h] = 0xFFFFFFFFu; sm.hleave[h] = 0u; sm.hbest[h] = ~0ull;
+        const uint4 empty = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, HEMPTY, 0x0000FFFFu);   // best = ~0, key, ml = (min 0xFFFF, leave 0)
+        uint4* tab = reinterpret_cast<uint4*>(sm.tab);
+        for (int h = tid; h < cfg.hash_cap; h += T) tab[h] = empty;
     }
     g.sync();
 
-    // ---- Map.move_robot for every robot, in robot order (map.py:160-202; evacuation_env_multi.py:60-63) ----
+    const uint32_t env_id = (uint32_t)(cfg.env_id_base + env);
+    const uint32_t tick = (uint32_t)sc[MQ_S_TICK];
+    const int fire_step = min(sc[MQ_S_FIRE_STEP], lay.n_fire_steps - 1);
+
+    // ---- Map.move_robot for every robot, in robot order (map.py:160-202; evacuation_env_multi.py:60-63).
+    //      Nobody reads the robots before the barrier that follows phase 1. ----
     if (tid == 0) {
         for (int r = 0; r < cfg.R; ++r) {
             int a = actions[(size_t)env * cfg.R + r];
@@ -365,262 +393,276 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
             if (r == 0) { sc[MQ_S_ROBOT_POS_X] = rob[0][0]; sc[MQ_S_ROBOT_POS_Y] = rob[0][1]; }   // map.py:200-201
         }
     }
-    g.sync();
 
-    const uint32_t env_id = (uint32_t)(cfg.env_id_base + env);
-    const uint32_t tick = (uint32_t)sc[MQ_S_TICK];
-    const int fire_step = min(sc[MQ_S_FIRE_STEP], lay.n_fire_steps - 1);
-
-    // ---- phase 1 (people.py:203-220): health, speed, accumulator; movers are compacted ------------------
-    for (int i0 = 0; i0 < N; i0 += T) {
-        const int i = i0 + tid;
-        bool mover = false;
-        if (i < N) {
-            const uint32_t p = st.pos[base + i];
-            uint32_t fl = st.flags[base + i];
-            double h = st.health[base + i];
-            if (!(fl & 3u)) {
-                const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
-                double a = st.acc[base + i];
-                const double danger = box_lookup(lay.ctr_box, lay.danger_ctr, fire_step, x, y);
-                if (danger > 0.0) {                                   // Person.update_health (people.py:61-88)
-                    const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
-                    const double u = u53(w4.x, w4.y);
-                    double loss;
-                    if (danger >= 0.8) loss = danger * 50.0 + (1.0 + (3.0 - 1.0) * u);
-                    else if (danger >= 0.5) loss = danger * 40.0 + (0.8 + (2.0 - 0.8) * u);
-                    else if (danger >= 0.2) loss = danger * 30.0 + (0.5 + (1.5 - 0.5) * u);
-                    else loss = danger * 20.0 + (0.2 + (1.0 - 0.2) * u);
-                    if (h < 50.0) loss *= 1.2;
-                    h -= loss;
-                    if (h <= 0.0) { h = 0.0; fl |= 2u; } else if (h <= 8.0) fl |= 2u;
-                    h = fmax(0.0, fmin(h, 100.0));
-                    st.health[base + i] = h;
-                    if (fl & 2u) st.flags[base + i] = (uint8_t)fl;
-                }
-                if (!(fl & 2u)) {
-                    // Person.update_state speed (people.py:38-44), then accumulator (people.py:216-220)
-                    const double speed = (h < 20.0) ? 0.4 : 1.0 * (0.3 + 0.7 * (h / 100.0));
-                    a += speed * 0.5;
-                    if (a >= 1.0) { a -= 1.0; mover = true; }
-                    st.acc[base + i] = a;
-                }
-            }
-            sm.pos[i] = p;
-            sm.fl[i] = (uint8_t)fl;
-            sm.mv[i] = 0u;
-            sm.health[i] = (fl & 2u) ? 0.0 : h;          // summand of evacuation_env.py:245 (dead -> +0.0)
+    // ---- phase 1 (people.py:203-220): health, speed, accumulator; movers are compacted.
+    //      State of PF persons per thread is fetched up front so the DRAM round trips overlap. ----
+    for (int i0 = 0; i0 < N; i0 += T * PF) {
+        uint32_t p_[PF], fl_[PF];
+        double h_[PF], a_[PF], dg_[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int i = i0 + k * T + tid;
+            p_[k] = 0; fl_[k] = 3u; h_[k] = 0.0; a_[k] = 0.0;
+            if (i < N) { p_[k] = st.pos[base + i]; fl_[k] = st.flags[base + i]; h_[k] = st.health[base + i]; a_[k] = st.acc[base + i]; }
         }
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mover);
-        if (bal) {
-            int wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&s_cnt[4], __popc(bal));
-            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-            if (mover) sm.mov[wbase + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)i;
-        }
-    }
-    g.sync();
-    const int n_mov = s_cnt[4];
-
-    // ---- phase 2 (people.py:221-230, 255-297): 4 lanes score the 8 directions of one mover ----------------
-    {
-        int rbx[MAXR], rby[MAXR];
 #pragma unroll
-        for (int r = 0; r < MAXR; ++r) { rbx[r] = rob[r < cfg.R ? r : 0][0]; rby[r] = rob[r < cfg.R ? r : 0][1]; }
-        const int q = lane & 3;
-        const int n_items = (n_mov * 4 + 31) & ~31;          // whole warps take part in the shuffles
-        for (int it = tid; it < n_items; it += T) {
-            const int mi = it >> 2;
-            const bool act = mi < n_mov;
-            int i = 0, x = 0, y = 0;
-            double best_score = -INFINITY;
-            int best_dir = 8;
-            if (act) {
-                i = sm.mov[mi];
-                const uint32_t p = sm.pos[i];
-                x = (int)(p & 0xFFFFu); y = (int)(p >> 16);
-                const double2 dpv2 = __ldg(reinterpret_cast<const double2*>(lay.dp5 + (size_t)(x * stride + y) * 8) + q);
-                const double dpv[2] = {dpv2.x, dpv2.y};
-                bool adm[2];
+        for (int k = 0; k < PF; ++k)
+            dg_[k] = (fl_[k] & 3u) ? 0.0 : box_lookup(lay.ctr_box, lay.danger_ctr, fire_step, (int)(p_[k] & 0xFFFFu), (int)(p_[k] >> 16));
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int d = q * 2 + k;
-                    adm[k] = (dpv[k] > -INFINITY) && !bm_get(sm.bm, wpr, x + c_dx[d], y + c_dy[d]);
-                }
-                if (adm[0] || adm[1]) {
-                    const uint4 w = philox4x32(env_id, tick, (uint32_t)i, (uint32_t)q, cfg.seed);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        if (!adm[k]) continue;
-                        const int d = q * 2 + k;
-                        const int nx = x + c_dx[d], ny = y + c_dy[d];
-                        int d2 = 0x7FFFFFFF;
-                        for (int r = 0; r < cfg.R; ++r) {
-                            const int ddx = nx - rbx[r], ddy = ny - rby[r];
-                            // robots may sit far off-map (evaluate_strategies.py:83 sets [1000,1000])
-                            const int qq = (abs(ddx) > 30000 || abs(ddy) > 30000) ? 0x7FFFFFFF : ddx * ddx + ddy * ddy;
-                            d2 = min(d2, qq);
-                        }
-                        const double eff = d2 < 25 ? c_repel[d2] : 0.0;
-                        const double u = k ? u53(w.z, w.w) : u53(w.x, w.y);
-                        const double noise = -0.1 + (0.1 - -0.1) * u;        // random.uniform(-0.1, 0.1)
-                        const double score = (dpv[k] + eff) + noise;           // people.py:287-291
-                        if (score > best_score) { best_score = score; best_dir = d; }
+        for (int k = 0; k < PF; ++k) {
+            const int i = i0 + k * T + tid;
+            if (i0 + k * T >= N) break;                       // uniform over the warp
+            bool mover = false;
+            if (i < N) {
+                uint32_t fl = fl_[k];
+                double h = h_[k];
+                if (!(fl & 3u)) {
+                    double a = a_[k];
+                    const double danger = dg_[k];
+                    if (danger > 0.0) {                                   // Person.update_health (people.py:61-88)
+                        const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
+                        const double u = u53(w4.x, w4.y);
+                        double loss;
+                        if (danger >= 0.8) loss = danger * 50.0 + (1.0 + (3.0 - 1.0) * u);
+                        else if (danger >= 0.5) loss = danger * 40.0 + (0.8 + (2.0 - 0.8) * u);
+                        else if (danger >= 0.2) loss = danger * 30.0 + (0.5 + (1.5 - 0.5) * u);
+                        else loss = danger * 20.0 + (0.2 + (1.0 - 0.2) * u);
+                        if (h < 50.0) loss *= 1.2;
+                        h -= loss;
+                        if (h <= 0.0) { h = 0.0; fl |= 2u; } else if (h <= 8.0) fl |= 2u;
+                        h = fmax(0.0, fmin(h, 100.0));
+                        st.health[base + i] = h;
+                        if (fl & 2u) st.flags[base + i] = (uint8_t)fl;
+                    }
+                    if (!(fl & 2u)) {
+                        // Person.update_state speed (people.py:38-44), then accumulator (people.py:216-220)
+                        const double speed = (h < 20.0) ? 0.4 : 1.0 * (0.3 + 0.7 * (h / 100.0));
+                        a += speed * 0.5;
+                        if (a >= 1.0) { a -= 1.0; mover = true; }
+                        st.acc[base + i] = a;
                     }
                 }
+                sm.pos[i] = p_[k];
+                sm.fl[i] = (uint8_t)fl;
+                sm.health[i] = (fl & 2u) ? 0.0 : h;          // summand of evacuation_env.py:245 (dead -> +0.0)
             }
-            // strict '>' in direction order (people.py:293): larger score wins, ties go to the lower direction
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score, o);
-                const int od = __shfl_xor_sync(0xFFFFFFFFu, best_dir, o);
-                if (os > best_score || (os == best_score && od < best_dir)) { best_score = os; best_dir = od; }
-            }
-            if (act && q == 0 && best_dir < 8) {
-                const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
-                const uint32_t t = (uint32_t)((x + c_dx[best_dir]) * stride + (y + c_dy[best_dir]));
-                uint32_t hh = hash_cell(t, cfg.hash_shift);
-                for (;;) {                                 // move_plan[(new_x,new_y)] (people.py:228-230)
-                    const uint32_t prev = atomicCAS(&sm.hkey[hh], HEMPTY, t);
-                    if (prev == HEMPTY || prev == t) break;
-                    hh = (hh + 1) & hmask;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mover);
+            if (bal) {
+                int wbase = 0;
+                if (lane == 0) wbase = atomicAdd(&s_cnt[4], __popc(bal));
+                wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+                if (mover) {
+                    const int mi = wbase + __popc(bal & ((1u << lane) - 1u));
+                    sm.mov[mi] = (uint16_t)i;
+                    sm.mv[mi] = 0xFFFFu;
                 }
-                atomicMin(&sm.hmin[hh], (uint32_t)i);
-                atomicMin(&sm.hbest[hh], ((unsigned long long)w4.z << 32) | (unsigned long long)i);
-                sm.mv[i] = (hh + 1u) | ((uint32_t)best_dir << 24);
             }
         }
     }
     g.sync();
 
-    // ---- phase 4a: winners leave their old cell (people.py:239-246,301) ---------------------------------
-    for (int mi = tid; mi < n_mov; mi += T) {
-        const int i = sm.mov[mi];
-        const uint32_t mv = sm.mv[i];
-        if (!mv) continue;
-        const uint32_t slot = (mv & 0xFFFFFFu) - 1u;
-        if ((uint32_t)sm.hbest[slot] != (uint32_t)i) continue;      // lost the shuffle: stays (people.py:248-249)
-        sm.mv[i] = mv | 0x80000000u;
-        const uint32_t key = sm.hmin[slot];
-        const uint32_t p = sm.pos[i];
-        const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
-        const uint32_t c_old = (uint32_t)(x * stride + y);
-        uint32_t hh = hash_cell(c_old, cfg.hash_shift);
-        bool found = false;
-        for (;;) {
-            const uint32_t k = sm.hkey[hh];
-            if (k == HEMPTY) break;
-            if (k == c_old) { found = true; break; }
-            hh = (hh + 1) & hmask;
-        }
-        if (found) atomicMax(&sm.hleave[hh], key + 1u);     // old cell is somebody's target: order decides
-        else bm_clear(sm.bm, wpr, x, y);                    // rmap[old] = 0
-    }
-    g.sync();
+    if (WPE > 1 && !g.worker()) {
+        // chain warp: the left-to-right health sum only needs phase 1; it overlaps with everything the workers do
+        if (lane == 0) s_sum[1] = health_chain(sm.health, N);
+    } else {
+        const int wt = tid;                 // worker thread id (workers are the first TW threads of the group)
+        const int n_mov = s_cnt[4];
 
-    // ---- phase 4b: winners enter their target (people.py:302-314) --------------------------------------
-    for (int mi = tid; mi < n_mov; mi += T) {
-        const int i = sm.mov[mi];
-        const uint32_t mv = sm.mv[i];
-        if (!(mv & 0x80000000u)) continue;
-        const uint32_t slot = (mv & 0xFFFFFFu) - 1u;
-        const int dir = (int)((mv >> 24) & 7u);
-        const uint32_t p = sm.pos[i];
-        const int nx = (int)(p & 0xFFFFu) + c_dx[dir], ny = (int)(p >> 16) + c_dy[dir];
-        const bool evac = (__ldg(lay.cellinfo + nx * stride + ny) & 8u) != 0;      // Map.checkSavefy (map.py:93-113)
-        if (sm.hmin[slot] + 1u > sm.hleave[slot] && !evac) bm_set(sm.bm, wpr, nx, ny);
-        else bm_clear(sm.bm, wpr, nx, ny);
-        const uint32_t np = (uint32_t)nx | ((uint32_t)ny << 16);
-        sm.pos[i] = np;
-        st.pos[base + i] = np;
-        if (evac) { const uint8_t f = sm.fl[i] | 1u; sm.fl[i] = f; st.flags[base + i] = f; }
-    }
-    g.sync();      // the proposal table is dead from here on: sm.dist may overwrite it
-
-    // ---- reward inputs (evacuation_env.py:174-233): counts, guidance, ordered list of distances --------
-    const int rpx = sc[MQ_S_ROBOT_POS_X], rpy = sc[MQ_S_ROBOT_POS_Y];
-    {
-        const int P = (N + T - 1) / T;
-        const int i0 = min(tid * P, N), i1 = min(i0 + P, N);
-        int live = 0, evac = 0, dead = 0, guid = 0;
-        for (int i = i0; i < i1; ++i) {
-            const uint32_t f = sm.fl[i];
-            evac += f & 1u; dead += (f >> 1) & 1u;
-            if (!(f & 3u)) ++live;
-        }
-        // exclusive scan of `live` over the group
-        int incl = live;
+        // ---- phase 2 (people.py:221-230, 255-297): 4 lanes score the 8 directions of one mover ----------------
+        {
+            int rbx[MAXR], rby[MAXR];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
-        int off = incl - live;
-        if (WPE > 1) {
-            if (lane == 31) s_wtot[warp] = incl;
-            g.sync();
-            for (int w = 0; w < warp; ++w) off += s_wtot[w];
+            for (int r = 0; r < MAXR; ++r) { rbx[r] = rob[r < cfg.R ? r : 0][0]; rby[r] = rob[r < cfg.R ? r : 0][1]; }
+            const int q = lane & 3;
+            const int n_items = (n_mov * 4 + 31) & ~31;          // whole warps take part in the shuffles
+            for (int it = wt; it < n_items; it += TW) {
+                const int mi = it >> 2;
+                const bool act = mi < n_mov;
+                int i = 0, x = 0, y = 0;
+                double best_score = -INFINITY;
+                int best_dir = 8;
+                if (act) {
+                    i = sm.mov[mi];
+                    const uint32_t p = sm.pos[i];
+                    x = (int)(p & 0xFFFFu); y = (int)(p >> 16);
+                    const double2 dpv2 = __ldg(reinterpret_cast<const double2*>(lay.dp5 + (size_t)(x * stride + y) * 8) + q);
+                    const double dpv[2] = {dpv2.x, dpv2.y};
+                    bool adm[2];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int d = q * 2 + k;
+                        adm[k] = (dpv[k] > -INFINITY) && !bm_get(sm.bm, wpr, x + move_dx(d), y + move_dy(d));
+                    }
+                    if (adm[0] || adm[1]) {
+                        const uint4 w = philox4x32(env_id, tick, (uint32_t)i, (uint32_t)q, cfg.seed);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            if (!adm[k]) continue;
+                            const int d = q * 2 + k;
+                            const int nx = x + move_dx(d), ny = y + move_dy(d);
+                            int d2 = 0x7FFFFFFF;
+#pragma unroll
+                            for (int r = 0; r < MAXR; ++r) {
+                                const int ddx = nx - rbx[r], ddy = ny - rby[r];
+                                // robots may sit far off-map (evaluate_strategies.py:83 sets [1000,1000])
+                                const int qq = (abs(ddx) > 30000 || abs(ddy) > 30000) ? 0x7FFFFFFF : ddx * ddx + ddy * ddy;
+                                d2 = min(d2, qq);               // r >= R repeats robot 0: harmless for the minimum
+                            }
+                            const double eff = d2 < 25 ? c_repel[d2] : 0.0;
+                            const double u = k ? u53(w.z, w.w) : u53(w.x, w.y);
+                            const double noise = -0.1 + (0.1 - -0.1) * u;        // random.uniform(-0.1, 0.1)
+                            const double score = (dpv[k] + eff) + noise;           // people.py:287-291
+                            if (score > best_score) { best_score = score; best_dir = d; }
+                        }
+                    }
+                }
+                // strict '>' in direction order (people.py:293): larger score wins, ties go to the lower direction
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score, o);
+                    const int od = __shfl_xor_sync(0xFFFFFFFFu, best_dir, o);
+                    if (os > best_score || (os == best_score && od < best_dir)) { best_score = os; best_dir = od; }
+                }
+                if (act && q == 0 && best_dir < 8) {
+                    const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
+                    const uint32_t t = (uint32_t)((x + move_dx(best_dir)) * stride + (y + move_dy(best_dir)));
+                    uint32_t hh = hash_cell(t, cfg.hash_shift);
+                    for (;;) {                                 // move_plan[(new_x,new_y)] (people.py:228-230)
+                        const uint32_t prev = atomicCAS(&sm.tab[hh].key, HEMPTY, t);
+                        if (prev == HEMPTY || prev == t) break;
+                        hh = (hh + 1) & hmask;
+                    }
+                    atomicMin(&sm.tab[hh].ml, (uint32_t)i);                      // leave half is still 0
+                    atomicMin(&sm.tab[hh].best, ((unsigned long long)w4.z << 32) | (unsigned long long)i);
+                    sm.mv[mi] = (uint16_t)(hh | ((uint32_t)best_dir << 12));
+                }
+            }
         }
-        for (int i = i0; i < i1; ++i) {
-            const uint32_t f = sm.fl[i];
-            if (f & 3u) continue;
+        g.wsync();
+
+        // ---- phase 4a: winners leave their old cell (people.py:239-246,301) ---------------------------------
+        for (int mi = wt; mi < n_mov; mi += TW) {
+            const uint32_t mv = sm.mv[mi];
+            if (mv == 0xFFFFu) continue;
+            const int i = sm.mov[mi];
+            const uint32_t slot = mv & 0xFFFu;
+            if ((uint32_t)sm.tab[slot].best != (uint32_t)i) continue;      // lost the shuffle: stays (people.py:248-249)
+            sm.mv[mi] = (uint16_t)(mv | 0x8000u);
+            const uint32_t key = sm.tab[slot].ml & 0xFFFFu;
             const uint32_t p = sm.pos[i];
             const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
-            // 2*(x+.5-rx) is an odd integer: compare squared distances exactly (sqrt is monotone, thresholds exact)
-            const long long X = 2LL * x + 1 - 2LL * rpx, Y = 2LL * y + 1 - 2LL * rpy;
-            const long long q4 = X * X + Y * Y;                             // 4 * dist^2
-            if (q4 <= 100) {                                                // dist_to_robot <= 5 (:202)
-                const long long EX = 2LL * x + 1 - 2LL * lay.obs_exit[0], EY = 2LL * y + 1 - 2LL * lay.obs_exit[1];
-                const long long e4 = EX * EX + EY * EY;
-                guid += e4 > 1600 ? 4 : (e4 > 400 ? 3 : 2);                 // 2.0 / 1.5 / 1.0 (:207-212)
-                if (sm.health[i] < 80.0) guid += 2;                         // +1.0 (:215-216)
+            const uint32_t c_old = (uint32_t)(x * stride + y);
+            uint32_t hh = hash_cell(c_old, cfg.hash_shift);
+            bool found = false;
+            for (;;) {
+                const uint32_t k = sm.tab[hh].key;
+                if (k == HEMPTY) break;
+                if (k == c_old) { found = true; break; }
+                hh = (hh + 1) & hmask;
             }
-            const double dx = ((double)x + 0.5) - (double)rpx, dy = ((double)y + 0.5) - (double)rpy;
-            sm.dist[off++] = sqrt(dx * dx + dy * dy);                       // np.linalg.norm (:228)
+            // old cell is somebody's target: order decides (the low half of ml is final since the barrier)
+            if (found) atomicMax(&sm.tab[hh].ml, ((key + 1u) << 16) | (sm.tab[hh].ml & 0xFFFFu));
+            else bm_clear(sm.bm, wpr, x, y);                    // rmap[old] = 0
         }
+        g.wsync();
+
+        // ---- phase 4b: winners enter their target (people.py:302-314) --------------------------------------
+        for (int mi = wt; mi < n_mov; mi += TW) {
+            const uint32_t mv = sm.mv[mi];
+            if (mv == 0xFFFFu || !(mv & 0x8000u)) continue;
+            const int i = sm.mov[mi];
+            const uint32_t ml = sm.tab[mv & 0xFFFu].ml;
+            const int dir = (int)((mv >> 12) & 7u);
+            const uint32_t p = sm.pos[i];
+            const int nx = (int)(p & 0xFFFFu) + move_dx(dir), ny = (int)(p >> 16) + move_dy(dir);
+            const bool evac = (__ldg(lay.cellinfo + nx * stride + ny) & 8u) != 0;      // Map.checkSavefy (map.py:93-113)
+            if ((ml & 0xFFFFu) + 1u > (ml >> 16) && !evac) bm_set(sm.bm, wpr, nx, ny);
+            else bm_clear(sm.bm, wpr, nx, ny);
+            const uint32_t np = (uint32_t)nx | ((uint32_t)ny << 16);
+            sm.pos[i] = np;
+            st.pos[base + i] = np;
+            if (evac) { const uint8_t f = sm.fl[i] | 1u; sm.fl[i] = f; st.flags[base + i] = f; }
+        }
+        g.wsync();      // the proposal table is dead from here on: sm.dist may overwrite it
+
+        // ---- reward inputs (evacuation_env.py:174-233): counts, guidance, ordered list of distances --------
+        const int rpx = sc[MQ_S_ROBOT_POS_X], rpy = sc[MQ_S_ROBOT_POS_Y];
+        {
+            const int P = (N + TW - 1) / TW;
+            const int i0 = min(wt * P, N), i1 = min(i0 + P, N);
+            int live = 0, evac = 0, dead = 0, guid = 0;
+            for (int i = i0; i < i1; ++i) {
+                const uint32_t f = sm.fl[i];
+                evac += f & 1u; dead += (f >> 1) & 1u;
+                if (!(f & 3u)) ++live;
+            }
+            // exclusive scan of `live` over the workers
+            int incl = live;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            evac += __shfl_xor_sync(0xFFFFFFFFu, evac, o);
-            dead += __shfl_xor_sync(0xFFFFFFFFu, dead, o);
-            guid += __shfl_xor_sync(0xFFFFFFFFu, guid, o);
-            live += __shfl_xor_sync(0xFFFFFFFFu, live, o);
-        }
-        if (lane == 0) {
-            if (WPE == 1) { s_cnt[0] = evac; s_cnt[1] = dead; s_cnt[2] = guid; s_cnt[3] = live; }
-            else { atomicAdd(&s_cnt[0], evac); atomicAdd(&s_cnt[1], dead); atomicAdd(&s_cnt[2], guid); atomicAdd(&s_cnt[3], live); }
-        }
-    }
-    g.sync();
-
-    // fire models step (evacuation_env.py:138-142; fire_model.py:63-67) — observation uses the new step
-    const int new_fire = min(sc[MQ_S_FIRE_STEP] + 1, lay.n_fire_steps - 1);
-
-    // ---- order-dependent fp64 sums: np.mean tree (warp 0) and the left-to-right sum() chain -----------------
-    // WPE > 1: warp 0 does the tree, lane 0 of warp 1 the chain, the other warps start on the outputs.
-    // WPE == 1: lane 31 runs the chain while lanes 0..7 of the same warp... no: a warp executes one path at a time,
-    // so the chain (lane 0) simply follows the tree.
-    if (warp == 0) {
-        const int n = s_cnt[3];
-        int nl = 0;
-        if (lane == 0) nl = enumerate_leaves(n, sm.leaf_off, sm.leaf_len);
-        nl = __shfl_sync(0xFFFFFFFFu, nl, 0);
-        __syncwarp();
-        const int gl = lane & 7, grp = lane >> 3;
-        const uint32_t gmask = 0xFFu << (grp * 8);
-        for (int l0 = 0; l0 < nl; l0 += 4) {
-            const int l = l0 + grp;
-            if (l < nl) {
-                const double s = leaf_sum8(sm.dist + sm.leaf_off[l], sm.leaf_len[l], gl, gmask);
-                if (gl == 0) sm.leaf_sum[l] = s;
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+            int off = incl - live;
+            if (WPE > 1) {
+                if (lane == 31) s_wtot[warp] = incl;
+                g.wsync();
+                for (int w = 0; w < warp; ++w) off += s_wtot[w];
+            }
+            for (int i = i0; i < i1; ++i) {
+                const uint32_t f = sm.fl[i];
+                if (f & 3u) continue;
+                const uint32_t p = sm.pos[i];
+                const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
+                // 2*(x+.5-rx) is an odd integer: compare squared distances exactly (sqrt is monotone, thresholds exact)
+                const long long X = 2LL * x + 1 - 2LL * rpx, Y = 2LL * y + 1 - 2LL * rpy;
+                const long long q4 = X * X + Y * Y;                             // 4 * dist^2
+                if (q4 <= 100) {                                                // dist_to_robot <= 5 (:202)
+                    const long long EX = 2LL * x + 1 - 2LL * lay.obs_exit[0], EY = 2LL * y + 1 - 2LL * lay.obs_exit[1];
+                    const long long e4 = EX * EX + EY * EY;
+                    guid += e4 > 1600 ? 4 : (e4 > 400 ? 3 : 2);                 // 2.0 / 1.5 / 1.0 (:207-212)
+                    if (sm.health[i] < 80.0) guid += 2;                         // +1.0 (:215-216)
+                }
+                const double dx = ((double)x + 0.5) - (double)rpx, dy = ((double)y + 0.5) - (double)rpy;
+                sm.dist[off++] = sqrt(dx * dx + dy * dy);                       // np.linalg.norm (:228)
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                evac += __shfl_xor_sync(0xFFFFFFFFu, evac, o);
+                dead += __shfl_xor_sync(0xFFFFFFFFu, dead, o);
+                guid += __shfl_xor_sync(0xFFFFFFFFu, guid, o);
+                live += __shfl_xor_sync(0xFFFFFFFFu, live, o);
+            }
+            if (lane == 0) {
+                if (WPE == 1) { s_cnt[0] = evac; s_cnt[1] = dead; s_cnt[2] = guid; s_cnt[3] = live; }
+                else { atomicAdd(&s_cnt[0], evac); atomicAdd(&s_cnt[1], dead); atomicAdd(&s_cnt[2], guid); atomicAdd(&s_cnt[3], live); }
             }
         }
-        __syncwarp();
-        if (lane == 0) s_sum[0] = combine_leaves(n, sm.leaf_sum);
+        g.wsync();
+
+        // ---- np.mean tree (warp 0); the other workers start on the outputs --------------------------------
+        if (warp == 0) {
+            const int n = s_cnt[3];
+            int nl = 0;
+            if (lane == 0) nl = enumerate_leaves(n, sm.leaf_off, sm.leaf_len);
+            nl = __shfl_sync(0xFFFFFFFFu, nl, 0);
+            __syncwarp();
+            const int gl = lane & 7, grp = lane >> 3;
+            const uint32_t gmask = 0xFFu << (grp * 8);
+            for (int l0 = 0; l0 < nl; l0 += 4) {
+                const int l = l0 + grp;
+                if (l < nl) {
+                    const double s = leaf_sum8(sm.dist + sm.leaf_off[l], sm.leaf_len[l], gl, gmask);
+                    if (gl == 0) sm.leaf_sum[l] = s;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                s_sum[0] = combine_leaves(n, sm.leaf_sum);
+                if (WPE == 1) s_sum[1] = health_chain(sm.health, N);
+            }
+        }
+        // fire models step (evacuation_env.py:138-142; fire_model.py:63-67) — the observation uses the new step
+        store_bitmap(wt, TW, lay, sm, st.rmap, env);
+        gather_obs(wt, TW, lay, cfg, sm, rob, rpx, rpy, min(sc[MQ_S_FIRE_STEP] + 1, lay.n_fire_steps - 1), obs, obs64, env);
     }
-    if ((WPE == 1 && lane == 0) || (WPE > 1 && warp == 1 && lane == 0)) {
-        double tot = 0.0;
-        for (int i = 0; i < N; ++i) tot += sm.health[i];       // left-to-right, dead contribute +0.0
-        s_sum[1] = tot;
-    }
-    store_bitmap<WPE>(g, lay, sm, st.rmap, env);
-    gather_obs<WPE>(g, lay, cfg, sm, rob, rpx, rpy, new_fire, obs, obs64, env);
     g.sync();
 
     // ---- _calculate_reward (evacuation_env.py:174-288), done (:150-157), scalars -----------------------
@@ -666,7 +708,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         const int done = (cur_evac + cur_dead == N) || (cur_step + 1 >= cfg.max_steps);
         reward_out[env] = reward;
         done_out[env] = (uint8_t)done;
-        sc[MQ_S_FIRE_STEP] = new_fire;
+        sc[MQ_S_FIRE_STEP] = min(sc[MQ_S_FIRE_STEP] + 1, lay.n_fire_steps - 1);
         sc[MQ_S_CUR_STEP] = cur_step + 1;
         sc[MQ_S_PREV_EVAC] = cur_evac; sc[MQ_S_PREV_DEAD] = cur_dead;
         sc[MQ_S_EVAC] = cur_evac; sc[MQ_S_DEAD] = cur_dead;
@@ -675,7 +717,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     }
     g.sync();
     if (s_cnt[5]) {
-        reset_env<WPE>(g, lay, cfg, st, sm, sc, rob, nullptr, obs, obs64, env);
+        reset_env<WPE, CW>(g, lay, cfg, st, sm, sc, rob, nullptr, obs, obs64, env);
     } else {
         if (tid < MQ_ENV_SCALARS) st.scalars[(size_t)env * MQ_ENV_SCALARS + tid] = sc[tid];
         if (tid < MAXR * 2) st.robots[(size_t)env * MAXR * 2 + tid] = rob[tid >> 1][tid & 1];
@@ -702,13 +744,14 @@ struct mq_env {
     mq::DevCfg cfg;
     mq::DevState st;
     void* d_dp5 = nullptr; void* d_cellinfo = nullptr; void* d_ctr = nullptr; void* d_int = nullptr;
-    int wpe = 8;            // warps per env
-    int blocks = 0;
+    int wpe = 8;            // warps per env: 1 (4 envs per 128-thread CTA) or 8 (one 256-thread CTA per env)
+    int blocks = 0, threads = 0;
     size_t smem = 0;        // dynamic shared memory per CTA
     int64_t launches = 0;
 };
 
 static int round_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+constexpr int SMALL_CW = 4;      // warps (= envs) per CTA in warp-per-env mode
 
 extern "C" int mq_env_state_sizes(const mq_env_cfg* cfg, const mq_layout* layout, int64_t* n_pad, int64_t* rmap_words) {
     MQ_REQUIRE(cfg && layout, "mq_env_state_sizes: null argument");
@@ -720,22 +763,24 @@ extern "C" int mq_env_state_sizes(const mq_env_cfg* cfg, const mq_layout* layout
     return MQ_OK;
 }
 
-template <int WPE>
+template <int WPE, int CW>
 static cudaError_t set_smem_attr(int bytes) {
-    cudaError_t e = cudaFuncSetAttribute(mq::env_step_kernel<WPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(mq::env_step_kernel<WPE, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mq::env_reset_kernel<WPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return cudaFuncSetAttribute(mq::env_reset_kernel<WPE, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layout* layout, const mq_env_state* state) {
     MQ_REQUIRE(out && cfg && layout && state, "mq_env_create: null argument");
     MQ_REQUIRE(cfg->n_envs > 0 && cfg->n_people > 0, "mq_env_create: n_envs and n_people must be positive");
-    MQ_REQUIRE(cfg->n_people < 65536, "mq_env_create: at most 65535 people per env");
     MQ_REQUIRE(cfg->n_robots >= 1 && cfg->n_robots <= MQ_MAX_ROBOTS, "mq_env_create: n_robots must be in 1..%d", MQ_MAX_ROBOTS);
     MQ_REQUIRE(layout->L >= 3 && layout->W >= 3 && layout->L <= 32000 && layout->W <= 32000, "mq_env_create: bad grid size");
     MQ_REQUIRE(layout->dp5 && layout->cellinfo && layout->danger_ctr && layout->danger_int, "mq_env_create: layout tables missing");
     MQ_REQUIRE(state->pos && state->health && state->acc && state->flags && state->rmap && state->robots && state->scalars,
                "mq_env_create: state buffers missing");
+    if (cfg->n_people > 3000)
+        return mq::fail(MQ_ERR_UNSUPPORTED, "mq_env_create: %d people per env: the shared-memory step kernel handles at most 3000; "
+                        "the tiled large-env kernel is not built yet", cfg->n_people);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return mq::fail(MQ_ERR_CUDA, "mq_env_create: no CUDA device (this build has no CPU fallback)");
@@ -783,7 +828,7 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     c.seed = cfg->seed; c.env_id_base = cfg->env_id_base; c.max_steps = cfg->max_steps;
     c.reset_robots = cfg->reset_robots; c.reset_fire = cfg->reset_fire; c.auto_reset = cfg->auto_reset;
     int want = c.N + c.N / 3 + 8;                      // load factor <= 0.75 even if everybody proposes a distinct cell
-    c.hash_cap = round_pow2(want < 64 ? 64 : want);
+    c.hash_cap = round_pow2(want < 64 ? 64 : want);    // <= 4096 (12-bit slot ids in Smem::mv)
     int lg = 0; while ((1 << lg) < c.hash_cap) ++lg;
     c.hash_shift = 32 - lg;
     c.n_leaf_max = c.N / 64 + 4;
@@ -795,11 +840,10 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     c.smem_per_env = (int)mq::carve(tmp, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
-    // warps per env: one warp for small envs (no CTA barriers), the whole CTA for big ones
-    e->wpe = c.N <= 256 ? 1 : (c.N <= 512 ? 2 : 8);
-    while (e->wpe < 8 && (size_t)c.smem_per_env * (mq::CTA_WARPS / e->wpe) + 2048 > (size_t)max_smem) e->wpe *= 2;
-    if (e->wpe == 4) e->wpe = 8;
-    const int groups = mq::CTA_WARPS / e->wpe;
+    // one warp per env for small envs (no CTA barriers, 4 envs per CTA), one CTA per env otherwise
+    e->wpe = (c.N <= 256 && (size_t)c.smem_per_env * SMALL_CW + 2048 <= (size_t)max_smem) ? 1 : 8;
+    const int groups = e->wpe == 1 ? SMALL_CW : 1;
+    e->threads = e->wpe == 1 ? 32 * SMALL_CW : 256;
     e->smem = (size_t)c.smem_per_env * groups;
     if ((int)e->smem + 2048 > max_smem) {
         size_t need = e->smem;
@@ -809,7 +853,7 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
                         "the tiled large-env kernel is not built yet", cfg->n_people, layout->L, layout->W, need, max_smem);
     }
     e->blocks = (c.n_envs + groups - 1) / groups;
-    ce = e->wpe == 1 ? set_smem_attr<1>((int)e->smem) : (e->wpe == 2 ? set_smem_attr<2>((int)e->smem) : set_smem_attr<8>((int)e->smem));
+    ce = e->wpe == 1 ? set_smem_attr<1, SMALL_CW>((int)e->smem) : set_smem_attr<8, 8>((int)e->smem);
     if (ce != cudaSuccess) {
         mq_env_destroy(e);
         return mq::fail(MQ_ERR_CUDA, "mq_env_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
@@ -837,9 +881,8 @@ extern "C" int mq_env_reset(mq_env* e, const uint8_t* env_mask, const int16_t* i
                             double* obs64_out, void* stream) {
     MQ_REQUIRE(e, "mq_env_reset: null handle");
     cudaStream_t s = (cudaStream_t)stream;
-    if (e->wpe == 1) mq::env_reset_kernel<1><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
-    else if (e->wpe == 2) mq::env_reset_kernel<2><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
-    else mq::env_reset_kernel<8><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
+    if (e->wpe == 1) mq::env_reset_kernel<1, SMALL_CW><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
+    else mq::env_reset_kernel<8, 8><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
     MQ_CUDA(cudaGetLastError());
     e->launches += 1;
     return MQ_OK;
@@ -849,9 +892,8 @@ extern "C" int mq_env_step(mq_env* e, const int32_t* actions, float* obs_out, do
                            uint8_t* done_out, void* stream) {
     MQ_REQUIRE(e && actions && reward_out && done_out, "mq_env_step: null argument");
     cudaStream_t s = (cudaStream_t)stream;
-    if (e->wpe == 1) mq::env_step_kernel<1><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
-    else if (e->wpe == 2) mq::env_step_kernel<2><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
-    else mq::env_step_kernel<8><<<e->blocks, mq::CTA_THREADS, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
+    if (e->wpe == 1) mq::env_step_kernel<1, SMALL_CW><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
+    else mq::env_step_kernel<8, 8><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
     MQ_CUDA(cudaGetLastError());
     e->launches += 1;
     return MQ_OK;
