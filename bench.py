@@ -276,6 +276,7 @@ def run_ours(args, wl):
     h2d = h_act[0].numel() * 4
     d2h = h_obs.numel() * 4 + h_rew.numel() * 8 + h_don.numel()
 
+    replay = run_replay_leg(args, dev) if args.replay_batch > 0 else None
     learner = None
     if args.loop_steps > 0:
         del envs, obs, rew, don
@@ -308,6 +309,8 @@ def run_ours(args, wl):
                                  "occupancy to 1 bit/cell and rewrites only changed person fields, so it moves fewer bytes"},
             "value_l2_resident": E * N * args.steps / (warm_ms * 1e-3),
         }
+        if replay is not None:
+            line["replay"] = replay
         if args.loop_steps > 0:
             line["learner"] = learner
         if world == 1 and not args.no_cpu:
@@ -322,6 +325,41 @@ def run_ours(args, wl):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_replay_leg(args, dev):
+    """Replay gather/scatter bandwidth (11,634 B per sampled transition, 2 x 5817 B per push)."""
+    import torch
+    from dqn_marl_b200.replay import ReplayRing
+    peaks, _ = measured_peaks()
+    cap, B, n_push = 1 << 19, args.replay_batch, 16384          # 6.1 GB ring: far larger than L2
+    ring = ReplayRing(cap, device=dev, seed=1)
+    s = torch.rand((n_push, 726), device=dev); ns = torch.rand((n_push, 726), device=dev)
+    a = torch.zeros(n_push, dtype=torch.int32, device=dev); r = torch.zeros(n_push, dtype=torch.float64, device=dev)
+    d = torch.zeros(n_push, dtype=torch.uint8, device=dev)
+    for _ in range(cap // n_push):
+        ring.push(s, a, r, ns, d)
+    out = ring.sample(B)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    torch.cuda.synchronize(dev); ev0.record()
+    for k in range(reps):
+        ring.sample(B, out=out)
+    ev1.record(); torch.cuda.synchronize(dev)
+    ms_s = ev0.elapsed_time(ev1) / reps
+    torch.cuda.synchronize(dev); ev0.record()
+    for k in range(reps):
+        ring.push(s, a, r, ns, d)
+    ev1.record(); torch.cuda.synchronize(dev)
+    ms_p = ev0.elapsed_time(ev1) / reps
+    gbs_s = 11634.0 * B / (ms_s * 1e-3) / 1e9
+    gbs_p = 2 * 5817.0 * n_push / (ms_p * 1e-3) / 1e9
+    res = {"sample": {"batch": B, "ms": ms_s, "transitions_per_s": B / (ms_s * 1e-3), "achieved_GBs": gbs_s, "frac_of_hbm_peak": gbs_s / peaks["hbm_gbs"]},
+           "push": {"n": n_push, "ms": ms_p, "transitions_per_s": n_push / (ms_p * 1e-3), "achieved_GBs": gbs_p, "frac_of_hbm_peak": gbs_p / peaks["hbm_gbs"]},
+           "ring_capacity": cap, "kernels": ["replay_sample_kernel", "replay_push_kernel"]}
+    del ring, out
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_learner_loop(args, wl, layout, dev, rank, world):
@@ -393,6 +431,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--loop-steps", type=int, default=8, help="steps of the full act/step/push/learn loop (0 = skip)")
     ap.add_argument("--learner-batch", type=int, default=4096)
+    ap.add_argument("--replay-batch", type=int, default=65536, help="replay sample batch of the bandwidth leg (0 = skip)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
