@@ -28,6 +28,7 @@ EXTRA = {
     "env.cu": ["-fmad=false", "-Xptxas", "-v"],
     "replay.cu": ["-Xptxas", "-v"],
     "qnet.cu": ["-Xptxas", "-v"],
+    "gemm_tc.cu": ["-Xptxas", "-v"],
 }
 
 

@@ -250,6 +250,13 @@ int mq_qnet_sync_target(mq_qnet* net, float tau, void* stream);
 int mq_qnet_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t counter, void* stream);
 int64_t mq_qnet_launch_count(const mq_qnet* net);
 
+/* ------------------------------------------------------------------------
+ * Stand-alone bf16 tensor-core GEMM (tcgen05 + TMEM + TMA), the building block of the Q-network's throughput
+ * path: C[M][N] f32 = A[M][K] bf16 * B[N][K]^T bf16 (both K-contiguous).  bn = tile width 128/64/32.
+ * ---------------------------------------------------------------------- */
+int mq_gemm_bf16(const void* A, const void* B, float* C, int32_t M, int32_t N, int32_t K, int32_t bn, int32_t splits,
+                 float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,38 @@
+"""Throughput of the stand-alone tcgen05 GEMM on the Q-network's shapes (B = 4096): TFLOP/s vs MEASURED_PEAKS bf16."""
+import ctypes as Ct
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dqn_marl_b200 import _lib
+
+lib = _lib.load()
+B = 4096
+M = B * 121
+shapes = [("fc1 fwd", B, 512, 15488, 128, 1), ("conv3 fwd", M, 128, 576, 128, 1), ("conv2 fwd", M, 64, 288, 64, 1),
+          ("fc1 dgrad", B, 15488, 512, 128, 1), ("fc1 wgrad", 512, 15488, B, 128, 1), ("conv3 dgrad", M, 64, 1152, 64, 1),
+          ("conv3 wgrad", 576, 128, M, 128, 96), ("conv2 wgrad", 288, 64, M, 64, 148), ("conv2 dgrad", M, 32, 576, 32, 1)]
+peak = 1629.4
+p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+if os.path.exists(p):
+    peak = json.load(open(p))["bf16_tflops"]
+st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+for name, m, n, k, bn, splits in shapes:
+    A = torch.randn((m, k), device="cuda").to(torch.bfloat16)
+    Bm = torch.randn((n, k), device="cuda").to(torch.bfloat16)
+    C = torch.empty((m, n), device="cuda")
+    ws = torch.empty((splits * m * n,), device="cuda") if splits > 1 else None
+    for _ in range(3):
+        _lib.check(lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(C), m, n, k, bn, splits, _lib.ptr(ws), st), "gemm")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    reps = 10
+    for _ in range(reps):
+        lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(C), m, n, k, bn, splits, _lib.ptr(ws), st)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
+    print(f"{name:12s} M={m:7d} N={n:6d} K={k:7d} bn={bn:3d} splits={splits:3d}  {ms:8.3f} ms  {tf:7.1f} TFLOP/s  {100*tf/peak:5.1f}% of {peak:.0f}")
