@@ -89,6 +89,8 @@ SIGNATURES = {
     "mq_qnet_sync_target": (C.c_int, [_vp, _f32, _vp]),
     "mq_qnet_dropout_mask": (C.c_int, [_vp, _i64, _f32, _u64, _u64, _vp]),
     "mq_qnet_launch_count": (_i64, [_vp]),
+    "mq_qnet_set_precision": (C.c_int, [_vp, _i32]),
+    "mq_qnet_params_changed": (C.c_int, [_vp]),
     "mq_gemm_bf16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
 }
 

@@ -132,6 +132,8 @@ class DQNAgent:
         memory_size = config.get("memory_size", 50000)
 
         self.net = QNet(dev, max_batch=max_batch or max(self.batch_size, 64), trainable=True)
+        # 'fp32' (default): CUDA-core path within 1e-5 of the reference; 'bf16': tcgen05 tensor-core path for throughput
+        self.precision = config.get("precision", "fp32")
         # PyTorch default init, same RNG consumption order as the reference (q_network, then target_network)
         online, _target = qp.TorchDQN(), qp.TorchDQN()
         self.net.load_state_dict(online.state_dict(), "online")
@@ -144,8 +146,8 @@ class DQNAgent:
         self._act_calls = 0
         self._mask_calls = 0
         self.update_target_network()
-        d = self.net.device
-        self._s1 = torch.zeros((1, 726), dtype=torch.float32, device=d)
+        if self.precision != "fp32":
+            self.net.set_precision(self.precision)
 
     # ------------------------------------------------------------------
     def _hparams(self, clip: float = 1.0) -> "_lib.MqHparams":

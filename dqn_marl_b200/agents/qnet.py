@@ -37,6 +37,7 @@ class QNet:
         with torch.cuda.device(dev):
             _lib.check(self.lib.mq_qnet_create(C.byref(h), dev.index, self.max_batch, C.byref(bind)), "mq_qnet_create")
         self._h = h
+        self.precision = "fp32"
         self._loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self._gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
 
@@ -61,6 +62,17 @@ class QNet:
     # -- parameters ------------------------------------------------------------------------------------
     def load_state_dict(self, sd, which="online"):
         qp.pack(sd, self.flat_p if which == "online" else self.flat_t)
+        self.params_changed()
+
+    def params_changed(self):
+        """Call after writing flat_p / flat_t directly (the bf16 operand copies are refreshed lazily)."""
+        _lib.check(self.lib.mq_qnet_params_changed(self._h), "mq_qnet_params_changed")
+
+    def set_precision(self, precision: str):
+        """'fp32' = CUDA-core parity path, 'bf16' = tcgen05 tensor-core path (conv2/conv3/fc1)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mq_qnet_set_precision(self._h, {"fp32": 0, "bf16": 1}[precision]), "mq_qnet_set_precision")
+        self.precision = precision
 
     def state_dict(self, which="online"):
         return qp.unpack(self.flat_p if which == "online" else self.flat_t)

@@ -19,7 +19,9 @@
 #include <new>
 #include "common.h"
 #include "gemm_f32.cuh"
+#include "gemm_tc.cuh"
 #include "philox.cuh"
+#include "qnet_bf16.cuh"
 
 namespace mq {
 
@@ -264,6 +266,14 @@ struct mq_qnet {
     float *partial = nullptr; size_t partial_cap = 0;
     float *norm_partial = nullptr, *gnorm = nullptr;
     int64_t launches = 0;
+    // ---- bf16 tensor-core path (precision = 1) ----
+    int precision = 0;                         // 0 = fp32 FFMA parity path, 1 = bf16 tcgen05 path
+    bool w_dirty[2] = {true, true};            // bf16 weight copies of [online, target] are stale
+    mq::bf::bf16 *w2f[2] = {nullptr, nullptr}, *w3f[2] = {nullptr, nullptr}, *w1f[2] = {nullptr, nullptr};   // forward operands
+    mq::bf::bf16 *w2d = nullptr, *w3d = nullptr, *w1t = nullptr;                                              // dgrad operands (online)
+    mq::bf::bf16 *A2 = nullptr, *A3 = nullptr, *a2b = nullptr, *a3b = nullptr;       // im2col rows, activations
+    mq::bf::bf16 *da3b = nullptr, *da2b = nullptr, *dh1b = nullptr, *dh1t = nullptr; // activation grads
+    mq::bf::bf16 *bufX = nullptr, *bufY = nullptr;                                   // [M][1152] and [M][128] scratch
 };
 
 namespace mq {
@@ -272,6 +282,97 @@ static void free_ws(mq_qnet* n) {
     float* ptrs[] = {n->a1, n->a2, n->a3, n->h1, n->h2, n->da1, n->da2, n->da3, n->dh1, n->dh2, n->q, n->dq, n->q_sa, n->maxq,
                      n->partial, n->norm_partial, n->gnorm};
     for (float* p : ptrs) cudaFree(p);
+    bf::bf16* bptrs[] = {n->w2f[0], n->w2f[1], n->w3f[0], n->w3f[1], n->w1f[0], n->w1f[1], n->w2d, n->w3d, n->w1t, n->A2, n->A3, n->a2b,
+                         n->a3b, n->da3b, n->da2b, n->dh1b, n->dh1t, n->bufX, n->bufY};
+    for (bf::bf16* p : bptrs) cudaFree(p);
+}
+
+// ---- bf16 path ----------------------------------------------------------------------------------------------------
+static int ew_blocks(long long total) { return (int)((total + 255) / 256); }
+
+static cudaError_t alloc_bf16(mq_qnet* n) {
+    if (n->A2) return cudaSuccess;
+    const size_t B = (size_t)n->max_batch, M = B * PIX, e = sizeof(bf::bf16);
+    cudaError_t ce = cudaSuccess;
+    auto alloc = [&](bf::bf16** p, size_t count) { if (ce == cudaSuccess) ce = cudaMalloc((void**)p, count * e); };
+    for (int w = 0; w < 2; ++w) { alloc(&n->w2f[w], (size_t)C2 * 9 * C1); alloc(&n->w3f[w], (size_t)C3 * 9 * C2); alloc(&n->w1f[w], (size_t)H1 * FLAT); }
+    alloc(&n->w2d, (size_t)C1 * 9 * C2); alloc(&n->w3d, (size_t)C2 * 9 * C3); alloc(&n->w1t, (size_t)FLAT * H1);
+    alloc(&n->A2, M * 9 * C1); alloc(&n->A3, M * 9 * C2); alloc(&n->a2b, M * C2); alloc(&n->a3b, M * C3);
+    if (n->tl.g[0]) {
+        alloc(&n->da3b, M * C3); alloc(&n->da2b, M * C2); alloc(&n->dh1b, B * H1); alloc(&n->dh1t, B * H1);
+        alloc(&n->bufX, M * 9 * C3); alloc(&n->bufY, M * C3);
+    }
+    return ce;
+}
+
+// fp32 master weights -> bf16 GEMM operands (after every optimizer step / target sync / load)
+static void refresh_weights(mq_qnet* n, int which, cudaStream_t s) {
+    if (!n->w_dirty[which]) return;
+    float* const* W = which ? n->tl.t : n->tl.p;
+    const bool bwd = which == 0 && n->tl.g[0];
+    bf::conv_weight_bf16_kernel<<<ew_blocks(9 * C1 * C2), 256, 0, s>>>(W[P_C2W], n->w2f[which], bwd ? n->w2d : nullptr, C1, C2);
+    bf::conv_weight_bf16_kernel<<<ew_blocks(9 * C2 * C3), 256, 0, s>>>(W[P_C3W], n->w3f[which], bwd ? n->w3d : nullptr, C2, C3);
+    bf::cast_transpose_kernel<<<ew_blocks((long long)H1 * FLAT), 256, 0, s>>>(W[P_F1W], n->w1f[which], bwd ? n->w1t : nullptr, H1, FLAT);
+    n->launches += 3;
+    n->w_dirty[which] = false;
+}
+
+template <int BN>
+static cudaError_t tc_gemm(mq_qnet* n, const bf::bf16* A, int lda, const bf::bf16* Bm, int ldb, int M, int N, int K, tc::Epilogue ep,
+                           bool allow_split, cudaStream_t s) {
+    int splits = 1;
+    const long long tiles = (long long)((M + tc::BM - 1) / tc::BM) * ((N + BN - 1) / BN);
+    if (allow_split && tiles < n->n_sms) {
+        splits = (int)((2LL * n->n_sms + tiles - 1) / tiles);
+        while (splits > 1 && (size_t)splits * M * N > n->partial_cap) --splits;
+    }
+    float* final_out = ep.out_f32;
+    if (splits > 1) ep.partial = n->partial;
+    cudaError_t e = tc::launch<BN, 4>(A, lda, Bm, ldb, M, N, K, ep, &splits, s);
+    n->launches += 1;
+    if (e == cudaSuccess && splits > 1) {
+        GemmParams p{};
+        p.M = M; p.N = N; p.C = final_out; p.ldc = ep.ldc; p.partial = n->partial; p.splits = splits;
+        p.bias = ep.bias; p.relu = ep.relu; p.drop = ep.drop; p.drop_scale = ep.drop_scale; p.mask_act = ep.mask_f32;
+        size_t total = (size_t)M * N;
+        int blocks = (int)((total + 255) / 256); if (blocks > 4 * n->n_sms) blocks = 4 * n->n_sms;
+        splitk_epilogue_kernel<<<blocks, 256, 0, s>>>(p);
+        n->launches += 1;
+    }
+    return e;
+}
+
+static void launch_colsum_bf16(mq_qnet* n, const bf::bf16* X, long long M, int N, float* out, cudaStream_t s);
+
+// forward with conv2 / conv3 / fc1 on the tensor cores; conv1, fc2 and the head stay fp32 (1.7 % of the flops)
+static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, long long B, const uint8_t* drop_mask, cudaStream_t s) {
+    float* const* W = which ? n->tl.t : n->tl.p;
+    const int M = (int)(B * PIX);
+    refresh_weights(n, which, s);
+    GemmParams p{};
+    p.batch = (int)B; p.partial = n->partial;
+    p.M = M; p.N = C1; p.K = 9 * CIN; p.A = obs; p.B = W[P_C1W]; p.ldb = C1; p.C = n->a1; p.ldc = C1; p.bias = W[P_C1B]; p.relu = 1;
+    n->launches += launch_gemm<A_IM2COL, B_ROW, 32, CIN>(p, n->partial_cap, n->n_sms, s);
+    bf::im2col_bf16_kernel<float, C1><<<ew_blocks((long long)M * 9 * (C1 / 8)), 256, 0, s>>>(n->a1, n->A2, M, 0);
+    tc::Epilogue ep{};
+    ep.out_bf16 = n->a2b; ep.ldc = C2; ep.bias = W[P_C2B]; ep.relu = 1;
+    cudaError_t e = tc_gemm<64>(n, n->A2, 9 * C1, n->w2f[which], 9 * C1, M, C2, 9 * C1, ep, false, s);
+    if (e != cudaSuccess) return e;
+    bf::im2col_bf16_kernel<bf::bf16, C2><<<ew_blocks((long long)M * 9 * (C2 / 8)), 256, 0, s>>>(n->a2b, n->A3, M, 0);
+    ep = tc::Epilogue{};
+    ep.out_bf16 = n->a3b; ep.ldc = C3; ep.bias = W[P_C3B]; ep.relu = 1;
+    e = tc_gemm<128>(n, n->A3, 9 * C2, n->w3f[which], 9 * C2, M, C3, 9 * C2, ep, false, s);
+    if (e != cudaSuccess) return e;
+    ep = tc::Epilogue{};
+    ep.out_f32 = n->h1; ep.ldc = H1; ep.bias = W[P_F1B]; ep.relu = 1; ep.drop = drop_mask; ep.drop_scale = 1.f / (1.f - 0.2f);
+    e = tc_gemm<128>(n, n->a3b, FLAT, n->w1f[which], FLAT, (int)B, H1, FLAT, ep, true, s);
+    if (e != cudaSuccess) return e;
+    n->launches += 2;
+    p = GemmParams{};
+    p.batch = (int)B; p.partial = n->partial; p.relu = 1;
+    p.M = (int)B; p.N = H2; p.K = H1; p.A = n->h1; p.lda = H1; p.B = W[P_F2W]; p.ldb = H1; p.C = n->h2; p.ldc = H2; p.bias = W[P_F2B];
+    n->launches += launch_gemm<A_ROW, B_COL, 64, 1>(p, n->partial_cap, n->n_sms, s);
+    return cudaGetLastError();
 }
 
 // forward of one network over B samples; activations land in the handle's workspace
@@ -305,6 +406,82 @@ static void launch_colsum(mq_qnet* n, const float* X, long long M, int N, float*
     colsum_partial_kernel<<<blocks, 256, 0, s>>>(X, M, N, rows, n->partial);
     colsum_final_kernel<<<(N + 255) / 256, 256, 0, s>>>(n->partial, blocks, N, out);
     n->launches += 2;
+}
+
+static void launch_colsum_bf16(mq_qnet* n, const bf::bf16* X, long long M, int N, float* out, cudaStream_t s) {
+    int rows = 256;
+    int blocks = (int)((M + rows - 1) / rows);
+    while ((size_t)blocks * N > n->partial_cap) { rows *= 2; blocks = (int)((M + rows - 1) / rows); }
+    bf::colsum_partial_bf16_kernel<<<blocks, 256, 0, s>>>(X, M, N, rows, n->partial);
+    colsum_final_kernel<<<(N + 255) / 256, 256, 0, s>>>(n->partial, blocks, N, out);
+    n->launches += 2;
+}
+
+static void transpose_bf16(mq_qnet* n, const bf::bf16* src, bf::bf16* dst, long long R, int C, cudaStream_t s) {
+    dim3 grid((unsigned)((R + 63) / 64), (unsigned)((C + 63) / 64));
+    bf::transpose_bf16_kernel<<<grid, 256, 0, s>>>(src, dst, R, C);
+    n->launches += 1;
+}
+
+// backward of the bf16 path.  Needs: forward_net_bf16(online) just ran (A2, A3, a1, a2b, a3b, h1, h2 hold the online
+// activations) and n->dq holds dL/dq.
+static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, const uint8_t* drop_online, cudaStream_t s) {
+    float* const* W = n->tl.p; float* const* G = n->tl.g;
+    const int M = (int)(B * PIX);
+    cudaError_t e;
+    fc3_wgrad_kernel<<<NA, H2, 0, s>>>(n->dq, n->h2, B, G[P_F3W], G[P_F3B]);
+    fc3_dgrad_kernel<<<(int)((B * H2 + 255) / 256), 256, 0, s>>>(n->dq, W[P_F3W], n->h2, B, n->dh2);
+    n->launches += 2;
+    GemmParams p{};
+    p.batch = (int)B; p.partial = n->partial;
+    p.M = H2; p.N = H1; p.K = (int)B; p.A = n->dh2; p.lda = H2; p.B = n->h1; p.ldb = H1; p.C = G[P_F2W]; p.ldc = H1;
+    n->launches += launch_gemm<A_COL, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    launch_colsum(n, n->dh2, B, H2, G[P_F2B], s);
+    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
+    p.M = (int)B; p.N = H1; p.K = H2; p.A = n->dh2; p.lda = H2; p.B = W[P_F2W]; p.ldb = H1; p.C = n->dh1; p.ldc = H1;
+    p.mask_act = n->h1; p.drop = drop_online; p.drop_scale = 1.f / (1.f - 0.2f);
+    n->launches += launch_gemm<A_ROW, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    launch_colsum(n, n->dh1, B, H1, G[P_F1B], s);
+    // fc1 on the tensor cores: dW1 = dh1^T a3 ; da3 = dh1 W1 (masked by a3 > 0)
+    bf::cast_transpose_kernel<<<ew_blocks(B * H1), 256, 0, s>>>(n->dh1, n->dh1b, n->dh1t, B, H1);
+    transpose_bf16(n, n->a3b, n->bufY, B, FLAT, s);                                   // a3^T [15488][B]
+    n->launches += 1;
+    tc::Epilogue ep{};
+    ep.out_f32 = G[P_F1W]; ep.ldc = FLAT;
+    if ((e = tc_gemm<128>(n, n->dh1t, (int)B, n->bufY, (int)B, H1, FLAT, (int)B, ep, false, s)) != cudaSuccess) return e;
+    ep = tc::Epilogue{};
+    ep.out_bf16 = n->da3b; ep.ldc = FLAT; ep.mask_bf16 = n->a3b;
+    if ((e = tc_gemm<128>(n, n->dh1b, H1, n->w1t, H1, (int)B, FLAT, H1, ep, false, s)) != cudaSuccess) return e;
+    // conv3: dWc3[(t,c)][n] = A3^T dY ; db ; da2 = im2col_flip(dY) Wd3^T (masked by a2 > 0)
+    launch_colsum_bf16(n, n->da3b, M, C3, G[P_C3B], s);
+    transpose_bf16(n, n->A3, n->bufX, M, 9 * C2, s);                                  // [576][M]
+    transpose_bf16(n, n->da3b, n->bufY, M, C3, s);                                    // [128][M]
+    ep = tc::Epilogue{};
+    ep.out_f32 = G[P_C3W]; ep.ldc = C3;
+    if ((e = tc_gemm<128>(n, n->bufX, M, n->bufY, M, 9 * C2, C3, M, ep, true, s)) != cudaSuccess) return e;
+    bf::im2col_bf16_kernel<bf::bf16, C3><<<ew_blocks((long long)M * 9 * (C3 / 8)), 256, 0, s>>>(n->da3b, n->bufX, M, 1);
+    n->launches += 1;
+    ep = tc::Epilogue{};
+    ep.out_bf16 = n->da2b; ep.ldc = C2; ep.mask_bf16 = n->a2b;
+    if ((e = tc_gemm<64>(n, n->bufX, 9 * C3, n->w3d, 9 * C3, M, C2, 9 * C3, ep, false, s)) != cudaSuccess) return e;
+    // conv2
+    launch_colsum_bf16(n, n->da2b, M, C2, G[P_C2B], s);
+    transpose_bf16(n, n->A2, n->bufX, M, 9 * C1, s);                                  // [288][M]
+    transpose_bf16(n, n->da2b, n->bufY, M, C2, s);                                    // [64][M]
+    ep = tc::Epilogue{};
+    ep.out_f32 = G[P_C2W]; ep.ldc = C2;
+    if ((e = tc_gemm<64>(n, n->bufX, M, n->bufY, M, 9 * C1, C2, M, ep, true, s)) != cudaSuccess) return e;
+    bf::im2col_bf16_kernel<bf::bf16, C2><<<ew_blocks((long long)M * 9 * (C2 / 8)), 256, 0, s>>>(n->da2b, n->bufX, M, 1);
+    n->launches += 1;
+    ep = tc::Epilogue{};
+    ep.out_f32 = n->da1; ep.ldc = C1; ep.mask_f32 = n->a1;
+    if ((e = tc_gemm<32>(n, n->bufX, 9 * C2, n->w2d, 9 * C2, M, C1, 9 * C2, ep, false, s)) != cudaSuccess) return e;
+    // conv1 (fp32, 1 % of the flops)
+    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
+    p.M = 9 * CIN; p.N = C1; p.K = M; p.A = state; p.B = n->da1; p.ldb = C1; p.C = G[P_C1W]; p.ldc = C1;
+    n->launches += launch_gemm<A_IM2COL_T, B_ROW, 32, CIN>(p, n->partial_cap, n->n_sms, s);
+    launch_colsum(n, n->da1, M, C1, G[P_C1B], s);
+    return cudaGetLastError();
 }
 
 }  // namespace mq
@@ -365,7 +542,12 @@ extern "C" int mq_qnet_forward(mq_qnet* n, int32_t which, const float* obs, int6
     MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_forward: batch %lld outside 1..%lld", (long long)B, n->max_batch);
     cudaStream_t s = (cudaStream_t)stream;
     float* const* W = which ? n->tl.t : n->tl.p;
-    mq::forward_net(n, W, obs, B, drop_mask, s);
+    if (n->precision == 1) {
+        cudaError_t e = mq::forward_net_bf16(n, which ? 1 : 0, obs, B, drop_mask, s);
+        if (e != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_forward (bf16 path): %s", cudaGetErrorString(e));
+    } else {
+        mq::forward_net(n, W, obs, B, drop_mask, s);
+    }
     const int blocks = (int)((B * 32 + 255) / 256);
     mq::qhead_kernel<<<blocks, 256, 0, s>>>(n->h2, W[mq::P_F3W], W[mq::P_F3B], B, 0, q_out, nullptr, nullptr, nullptr, 0.f, 0, 0, 0, 1);
     n->launches += 1;
@@ -378,7 +560,12 @@ extern "C" int mq_qnet_act(mq_qnet* n, const float* obs, int64_t B, float eps, u
     MQ_REQUIRE(n && obs && action_out && n_robots >= 1, "mq_qnet_act: bad argument");
     MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_act: batch %lld outside 1..%lld", (long long)B, n->max_batch);
     cudaStream_t s = (cudaStream_t)stream;
-    mq::forward_net(n, n->tl.p, obs, B, drop_mask, s);
+    if (n->precision == 1) {
+        cudaError_t e = mq::forward_net_bf16(n, 0, obs, B, drop_mask, s);
+        if (e != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_act (bf16 path): %s", cudaGetErrorString(e));
+    } else {
+        mq::forward_net(n, n->tl.p, obs, B, drop_mask, s);
+    }
     const int blocks = (int)((B * 32 + 255) / 256);
     mq::qhead_kernel<<<blocks, 256, 0, s>>>(n->h2, n->tl.p[mq::P_F3W], n->tl.p[mq::P_F3B], B, 1, q_out, nullptr, nullptr, action_out, eps,
                                             seed, env_id_base, tick, n_robots);
@@ -397,16 +584,27 @@ extern "C" int mq_qnet_td_backward(mq_qnet* n, const float* state, const int64_t
     cudaStream_t s = (cudaStream_t)stream;
     const int hb = (int)((B * 32 + 255) / 256);
     // next_q = target_network(next_states).max(1)[0]   (dqn_agent.py:146-147)
-    forward_net(n, n->tl.t, next_state, B, drop_target, s);
+    const bool bf16 = n->precision == 1;
+    MQ_REQUIRE(!bf16 || B % 8 == 0, "mq_qnet_td_backward: the bf16 path needs a batch that is a multiple of 8 (got %lld)", (long long)B);
+    cudaError_t fe = cudaSuccess;
+    if (bf16) fe = forward_net_bf16(n, 1, next_state, B, drop_target, s);
+    else forward_net(n, n->tl.t, next_state, B, drop_target, s);
     qhead_kernel<<<hb, 256, 0, s>>>(n->h2, n->tl.t[P_F3W], n->tl.t[P_F3B], B, 3, nullptr, nullptr, n->maxq, nullptr, 0.f, 0, 0, 0, 1);
     // current_q = q_network(states).gather(1, actions)   (dqn_agent.py:143)
-    forward_net(n, n->tl.p, state, B, drop_online, s);
+    if (bf16 && fe == cudaSuccess) fe = forward_net_bf16(n, 0, state, B, drop_online, s);
+    else if (!bf16) forward_net(n, n->tl.p, state, B, drop_online, s);
+    if (fe != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_td_backward (bf16 forward): %s", cudaGetErrorString(fe));
     qhead_kernel<<<hb, 256, 0, s>>>(n->h2, n->tl.p[P_F3W], n->tl.p[P_F3B], B, 2, nullptr, (const long long*)action, n->q_sa, nullptr, 0.f,
                                     0, 0, 0, 1);
     td_loss_kernel<<<1, 1024, 0, s>>>(n->q_sa, n->maxq, reward, done, (const long long*)action, B, hp->gamma, hp->huber, n->dq, loss_out);
     n->launches += 3;
 
     // ---- backward (loss.backward(), dqn_agent.py:154-155) ----
+    if (bf16) {
+        cudaError_t be = backward_bf16(n, state, B, drop_online, s);
+        if (be != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_td_backward (bf16 backward): %s", cudaGetErrorString(be));
+        return MQ_OK;
+    }
     float* const* W = n->tl.p; float* const* G = n->tl.g;
     fc3_wgrad_kernel<<<NA, H2, 0, s>>>(n->dq, n->h2, B, G[P_F3W], G[P_F3B]);
     fc3_dgrad_kernel<<<(int)((B * H2 + 255) / 256), 256, 0, s>>>(n->dq, W[P_F3W], n->h2, B, n->dh2);
@@ -471,6 +669,7 @@ extern "C" int mq_qnet_clip_adam(mq_qnet* n, const mq_hparams* hp, float grad_sc
                                                           step_size, bc2_sqrt);
     if (gnorm_out) MQ_CUDA(cudaMemcpyAsync(gnorm_out, n->gnorm, sizeof(float), cudaMemcpyDeviceToDevice, s));
     n->launches += 3;
+    n->w_dirty[0] = true;
     MQ_CUDA(cudaGetLastError());
     return MQ_OK;
 }
@@ -479,6 +678,7 @@ extern "C" int mq_qnet_sync_target(mq_qnet* n, float tau, void* stream) {
     MQ_REQUIRE(n, "mq_qnet_sync_target: null handle");
     mq::sync_target_kernel<<<(int)n->total_chunks, 256, 0, (cudaStream_t)stream>>>(n->tl, tau);
     n->launches += 1;
+    n->w_dirty[1] = true;
     MQ_CUDA(cudaGetLastError());
     return MQ_OK;
 }
@@ -489,5 +689,24 @@ extern "C" int mq_qnet_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t 
     const long long groups = (n + 3) / 4;
     mq::dropout_mask_kernel<<<(int)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mask, n, threshold, seed, counter);
     MQ_CUDA(cudaGetLastError());
+    return MQ_OK;
+}
+
+extern "C" int mq_qnet_set_precision(mq_qnet* n, int32_t precision) {
+    MQ_REQUIRE(n && (precision == 0 || precision == 1), "mq_qnet_set_precision: precision must be 0 (fp32) or 1 (bf16 tensor cores)");
+    if (precision == 1) {
+        MQ_CUDA(cudaSetDevice(n->device));
+        cudaError_t e = mq::alloc_bf16(n);
+        if (e != cudaSuccess) return mq::fail(MQ_ERR_ALLOC, "mq_qnet_set_precision: bf16 workspace allocation failed: %s", cudaGetErrorString(e));
+        if (!mq::tc::encode_fn()) return mq::fail(MQ_ERR_UNSUPPORTED, "mq_qnet_set_precision: cuTensorMapEncodeTiled is not available in this driver");
+    }
+    n->precision = precision;
+    n->w_dirty[0] = n->w_dirty[1] = true;
+    return MQ_OK;
+}
+
+extern "C" int mq_qnet_params_changed(mq_qnet* n) {
+    MQ_REQUIRE(n, "mq_qnet_params_changed: null handle");
+    n->w_dirty[0] = n->w_dirty[1] = true;
     return MQ_OK;
 }

@@ -248,6 +248,12 @@ int mq_qnet_clip_adam(mq_qnet* net, const mq_hparams* hp, float grad_scale, floa
 int mq_qnet_sync_target(mq_qnet* net, float tau, void* stream);
 /* nn.Dropout(0.2) keep-mask from keyed draws: mask dev u8 [n], keep probability 1-p (dqn_agent.py:33,57) */
 int mq_qnet_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t counter, void* stream);
+/* precision 0 = fp32 FFMA parity path (default, Q/loss within 1e-5 of the reference's fp32 agent);
+ * precision 1 = bf16 tcgen05/TMEM path for conv2, conv3 and fc1 forward + backward (fp32 accumulation, fp32 master
+ * weights and optimizer; reported separately).  Allocates the bf16 workspaces on first use. */
+int mq_qnet_set_precision(mq_qnet* net, int32_t precision);
+/* tell the library that the caller overwrote the bound parameter tensors (load_state_dict / checkpoint load) */
+int mq_qnet_params_changed(mq_qnet* net);
 int64_t mq_qnet_launch_count(const mq_qnet* net);
 
 /* ------------------------------------------------------------------------

@@ -216,3 +216,38 @@ def test_dqn_agent_facade_reference_surface(tmp_path):
     for i in range(40):
         agent3.remember(rng.random((11, 11, 6)), 1, 0.0, rng.random((11, 11, 6)), False)
     assert agent3.learn() is None
+
+
+def test_bf16_tensor_core_path_tracks_fp32():
+    """The tcgen05 bf16 path (conv2/conv3/fc1 on tensor cores, fp32 accumulate / master weights) against the fp32
+    parity path on the same weights and batch: Q within 2e-2 of the Q scale, loss within 1e-2, gradients aligned."""
+    from dqn_marl_b200.agents import qnet_params as qp
+    q, t = torch_ref.build_nets(21, 22)
+    B = 256
+    gen = torch.Generator().manual_seed(4)
+    states = (torch.rand((B, 11, 11, 6), generator=gen) < 0.3).float() * torch.rand((B, 11, 11, 6), generator=gen)
+    nstates = (torch.rand((B, 11, 11, 6), generator=gen) < 0.3).float()
+    d = "cuda:0"
+    batch = dict(states=states.to(d), actions=torch.randint(0, 5, (B,), generator=gen).to(d), rewards=(torch.randn(B, generator=gen) * 0.1).to(d),
+                 next_states=nstates.to(d), dones=(torch.rand(B, generator=gen) < 0.1).to(torch.uint8).to(d))
+    mask = (torch.rand((B, 512), generator=gen) >= 0.2).to(torch.uint8).to(d)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        net = _qnet(q, t, max_batch=B)
+        net.set_precision(prec)
+        qv = net.forward(batch["states"]).cpu()
+        loss = net.td_backward(batch, _hp(1), mask, mask).item()
+        grads = {k: v.cpu() for k, v in qp.unpack(net.flat_g).items()}
+        gnorm = net.clip_adam(_hp(1)).item()
+        res[prec] = (qv, loss, grads, gnorm, net.flat_p.clone().cpu())
+    q32, l32, g32, n32, p32 = res["fp32"]
+    q16, l16, g16, n16, p16 = res["bf16"]
+    assert (q32 - q16).abs().max() <= 2e-2 * q32.abs().max()
+    assert abs(l32 - l16) <= 1e-2 * abs(l32)
+    assert abs(n32 - n16) <= 3e-2 * n32
+    for k in g32:
+        a, b = g32[k].flatten().double(), g16[k].flatten().double()
+        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+        assert cos > 0.995, (k, cos)
+        assert abs(float(b.norm() / a.norm()) - 1.0) < 5e-2, (k, float(b.norm() / a.norm()))
+    assert (p32 - p16).abs().max() <= 2.1e-4          # one Adam step moves a weight by at most lr = 1e-4 in either path
