@@ -277,11 +277,13 @@ def run_ours(args, wl):
     d2h = h_obs.numel() * 4 + h_rew.numel() * 8 + h_don.numel()
 
     replay = run_replay_leg(args, dev) if args.replay_batch > 0 else None
-    learner = None
+    learner = learner_fp32 = None
     if args.loop_steps > 0:
         del envs, obs, rew, don
         torch.cuda.empty_cache()
-        learner = run_learner_loop(args, wl, layout, dev, rank, world)
+        learner = run_learner_loop(args, wl, layout, dev, rank, world, "bf16")
+        torch.cuda.empty_cache()
+        learner_fp32 = run_learner_loop(args, wl, layout, dev, rank, world, "fp32") if args.fp32_loop else None
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
@@ -313,6 +315,8 @@ def run_ours(args, wl):
             line["replay"] = replay
         if args.loop_steps > 0:
             line["learner"] = learner
+            if learner_fp32 is not None:
+                line["learner_fp32"] = learner_fp32
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             n_cpu_envs = min(E, 1024)
@@ -362,7 +366,7 @@ def run_replay_leg(args, dev):
     return res
 
 
-def run_learner_loop(args, wl, layout, dev, rank, world):
+def run_learner_loop(args, wl, layout, dev, rank, world, precision="bf16"):
     """Secondary metric of BASELINE.json: learner transitions/s in the full act -> step -> push -> learn loop
     (train_dqn.py:98-125 batched), fp32 parity path of the Q-network, gradient all-reduce over NCCL when N > 1."""
     import torch
@@ -371,7 +375,7 @@ def run_learner_loop(args, wl, layout, dev, rank, world):
     E, N, B = wl["envs"], wl["people"], args.learner_batch
     torch.manual_seed(0)
     tr = VecTrainer(layout, E, N, dev, dict(batch_size=B, learning_rate=1e-4, gamma=0.99, epsilon=1.0, epsilon_min=0.02,
-                                             epsilon_decay=0.9995, dropout="train"),
+                                             epsilon_decay=0.9995, dropout="train", precision=precision),
                     env_id_base=rank * E, seed=2026, replay_capacity=max(1 << 17, 4 * E))
     for _ in range(3):
         tr.step()
@@ -415,7 +419,8 @@ def run_learner_loop(args, wl, layout, dev, rank, world):
             "unit": "transitions/s", "batch_per_gpu": B, "loop_steps": K, "ms_per_loop_step": total_ms / K,
             "env_agent_steps_per_s_in_loop": world * E * N * K / (total_ms * 1e-3),
             "segments_ms": {"act": seg[0] / K, "env_step": seg[1] / K, "replay_push": seg[2] / K, "sample+learn": learn_ms},
-            "qnet_dtype": "f32 (parity path, CUDA-core FFMA)", "learn_tflops": 155.4e6 * B / (learn_ms * 1e-3) / 1e12,
+            "qnet_dtype": "bf16 tcgen05 tensor cores (conv2/conv3/fc1), fp32 accumulate + master weights" if precision == "bf16"
+            else "f32 (parity path, CUDA-core FFMA)", "learn_tflops": 155.4e6 * B / (learn_ms * 1e-3) / 1e12,
             "act_tflops": 38.85e6 * E / (seg[0] / K * 1e-3) / 1e12, "gpu_launches": int(launches),
             "allreduce": "nccl all-reduce of the flat 8,157,093-float gradient per learn step" if world > 1 else None}
 
@@ -431,6 +436,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--loop-steps", type=int, default=8, help="steps of the full act/step/push/learn loop (0 = skip)")
     ap.add_argument("--learner-batch", type=int, default=4096)
+    ap.add_argument("--fp32-loop", type=int, default=1, help="also run the loop with the fp32 parity path")
     ap.add_argument("--replay-batch", type=int, default=65536, help="replay sample batch of the bandwidth leg (0 = skip)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -28,7 +28,7 @@ extern "C" int mq_gemm_bf16(const void* A, const void* B, float* C, int32_t M, i
     cudaError_t e;
     const __nv_bfloat16* a = (const __nv_bfloat16*)A;
     const __nv_bfloat16* b = (const __nv_bfloat16*)B;
-    if (bn == 128) e = mq::tc::launch<128, 4>(a, K, b, K, M, N, K, ep, &sp, s);
+    if (bn == 128) e = mq::tc::launch<128, 3>(a, K, b, K, M, N, K, ep, &sp, s);
     else if (bn == 64) e = mq::tc::launch<64, 4>(a, K, b, K, M, N, K, ep, &sp, s);
     else if (bn == 32) e = mq::tc::launch<32, 4>(a, K, b, K, M, N, K, ep, &sp, s);
     else return mq::fail(MQ_ERR_ARG, "mq_gemm_bf16: bn must be 128, 64 or 32");

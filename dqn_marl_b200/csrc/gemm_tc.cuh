@@ -181,29 +181,102 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int m = m0 + q * 32 + lane;
+        // fast path: no per-element masks, full 32-column chunks, 16-byte aligned rows -> vector stores
+        const bool plain = !ep.mask_bf16 && !ep.mask_f32 && !ep.drop && (ep.ldc % 8 == 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            if (m < M && num_kb > 0) {
-                if (ep.partial) {
-                    float* dst = ep.partial + ((size_t)blockIdx.z * M + m) * N + n0 + c0;
+            if (m >= M || num_kb <= 0) continue;
+            const int nb = n0 + c0;
+            if (nb >= N) continue;
+            if (ep.partial) {
+                float* dst = ep.partial + ((size_t)blockIdx.z * M + m) * N + nb;
+                if (nb + 32 <= N && (N % 4 == 0)) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (n0 + c0 + j < N) dst[j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (nb + j < N) dst[j] = __uint_as_float(r[j]);
+                }
+                continue;
+            }
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (ep.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < N) v[j] += __ldg(ep.bias + nb + j);
+            }
+            if (ep.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            const size_t o = (size_t)m * ep.ldc + nb;
+            if (plain && nb + 32 <= N) {
+                if (ep.out_bf16) {
+                    uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + o);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                        dst[j / 8] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                                *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+                    }
+                }
+                if (ep.out_f32) {
+                    float4* dst = reinterpret_cast<float4*>(ep.out_f32 + o);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) dst[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            } else {
+                if (ep.mask_bf16 && nb + 32 <= N && (ep.ldc % 8 == 0)) {
+                    const uint4* mk = reinterpret_cast<const uint4*>(ep.mask_bf16 + o);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        const uint4 w = mk[j / 8];
+                        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ws[k]);
+                            if (!(__low2float(b2) > 0.f)) v[j + 2 * k] = 0.f;
+                            if (!(__high2float(b2) > 0.f)) v[j + 2 * k + 1] = 0.f;
+                        }
+                    }
+                } else if (ep.mask_bf16) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (nb + j < N && !(__bfloat162float(ep.mask_bf16[o + j]) > 0.f)) v[j] = 0.f;
+                }
+                if (ep.mask_f32) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (nb + j < N && !(ep.mask_f32[o + j] > 0.f)) v[j] = 0.f;
+                }
+                if (ep.drop) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) if (nb + j < N) v[j] = ep.drop[(size_t)m * N + nb + j] ? v[j] * ep.drop_scale : 0.f;
+                }
+                if (nb + 32 <= N && (ep.ldc % 8 == 0)) {
+                    if (ep.out_bf16) {
+                        uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + o);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            dst[j / 8] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                                    *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+                        }
+                    }
+                    if (ep.out_f32) {
+                        float4* dst = reinterpret_cast<float4*>(ep.out_f32 + o);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) dst[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int n = n0 + c0 + j;
-                        if (n >= N) continue;
-                        float v = __uint_as_float(r[j]);
-                        if (ep.bias) v += __ldg(ep.bias + n);
-                        if (ep.relu) v = fmaxf(v, 0.f);
-                        const size_t o = (size_t)m * ep.ldc + n;
-                        if (ep.mask_bf16) v = (__bfloat162float(ep.mask_bf16[o]) > 0.f) ? v : 0.f;
-                        if (ep.mask_f32) v = (ep.mask_f32[o] > 0.f) ? v : 0.f;
-                        if (ep.drop) v = ep.drop[(size_t)m * N + n] ? v * ep.drop_scale : 0.f;
-                        if (ep.out_f32) ep.out_f32[o] = v;
-                        if (ep.out_bf16) ep.out_bf16[o] = __float2bfloat16(v);
+                        if (nb + j >= N) continue;
+                        if (ep.out_f32) ep.out_f32[o + j] = v[j];
+                        if (ep.out_bf16) ep.out_bf16[o + j] = __float2bfloat16(v[j]);
                     }
                 }
             }

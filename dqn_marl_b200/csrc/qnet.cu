@@ -110,18 +110,20 @@ td_loss_kernel(const float* __restrict__ q_sa, const float* __restrict__ maxq_ne
 }
 
 // ---- fc3 backward: dW3[a][k] = sum_b dq[b][a] h2[b][k];  db3[a] = sum_b dq[b][a];  dh2 = (dq W3) * (h2 > 0) --------
+constexpr int FC3_CHUNK = 64;      // batch rows per block of the fc3 weight gradient
 __global__ void __launch_bounds__(256)
-fc3_wgrad_kernel(const float* __restrict__ dq, const float* __restrict__ h2, long long B, float* __restrict__ dw3,
-                 float* __restrict__ db3) {
-    // grid = NA blocks; thread k owns dW3[a][k]; fixed b order: deterministic
+fc3_wgrad_kernel(const float* __restrict__ dq, const float* __restrict__ h2, long long B, float* __restrict__ part_w,
+                 float* __restrict__ part_b) {
+    // grid = (NA, chunks); thread k owns dW3[a][k] of this chunk; fixed b order inside a chunk: deterministic
     const int a = blockIdx.x, k = threadIdx.x;
+    const long long b0 = (long long)blockIdx.y * FC3_CHUNK, b1 = b0 + FC3_CHUNK < B ? b0 + FC3_CHUNK : B;
     float acc = 0.f, accb = 0.f;
-    for (long long b = 0; b < B; ++b) {
+    for (long long b = b0; b < b1; ++b) {
         const float g = __ldg(dq + b * NA + a);
         if (g != 0.f) { acc = fmaf(g, __ldg(h2 + b * H2 + k), acc); accb += g; }
     }
-    dw3[a * H2 + k] = acc;
-    if (k == 0) db3[a] = accb;
+    part_w[((size_t)blockIdx.y * NA + a) * H2 + k] = acc;
+    if (k == 0) part_b[(size_t)blockIdx.y * NA + a] = accb;
 }
 __global__ void __launch_bounds__(256)
 fc3_dgrad_kernel(const float* __restrict__ dq, const float* __restrict__ w3, const float* __restrict__ h2, long long B,
@@ -147,13 +149,16 @@ colsum_partial_kernel(const float* __restrict__ X, long long M, int N, int rows_
         partial[(size_t)blockIdx.x * N + n] = acc;
     }
 }
+// one warp per column: lanes stride over the partial rows, fixed shuffle tree: deterministic
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int blocks, int N, float* __restrict__ out) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (n >= N) return;
     float acc = 0.f;
-    for (int b = 0; b < blocks; ++b) acc += partial[(size_t)b * N + n];
-    out[n] = acc;
+    for (int b = lane; b < blocks; b += 32) acc += partial[(size_t)b * N + n];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) out[n] = acc;
 }
 
 // ---- global grad norm (clip_grad_norm_, dqn_agent.py:158) + Adam (:85,160), multi-tensor ---------------------
@@ -328,7 +333,7 @@ static cudaError_t tc_gemm(mq_qnet* n, const bf::bf16* A, int lda, const bf::bf1
     }
     float* final_out = ep.out_f32;
     if (splits > 1) ep.partial = n->partial;
-    cudaError_t e = tc::launch<BN, 4>(A, lda, Bm, ldb, M, N, K, ep, &splits, s);
+    cudaError_t e = tc::launch<BN, (BN == 128 ? 3 : 4)>(A, lda, Bm, ldb, M, N, K, ep, &splits, s);
     n->launches += 1;
     if (e == cudaSuccess && splits > 1) {
         GemmParams p{};
@@ -404,7 +409,7 @@ static void launch_colsum(mq_qnet* n, const float* X, long long M, int N, float*
     int blocks = (int)((M + rows - 1) / rows);
     while ((size_t)blocks * N > n->partial_cap) { rows *= 2; blocks = (int)((M + rows - 1) / rows); }
     colsum_partial_kernel<<<blocks, 256, 0, s>>>(X, M, N, rows, n->partial);
-    colsum_final_kernel<<<(N + 255) / 256, 256, 0, s>>>(n->partial, blocks, N, out);
+    colsum_final_kernel<<<(N * 32 + 255) / 256, 256, 0, s>>>(n->partial, blocks, N, out);
     n->launches += 2;
 }
 
@@ -413,7 +418,7 @@ static void launch_colsum_bf16(mq_qnet* n, const bf::bf16* X, long long M, int N
     int blocks = (int)((M + rows - 1) / rows);
     while ((size_t)blocks * N > n->partial_cap) { rows *= 2; blocks = (int)((M + rows - 1) / rows); }
     bf::colsum_partial_bf16_kernel<<<blocks, 256, 0, s>>>(X, M, N, rows, n->partial);
-    colsum_final_kernel<<<(N + 255) / 256, 256, 0, s>>>(n->partial, blocks, N, out);
+    colsum_final_kernel<<<(N * 32 + 255) / 256, 256, 0, s>>>(n->partial, blocks, N, out);
     n->launches += 2;
 }
 
@@ -429,7 +434,14 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
     float* const* W = n->tl.p; float* const* G = n->tl.g;
     const int M = (int)(B * PIX);
     cudaError_t e;
-    fc3_wgrad_kernel<<<NA, H2, 0, s>>>(n->dq, n->h2, B, G[P_F3W], G[P_F3B]);
+    {
+        const int chunks = (int)((B + FC3_CHUNK - 1) / FC3_CHUNK);
+        float* pw = n->partial; float* pb = n->partial + (size_t)chunks * NA * H2;
+        fc3_wgrad_kernel<<<dim3(NA, chunks), H2, 0, s>>>(n->dq, n->h2, B, pw, pb);
+        colsum_final_kernel<<<(NA * H2 * 32 + 255) / 256, 256, 0, s>>>(pw, chunks, NA * H2, G[P_F3W]);
+        colsum_final_kernel<<<(NA * 32 + 255) / 256, 256, 0, s>>>(pb, chunks, NA, G[P_F3B]);
+        n->launches += 2;
+    }
     fc3_dgrad_kernel<<<(int)((B * H2 + 255) / 256), 256, 0, s>>>(n->dq, W[P_F3W], n->h2, B, n->dh2);
     n->launches += 2;
     GemmParams p{};
@@ -606,7 +618,14 @@ extern "C" int mq_qnet_td_backward(mq_qnet* n, const float* state, const int64_t
         return MQ_OK;
     }
     float* const* W = n->tl.p; float* const* G = n->tl.g;
-    fc3_wgrad_kernel<<<NA, H2, 0, s>>>(n->dq, n->h2, B, G[P_F3W], G[P_F3B]);
+    {
+        const int chunks = (int)((B + FC3_CHUNK - 1) / FC3_CHUNK);
+        float* pw = n->partial; float* pb = n->partial + (size_t)chunks * NA * H2;
+        fc3_wgrad_kernel<<<dim3(NA, chunks), H2, 0, s>>>(n->dq, n->h2, B, pw, pb);
+        colsum_final_kernel<<<(NA * H2 * 32 + 255) / 256, 256, 0, s>>>(pw, chunks, NA * H2, G[P_F3W]);
+        colsum_final_kernel<<<(NA * 32 + 255) / 256, 256, 0, s>>>(pb, chunks, NA, G[P_F3B]);
+        n->launches += 2;
+    }
     fc3_dgrad_kernel<<<(int)((B * H2 + 255) / 256), 256, 0, s>>>(n->dq, W[P_F3W], n->h2, B, n->dh2);
     n->launches += 2;
     GemmParams p{};

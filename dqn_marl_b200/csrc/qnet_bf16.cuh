@@ -47,20 +47,37 @@ im2col_bf16_kernel(const Tin* __restrict__ src, bf16* __restrict__ dst, long lon
     *reinterpret_cast<uint4*>(dst + (m * 9 + tap) * C + c8 * 8) = *reinterpret_cast<const uint4*>(v);
 }
 
-// [R][C] -> [C][R], 64 x 64 tiles through shared memory
+// [R][C] -> [C][R], 64 x 64 tiles through shared memory, 16-byte global accesses on both sides
+// (C % 8 == 0 and R % 8 == 0 on the fast path; callers guarantee it: B is a multiple of 8)
 __global__ void __launch_bounds__(256)
 transpose_bf16_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long long R, int C) {
-    __shared__ bf16 tile[64][66];
+    __shared__ __align__(16) bf16 tile[64][72];
     const long long r0 = (long long)blockIdx.x * 64;
     const int c0 = blockIdx.y * 64;
-    for (int k = threadIdx.x; k < 64 * 64; k += 256) {
-        const int r = k >> 6, c = k & 63;
-        tile[r][c] = (r0 + r < R && c0 + c < C) ? src[(r0 + r) * C + c0 + c] : __float2bfloat16(0.f);
+    const bool vec = (C % 8 == 0) && (R % 8 == 0);
+    for (int k = threadIdx.x; k < 64 * 8; k += 256) {       // 64 rows x 8 chunks of 8 elements
+        const int r = k >> 3, c = (k & 7) * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (r0 + r < R && c0 + c < C) {
+            if (vec) v = *reinterpret_cast<const uint4*>(src + (r0 + r) * C + c0 + c);
+            else {
+                __align__(16) bf16 t[8];
+                for (int q = 0; q < 8; ++q) t[q] = (c0 + c + q < C) ? src[(r0 + r) * C + c0 + c + q] : __float2bfloat16(0.f);
+                v = *reinterpret_cast<const uint4*>(t);
+            }
+        }
+        *reinterpret_cast<uint4*>(&tile[r][c]) = v;
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < 64 * 64; k += 256) {
-        const int c = k >> 6, r = k & 63;
-        if (r0 + r < R && c0 + c < C) dst[(long long)(c0 + c) * R + r0 + r] = tile[r][c];
+    for (int k = threadIdx.x; k < 64 * 8; k += 256) {       // 64 output rows (columns of src) x 8 chunks of 8 source rows
+        const int c = k >> 3, r = (k & 7) * 8;
+        if (c0 + c >= C || r0 + r >= R) continue;
+        __align__(16) bf16 t[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t[q] = tile[r + q][c];
+        bf16* d = dst + (long long)(c0 + c) * R + r0 + r;
+        if (vec) *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(t);
+        else for (int q = 0; q < 8; ++q) if (r0 + r + q < R) d[q] = t[q];
     }
 }
 
