@@ -53,6 +53,8 @@ struct DevCfg {
     int env_id_base, max_steps, reset_robots, reset_fire, auto_reset;
     int hash_cap, hash_shift, n_leaf_max;
     int smem_per_env;
+    unsigned char* scratch;            // BIG envs: per-env global scratch for everything but the occupancy bitmap
+    long long scratch_per_env;
     double evac_reward, death_penalty, death_acc_penalty, alive_bonus;
 };
 
@@ -77,31 +79,43 @@ struct Smem {
     double* health; double* dist; double* leaf_sum;
     uint32_t* bm; uint32_t* pos;
     int* leaf_off; int* leaf_len;
-    uint16_t* mov; uint16_t* mv;
+    uint16_t* mov; uint32_t* mv;
     uint8_t* fl;
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline size_t carve(Smem& s, unsigned char* base, int N, int cap, int words, int nleaf) {
-    size_t o = 0;
+// Small envs: everything in shared memory (returns the shared bytes).  BIG envs (gbase != nullptr): only the
+// occupancy bitmap and the pairwise-sum leaf tables stay in shared memory, the per-person arrays and the proposal
+// table live in a per-env global scratch area (returns the shared bytes; *gbytes receives the scratch bytes).
+__host__ __device__ inline size_t carve(Smem& s, unsigned char* base, unsigned char* gbase, int N, int cap, int words, int nleaf,
+                                        size_t* gbytes = nullptr) {
+    size_t o = 0, go = 0;
+    unsigned char* pb = gbase ? gbase : base;          // where the per-person arrays go
+    size_t& po = gbase ? go : o;
     const size_t table = (size_t)cap * sizeof(Slot);
     const size_t distb = sizeof(double) * (size_t)N;
-    s.tab = (Slot*)(base + o);
-    s.dist = (double*)(base + o);
-    o += align_up(table > distb ? table : distb, 16);
-    s.health = (double*)(base + o); o += sizeof(double) * N;
+    s.tab = (Slot*)(pb + po);
+    s.dist = (double*)(pb + po);
+    if (gbase) { po += align_up(table, 16); s.dist = (double*)(pb + po); po += align_up(distb, 16); }
+    else po += align_up(table > distb ? table : distb, 16);
+    s.health = (double*)(pb + po); po += align_up(sizeof(double) * N, 16);
+    s.pos = (uint32_t*)(pb + po); po += align_up(sizeof(uint32_t) * N, 16);
+    s.mv = (uint32_t*)(pb + po); po += align_up(sizeof(uint32_t) * N, 16);
+    s.mov = (uint16_t*)(pb + po); po += align_up(sizeof(uint16_t) * N, 16);
+    s.fl = (uint8_t*)(pb + po); po += align_up(N, 16);
     s.leaf_sum = (double*)(base + o); o += sizeof(double) * nleaf;
     o = align_up(o, 16);
     s.bm = (uint32_t*)(base + o); o += sizeof(uint32_t) * align_up(words, 4);
-    s.pos = (uint32_t*)(base + o); o += sizeof(uint32_t) * N;
     s.leaf_off = (int*)(base + o); o += sizeof(int) * nleaf;
     s.leaf_len = (int*)(base + o); o += sizeof(int) * nleaf;
-    s.mov = (uint16_t*)(base + o); o += sizeof(uint16_t) * align_up(N, 2);
-    s.mv = (uint16_t*)(base + o); o += sizeof(uint16_t) * align_up(N, 2);
-    s.fl = (uint8_t*)(base + o); o += align_up(N, 16);
+    if (gbytes) *gbytes = align_up(go, 256);
     return align_up(o, 16);
 }
+
+// proposal-table reads: atomics act at L2, so BIG (global-memory) tables are read around L1
+template <bool BIG> __device__ __forceinline__ uint32_t tab_ld(const uint32_t* p) { return BIG ? __ldcg(p) : *p; }
+template <bool BIG> __device__ __forceinline__ unsigned long long tab_ld(const unsigned long long* p) { return BIG ? __ldcg(p) : *p; }
 
 // group = the WPE warps that own one env; CW = warps per CTA.  With WPE == 8 the last warp is the "chain warp": it
 // takes part in the load phases, then runs the sequential health sum while the 7 worker warps do everything else.
@@ -235,7 +249,7 @@ __device__ void reset_env(const Group<WPE, CW>& g, const DevLayout& lay, const D
     gather_obs(tid, T, lay, cfg, sm, rob, sc[MQ_S_ROBOT_POS_X], sc[MQ_S_ROBOT_POS_Y], sc[MQ_S_FIRE_STEP], obs, obs64, env);
 }
 
-template <int WPE, int CW>
+template <int WPE, int CW, bool BIG>
 __global__ void __launch_bounds__(32 * CW)
 env_reset_kernel(DevLayout lay, DevCfg cfg, DevState st, const uint8_t* env_mask, const int16_t* inject, float* obs,
                  double* obs64) {
@@ -248,7 +262,8 @@ env_reset_kernel(DevLayout lay, DevCfg cfg, DevState st, const uint8_t* env_mask
     if (env >= cfg.n_envs) return;
     if (env_mask && !env_mask[env]) return;
     Smem sm;
-    carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, cfg.N, cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
+    carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
+          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
     int* sc = s_sc[g.gid];
     int(*rob)[2] = s_rob[g.gid];
     if (g.gtid < MQ_ENV_SCALARS) sc[g.gtid] = st.scalars[(size_t)env * MQ_ENV_SCALARS + g.gtid];
@@ -328,8 +343,8 @@ __device__ __forceinline__ double health_chain(const double* h, int N) {
 // ---------------------------------------------------------------------------------------------
 constexpr int PF = 4;     // persons per thread whose state is fetched before any of them is processed
 
-template <int WPE, int CW>
-__global__ void __launch_bounds__(32 * CW, WPE == 1 ? 7 : 3)      // 28 env-warps / 3 env-CTAs resident per SM
+template <int WPE, int CW, bool BIG>
+__global__ void __launch_bounds__(32 * CW, WPE == 1 ? 7 : (BIG ? 1 : 3))      // 28 env-warps / 3 env-CTAs resident per SM
 env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ actions, float* obs, double* obs64,
                 double* reward_out, uint8_t* done_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -347,7 +362,8 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     const int env = blockIdx.x * GROUPS + g.gid;
     if (env >= cfg.n_envs) return;              // whole group leaves together (GROUPS == 1 when WPE == CW)
     Smem sm;
-    carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, cfg.N, cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
+    carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
+          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
     int* sc = s_sc[g.gid];
     int(*rob)[2] = s_rob[g.gid];
     int* s_cnt = s_cnt_all[g.gid];
@@ -454,7 +470,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                 if (mover) {
                     const int mi = wbase + __popc(bal & ((1u << lane) - 1u));
                     sm.mov[mi] = (uint16_t)i;
-                    sm.mv[mi] = 0xFFFFu;
+                    sm.mv[mi] = 0xFFFFFFFFu;
                 }
             }
         }
@@ -534,7 +550,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                     }
                     atomicMin(&sm.tab[hh].ml, (uint32_t)i);                      // leave half is still 0
                     atomicMin(&sm.tab[hh].best, ((unsigned long long)w4.z << 32) | (unsigned long long)i);
-                    sm.mv[mi] = (uint16_t)(hh | ((uint32_t)best_dir << 12));
+                    sm.mv[mi] = hh | ((uint32_t)best_dir << 20);
                 }
             }
         }
@@ -543,25 +559,25 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         // ---- phase 4a: winners leave their old cell (people.py:239-246,301) ---------------------------------
         for (int mi = wt; mi < n_mov; mi += TW) {
             const uint32_t mv = sm.mv[mi];
-            if (mv == 0xFFFFu) continue;
+            if (mv == 0xFFFFFFFFu) continue;
             const int i = sm.mov[mi];
-            const uint32_t slot = mv & 0xFFFu;
-            if ((uint32_t)sm.tab[slot].best != (uint32_t)i) continue;      // lost the shuffle: stays (people.py:248-249)
-            sm.mv[mi] = (uint16_t)(mv | 0x8000u);
-            const uint32_t key = sm.tab[slot].ml & 0xFFFFu;
+            const uint32_t slot = mv & 0xFFFFFu;
+            if ((uint32_t)tab_ld<BIG>(&sm.tab[slot].best) != (uint32_t)i) continue;      // lost the shuffle: stays (people.py:248-249)
+            sm.mv[mi] = mv | 0x80000000u;
+            const uint32_t key = tab_ld<BIG>(&sm.tab[slot].ml) & 0xFFFFu;
             const uint32_t p = sm.pos[i];
             const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
             const uint32_t c_old = (uint32_t)(x * stride + y);
             uint32_t hh = hash_cell(c_old, cfg.hash_shift);
             bool found = false;
             for (;;) {
-                const uint32_t k = sm.tab[hh].key;
+                const uint32_t k = tab_ld<BIG>(&sm.tab[hh].key);
                 if (k == HEMPTY) break;
                 if (k == c_old) { found = true; break; }
                 hh = (hh + 1) & hmask;
             }
             // old cell is somebody's target: order decides (the low half of ml is final since the barrier)
-            if (found) atomicMax(&sm.tab[hh].ml, ((key + 1u) << 16) | (sm.tab[hh].ml & 0xFFFFu));
+            if (found) atomicMax(&sm.tab[hh].ml, ((key + 1u) << 16) | (tab_ld<BIG>(&sm.tab[hh].ml) & 0xFFFFu));
             else bm_clear(sm.bm, wpr, x, y);                    // rmap[old] = 0
         }
         g.wsync();
@@ -569,10 +585,10 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         // ---- phase 4b: winners enter their target (people.py:302-314) --------------------------------------
         for (int mi = wt; mi < n_mov; mi += TW) {
             const uint32_t mv = sm.mv[mi];
-            if (mv == 0xFFFFu || !(mv & 0x8000u)) continue;
+            if (mv == 0xFFFFFFFFu || !(mv & 0x80000000u)) continue;
             const int i = sm.mov[mi];
-            const uint32_t ml = sm.tab[mv & 0xFFFu].ml;
-            const int dir = (int)((mv >> 12) & 7u);
+            const uint32_t ml = tab_ld<BIG>(&sm.tab[mv & 0xFFFFFu].ml);
+            const int dir = (int)((mv >> 20) & 7u);
             const uint32_t p = sm.pos[i];
             const int nx = (int)(p & 0xFFFFu) + move_dx(dir), ny = (int)(p >> 16) + move_dy(dir);
             const bool evac = (__ldg(lay.cellinfo + nx * stride + ny) & 8u) != 0;      // Map.checkSavefy (map.py:93-113)
@@ -745,6 +761,8 @@ struct mq_env {
     mq::DevState st;
     void* d_dp5 = nullptr; void* d_cellinfo = nullptr; void* d_ctr = nullptr; void* d_int = nullptr;
     int wpe = 8;            // warps per env: 1 (4 envs per 128-thread CTA) or 8 (one 256-thread CTA per env)
+    bool big = false;       // per-person arrays + proposal table in global scratch (envs too large for shared memory)
+    void* d_scratch = nullptr;
     int blocks = 0, threads = 0;
     size_t smem = 0;        // dynamic shared memory per CTA
     int64_t launches = 0;
@@ -763,11 +781,11 @@ extern "C" int mq_env_state_sizes(const mq_env_cfg* cfg, const mq_layout* layout
     return MQ_OK;
 }
 
-template <int WPE, int CW>
+template <int WPE, int CW, bool BIG>
 static cudaError_t set_smem_attr(int bytes) {
-    cudaError_t e = cudaFuncSetAttribute(mq::env_step_kernel<WPE, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaError_t e = cudaFuncSetAttribute(mq::env_step_kernel<WPE, CW, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mq::env_reset_kernel<WPE, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return cudaFuncSetAttribute(mq::env_reset_kernel<WPE, CW, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layout* layout, const mq_env_state* state) {
@@ -778,9 +796,7 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     MQ_REQUIRE(layout->dp5 && layout->cellinfo && layout->danger_ctr && layout->danger_int, "mq_env_create: layout tables missing");
     MQ_REQUIRE(state->pos && state->health && state->acc && state->flags && state->rmap && state->robots && state->scalars,
                "mq_env_create: state buffers missing");
-    if (cfg->n_people > 3000)
-        return mq::fail(MQ_ERR_UNSUPPORTED, "mq_env_create: %d people per env: the shared-memory step kernel handles at most 3000; "
-                        "the tiled large-env kernel is not built yet", cfg->n_people);
+    MQ_REQUIRE(cfg->n_people <= 65000, "mq_env_create: at most 65000 people per env (16-bit list indices)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return mq::fail(MQ_ERR_CUDA, "mq_env_create: no CUDA device (this build has no CPU fallback)");
@@ -828,7 +844,7 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     c.seed = cfg->seed; c.env_id_base = cfg->env_id_base; c.max_steps = cfg->max_steps;
     c.reset_robots = cfg->reset_robots; c.reset_fire = cfg->reset_fire; c.auto_reset = cfg->auto_reset;
     int want = c.N + c.N / 3 + 8;                      // load factor <= 0.75 even if everybody proposes a distinct cell
-    c.hash_cap = round_pow2(want < 64 ? 64 : want);    // <= 4096 (12-bit slot ids in Smem::mv)
+    c.hash_cap = round_pow2(want < 64 ? 64 : want);    // < 2^20 (20-bit slot ids in Smem::mv)
     int lg = 0; while ((1 << lg) < c.hash_cap) ++lg;
     c.hash_shift = 32 - lg;
     c.n_leaf_max = c.N / 64 + 4;
@@ -837,11 +853,25 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     e->st = {state->pos, state->health, state->acc, state->flags, state->rmap, state->robots, state->scalars};
 
     mq::Smem tmp;
-    c.smem_per_env = (int)mq::carve(tmp, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
-    // one warp per env for small envs (no CTA barriers, 4 envs per CTA), one CTA per env otherwise
+    c.scratch = nullptr; c.scratch_per_env = 0;
+    c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max);
+    // one warp per env for small envs (no CTA barriers, 4 envs per CTA), one CTA per env otherwise; envs whose
+    // person arrays do not fit shared memory keep only the occupancy bitmap there (BIG)
     e->wpe = (c.N <= 256 && (size_t)c.smem_per_env * SMALL_CW + 2048 <= (size_t)max_smem) ? 1 : 8;
+    e->big = e->wpe == 8 && (size_t)c.smem_per_env + 2048 > (size_t)max_smem;
+    if (e->big) {
+        size_t gbytes = 0;
+        c.smem_per_env = (int)mq::carve(tmp, nullptr, (unsigned char*)16, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, &gbytes);
+        c.scratch_per_env = (long long)gbytes;
+        if ((ce = cudaMalloc(&e->d_scratch, gbytes * (size_t)c.n_envs)) != cudaSuccess) {
+            mq_env_destroy(e);
+            return mq::fail(MQ_ERR_ALLOC, "mq_env_create: %zu B of scratch for %d large envs: %s", gbytes * (size_t)c.n_envs, c.n_envs,
+                            cudaGetErrorString(ce));
+        }
+        c.scratch = (unsigned char*)e->d_scratch;
+    }
     const int groups = e->wpe == 1 ? SMALL_CW : 1;
     e->threads = e->wpe == 1 ? 32 * SMALL_CW : 256;
     e->smem = (size_t)c.smem_per_env * groups;
@@ -849,11 +879,12 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
         size_t need = e->smem;
         mq_env_destroy(e);
         return mq::fail(MQ_ERR_UNSUPPORTED,
-                        "mq_env_create: env of %d people on a %dx%d grid needs %zu B of shared memory per CTA (limit %d); "
-                        "the tiled large-env kernel is not built yet", cfg->n_people, layout->L, layout->W, need, max_smem);
+                        "mq_env_create: the occupancy bitmap of a %dx%d grid needs %zu B of shared memory per CTA (limit %d)",
+                        layout->L, layout->W, need, max_smem);
     }
     e->blocks = (c.n_envs + groups - 1) / groups;
-    ce = e->wpe == 1 ? set_smem_attr<1, SMALL_CW>((int)e->smem) : set_smem_attr<8, 8>((int)e->smem);
+    ce = e->wpe == 1 ? set_smem_attr<1, SMALL_CW, false>((int)e->smem)
+                     : (e->big ? set_smem_attr<8, 8, true>((int)e->smem) : set_smem_attr<8, 8, false>((int)e->smem));
     if (ce != cudaSuccess) {
         mq_env_destroy(e);
         return mq::fail(MQ_ERR_CUDA, "mq_env_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
@@ -864,7 +895,7 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
 
 extern "C" int mq_env_destroy(mq_env* e) {
     if (!e) return MQ_OK;
-    cudaFree(e->d_dp5); cudaFree(e->d_cellinfo); cudaFree(e->d_ctr); cudaFree(e->d_int);
+    cudaFree(e->d_dp5); cudaFree(e->d_cellinfo); cudaFree(e->d_ctr); cudaFree(e->d_int); cudaFree(e->d_scratch);
     delete e;
     return MQ_OK;
 }
@@ -881,8 +912,9 @@ extern "C" int mq_env_reset(mq_env* e, const uint8_t* env_mask, const int16_t* i
                             double* obs64_out, void* stream) {
     MQ_REQUIRE(e, "mq_env_reset: null handle");
     cudaStream_t s = (cudaStream_t)stream;
-    if (e->wpe == 1) mq::env_reset_kernel<1, SMALL_CW><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
-    else mq::env_reset_kernel<8, 8><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
+    if (e->wpe == 1) mq::env_reset_kernel<1, SMALL_CW, false><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
+    else if (e->big) mq::env_reset_kernel<8, 8, true><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
+    else mq::env_reset_kernel<8, 8, false><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
     MQ_CUDA(cudaGetLastError());
     e->launches += 1;
     return MQ_OK;
@@ -892,8 +924,9 @@ extern "C" int mq_env_step(mq_env* e, const int32_t* actions, float* obs_out, do
                            uint8_t* done_out, void* stream) {
     MQ_REQUIRE(e && actions && reward_out && done_out, "mq_env_step: null argument");
     cudaStream_t s = (cudaStream_t)stream;
-    if (e->wpe == 1) mq::env_step_kernel<1, SMALL_CW><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
-    else mq::env_step_kernel<8, 8><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
+    if (e->wpe == 1) mq::env_step_kernel<1, SMALL_CW, false><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
+    else if (e->big) mq::env_step_kernel<8, 8, true><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
+    else mq::env_step_kernel<8, 8, false><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
     MQ_CUDA(cudaGetLastError());
     e->launches += 1;
     return MQ_OK;

@@ -237,3 +237,18 @@ def test_reference_facade_replays_golden(name):
     assert pm["evacuated"] + pm["dead"] + pm["remaining"] == m["n_people"]
     assert np.array_equal(env.people.rmap != 0, np.unpackbits(g["rmap"][F - 1])[:(m["width"] + 2) * (m["height"] + 2)].reshape(m["width"] + 2, -1) != 0)
     assert env.map.Check_Valid(5, 5) and not env.map.Check_Valid(19, 15) and not env.map.Check_Valid(0, 3)
+
+
+def test_large_env_global_scratch_matches_oracle():
+    """Envs whose person arrays do not fit shared memory (6000 people): proposal table and per-person arrays live in
+    global scratch, only the occupancy bitmap is staged in shared memory."""
+    from dqn_marl_b200.layout import Layout
+    lay = Layout.synthetic(160, 160, n_exits=4, seed=11)
+    _run_vs_oracle(lay, n_envs=2, N=6000, seed=13, steps=14, check_every=2)
+
+
+def test_c5_shape_matches_oracle():
+    """BASELINE.json configs[4] shape: 1024x1024 multi-exit grid, 20000 people per env."""
+    from dqn_marl_b200.layout import Layout
+    lay = Layout.synthetic(1024, 1024, n_exits=8, wall_fill=0.15, seed=2024)
+    _run_vs_oracle(lay, n_envs=2, N=20000, seed=5, steps=6, check_every=1)
