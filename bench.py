@@ -42,6 +42,8 @@ WORKLOADS = {
                desc="CA-dqn1 single room 36x30, 150 people/env, 4096 envs, env-step only (BASELINE.json configs[1])"),
     "c3": dict(L=256, W=256, people=1000, envs=16384, synthetic=True,
                desc="synthetic Louvre layout 256x256, 1000 people/env, 16384 envs, env-step only (BASELINE.json configs[2] env part)"),
+    "c5": dict(L=1024, W=1024, people=20000, envs=512, synthetic=True, exits=8, wall_fill=0.15,
+               desc="stress: synthetic 1024x1024 multi-exit museum grid, 20000 people/env, 512 envs per GPU, env-step only (BASELINE.json configs[4] env part)"),
 }
 L2_BYTES = 126e6
 
@@ -117,7 +119,7 @@ class ClockSampler:
 def make_layout(wl):
     from dqn_marl_b200.layout import Layout
     if wl["synthetic"]:
-        return Layout.synthetic(wl["L"], wl["W"], n_exits=1, seed=2024)
+        return Layout.synthetic(wl["L"], wl["W"], n_exits=wl.get("exits", 1), wall_fill=wl.get("wall_fill", 0.10), seed=2024)
     return Layout.reference_room(wl["L"], wl["W"])
 
 
