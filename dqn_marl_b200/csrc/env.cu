@@ -22,6 +22,7 @@
 //     the winners that left it; a left cell that is nobody's target is simply cleared.
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include "common.h"
@@ -31,7 +32,6 @@ namespace mq {
 
 constexpr int MAXR = MQ_MAX_ROBOTS;
 constexpr uint32_t HEMPTY = 0xFFFFFFFFu;
-constexpr int MAX_CTA_THREADS = 256;
 
 struct DevLayout {
     int L, W, stride, G, wpr, rmap_words;
@@ -344,7 +344,7 @@ __device__ __forceinline__ double health_chain(const double* h, int N) {
 constexpr int PF = 4;     // persons per thread whose state is fetched before any of them is processed
 
 template <int WPE, int CW, bool BIG>
-__global__ void __launch_bounds__(32 * CW, WPE == 1 ? 7 : (BIG ? 1 : 3))      // 28 env-warps / 3 env-CTAs resident per SM
+__global__ void __launch_bounds__(32 * CW, WPE == 1 ? 7 : (BIG ? 1 : 3))      // 28 env-warps / 3 env-CTAs resident per SM (BIG: one)
 env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ actions, float* obs, double* obs64,
                 double* reward_out, uint8_t* done_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -760,8 +760,9 @@ struct mq_env {
     mq::DevCfg cfg;
     mq::DevState st;
     void* d_dp5 = nullptr; void* d_cellinfo = nullptr; void* d_ctr = nullptr; void* d_int = nullptr;
-    int wpe = 8;            // warps per env: 1 (4 envs per 128-thread CTA) or 8 (one 256-thread CTA per env)
+    int wpe = 8;            // warps per env: 1 (4 envs per 128-thread CTA), 8 (one 256-thread CTA per env), 16 / 32 (BIG)
     bool big = false;       // per-person arrays + proposal table in global scratch (envs too large for shared memory)
+    int variant = 0;        // index into the kernel variant table
     void* d_scratch = nullptr;
     int blocks = 0, threads = 0;
     size_t smem = 0;        // dynamic shared memory per CTA
@@ -770,6 +771,7 @@ struct mq_env {
 
 static int round_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 constexpr int SMALL_CW = 4;      // warps (= envs) per CTA in warp-per-env mode
+constexpr int BIG_WPE = 32;      // warps per env (= per CTA) of the BIG variant
 
 extern "C" int mq_env_state_sizes(const mq_env_cfg* cfg, const mq_layout* layout, int64_t* n_pad, int64_t* rmap_words) {
     MQ_REQUIRE(cfg && layout, "mq_env_state_sizes: null argument");
@@ -781,11 +783,18 @@ extern "C" int mq_env_state_sizes(const mq_env_cfg* cfg, const mq_layout* layout
     return MQ_OK;
 }
 
-template <int WPE, int CW, bool BIG>
-static cudaError_t set_smem_attr(int bytes) {
-    cudaError_t e = cudaFuncSetAttribute(mq::env_step_kernel<WPE, CW, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mq::env_reset_kernel<WPE, CW, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+// kernel variants: (warps per env, warps per CTA, BIG)
+typedef void (*StepFn)(mq::DevLayout, mq::DevCfg, mq::DevState, const int*, float*, double*, double*, uint8_t*);
+typedef void (*ResetFn)(mq::DevLayout, mq::DevCfg, mq::DevState, const uint8_t*, const int16_t*, float*, double*);
+struct Variant { int wpe, cw; bool big; StepFn step; ResetFn reset; };
+#define MQ_VARIANT(WPE, CW, BIG) {WPE, CW, BIG, mq::env_step_kernel<WPE, CW, BIG>, mq::env_reset_kernel<WPE, CW, BIG>}
+static const Variant k_variants[] = {
+    MQ_VARIANT(1, SMALL_CW, false), MQ_VARIANT(8, 8, false), MQ_VARIANT(8, 8, true), MQ_VARIANT(16, 16, true), MQ_VARIANT(32, 32, true),
+};
+static int find_variant(int wpe, bool big) {
+    for (int i = 0; i < (int)(sizeof(k_variants) / sizeof(k_variants[0])); ++i)
+        if (k_variants[i].wpe == wpe && k_variants[i].big == big) return i;
+    return -1;
 }
 
 extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layout* layout, const mq_env_state* state) {
@@ -862,6 +871,8 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     e->wpe = (c.N <= 256 && (size_t)c.smem_per_env * SMALL_CW + 2048 <= (size_t)max_smem) ? 1 : 8;
     e->big = e->wpe == 8 && (size_t)c.smem_per_env + 2048 > (size_t)max_smem;
     if (e->big) {
+        e->wpe = BIG_WPE;                              // one CTA per SM (shared-memory bound): make it a wide one
+        if (const char* v = getenv("MQ_BIG_WPE")) { int w = atoi(v); if (w == 8 || w == 16 || w == 32) e->wpe = w; }
         size_t gbytes = 0;
         c.smem_per_env = (int)mq::carve(tmp, nullptr, (unsigned char*)16, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, &gbytes);
         c.scratch_per_env = (long long)gbytes;
@@ -872,8 +883,9 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
         }
         c.scratch = (unsigned char*)e->d_scratch;
     }
+    e->variant = find_variant(e->wpe, e->big);
     const int groups = e->wpe == 1 ? SMALL_CW : 1;
-    e->threads = e->wpe == 1 ? 32 * SMALL_CW : 256;
+    e->threads = 32 * k_variants[e->variant].cw;
     e->smem = (size_t)c.smem_per_env * groups;
     if ((int)e->smem + 2048 > max_smem) {
         size_t need = e->smem;
@@ -883,8 +895,9 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
                         layout->L, layout->W, need, max_smem);
     }
     e->blocks = (c.n_envs + groups - 1) / groups;
-    ce = e->wpe == 1 ? set_smem_attr<1, SMALL_CW, false>((int)e->smem)
-                     : (e->big ? set_smem_attr<8, 8, true>((int)e->smem) : set_smem_attr<8, 8, false>((int)e->smem));
+    ce = cudaFuncSetAttribute((const void*)k_variants[e->variant].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem);
+    if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute((const void*)k_variants[e->variant].reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem);
     if (ce != cudaSuccess) {
         mq_env_destroy(e);
         return mq::fail(MQ_ERR_CUDA, "mq_env_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
@@ -912,9 +925,7 @@ extern "C" int mq_env_reset(mq_env* e, const uint8_t* env_mask, const int16_t* i
                             double* obs64_out, void* stream) {
     MQ_REQUIRE(e, "mq_env_reset: null handle");
     cudaStream_t s = (cudaStream_t)stream;
-    if (e->wpe == 1) mq::env_reset_kernel<1, SMALL_CW, false><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
-    else if (e->big) mq::env_reset_kernel<8, 8, true><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
-    else mq::env_reset_kernel<8, 8, false><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
+    k_variants[e->variant].reset<<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
     MQ_CUDA(cudaGetLastError());
     e->launches += 1;
     return MQ_OK;
@@ -924,9 +935,7 @@ extern "C" int mq_env_step(mq_env* e, const int32_t* actions, float* obs_out, do
                            uint8_t* done_out, void* stream) {
     MQ_REQUIRE(e && actions && reward_out && done_out, "mq_env_step: null argument");
     cudaStream_t s = (cudaStream_t)stream;
-    if (e->wpe == 1) mq::env_step_kernel<1, SMALL_CW, false><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
-    else if (e->big) mq::env_step_kernel<8, 8, true><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
-    else mq::env_step_kernel<8, 8, false><<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
+    k_variants[e->variant].step<<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
     MQ_CUDA(cudaGetLastError());
     e->launches += 1;
     return MQ_OK;

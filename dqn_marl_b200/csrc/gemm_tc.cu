@@ -41,3 +41,72 @@ extern "C" int mq_gemm_bf16(const void* A, const void* B, float* C, int32_t M, i
     }
     return MQ_OK;
 }
+
+static int finish_split(float* workspace, int sp, size_t total, float* C, cudaStream_t s) {
+    if (sp > 1) {
+        int blocks = (int)((total + 255) / 256); if (blocks > 1184) blocks = 1184;
+        mq::tc_splitk_reduce_kernel<<<blocks, 256, 0, s>>>(workspace, sp, total, C);
+        MQ_CUDA(cudaGetLastError());
+    }
+    return MQ_OK;
+}
+
+// C[M][N] (fp32) = At[K][M]^T * Bt[K][N]: both operands bf16 with K as the ROW index (MN-major UMMA descriptors) —
+// the weight-gradient shapes (K = batch rows) without a transpose.  M, N multiples of 8.
+extern "C" int mq_gemm_bf16_tn(const void* At, const void* Bt, float* C, int32_t M, int32_t N, int32_t K, int32_t splits, float* workspace,
+                               void* stream) {
+    MQ_REQUIRE(At && Bt && C && M > 0 && N > 0 && K > 0, "mq_gemm_bf16_tn: bad argument");
+    MQ_REQUIRE(M % 8 == 0 && N % 8 == 0, "mq_gemm_bf16_tn: M and N must be multiples of 8 (TMA row pitch of 16 bytes)");
+    MQ_REQUIRE(splits <= 1 || workspace, "mq_gemm_bf16_tn: split-K needs a workspace");
+    cudaStream_t s = (cudaStream_t)stream;
+    mq::tc::Epilogue ep{};
+    ep.out_f32 = C; ep.ldc = N; ep.partial = splits > 1 ? workspace : nullptr;
+    int sp = splits < 1 ? 1 : splits;
+    cudaError_t e = mq::tc::launch_tn<128, 3>((const __nv_bfloat16*)At, M, (const __nv_bfloat16*)Bt, N, M, N, K, ep, &sp, s);
+    if (e != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_gemm_bf16_tn: launch failed: %s", cudaGetErrorString(e));
+    return finish_split(workspace, sp, (size_t)M * N, C, s);
+}
+
+// Y[B*121][Cout] (fp32) = conv3x3/pad1 of X [B][11][11][Cin] (bf16, NHWC) with Wk[Cout][9*Cin] (bf16, taps (kh,kw,c)); implicit
+// GEMM, the im2col matrix is never written: each tap is a shifted, zero-filled 4-D TMA box.  flip = 1 mirrors the taps
+// (data gradient).  Cin must be a multiple of 32 (32 -> 64B swizzle, else 128B swizzle); bn = 128 / 64 / 32.
+extern "C" int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, int64_t batch, int32_t Cin, int32_t Cout, int32_t flip, int32_t bn,
+                               void* stream) {
+    MQ_REQUIRE(X && Wk && Y && batch > 0 && Cin > 0 && Cout > 0, "mq_conv3x3_bf16: bad argument");
+    MQ_REQUIRE(Cin % 32 == 0, "mq_conv3x3_bf16: Cin must be a multiple of 32");
+    cudaStream_t s = (cudaStream_t)stream;
+    mq::tc::Epilogue ep{};
+    ep.out_f32 = Y; ep.ldc = Cout;
+    const __nv_bfloat16* x = (const __nv_bfloat16*)X;
+    const __nv_bfloat16* w = (const __nv_bfloat16*)Wk;
+    cudaError_t e;
+    if (Cin % 64 == 0) {
+        if (bn == 128) e = mq::tc::launch_conv<128, 4, 64>(x, w, batch, Cin, Cout, flip, ep, s);
+        else if (bn == 64) e = mq::tc::launch_conv<64, 4, 64>(x, w, batch, Cin, Cout, flip, ep, s);
+        else if (bn == 32) e = mq::tc::launch_conv<32, 4, 64>(x, w, batch, Cin, Cout, flip, ep, s);
+        else return mq::fail(MQ_ERR_ARG, "mq_conv3x3_bf16: bn must be 128, 64 or 32");
+    } else {
+        if (bn == 64) e = mq::tc::launch_conv<64, 6, 32>(x, w, batch, Cin, Cout, flip, ep, s);
+        else return mq::fail(MQ_ERR_ARG, "mq_conv3x3_bf16: Cin = 32 (mod 64) supports bn = 64 only");
+    }
+    if (e != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_conv3x3_bf16: launch failed: %s", cudaGetErrorString(e));
+    return MQ_OK;
+}
+
+// dW[9*Cin][Cout] (fp32) = im2col(X)^T * dY: X [B][11][11][Cin] bf16, dY [B*121][Cout] bf16; Cin % 64 == 0, Cout % 8 == 0.
+// splits > 1 partitions the samples; workspace >= splits * 9*Cin * Cout floats.
+extern "C" int mq_conv3x3_wgrad_bf16(const void* X, const void* dY, float* dW, int64_t batch, int32_t Cin, int32_t Cout, int32_t splits,
+                                     float* workspace, void* stream) {
+    MQ_REQUIRE(X && dY && dW && batch > 0, "mq_conv3x3_wgrad_bf16: bad argument");
+    MQ_REQUIRE(Cin % 64 == 0 && Cout % 8 == 0, "mq_conv3x3_wgrad_bf16: Cin must be a multiple of 64 and Cout of 8");
+    MQ_REQUIRE(splits <= 1 || workspace, "mq_conv3x3_wgrad_bf16: split needs a workspace");
+    cudaStream_t s = (cudaStream_t)stream;
+    mq::tc::Epilogue ep{};
+    ep.out_f32 = dW; ep.ldc = Cout; ep.partial = splits > 1 ? workspace : nullptr;
+    int sp = splits < 1 ? 1 : splits;
+    cudaError_t e;
+    if (Cout > 64) e = mq::tc::launch_conv_wgrad<128, 3>((const __nv_bfloat16*)X, (const __nv_bfloat16*)dY, batch, Cin, Cout, ep, &sp, s);
+    else e = mq::tc::launch_conv_wgrad<64, 4>((const __nv_bfloat16*)X, (const __nv_bfloat16*)dY, batch, Cin, Cout, ep, &sp, s);
+    if (e != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_conv3x3_wgrad_bf16: launch failed: %s", cudaGetErrorString(e));
+    return finish_split(workspace, sp, (size_t)9 * Cin * Cout, dW, s);
+}

@@ -2,7 +2,14 @@
 // tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) with the fp32 accumulator in TMEM ->
 // tcgen05.ld -> fused epilogue -> global.   Hand-written PTX, no CUTLASS.
 //
-//   C[M][N] = A[M][K] * B[N][K]^T          A, B bf16, both K-major (row-major with K contiguous)
+//   gemm_bf16_tc_kernel   C[M][N] = A[M][K] * B[N][K]^T     A, B bf16, both K-major (row-major with K contiguous)
+//       CONV = true: A is never materialised.  It is the im2col view of an NHWC activation [B][11][11][C] of a 3x3 / pad 1
+//       convolution: the K-block of tap (di, dj) is ONE 4-D TMA box {BK channels, 11, 11, 1 sample} whose origin is shifted
+//       by (dj, di); the out-of-bounds part of the box is zero-filled by TMA = the padding.  One sample (121 rows, padded to
+//       the 128-row MMA tile) per CTA.  `flip` mirrors the taps (dgrad).
+//   gemm_bf16_tn_kernel   C[M][N] = At[K][M]^T * Bt[K][N]   both operands MN-major (K is the row index): the weight-gradient
+//       shapes (K = batch rows) run without any transpose.  CONV = true: At is the shifted 4-D box view again (one sample =
+//       one 128-row K-block whose last 7 rows stay zero), Bt = dY rows of the sample.
 //
 // This is the throughput path of the Q-network (DQNNetwork, Louvre_Evacuation/agents/dqn_agent.py:15-61): the
 // contractions with >= 16k rows (conv2/conv3 as GEMMs over im2col rows, fc1) run here; the fp32 FFMA kernels of
@@ -18,7 +25,8 @@
 namespace mq {
 namespace tc {
 
-constexpr int BM = 128, BK = 64, UMMA_K = 16, THREADS = 192;
+constexpr int BM = 128, UMMA_K = 16, THREADS = 192;
+constexpr int PIXELS = 121;      // 11 x 11 window of the Q-network's convolutions
 
 struct Epilogue {
     float* out_f32;              // [M][ldc] or null
@@ -56,20 +64,26 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer) : "memory");
 }
-// shared-memory matrix descriptor: K-major tile of [rows][64 bf16] written by TMA with SWIZZLE_128B
-// (8-row x 128-byte swizzle atoms, 1024 B apart)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// shared-memory matrix descriptor of a tile written by TMA with a 128B (layout 2) or 64B (layout 4) swizzle.
+//   K-major  tile [rows][BK]: swizzle atoms of 8 rows, `sbo` bytes apart (8 * row bytes); lbo unused
+//   MN-major tile [k rows][64 mn]: atoms of 8 k-rows x 128 B, `sbo` = 1024 B apart along K, `lbo` = distance between
+//   the 64-wide MN slabs
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t sbo = 1024u, uint32_t lbo = 0u, uint64_t layout = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // start address
-    d |= (uint64_t)0 << 16;                                // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024u >> 4) << 32;                     // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)((lbo & 0x3FFFFu) >> 4) << 16;          // leading byte offset
+    d |= (uint64_t)((sbo & 0x3FFFFu) >> 4) << 32;          // stride byte offset
     d |= (uint64_t)1 << 46;                                // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                                // SWIZZLE_128B
+    d |= layout << 61;                                     // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
     return d;
 }
-// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, M = 128, N = n; mn_major sets both transpose bits
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major = false) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? (3u << 15) : 0u) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -95,47 +109,164 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BN, int STAGES>
+// ---- epilogue of one 128 x BN accumulator tile: TMEM -> registers -> fused ops -> global -----------------------------
+// Executed by the four epilogue warps; q = TMEM lane quadrant of the warp.  `row` = global output row of this thread
+// (valid iff row_ok), `n0` = first output column of the tile.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const Epilogue& ep, uint32_t tmem_base, int q, bool row_ok, long long row, int n0,
+                                              long long M, int N, int split) {
+    // fast path: no per-element masks, full 32-column chunks, 16-byte aligned rows -> vector stores
+    const bool plain = !ep.mask_bf16 && !ep.mask_f32 && !ep.drop && (ep.ldc % 8 == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        if (!row_ok) continue;
+        const int nb = n0 + c0;
+        if (nb >= N) continue;
+        if (ep.partial) {
+            float* dst = ep.partial + ((size_t)split * M + row) * N + nb;
+            if (nb + 32 <= N && (N % 4 == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < N) dst[j] = __uint_as_float(r[j]);
+            }
+            continue;
+        }
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (ep.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < N) v[j] += __ldg(ep.bias + nb + j);
+        }
+        if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        const size_t o = (size_t)row * ep.ldc + nb;
+        const bool vec = nb + 32 <= N && (ep.ldc % 8 == 0);
+        if (!plain) {
+            if (ep.mask_bf16 && vec) {
+                const uint4* mk = reinterpret_cast<const uint4*>(ep.mask_bf16 + o);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const uint4 w = mk[j / 8];
+                    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ws[k]);
+                        if (!(__low2float(b2) > 0.f)) v[j + 2 * k] = 0.f;
+                        if (!(__high2float(b2) > 0.f)) v[j + 2 * k + 1] = 0.f;
+                    }
+                }
+            } else if (ep.mask_bf16) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < N && !(__bfloat162float(ep.mask_bf16[o + j]) > 0.f)) v[j] = 0.f;
+            }
+            if (ep.mask_f32) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < N && !(ep.mask_f32[o + j] > 0.f)) v[j] = 0.f;
+            }
+            if (ep.drop) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < N) v[j] = ep.drop[(size_t)row * N + nb + j] ? v[j] * ep.drop_scale : 0.f;
+            }
+        }
+        if (vec) {
+            if (ep.out_bf16) {
+                uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + o);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                    dst[j / 8] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
+                                            *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
+                }
+            }
+            if (ep.out_f32) {
+                float4* dst = reinterpret_cast<float4*>(ep.out_f32 + o);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) dst[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (nb + j >= N) continue;
+                if (ep.out_f32) ep.out_f32[o + j] = v[j];
+                if (ep.out_bf16) ep.out_bf16[o + j] = __float2bfloat16(v[j]);
+            }
+        }
+    }
+}
+
+// common prologue: barriers, tensor-map prefetch, TMEM allocation
+struct Pipe {
+    uint64_t *full_bar, *empty_bar, *tmem_full_bar;
+    uint32_t* tmem_ptr;
+};
+template <int STAGES>
+__device__ __forceinline__ uint32_t pipe_init(Pipe& pp, unsigned char* bars, const CUtensorMap* ta, const CUtensorMap* tb, uint32_t tmem_cols) {
+    pp.full_bar = (uint64_t*)bars;
+    pp.empty_bar = pp.full_bar + STAGES;
+    pp.tmem_full_bar = pp.empty_bar + STAGES;
+    pp.tmem_ptr = (uint32_t*)(pp.tmem_full_bar + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&pp.full_bar[s], 1); mbar_init(&pp.empty_bar[s], 1); }
+        mbar_init(pp.tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(ta) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(tb) : "memory");
+    }
+    if (warp == 1) {      // TMEM allocation by one full warp
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(pp.tmem_ptr)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    return *pp.tmem_ptr;
+}
+__device__ __forceinline__ void pipe_fini(uint32_t tmem_base, uint32_t tmem_cols) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+}
+
+// =====================================================================================================================
+// K-major kernel.  BK = 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B, the 32-channel activations of conv2).
+// =====================================================================================================================
+struct ConvArgs { int cblocks; int flip; };     // K-blocks per tap (= Cin / BK); mirrored taps
+
+template <int BN, int STAGES, int BK>
 struct SmemLayout {
     static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BK, bool CONV>
 __global__ void __launch_bounds__(THREADS)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K,
-                    int k_chunk, Epilogue ep) {
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, long long M, int N, int K,
+                    int k_chunk, ConvArgs cv, Epilogue ep) {
     extern __shared__ unsigned char smem_raw[];
-    using L = SmemLayout<BN, STAGES>;
-    unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // SWIZZLE_128B: 1024 B alignment
-    uint64_t* full_bar = (uint64_t*)(tiles + STAGES * L::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
-    uint32_t* tmem_ptr = (uint32_t*)(tmem_full_bar + 1);
+    using L = SmemLayout<BN, STAGES, BK>;
+    constexpr uint64_t LAYOUT = BK == 64 ? 2 : 4;
+    constexpr uint32_t SBO = 8 * BK * 2;
+    unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // swizzle atoms: 1024 B alignment
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    Pipe pp;
+    const uint32_t tmem_base = pipe_init<STAGES>(pp, tiles + STAGES * L::STAGE_BYTES, &tmap_a, &tmap_b, TMEM_COLS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m_tile = blockIdx.y, n0 = blockIdx.x * BN;       // CONV: m_tile = sample
     const int k_begin = blockIdx.z * k_chunk;
     const int k_end = min(K, k_begin + k_chunk);
     const int num_kb = (k_end - k_begin + BK - 1) / BK;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-
-    if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
-    }
-    if (warp == 1) {      // TMEM allocation by one full warp
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -143,13 +274,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t phase = 1;          // fresh barriers: the first pass over the ring does not wait
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
-                mbar_wait(&empty_bar[s], phase);
+                mbar_wait(&pp.empty_bar[s], phase);
                 unsigned char* a_dst = tiles + s * L::STAGE_BYTES;
                 unsigned char* b_dst = a_dst + L::A_BYTES;
-                mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
                 const int k = k_begin + kb * BK;
-                tma_load_2d(a_dst, &tmap_a, &full_bar[s], k, m0);
-                tma_load_2d(b_dst, &tmap_b, &full_bar[s], k, n0);
+                if (CONV) {
+                    mbar_expect_tx(&pp.full_bar[s], PIXELS * BK * 2 + L::B_BYTES);
+                    const int kbg = k / BK, tap = kbg / cv.cblocks, cb = kbg - tap * cv.cblocks;
+                    int di = tap / 3 - 1, dj = tap % 3 - 1;
+                    if (cv.flip) { di = -di; dj = -dj; }
+                    tma_load_4d(a_dst, &tmap_a, &pp.full_bar[s], cb * BK, dj, di, m_tile);
+                } else {
+                    mbar_expect_tx(&pp.full_bar[s], L::STAGE_BYTES);
+                    tma_load_2d(a_dst, &tmap_a, &pp.full_bar[s], k, m_tile * BM);
+                }
+                tma_load_2d(b_dst, &tmap_b, &pp.full_bar[s], k, n0);
                 if (s == STAGES - 1) phase ^= 1;
             }
         }
@@ -160,133 +299,132 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
-                mbar_wait(&full_bar[s], phase);
+                mbar_wait(&pp.full_bar[s], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
                 const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2);
-                    const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2);
+                    const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
+                    const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
                     umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                 }
-                umma_commit(&empty_bar[s]);          // frees the stage once these MMAs have read it
+                umma_commit(&pp.empty_bar[s]);          // frees the stage once these MMAs have read it
                 if (s == STAGES - 1) phase ^= 1;
             }
-            umma_commit(tmem_full_bar);              // accumulator complete
+            umma_commit(pp.tmem_full_bar);              // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
         const int q = warp & 3;
-        mbar_wait(tmem_full_bar, 0);
+        mbar_wait(pp.tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int m = m0 + q * 32 + lane;
-        // fast path: no per-element masks, full 32-column chunks, 16-byte aligned rows -> vector stores
-        const bool plain = !ep.mask_bf16 && !ep.mask_f32 && !ep.drop && (ep.ldc % 8 == 0);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            if (m >= M || num_kb <= 0) continue;
-            const int nb = n0 + c0;
-            if (nb >= N) continue;
-            if (ep.partial) {
-                float* dst = ep.partial + ((size_t)blockIdx.z * M + m) * N + nb;
-                if (nb + 32 <= N && (N % 4 == 0)) {
+        const int r = q * 32 + lane;
+        const long long row = CONV ? (long long)m_tile * PIXELS + r : (long long)m_tile * BM + r;
+        const bool ok = (CONV ? r < PIXELS : true) && row < M && num_kb > 0;
+        epilogue_tile<BN>(ep, tmem_base, q, ok, row, n0, M, N, blockIdx.z);
+    }
+    pipe_fini(tmem_base, TMEM_COLS);
+}
+
+// =====================================================================================================================
+// MN-major ("TN") kernel: C[M][N] = sum_k At[k][m] * Bt[k][n].  A stage holds BKR k-rows: 2 A slabs and BN/64 B slabs of
+// [BKR][64] bf16 (128-byte rows, SWIZZLE_128B).  CONV: one stage = one sample (121 of the 128 rows are loaded, the rest
+// stay zero); the A slab of output rows m0 + 64 j is tap (m / Cin), channels (m % Cin) .. +64 of the shifted activation.
+// =====================================================================================================================
+template <int BN, int STAGES, int BKR>
+struct SmemLayoutTN {
+    static constexpr int SLAB = BKR * 128;
+    static constexpr int A_BYTES = 2 * SLAB, B_BYTES = (BN / 64) * SLAB;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN, int STAGES, int BKR, bool CONV>
+__global__ void __launch_bounds__(THREADS)
+gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K,
+                    int k_chunk, int cin, Epilogue ep) {
+    extern __shared__ unsigned char smem_raw[];
+    using L = SmemLayoutTN<BN, STAGES, BKR>;
+    static_assert(BN % 64 == 0 && BKR % UMMA_K == 0, "tile shape");
+    unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr uint32_t TMEM_COLS = BN;
+    if (CONV) {     // rows 121..127 of every slab are never written by TMA: they must read as zero
+        constexpr int SLABS = STAGES * (2 + BN / 64), PADB = (BKR - PIXELS) * 128;
+        for (int i = threadIdx.x; i < SLABS * (PADB / 16); i += THREADS) {
+            const int sl = i / (PADB / 16), o = i - sl * (PADB / 16);
+            *reinterpret_cast<uint4*>(tiles + (size_t)sl * L::SLAB + PIXELS * 128 + o * 16) = make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    Pipe pp;
+    const uint32_t tmem_base = pipe_init<STAGES>(pp, tiles + STAGES * L::STAGE_BYTES, &tmap_a, &tmap_b, TMEM_COLS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // K is counted in rows (2-D) or samples (CONV)
+    const int k_begin = blockIdx.z * k_chunk;
+    const int k_end = min(K, k_begin + k_chunk);
+    const int num_kb = CONV ? (k_end - k_begin) : (k_end - k_begin + BKR - 1) / BKR;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t phase = 1;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&pp.empty_bar[s], phase);
+                unsigned char* a_dst = tiles + s * L::STAGE_BYTES;
+                unsigned char* b_dst = a_dst + L::A_BYTES;
+                if (CONV) {
+                    const int sample = k_begin + kb;
+                    const int a_slabs = (m0 + 64 < M) ? 2 : 1;
+                    mbar_expect_tx(&pp.full_bar[s], (a_slabs + BN / 64) * PIXELS * 128);
+                    for (int j = 0; j < a_slabs; ++j) {
+                        const int m = m0 + 64 * j, tap = m / cin, c0 = m - tap * cin;
+                        tma_load_4d(a_dst + j * L::SLAB, &tmap_a, &pp.full_bar[s], c0, tap % 3 - 1, tap / 3 - 1, sample);
+                    }
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * L::SLAB, &tmap_b, &pp.full_bar[s], n0 + 64 * j, sample * PIXELS);
                 } else {
+                    const int k = k_begin + kb * BKR;
+                    mbar_expect_tx(&pp.full_bar[s], L::STAGE_BYTES);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) if (nb + j < N) dst[j] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 2; ++j) tma_load_2d(a_dst + j * L::SLAB, &tmap_a, &pp.full_bar[s], m0 + 64 * j, k);
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * L::SLAB, &tmap_b, &pp.full_bar[s], n0 + 64 * j, k);
                 }
-                continue;
-            }
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (ep.bias) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (nb + j < N) v[j] += __ldg(ep.bias + nb + j);
-            }
-            if (ep.relu) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            const size_t o = (size_t)m * ep.ldc + nb;
-            if (plain && nb + 32 <= N) {
-                if (ep.out_bf16) {
-                    uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + o);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                        dst[j / 8] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                                                *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-                    }
-                }
-                if (ep.out_f32) {
-                    float4* dst = reinterpret_cast<float4*>(ep.out_f32 + o);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) dst[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-            } else {
-                if (ep.mask_bf16 && nb + 32 <= N && (ep.ldc % 8 == 0)) {
-                    const uint4* mk = reinterpret_cast<const uint4*>(ep.mask_bf16 + o);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        const uint4 w = mk[j / 8];
-                        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ws[k]);
-                            if (!(__low2float(b2) > 0.f)) v[j + 2 * k] = 0.f;
-                            if (!(__high2float(b2) > 0.f)) v[j + 2 * k + 1] = 0.f;
-                        }
-                    }
-                } else if (ep.mask_bf16) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (nb + j < N && !(__bfloat162float(ep.mask_bf16[o + j]) > 0.f)) v[j] = 0.f;
-                }
-                if (ep.mask_f32) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (nb + j < N && !(ep.mask_f32[o + j] > 0.f)) v[j] = 0.f;
-                }
-                if (ep.drop) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) if (nb + j < N) v[j] = ep.drop[(size_t)m * N + nb + j] ? v[j] * ep.drop_scale : 0.f;
-                }
-                if (nb + 32 <= N && (ep.ldc % 8 == 0)) {
-                    if (ep.out_bf16) {
-                        uint4* dst = reinterpret_cast<uint4*>(ep.out_bf16 + o);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                            dst[j / 8] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), *reinterpret_cast<uint32_t*>(&p1),
-                                                    *reinterpret_cast<uint32_t*>(&p2), *reinterpret_cast<uint32_t*>(&p3));
-                        }
-                    }
-                    if (ep.out_f32) {
-                        float4* dst = reinterpret_cast<float4*>(ep.out_f32 + o);
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) dst[j / 4] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (nb + j >= N) continue;
-                        if (ep.out_f32) ep.out_f32[o + j] = v[j];
-                        if (ep.out_bf16) ep.out_bf16[o + j] = __float2bfloat16(v[j]);
-                    }
-                }
+                if (s == STAGES - 1) phase ^= 1;
             }
         }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, true);
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&pp.full_bar[s], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
+                const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+                for (int k = 0; k < BKR / UMMA_K; ++k) {
+                    const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 128, 1024u, (uint32_t)L::SLAB, 2);
+                    const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 128, 1024u, (uint32_t)L::SLAB, 2);
+                    umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&pp.empty_bar[s]);
+                if (s == STAGES - 1) phase ^= 1;
+            }
+            umma_commit(pp.tmem_full_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(pp.tmem_full_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const long long row = m0 + q * 32 + lane;
+        epilogue_tile<BN>(ep, tmem_base, q, row < M && num_kb > 0, row, n0, M, N, blockIdx.z);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
-    }
+    pipe_fini(tmem_base, TMEM_COLS);
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
@@ -305,29 +443,51 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2D bf16 row-major matrix [rows][cols] (cols contiguous, leading dimension ld elements), box = [box_rows][64]
-inline bool make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+// 2D bf16 row-major matrix [rows][cols] (cols contiguous, leading dimension ld elements), box = [box_rows][box_cols];
+// box_cols = 64 -> SWIZZLE_128B, 32 -> SWIZZLE_64B
+inline bool make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols = 64) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// NHWC activation [B][11][11][C] bf16 as a 4-D tensor (C, x, y, b); box = {box_c channels, 11, 11, 1}: one sample's window,
+// shifted by the tap through the box origin, zero-filled outside the 11 x 11 image
+inline bool make_tmap_act(CUtensorMap* out, const void* base, uint64_t batch, uint64_t C, uint32_t box_c) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {C, 11, 11, batch};
+    cuuint64_t strides[3] = {C * 2, 11 * C * 2, 121 * C * 2};
+    cuuint32_t box[4] = {box_c, 11, 11, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <typename KernelT>
+inline cudaError_t ensure_smem(KernelT kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+// C[M][N] = A[M][K] B[N][K]^T
 template <int BN, int STAGES>
 inline cudaError_t launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K, Epilogue ep,
                           int* splits_inout, cudaStream_t stream) {
+    constexpr int BK = 64;
     int splits = splits_inout ? *splits_inout : 1;
     CUtensorMap ta, tb;
     if (!make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM) || !make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN))
         return cudaErrorInvalidValue;
-    using L = SmemLayout<BN, STAGES>;
+    using L = SmemLayout<BN, STAGES, BK>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        cudaError_t e = ensure_smem(gemm_bf16_tc_kernel<BN, STAGES, BK, false>, L::TOTAL);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -340,7 +500,91 @@ inline cudaError_t launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* 
     if (splits > 1 && !ep.partial) return cudaErrorInvalidValue;
     if (splits == 1) ep.partial = nullptr;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
-    gemm_bf16_tc_kernel<BN, STAGES><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, N, K, chunk_tiles * BK, ep);
+    gemm_bf16_tc_kernel<BN, STAGES, BK, false><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, N, K, chunk_tiles * BK, ConvArgs{1, 0}, ep);
+    return cudaGetLastError();
+}
+
+// 3x3 / pad 1 convolution over 11 x 11 windows as an implicit GEMM: Y[B*121][Cout] = im2col(X [B][11][11][Cin]) * Wk[Cout][9*Cin]^T
+// (taps in (kh, kw, c) order; flip = mirrored taps = the data-gradient convolution).  BK = 64 needs Cin % 64 == 0, BK = 32 Cin % 32 == 0.
+template <int BN, int STAGES, int BK>
+inline cudaError_t launch_conv(const __nv_bfloat16* X, const __nv_bfloat16* Wk, long long batch, int Cin, int Cout, int flip, Epilogue ep,
+                               cudaStream_t stream) {
+    if (Cin % BK != 0 || batch <= 0) return cudaErrorInvalidValue;
+    CUtensorMap ta, tb;
+    if (!make_tmap_act(&ta, X, (uint64_t)batch, (uint64_t)Cin, BK) ||
+        !make_tmap(&tb, Wk, (uint64_t)Cout, (uint64_t)9 * Cin, (uint64_t)9 * Cin, BN, BK))
+        return cudaErrorInvalidValue;
+    using L = SmemLayout<BN, STAGES, BK>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = ensure_smem(gemm_bf16_tc_kernel<BN, STAGES, BK, true>, L::TOTAL);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    ep.partial = nullptr;
+    dim3 grid((Cout + BN - 1) / BN, (unsigned)batch, 1);
+    gemm_bf16_tc_kernel<BN, STAGES, BK, true><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, batch * PIXELS, Cout, 9 * Cin, 9 * Cin,
+                                                                                 ConvArgs{Cin / BK, flip}, ep);
+    return cudaGetLastError();
+}
+
+// C[M][N] = At[K][M]^T Bt[K][N]   (M % 8 == 0 and N % 8 == 0: TMA row pitch)
+template <int BN, int STAGES>
+inline cudaError_t launch_tn(const __nv_bfloat16* At, int lda, const __nv_bfloat16* Bt, int ldb, int M, int N, int K, Epilogue ep,
+                             int* splits_inout, cudaStream_t stream) {
+    constexpr int BKR = 64;
+    int splits = splits_inout ? *splits_inout : 1;
+    CUtensorMap ta, tb;
+    if (!make_tmap(&ta, At, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BKR) || !make_tmap(&tb, Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BKR))
+        return cudaErrorInvalidValue;
+    using L = SmemLayoutTN<BN, STAGES, BKR>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = ensure_smem(gemm_bf16_tn_kernel<BN, STAGES, BKR, false>, L::TOTAL);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int k_tiles = (K + BKR - 1) / BKR;
+    if (splits < 1) splits = 1;
+    if (splits > k_tiles) splits = k_tiles;
+    const int chunk_tiles = (k_tiles + splits - 1) / splits;
+    splits = (k_tiles + chunk_tiles - 1) / chunk_tiles;
+    if (splits_inout) *splits_inout = splits;
+    if (splits > 1 && !ep.partial) return cudaErrorInvalidValue;
+    if (splits == 1) ep.partial = nullptr;
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
+    gemm_bf16_tn_kernel<BN, STAGES, BKR, false><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, N, K, chunk_tiles * BKR, 0, ep);
+    return cudaGetLastError();
+}
+
+// weight gradient of the 3x3 convolution: dW[9*Cin][Cout] = im2col(X)^T dY, X [B][11][11][Cin], dY [B*121][Cout]; split over samples
+template <int BN, int STAGES>
+inline cudaError_t launch_conv_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* dY, long long batch, int Cin, int Cout, Epilogue ep,
+                                     int* splits_inout, cudaStream_t stream) {
+    constexpr int BKR = 128;
+    if (Cin % 64 != 0 || Cout % 8 != 0 || batch <= 0) return cudaErrorInvalidValue;
+    int splits = splits_inout ? *splits_inout : 1;
+    CUtensorMap ta, tb;
+    if (!make_tmap_act(&ta, X, (uint64_t)batch, (uint64_t)Cin, 64) ||
+        !make_tmap(&tb, dY, (uint64_t)batch * PIXELS, (uint64_t)Cout, (uint64_t)Cout, PIXELS))
+        return cudaErrorInvalidValue;
+    using L = SmemLayoutTN<BN, STAGES, BKR>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = ensure_smem(gemm_bf16_tn_kernel<BN, STAGES, BKR, true>, L::TOTAL);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int M = 9 * Cin;
+    if (splits < 1) splits = 1;
+    if (splits > batch) splits = (int)batch;
+    const int chunk = (int)((batch + splits - 1) / splits);
+    splits = (int)((batch + chunk - 1) / chunk);
+    if (splits_inout) *splits_inout = splits;
+    if (splits > 1 && !ep.partial) return cudaErrorInvalidValue;
+    if (splits == 1) ep.partial = nullptr;
+    dim3 grid((Cout + BN - 1) / BN, (M + BM - 1) / BM, splits);
+    gemm_bf16_tn_kernel<BN, STAGES, BKR, true><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, Cout, (int)batch, chunk, Cin, ep);
     return cudaGetLastError();
 }
 

@@ -263,6 +263,24 @@ int64_t mq_qnet_launch_count(const mq_qnet* net);
 int mq_gemm_bf16(const void* A, const void* B, float* C, int32_t M, int32_t N, int32_t K, int32_t bn, int32_t splits,
                  float* workspace, void* stream);
 
+/* C[M][N] f32 = At[K][M]^T * Bt[K][N]: both bf16 operands stored with K as the row index (MN-major UMMA descriptors).
+ * The weight-gradient shapes of DQNAgent.learn (dqn_agent.py:153, loss.backward) reduce over the batch rows; this form
+ * needs no transposed copy.  M and N multiples of 8. */
+int mq_gemm_bf16_tn(const void* At, const void* Bt, float* C, int32_t M, int32_t N, int32_t K, int32_t splits, float* workspace,
+                    void* stream);
+
+/* 3x3 / padding 1 convolution over the 11x11 observation window as an implicit GEMM (nn.Conv2d(.., 3, padding=1) of
+ * DQNNetwork, dqn_agent.py:22-24,48-50): Y[batch*121][Cout] f32 = im2col(X) * Wk^T with X [batch][11][11][Cin] bf16 (NHWC)
+ * and Wk [Cout][9*Cin] bf16 (taps in (kh, kw, c) order).  The im2col matrix is never written: every tap is one shifted,
+ * zero-filled 4-D TMA box.  flip = 1 mirrors the taps (the data-gradient convolution of loss.backward()). */
+int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, int64_t batch, int32_t Cin, int32_t Cout, int32_t flip, int32_t bn,
+                    void* stream);
+
+/* Weight gradient of that convolution: dW[9*Cin][Cout] f32 = im2col(X)^T * dY, dY [batch*121][Cout] bf16.  splits > 1
+ * partitions the samples (workspace >= splits * 9*Cin*Cout floats). */
+int mq_conv3x3_wgrad_bf16(const void* X, const void* dY, float* dW, int64_t batch, int32_t Cin, int32_t Cout, int32_t splits,
+                          float* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,3 +35,75 @@ def test_gemm_matches_torch(M, N, K, bn):
 @pytest.mark.parametrize("M,N,K,bn,splits", [(576, 128, 8192, 128, 8), (288, 64, 4000, 64, 5), (512, 1024, 4096, 128, 3)])
 def test_gemm_split_k(M, N, K, bn, splits):
     _run(M, N, K, bn, splits)
+
+
+def _stream():
+    import ctypes as Ct
+    return Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(128, 128, 64, 1), (128, 128, 256, 1), (512, 1024, 4096, 1), (512, 15488, 512, 1),
+                                          (256, 384, 1000, 1), (576, 128, 8192, 8), (512, 256, 4100, 3)])
+def test_gemm_tn_matches_torch(M, N, K, splits):
+    """MN-major operands (K = row index): C = At^T Bt, the weight-gradient form."""
+    from dqn_marl_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda:0"); g.manual_seed(M + N + K)
+    At = torch.randn((K, M), generator=g, device="cuda:0").to(torch.bfloat16)
+    Bt = torch.randn((K, N), generator=g, device="cuda:0").to(torch.bfloat16)
+    C = torch.full((M, N), float("nan"), device="cuda:0")
+    ws = torch.empty((splits * M * N,), device="cuda:0") if splits > 1 else None
+    _lib.check(lib.mq_gemm_bf16_tn(_lib.ptr(At), _lib.ptr(Bt), _lib.ptr(C), M, N, K, splits, _lib.ptr(ws), _stream()), "mq_gemm_bf16_tn")
+    torch.cuda.synchronize()
+    ref = At.float().t() @ Bt.float()
+    err = (C - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, (M, N, K, splits, err, scale)
+
+
+def _conv_ref(X, Wk, Cin, Cout, flip):
+    """X [B][11][11][Cin], Wk [Cout][9*Cin] with taps (kh, kw, c) -> [B*121][Cout] by torch conv2d on the same bf16 values."""
+    w = Wk.float().reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)          # [Cout][Cin][kh][kw]
+    if flip:
+        w = w.flip(2, 3)
+    y = torch.nn.functional.conv2d(X.float().permute(0, 3, 1, 2), w, padding=1)
+    return y.permute(0, 2, 3, 1).reshape(-1, Cout)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,bn,flip", [(1, 64, 128, 128, 0), (5, 64, 128, 128, 0), (64, 64, 128, 128, 1), (37, 128, 64, 64, 1),
+                                                (16, 64, 32, 32, 1), (33, 32, 64, 64, 0), (300, 64, 128, 128, 0)])
+def test_implicit_conv_matches_torch(B, Cin, Cout, bn, flip):
+    """3x3/pad-1 convolution as an implicit GEMM over shifted, zero-filled 4-D TMA boxes (no im2col buffer)."""
+    from dqn_marl_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda:0"); g.manual_seed(B * 7 + Cin)
+    X = torch.randn((B, 11, 11, Cin), generator=g, device="cuda:0").to(torch.bfloat16)
+    Wk = (torch.randn((Cout, 9 * Cin), generator=g, device="cuda:0") / 8).to(torch.bfloat16)
+    Y = torch.full((B * 121, Cout), float("nan"), device="cuda:0")
+    _lib.check(lib.mq_conv3x3_bf16(_lib.ptr(X), _lib.ptr(Wk), _lib.ptr(Y), B, Cin, Cout, flip, bn, _stream()), "mq_conv3x3_bf16")
+    torch.cuda.synchronize()
+    ref = _conv_ref(X, Wk, Cin, Cout, flip)
+    err = (Y - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, (B, Cin, Cout, bn, flip, err, scale)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,splits", [(1, 64, 128, 1), (9, 64, 128, 1), (100, 64, 128, 7), (64, 128, 64, 4), (257, 64, 128, 29)])
+def test_conv_wgrad_matches_torch(B, Cin, Cout, splits):
+    """dW[(kh,kw,c)][n] = sum over samples and pixels of X[b, i+kh-1, j+kw-1, c] * dY[b, i, j, n] (MN-major implicit GEMM)."""
+    from dqn_marl_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator(device="cuda:0"); g.manual_seed(B + Cout)
+    X = torch.randn((B, 11, 11, Cin), generator=g, device="cuda:0").to(torch.bfloat16)
+    dY = torch.randn((B * 121, Cout), generator=g, device="cuda:0").to(torch.bfloat16)
+    dW = torch.full((9 * Cin, Cout), float("nan"), device="cuda:0")
+    ws = torch.empty((splits * 9 * Cin * Cout,), device="cuda:0") if splits > 1 else None
+    _lib.check(lib.mq_conv3x3_wgrad_bf16(_lib.ptr(X), _lib.ptr(dY), _lib.ptr(dW), B, Cin, Cout, splits, _lib.ptr(ws), _stream()),
+               "mq_conv3x3_wgrad_bf16")
+    torch.cuda.synchronize()
+    cols = torch.nn.functional.unfold(X.float().permute(0, 3, 1, 2), 3, padding=1)         # [B][Cin*9][121], (c, kh, kw) order
+    cols = cols.reshape(B, Cin, 9, 121).permute(0, 3, 2, 1).reshape(B * 121, 9 * Cin)      # rows (b, pixel), cols (tap, c)
+    ref = cols.t() @ dY.float()
+    err = (dW - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-3 * scale + 1e-3, (B, Cin, Cout, splits, err, scale)
