@@ -11,6 +11,7 @@
 // skinny shapes (fc1 at small batch, every wgrad), partials reduced by `splitk_epilogue_kernel`.
 #pragma once
 #include <cstdint>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 namespace mq {
@@ -21,6 +22,7 @@ enum BMode { B_ROW = 0, B_COL = 1, B_CONVW_T = 2 };
 struct GemmParams {
     int M, N, K;
     const float* A; const float* B; float* C;
+    __nv_bfloat16* Cb;           // optional bf16 copy of C (same ld): operand of the tensor-core path
     int lda, ldb, ldc;
     int batch;                   // conv: number of images (M or K = batch * 121)
     // epilogue: C = f(acc + bias[n]) with optional relu, * (mask_act[m][n] > 0), * drop[m][n] * drop_scale
@@ -169,7 +171,11 @@ gemm_f32_kernel(GemmParams p) {
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
                 const int n = n0 + col_of(j);
-                if (n < p.N) p.C[(size_t)m * p.ldc + n] = epilogue_value(p, acc[i][j], m, n);
+                if (n < p.N) {
+                    const float v = epilogue_value(p, acc[i][j], m, n);
+                    p.C[(size_t)m * p.ldc + n] = v;
+                    if (p.Cb) p.Cb[(size_t)m * p.ldc + n] = __float2bfloat16(v);
+                }
             }
         }
     }
@@ -181,7 +187,9 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(GemmParams p) {
         const int m = (int)(idx / p.N), n = (int)(idx - (size_t)m * p.N);
         float v = 0.f;
         for (int s = 0; s < p.splits; ++s) v += p.partial[(size_t)s * total + idx];     // fixed order: deterministic
-        p.C[(size_t)m * p.ldc + n] = epilogue_value(p, v, m, n);
+        v = epilogue_value(p, v, m, n);
+        p.C[(size_t)m * p.ldc + n] = v;
+        if (p.Cb) p.Cb[(size_t)m * p.ldc + n] = __float2bfloat16(v);
     }
 }
 

@@ -332,28 +332,43 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 // [BKR][64] bf16 (128-byte rows, SWIZZLE_128B).  CONV: one stage = one sample (121 of the 128 rows are loaded, the rest
 // stay zero); the A slab of output rows m0 + 64 j is tap (m / Cin), channels (m % Cin) .. +64 of the shifted activation.
 // =====================================================================================================================
-template <int BN, int STAGES, int BKR>
+template <int BN, int STAGES, int BKR, int AW>
 struct SmemLayoutTN {
-    static constexpr int SLAB = BKR * 128;
-    static constexpr int A_BYTES = 2 * SLAB, B_BYTES = (BN / 64) * SLAB;
+    static constexpr int A_SLAB = BKR * AW * 2, A_SLABS = BM / AW;        // AW = 64: 128 B rows (SWIZZLE_128B); 32: 64 B rows (SWIZZLE_64B)
+    static constexpr int B_SLAB = BKR * 128, B_SLABS = BN / 64;
+    static constexpr int A_BYTES = A_SLABS * A_SLAB, B_BYTES = B_SLABS * B_SLAB;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
 };
 
-template <int BN, int STAGES, int BKR, bool CONV>
+template <int BN, int STAGES, int BKR, bool CONV, int AW>
 __global__ void __launch_bounds__(THREADS)
 gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, int M, int N, int K,
                     int k_chunk, int cin, Epilogue ep) {
     extern __shared__ unsigned char smem_raw[];
-    using L = SmemLayoutTN<BN, STAGES, BKR>;
-    static_assert(BN % 64 == 0 && BKR % UMMA_K == 0, "tile shape");
+    using L = SmemLayoutTN<BN, STAGES, BKR, AW>;
+    static_assert(BN % 64 == 0 && BKR % UMMA_K == 0 && (AW == 64 || AW == 32), "tile shape");
+    constexpr uint32_t A_ROW = AW * 2;                  // bytes per k-row of an A slab
+    constexpr uint64_t A_LAYOUT = AW == 64 ? 2 : 4;
     unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr uint32_t TMEM_COLS = BN;
-    if (CONV) {     // rows 121..127 of every slab are never written by TMA: they must read as zero
-        constexpr int SLABS = STAGES * (2 + BN / 64), PADB = (BKR - PIXELS) * 128;
-        for (int i = threadIdx.x; i < SLABS * (PADB / 16); i += THREADS) {
-            const int sl = i / (PADB / 16), o = i - sl * (PADB / 16);
-            *reinterpret_cast<uint4*>(tiles + (size_t)sl * L::SLAB + PIXELS * 128 + o * 16) = make_uint4(0, 0, 0, 0);
+    if (CONV) {     // rows 121..BKR-1 of every slab are never written by TMA: they must read as zero
+        constexpr int PAD = BKR - PIXELS;
+        for (int i = threadIdx.x; i < STAGES * (L::A_SLABS * PAD * (int)A_ROW + L::B_SLABS * PAD * 128) / 16; i += THREADS) {
+            const int per_stage = (L::A_SLABS * PAD * (int)A_ROW + L::B_SLABS * PAD * 128) / 16;
+            const int st = i / per_stage;
+            int o = i - st * per_stage;
+            unsigned char* base = tiles + (size_t)st * L::STAGE_BYTES;
+            unsigned char* dst;
+            if (o < L::A_SLABS * PAD * (int)A_ROW / 16) {
+                const int sl = o / (PAD * (int)A_ROW / 16); o -= sl * (PAD * (int)A_ROW / 16);
+                dst = base + sl * L::A_SLAB + PIXELS * A_ROW + o * 16;
+            } else {
+                o -= L::A_SLABS * PAD * (int)A_ROW / 16;
+                const int sl = o / (PAD * 128 / 16); o -= sl * (PAD * 128 / 16);
+                dst = base + L::A_BYTES + sl * L::B_SLAB + PIXELS * 128 + o * 16;
+            }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -377,21 +392,21 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 unsigned char* b_dst = a_dst + L::A_BYTES;
                 if (CONV) {
                     const int sample = k_begin + kb;
-                    const int a_slabs = (m0 + 64 < M) ? 2 : 1;
-                    mbar_expect_tx(&pp.full_bar[s], (a_slabs + BN / 64) * PIXELS * 128);
+                    const int a_slabs = min(L::A_SLABS, (M - m0 + AW - 1) / AW);
+                    mbar_expect_tx(&pp.full_bar[s], a_slabs * PIXELS * A_ROW + L::B_SLABS * PIXELS * 128);
                     for (int j = 0; j < a_slabs; ++j) {
-                        const int m = m0 + 64 * j, tap = m / cin, c0 = m - tap * cin;
-                        tma_load_4d(a_dst + j * L::SLAB, &tmap_a, &pp.full_bar[s], c0, tap % 3 - 1, tap / 3 - 1, sample);
+                        const int m = m0 + AW * j, tap = m / cin, c0 = m - tap * cin;
+                        tma_load_4d(a_dst + j * L::A_SLAB, &tmap_a, &pp.full_bar[s], c0, tap % 3 - 1, tap / 3 - 1, sample);
                     }
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * L::SLAB, &tmap_b, &pp.full_bar[s], n0 + 64 * j, sample * PIXELS);
+                    for (int j = 0; j < L::B_SLABS; ++j) tma_load_2d(b_dst + j * L::B_SLAB, &tmap_b, &pp.full_bar[s], n0 + 64 * j, sample * PIXELS);
                 } else {
                     const int k = k_begin + kb * BKR;
                     mbar_expect_tx(&pp.full_bar[s], L::STAGE_BYTES);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) tma_load_2d(a_dst + j * L::SLAB, &tmap_a, &pp.full_bar[s], m0 + 64 * j, k);
+                    for (int j = 0; j < L::A_SLABS; ++j) tma_load_2d(a_dst + j * L::A_SLAB, &tmap_a, &pp.full_bar[s], m0 + AW * j, k);
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(b_dst + j * L::SLAB, &tmap_b, &pp.full_bar[s], n0 + 64 * j, k);
+                    for (int j = 0; j < L::B_SLABS; ++j) tma_load_2d(b_dst + j * L::B_SLAB, &tmap_b, &pp.full_bar[s], n0 + 64 * j, k);
                 }
                 if (s == STAGES - 1) phase ^= 1;
             }
@@ -408,8 +423,8 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const uint32_t b_addr = a_addr + L::A_BYTES;
 #pragma unroll
                 for (int k = 0; k < BKR / UMMA_K; ++k) {
-                    const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 128, 1024u, (uint32_t)L::SLAB, 2);
-                    const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 128, 1024u, (uint32_t)L::SLAB, 2);
+                    const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * A_ROW, 8 * A_ROW, (uint32_t)L::A_SLAB, A_LAYOUT);
+                    const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 128, 1024u, (uint32_t)L::B_SLAB, 2);
                     umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&pp.empty_bar[s]);
@@ -537,10 +552,10 @@ inline cudaError_t launch_tn(const __nv_bfloat16* At, int lda, const __nv_bfloat
     CUtensorMap ta, tb;
     if (!make_tmap(&ta, At, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BKR) || !make_tmap(&tb, Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BKR))
         return cudaErrorInvalidValue;
-    using L = SmemLayoutTN<BN, STAGES, BKR>;
+    using L = SmemLayoutTN<BN, STAGES, BKR, 64>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = ensure_smem(gemm_bf16_tn_kernel<BN, STAGES, BKR, false>, L::TOTAL);
+        cudaError_t e = ensure_smem(gemm_bf16_tn_kernel<BN, STAGES, BKR, false, 64>, L::TOTAL);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -553,25 +568,26 @@ inline cudaError_t launch_tn(const __nv_bfloat16* At, int lda, const __nv_bfloat
     if (splits > 1 && !ep.partial) return cudaErrorInvalidValue;
     if (splits == 1) ep.partial = nullptr;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
-    gemm_bf16_tn_kernel<BN, STAGES, BKR, false><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, N, K, chunk_tiles * BKR, 0, ep);
+    gemm_bf16_tn_kernel<BN, STAGES, BKR, false, 64><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, N, K, chunk_tiles * BKR, 0, ep);
     return cudaGetLastError();
 }
 
-// weight gradient of the 3x3 convolution: dW[9*Cin][Cout] = im2col(X)^T dY, X [B][11][11][Cin], dY [B*121][Cout]; split over samples
-template <int BN, int STAGES>
+// weight gradient of the 3x3 convolution: dW[9*Cin][Cout] = im2col(X)^T dY, X [B][11][11][Cin], dY [B*121][Cout]; split over samples.
+// AW = width of an A slab: 64 (Cin % 64 == 0) or 32 (Cin % 32 == 0, 64-byte swizzle)
+template <int BN, int STAGES, int AW>
 inline cudaError_t launch_conv_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* dY, long long batch, int Cin, int Cout, Epilogue ep,
                                      int* splits_inout, cudaStream_t stream) {
     constexpr int BKR = 128;
-    if (Cin % 64 != 0 || Cout % 8 != 0 || batch <= 0) return cudaErrorInvalidValue;
+    if (Cin % AW != 0 || Cout % 8 != 0 || batch <= 0) return cudaErrorInvalidValue;
     int splits = splits_inout ? *splits_inout : 1;
     CUtensorMap ta, tb;
-    if (!make_tmap_act(&ta, X, (uint64_t)batch, (uint64_t)Cin, 64) ||
+    if (!make_tmap_act(&ta, X, (uint64_t)batch, (uint64_t)Cin, AW) ||
         !make_tmap(&tb, dY, (uint64_t)batch * PIXELS, (uint64_t)Cout, (uint64_t)Cout, PIXELS))
         return cudaErrorInvalidValue;
-    using L = SmemLayoutTN<BN, STAGES, BKR>;
+    using L = SmemLayoutTN<BN, STAGES, BKR, AW>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = ensure_smem(gemm_bf16_tn_kernel<BN, STAGES, BKR, true>, L::TOTAL);
+        cudaError_t e = ensure_smem(gemm_bf16_tn_kernel<BN, STAGES, BKR, true, AW>, L::TOTAL);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -584,7 +600,7 @@ inline cudaError_t launch_conv_wgrad(const __nv_bfloat16* X, const __nv_bfloat16
     if (splits > 1 && !ep.partial) return cudaErrorInvalidValue;
     if (splits == 1) ep.partial = nullptr;
     dim3 grid((Cout + BN - 1) / BN, (M + BM - 1) / BM, splits);
-    gemm_bf16_tn_kernel<BN, STAGES, BKR, true><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, Cout, (int)batch, chunk, Cin, ep);
+    gemm_bf16_tn_kernel<BN, STAGES, BKR, true, AW><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, Cout, (int)batch, chunk, Cin, ep);
     return cudaGetLastError();
 }
 

@@ -276,9 +276,8 @@ struct mq_qnet {
     bool w_dirty[2] = {true, true};            // bf16 weight copies of [online, target] are stale
     mq::bf::bf16 *w2f[2] = {nullptr, nullptr}, *w3f[2] = {nullptr, nullptr}, *w1f[2] = {nullptr, nullptr};   // forward operands
     mq::bf::bf16 *w2d = nullptr, *w3d = nullptr, *w1t = nullptr;                                              // dgrad operands (online)
-    mq::bf::bf16 *A2 = nullptr, *A3 = nullptr, *a2b = nullptr, *a3b = nullptr;       // im2col rows, activations
-    mq::bf::bf16 *da3b = nullptr, *da2b = nullptr, *dh1b = nullptr, *dh1t = nullptr; // activation grads
-    mq::bf::bf16 *bufX = nullptr, *bufY = nullptr;                                   // [M][1152] and [M][128] scratch
+    mq::bf::bf16 *a1b = nullptr, *a2b = nullptr, *a3b = nullptr;                     // NHWC activations (TMA operands)
+    mq::bf::bf16 *da3b = nullptr, *da2b = nullptr, *dh1b = nullptr;                  // activation grads
 };
 
 namespace mq {
@@ -287,8 +286,8 @@ static void free_ws(mq_qnet* n) {
     float* ptrs[] = {n->a1, n->a2, n->a3, n->h1, n->h2, n->da1, n->da2, n->da3, n->dh1, n->dh2, n->q, n->dq, n->q_sa, n->maxq,
                      n->partial, n->norm_partial, n->gnorm};
     for (float* p : ptrs) cudaFree(p);
-    bf::bf16* bptrs[] = {n->w2f[0], n->w2f[1], n->w3f[0], n->w3f[1], n->w1f[0], n->w1f[1], n->w2d, n->w3d, n->w1t, n->A2, n->A3, n->a2b,
-                         n->a3b, n->da3b, n->da2b, n->dh1b, n->dh1t, n->bufX, n->bufY};
+    bf::bf16* bptrs[] = {n->w2f[0], n->w2f[1], n->w3f[0], n->w3f[1], n->w1f[0], n->w1f[1], n->w2d, n->w3d, n->w1t, n->a1b, n->a2b,
+                         n->a3b, n->da3b, n->da2b, n->dh1b};
     for (bf::bf16* p : bptrs) cudaFree(p);
 }
 
@@ -296,17 +295,14 @@ static void free_ws(mq_qnet* n) {
 static int ew_blocks(long long total) { return (int)((total + 255) / 256); }
 
 static cudaError_t alloc_bf16(mq_qnet* n) {
-    if (n->A2) return cudaSuccess;
+    if (n->a1b) return cudaSuccess;
     const size_t B = (size_t)n->max_batch, M = B * PIX, e = sizeof(bf::bf16);
     cudaError_t ce = cudaSuccess;
     auto alloc = [&](bf::bf16** p, size_t count) { if (ce == cudaSuccess) ce = cudaMalloc((void**)p, count * e); };
     for (int w = 0; w < 2; ++w) { alloc(&n->w2f[w], (size_t)C2 * 9 * C1); alloc(&n->w3f[w], (size_t)C3 * 9 * C2); alloc(&n->w1f[w], (size_t)H1 * FLAT); }
     alloc(&n->w2d, (size_t)C1 * 9 * C2); alloc(&n->w3d, (size_t)C2 * 9 * C3); alloc(&n->w1t, (size_t)FLAT * H1);
-    alloc(&n->A2, M * 9 * C1); alloc(&n->A3, M * 9 * C2); alloc(&n->a2b, M * C2); alloc(&n->a3b, M * C3);
-    if (n->tl.g[0]) {
-        alloc(&n->da3b, M * C3); alloc(&n->da2b, M * C2); alloc(&n->dh1b, B * H1); alloc(&n->dh1t, B * H1);
-        alloc(&n->bufX, M * 9 * C3); alloc(&n->bufY, M * C3);
-    }
+    alloc(&n->a1b, M * C1); alloc(&n->a2b, M * C2); alloc(&n->a3b, M * C3);
+    if (n->tl.g[0]) { alloc(&n->da3b, M * C3); alloc(&n->da2b, M * C2); alloc(&n->dh1b, B * H1); }
     return ce;
 }
 
@@ -356,17 +352,16 @@ static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, lon
     refresh_weights(n, which, s);
     GemmParams p{};
     p.batch = (int)B; p.partial = n->partial;
-    p.M = M; p.N = C1; p.K = 9 * CIN; p.A = obs; p.B = W[P_C1W]; p.ldb = C1; p.C = n->a1; p.ldc = C1; p.bias = W[P_C1B]; p.relu = 1;
+    p.M = M; p.N = C1; p.K = 9 * CIN; p.A = obs; p.B = W[P_C1W]; p.ldb = C1; p.C = n->a1; p.Cb = n->a1b; p.ldc = C1; p.bias = W[P_C1B]; p.relu = 1;
     n->launches += launch_gemm<A_IM2COL, B_ROW, 32, CIN>(p, n->partial_cap, n->n_sms, s);
-    bf::im2col_bf16_kernel<float, C1><<<ew_blocks((long long)M * 9 * (C1 / 8)), 256, 0, s>>>(n->a1, n->A2, M, 0);
+    // conv2 / conv3: implicit GEMMs, every tap a shifted zero-filled TMA box of the NHWC activation (no im2col buffer)
     tc::Epilogue ep{};
     ep.out_bf16 = n->a2b; ep.ldc = C2; ep.bias = W[P_C2B]; ep.relu = 1;
-    cudaError_t e = tc_gemm<64>(n, n->A2, 9 * C1, n->w2f[which], 9 * C1, M, C2, 9 * C1, ep, false, s);
+    cudaError_t e = tc::launch_conv<64, 6, 32>(n->a1b, n->w2f[which], B, C1, C2, 0, ep, s);
     if (e != cudaSuccess) return e;
-    bf::im2col_bf16_kernel<bf::bf16, C2><<<ew_blocks((long long)M * 9 * (C2 / 8)), 256, 0, s>>>(n->a2b, n->A3, M, 0);
     ep = tc::Epilogue{};
     ep.out_bf16 = n->a3b; ep.ldc = C3; ep.bias = W[P_C3B]; ep.relu = 1;
-    e = tc_gemm<128>(n, n->A3, 9 * C2, n->w3f[which], 9 * C2, M, C3, 9 * C2, ep, false, s);
+    e = tc::launch_conv<128, 4, 64>(n->a2b, n->w3f[which], B, C2, C3, 0, ep, s);
     if (e != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_f32 = n->h1; ep.ldc = H1; ep.bias = W[P_F1B]; ep.relu = 1; ep.drop = drop_mask; ep.drop_scale = 1.f / (1.f - 0.2f);
@@ -422,13 +417,29 @@ static void launch_colsum_bf16(mq_qnet* n, const bf::bf16* X, long long M, int N
     n->launches += 2;
 }
 
-static void transpose_bf16(mq_qnet* n, const bf::bf16* src, bf::bf16* dst, long long R, int C, cudaStream_t s) {
-    dim3 grid((unsigned)((R + 63) / 64), (unsigned)((C + 63) / 64));
-    bf::transpose_bf16_kernel<<<grid, 256, 0, s>>>(src, dst, R, C);
+// conv weight gradient on the tensor cores: split over samples so that ~one wave of CTAs runs, deterministic reduce
+template <int BN, int STAGES, int AW>
+static cudaError_t conv_wgrad(mq_qnet* n, const bf::bf16* X, const bf::bf16* dY, long long B, int Cin, int Cout, float* out, cudaStream_t s) {
+    const int M = 9 * Cin;
+    const int tiles = ((M + tc::BM - 1) / tc::BM) * ((Cout + BN - 1) / BN);
+    int splits = (n->n_sms + tiles - 1) / tiles;
+    while (splits > 1 && (size_t)splits * M * Cout > n->partial_cap) --splits;
+    tc::Epilogue ep{};
+    ep.out_f32 = out; ep.ldc = Cout; ep.partial = n->partial;
+    cudaError_t e = tc::launch_conv_wgrad<BN, STAGES, AW>(X, dY, B, Cin, Cout, ep, &splits, s);
     n->launches += 1;
+    if (e == cudaSuccess && splits > 1) {
+        GemmParams p{};
+        p.M = M; p.N = Cout; p.C = out; p.ldc = Cout; p.partial = n->partial; p.splits = splits;
+        size_t total = (size_t)M * Cout;
+        int blocks = (int)((total + 255) / 256); if (blocks > 4 * n->n_sms) blocks = 4 * n->n_sms;
+        splitk_epilogue_kernel<<<blocks, 256, 0, s>>>(p);
+        n->launches += 1;
+    }
+    return e;
 }
 
-// backward of the bf16 path.  Needs: forward_net_bf16(online) just ran (A2, A3, a1, a2b, a3b, h1, h2 hold the online
+// backward of the bf16 path.  Needs: forward_net_bf16(online) just ran (a1, a1b, a2b, a3b, h1, h2 hold the online
 // activations) and n->dq holds dL/dq.
 static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, const uint8_t* drop_online, cudaStream_t s) {
     float* const* W = n->tl.p; float* const* G = n->tl.g;
@@ -451,43 +462,33 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
     launch_colsum(n, n->dh2, B, H2, G[P_F2B], s);
     p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
     p.M = (int)B; p.N = H1; p.K = H2; p.A = n->dh2; p.lda = H2; p.B = W[P_F2W]; p.ldb = H1; p.C = n->dh1; p.ldc = H1;
-    p.mask_act = n->h1; p.drop = drop_online; p.drop_scale = 1.f / (1.f - 0.2f);
+    p.mask_act = n->h1; p.drop = drop_online; p.drop_scale = 1.f / (1.f - 0.2f); p.Cb = n->dh1b;
     n->launches += launch_gemm<A_ROW, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
     launch_colsum(n, n->dh1, B, H1, G[P_F1B], s);
-    // fc1 on the tensor cores: dW1 = dh1^T a3 ; da3 = dh1 W1 (masked by a3 > 0)
-    bf::cast_transpose_kernel<<<ew_blocks(B * H1), 256, 0, s>>>(n->dh1, n->dh1b, n->dh1t, B, H1);
-    transpose_bf16(n, n->a3b, n->bufY, B, FLAT, s);                                   // a3^T [15488][B]
-    n->launches += 1;
+    // fc1 on the tensor cores: dW1 = dh1^T a3 (both operands MN-major: no transposes) ; da3 = dh1 W1 (masked by a3 > 0)
     tc::Epilogue ep{};
     ep.out_f32 = G[P_F1W]; ep.ldc = FLAT;
-    if ((e = tc_gemm<128>(n, n->dh1t, (int)B, n->bufY, (int)B, H1, FLAT, (int)B, ep, false, s)) != cudaSuccess) return e;
+    {
+        int one = 1;
+        if ((e = tc::launch_tn<128, 3>(n->dh1b, H1, n->a3b, FLAT, H1, FLAT, (int)B, ep, &one, s)) != cudaSuccess) return e;
+        n->launches += 1;
+    }
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da3b; ep.ldc = FLAT; ep.mask_bf16 = n->a3b;
     if ((e = tc_gemm<128>(n, n->dh1b, H1, n->w1t, H1, (int)B, FLAT, H1, ep, false, s)) != cudaSuccess) return e;
-    // conv3: dWc3[(t,c)][n] = A3^T dY ; db ; da2 = im2col_flip(dY) Wd3^T (masked by a2 > 0)
+    // conv3: dWc3[(t,c)][n] = im2col(a2)^T dY (implicit, split over samples) ; db ; da2 = conv_flip(dY, Wd3) (masked by a2 > 0)
     launch_colsum_bf16(n, n->da3b, M, C3, G[P_C3B], s);
-    transpose_bf16(n, n->A3, n->bufX, M, 9 * C2, s);                                  // [576][M]
-    transpose_bf16(n, n->da3b, n->bufY, M, C3, s);                                    // [128][M]
-    ep = tc::Epilogue{};
-    ep.out_f32 = G[P_C3W]; ep.ldc = C3;
-    if ((e = tc_gemm<128>(n, n->bufX, M, n->bufY, M, 9 * C2, C3, M, ep, true, s)) != cudaSuccess) return e;
-    bf::im2col_bf16_kernel<bf::bf16, C3><<<ew_blocks((long long)M * 9 * (C3 / 8)), 256, 0, s>>>(n->da3b, n->bufX, M, 1);
-    n->launches += 1;
+    if ((e = conv_wgrad<128, 3, 64>(n, n->a2b, n->da3b, B, C2, C3, G[P_C3W], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da2b; ep.ldc = C2; ep.mask_bf16 = n->a2b;
-    if ((e = tc_gemm<64>(n, n->bufX, 9 * C3, n->w3d, 9 * C3, M, C2, 9 * C3, ep, false, s)) != cudaSuccess) return e;
+    if ((e = tc::launch_conv<64, 4, 64>(n->da3b, n->w3d, B, C3, C2, 1, ep, s)) != cudaSuccess) return e;
     // conv2
     launch_colsum_bf16(n, n->da2b, M, C2, G[P_C2B], s);
-    transpose_bf16(n, n->A2, n->bufX, M, 9 * C1, s);                                  // [288][M]
-    transpose_bf16(n, n->da2b, n->bufY, M, C2, s);                                    // [64][M]
-    ep = tc::Epilogue{};
-    ep.out_f32 = G[P_C2W]; ep.ldc = C2;
-    if ((e = tc_gemm<64>(n, n->bufX, M, n->bufY, M, 9 * C1, C2, M, ep, true, s)) != cudaSuccess) return e;
-    bf::im2col_bf16_kernel<bf::bf16, C2><<<ew_blocks((long long)M * 9 * (C2 / 8)), 256, 0, s>>>(n->da2b, n->bufX, M, 1);
-    n->launches += 1;
+    if ((e = conv_wgrad<64, 4, 32>(n, n->a1b, n->da2b, B, C1, C2, G[P_C2W], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_f32 = n->da1; ep.ldc = C1; ep.mask_f32 = n->a1;
-    if ((e = tc_gemm<32>(n, n->bufX, 9 * C2, n->w2d, 9 * C2, M, C1, 9 * C2, ep, false, s)) != cudaSuccess) return e;
+    if ((e = tc::launch_conv<32, 4, 64>(n->da2b, n->w2d, B, C2, C1, 1, ep, s)) != cudaSuccess) return e;
+    n->launches += 2;
     // conv1 (fp32, 1 % of the flops)
     p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
     p.M = 9 * CIN; p.N = C1; p.K = M; p.A = state; p.B = n->da1; p.ldb = C1; p.C = G[P_C1W]; p.ldc = C1;

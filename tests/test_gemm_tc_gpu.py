@@ -88,7 +88,8 @@ def test_implicit_conv_matches_torch(B, Cin, Cout, bn, flip):
     assert err <= 2e-3 * scale + 1e-3, (B, Cin, Cout, bn, flip, err, scale)
 
 
-@pytest.mark.parametrize("B,Cin,Cout,splits", [(1, 64, 128, 1), (9, 64, 128, 1), (100, 64, 128, 7), (64, 128, 64, 4), (257, 64, 128, 29)])
+@pytest.mark.parametrize("B,Cin,Cout,splits", [(1, 64, 128, 1), (9, 64, 128, 1), (100, 64, 128, 7), (64, 128, 64, 4), (257, 64, 128, 29),
+                                               (3, 32, 64, 1), (130, 32, 64, 9)])
 def test_conv_wgrad_matches_torch(B, Cin, Cout, splits):
     """dW[(kh,kw,c)][n] = sum over samples and pixels of X[b, i+kh-1, j+kw-1, c] * dY[b, i, j, n] (MN-major implicit GEMM)."""
     from dqn_marl_b200 import _lib
