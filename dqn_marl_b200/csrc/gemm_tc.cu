@@ -69,7 +69,8 @@ extern "C" int mq_gemm_bf16_tn(const void* At, const void* Bt, float* C, int32_t
 
 // Y[B*121][Cout] (fp32) = conv3x3/pad1 of X [B][11][11][Cin] (bf16, NHWC) with Wk[Cout][9*Cin] (bf16, taps (kh,kw,c)); implicit
 // GEMM, the im2col matrix is never written: each tap is a shifted, zero-filled 4-D TMA box.  flip = 1 mirrors the taps
-// (data gradient).  Cin must be a multiple of 32 (32 -> 64B swizzle, else 128B swizzle); bn = 128 / 64 / 32.
+// (data gradient).  Cin must be a multiple of 32 (32 -> 64B swizzle, else 128B swizzle); bn = 128 / 64 / 32 = tile width of the
+// one-sample-per-CTA kernel, bn = 0 = persistent kernel with the weights resident in shared memory.
 extern "C" int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, int64_t batch, int32_t Cin, int32_t Cout, int32_t flip, int32_t bn,
                                void* stream) {
     MQ_REQUIRE(X && Wk && Y && batch > 0 && Cin > 0 && Cout > 0, "mq_conv3x3_bf16: bad argument");
@@ -80,7 +81,16 @@ extern "C" int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, int64_t 
     const __nv_bfloat16* x = (const __nv_bfloat16*)X;
     const __nv_bfloat16* w = (const __nv_bfloat16*)Wk;
     cudaError_t e;
-    if (Cin % 64 == 0) {
+    if (bn == 0) {          // persistent kernel: weights resident in shared memory, Cout = tile width
+        int dev = 0, n_sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (Cin % 64 == 0 && Cout == 128) e = mq::tc::launch_conv_persistent<128, 64, 4>(x, w, batch, Cin, Cout, flip, ep, n_sms, s);
+        else if (Cin % 64 == 0 && Cout == 64) e = mq::tc::launch_conv_persistent<64, 64, 4>(x, w, batch, Cin, Cout, flip, ep, n_sms, s);
+        else if (Cin % 64 == 0 && Cout == 32) e = mq::tc::launch_conv_persistent<32, 64, 4>(x, w, batch, Cin, Cout, flip, ep, n_sms, s);
+        else if (Cout == 64) e = mq::tc::launch_conv_persistent<64, 32, 6>(x, w, batch, Cin, Cout, flip, ep, n_sms, s);
+        else return mq::fail(MQ_ERR_ARG, "mq_conv3x3_bf16: the persistent kernel (bn = 0) supports Cout = 128/64/32 (Cin %% 64 == 0) or Cout = 64");
+    } else if (Cin % 64 == 0) {
         if (bn == 128) e = mq::tc::launch_conv<128, 4, 64>(x, w, batch, Cin, Cout, flip, ep, s);
         else if (bn == 64) e = mq::tc::launch_conv<64, 4, 64>(x, w, batch, Cin, Cout, flip, ep, s);
         else if (bn == 32) e = mq::tc::launch_conv<32, 4, 64>(x, w, batch, Cin, Cout, flip, ep, s);

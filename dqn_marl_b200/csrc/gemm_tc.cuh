@@ -328,6 +328,115 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // =====================================================================================================================
+// Persistent implicit-GEMM convolution: the whole weight matrix Wk[BN][9*Cin] stays in shared memory (<= 147 KB for the
+// Q-network's layers), every CTA walks over samples (one 121-row tile each): the A ring streams the shifted boxes, the
+// accumulator is double-buffered in TMEM so the epilogue of sample t overlaps the MMAs of sample t+1.
+// =====================================================================================================================
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int BK, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1)
+conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, long long batch, int nkb,
+                            ConvArgs cv, Epilogue ep) {
+    extern __shared__ unsigned char smem_raw[];
+    constexpr uint64_t LAYOUT = BK == 64 ? 2 : 4;
+    constexpr uint32_t SBO = 8 * BK * 2;
+    constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
+    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    unsigned char* wtile = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = wtile + (size_t)nkb * W_BYTES;
+    uint64_t* full_bar = (uint64_t*)(ring + STAGES * A_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;           // [2]
+    uint64_t* w_full = tmem_empty + 2;
+    uint32_t* tmem_ptr = (uint32_t*)(w_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        mbar_init(w_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(w_full, (uint32_t)nkb * W_BYTES);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(wtile + (size_t)kb * W_BYTES, &tmap_w, w_full, kb * BK, 0);
+            long long g = 0;
+            for (long long sample = blockIdx.x; sample < batch; sample += gridDim.x) {
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % STAGES);
+                    mbar_wait(&empty_bar[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
+                    mbar_expect_tx(&full_bar[s], PIXELS * BK * 2);
+                    const int tap = kb / cv.cblocks, cb = kb - tap * cv.cblocks;
+                    int di = tap / 3 - 1, dj = tap % 3 - 1;
+                    if (cv.flip) { di = -di; dj = -dj; }
+                    tma_load_4d(ring + s * A_BYTES, &tmap_a, &full_bar[s], cb * BK, dj, di, (int)sample);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            mbar_wait(w_full, 0);
+            long long g = 0;
+            int it = 0;
+            for (long long sample = blockIdx.x; sample < batch; sample += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));       // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % STAGES);
+                    mbar_wait(&full_bar[s], (uint32_t)((g / STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(ring + s * A_BYTES);
+                    const uint32_t b_addr = smem_u32(wtile + (size_t)kb * W_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
+                        const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
+                        umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        int it = 0;
+        for (long long sample = blockIdx.x; sample < batch; sample += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, r < PIXELS, sample * PIXELS + r, 0, batch * PIXELS, BN, 0);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+// =====================================================================================================================
 // MN-major ("TN") kernel: C[M][N] = sum_k At[k][m] * Bt[k][n].  A stage holds BKR k-rows: 2 A slabs and BN/64 B slabs of
 // [BKR][64] bf16 (128-byte rows, SWIZZLE_128B).  CONV: one stage = one sample (121 of the 128 rows are loaded, the rest
 // stay zero); the A slab of output rows m0 + 64 j is tap (m / Cin), channels (m % Cin) .. +64 of the shifted activation.
@@ -540,6 +649,30 @@ inline cudaError_t launch_conv(const __nv_bfloat16* X, const __nv_bfloat16* Wk, 
     dim3 grid((Cout + BN - 1) / BN, (unsigned)batch, 1);
     gemm_bf16_tc_kernel<BN, STAGES, BK, true><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, batch * PIXELS, Cout, 9 * Cin, 9 * Cin,
                                                                                  ConvArgs{Cin / BK, flip}, ep);
+    return cudaGetLastError();
+}
+
+// Persistent form of launch_conv (Cout == BN): weights resident in shared memory, one CTA per SM walking over the samples.
+template <int BN, int BK, int STAGES>
+inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfloat16* Wk, long long batch, int Cin, int Cout, int flip,
+                                          Epilogue ep, int n_sms, cudaStream_t stream) {
+    if (Cin % BK != 0 || batch <= 0 || Cout != BN) return cudaErrorInvalidValue;
+    CUtensorMap ta, tw;
+    if (!make_tmap_act(&ta, X, (uint64_t)batch, (uint64_t)Cin, BK) ||
+        !make_tmap(&tw, Wk, (uint64_t)Cout, (uint64_t)9 * Cin, (uint64_t)9 * Cin, BN, BK))
+        return cudaErrorInvalidValue;
+    const int nkb = 9 * Cin / BK;
+    const int smem = nkb * BN * BK * 2 + STAGES * BM * BK * 2 + 1024 + 256;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    static int attr_bytes = 0;
+    if (smem > attr_bytes) {
+        cudaError_t e = ensure_smem(conv_bf16_persistent_kernel<BN, BK, STAGES>, smem);
+        if (e != cudaSuccess) return e;
+        attr_bytes = smem;
+    }
+    ep.partial = nullptr;
+    const int grid = (int)(batch < n_sms ? batch : n_sms);
+    conv_bf16_persistent_kernel<BN, BK, STAGES><<<grid, THREADS, smem, stream>>>(ta, tw, batch, nkb, ConvArgs{Cin / BK, flip}, ep);
     return cudaGetLastError();
 }
 

@@ -354,14 +354,15 @@ static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, lon
     p.batch = (int)B; p.partial = n->partial;
     p.M = M; p.N = C1; p.K = 9 * CIN; p.A = obs; p.B = W[P_C1W]; p.ldb = C1; p.C = n->a1; p.Cb = n->a1b; p.ldc = C1; p.bias = W[P_C1B]; p.relu = 1;
     n->launches += launch_gemm<A_IM2COL, B_ROW, 32, CIN>(p, n->partial_cap, n->n_sms, s);
-    // conv2 / conv3: implicit GEMMs, every tap a shifted zero-filled TMA box of the NHWC activation (no im2col buffer)
+    // conv2 / conv3: persistent implicit GEMMs (weights resident in shared memory), every tap a shifted zero-filled TMA box
+    // of the NHWC activation (no im2col buffer)
     tc::Epilogue ep{};
     ep.out_bf16 = n->a2b; ep.ldc = C2; ep.bias = W[P_C2B]; ep.relu = 1;
-    cudaError_t e = tc::launch_conv<64, 6, 32>(n->a1b, n->w2f[which], B, C1, C2, 0, ep, s);
+    cudaError_t e = tc::launch_conv_persistent<64, 32, 6>(n->a1b, n->w2f[which], B, C1, C2, 0, ep, n->n_sms, s);
     if (e != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->a3b; ep.ldc = C3; ep.bias = W[P_C3B]; ep.relu = 1;
-    e = tc::launch_conv<128, 4, 64>(n->a2b, n->w3f[which], B, C2, C3, 0, ep, s);
+    e = tc::launch_conv_persistent<128, 64, 4>(n->a2b, n->w3f[which], B, C2, C3, 0, ep, n->n_sms, s);
     if (e != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_f32 = n->h1; ep.ldc = H1; ep.bias = W[P_F1B]; ep.relu = 1; ep.drop = drop_mask; ep.drop_scale = 1.f / (1.f - 0.2f);
@@ -481,13 +482,13 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
     if ((e = conv_wgrad<128, 3, 64>(n, n->a2b, n->da3b, B, C2, C3, G[P_C3W], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da2b; ep.ldc = C2; ep.mask_bf16 = n->a2b;
-    if ((e = tc::launch_conv<64, 4, 64>(n->da3b, n->w3d, B, C3, C2, 1, ep, s)) != cudaSuccess) return e;
+    if ((e = tc::launch_conv_persistent<64, 64, 4>(n->da3b, n->w3d, B, C3, C2, 1, ep, n->n_sms, s)) != cudaSuccess) return e;
     // conv2
     launch_colsum_bf16(n, n->da2b, M, C2, G[P_C2B], s);
     if ((e = conv_wgrad<64, 4, 32>(n, n->a1b, n->da2b, B, C1, C2, G[P_C2W], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_f32 = n->da1; ep.ldc = C1; ep.mask_f32 = n->a1;
-    if ((e = tc::launch_conv<32, 4, 64>(n->da2b, n->w2d, B, C2, C1, 1, ep, s)) != cudaSuccess) return e;
+    if ((e = tc::launch_conv_persistent<32, 64, 4>(n->da2b, n->w2d, B, C2, C1, 1, ep, n->n_sms, s)) != cudaSuccess) return e;
     n->launches += 2;
     // conv1 (fp32, 1 % of the flops)
     p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;

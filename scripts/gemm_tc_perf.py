@@ -36,3 +36,39 @@ for name, m, n, k, bn, splits in shapes:
     ms = e0.elapsed_time(e1) / reps
     tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
     print(f"{name:12s} M={m:7d} N={n:6d} K={k:7d} bn={bn:3d} splits={splits:3d}  {ms:8.3f} ms  {tf:7.1f} TFLOP/s  {100*tf/peak:5.1f}% of {peak:.0f}")
+
+print("--- implicit convolutions (one-sample-per-CTA kernel vs persistent kernel) and MN-major weight gradients")
+def timeit(fn, reps=10):
+    for _ in range(3):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+for name, cin, cout, flip, bn in [("conv3 fwd", 64, 128, 0, 128), ("conv3 dgrad", 128, 64, 1, 64), ("conv2 fwd", 32, 64, 0, 64),
+                                  ("conv2 dgrad", 64, 32, 1, 32)]:
+    X = torch.randn((B, 11, 11, cin), device="cuda").to(torch.bfloat16)
+    Wk = torch.randn((cout, 9 * cin), device="cuda").to(torch.bfloat16)
+    Y = torch.empty((M, cout), device="cuda")
+    fl = 2.0 * M * cout * 9 * cin
+    for label, b in (("tile", bn), ("persistent", 0)):
+        ms = timeit(lambda: _lib.check(lib.mq_conv3x3_bf16(_lib.ptr(X), _lib.ptr(Wk), _lib.ptr(Y), B, cin, cout, flip, b, st), "conv"))
+        tf = fl / (ms * 1e-3) / 1e12
+        print(f"{name:12s} {label:10s} Cin={cin:3d} Cout={cout:3d}  {ms:8.3f} ms  {tf:7.1f} TFLOP/s  {100*tf/peak:5.1f}% of {peak:.0f}")
+for name, cin, cout, splits in [("conv3 wgrad", 64, 128, 30), ("conv2 wgrad", 32, 64, 50)]:
+    X = torch.randn((B, 11, 11, cin), device="cuda").to(torch.bfloat16)
+    dY = torch.randn((M, cout), device="cuda").to(torch.bfloat16)
+    dW = torch.empty((9 * cin, cout), device="cuda")
+    ws = torch.empty((splits * 9 * cin * cout,), device="cuda")
+    ms = timeit(lambda: _lib.check(lib.mq_conv3x3_wgrad_bf16(_lib.ptr(X), _lib.ptr(dY), _lib.ptr(dW), B, cin, cout, splits, _lib.ptr(ws), st), "wgrad"))
+    tf = 2.0 * M * cout * 9 * cin / (ms * 1e-3) / 1e12
+    print(f"{name:12s} implicit TN splits={splits:3d}  {ms:8.3f} ms  {tf:7.1f} TFLOP/s  {100*tf/peak:5.1f}% of {peak:.0f}")
+At = torch.randn((B, 512), device="cuda").to(torch.bfloat16)
+Bt = torch.randn((B, 15488), device="cuda").to(torch.bfloat16)
+C = torch.empty((512, 15488), device="cuda")
+ms = timeit(lambda: _lib.check(lib.mq_gemm_bf16_tn(_lib.ptr(At), _lib.ptr(Bt), _lib.ptr(C), 512, 15488, B, 1, None, st), "tn"))
+tf = 2.0 * 512 * 15488 * B / (ms * 1e-3) / 1e12
+print(f"fc1 wgrad    MN-major TN            {ms:8.3f} ms  {tf:7.1f} TFLOP/s  {100*tf/peak:5.1f}% of {peak:.0f}")

@@ -71,7 +71,9 @@ def _conv_ref(X, Wk, Cin, Cout, flip):
 
 
 @pytest.mark.parametrize("B,Cin,Cout,bn,flip", [(1, 64, 128, 128, 0), (5, 64, 128, 128, 0), (64, 64, 128, 128, 1), (37, 128, 64, 64, 1),
-                                                (16, 64, 32, 32, 1), (33, 32, 64, 64, 0), (300, 64, 128, 128, 0)])
+                                                (16, 64, 32, 32, 1), (33, 32, 64, 64, 0), (300, 64, 128, 128, 0),
+                                                (1, 64, 128, 0, 0), (700, 64, 128, 0, 0), (333, 128, 64, 0, 1), (450, 64, 32, 0, 1),
+                                                (301, 32, 64, 0, 0)])
 def test_implicit_conv_matches_torch(B, Cin, Cout, bn, flip):
     """3x3/pad-1 convolution as an implicit GEMM over shifted, zero-filled 4-D TMA boxes (no im2col buffer)."""
     from dqn_marl_b200 import _lib
