@@ -67,17 +67,17 @@ extern "C" int mq_gemm_bf16_tn(const void* At, const void* Bt, float* C, int32_t
     return finish_split(workspace, sp, (size_t)M * N, C, s);
 }
 
-// Y[B*121][Cout] (fp32) = conv3x3/pad1 of X [B][11][11][Cin] (bf16, NHWC) with Wk[Cout][9*Cin] (bf16, taps (kh,kw,c)); implicit
+// Y[B*121][Cout] (fp32 in Y and / or bf16 in Y_bf16) = conv3x3/pad1 of X [B][11][11][Cin] (bf16, NHWC) with Wk[Cout][9*Cin] (bf16, taps (kh,kw,c)); implicit
 // GEMM, the im2col matrix is never written: each tap is a shifted, zero-filled 4-D TMA box.  flip = 1 mirrors the taps
 // (data gradient).  Cin must be a multiple of 32 (32 -> 64B swizzle, else 128B swizzle); bn = 128 / 64 / 32 = tile width of the
 // one-sample-per-CTA kernel, bn = 0 = persistent kernel with the weights resident in shared memory.
-extern "C" int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, int64_t batch, int32_t Cin, int32_t Cout, int32_t flip, int32_t bn,
-                               void* stream) {
-    MQ_REQUIRE(X && Wk && Y && batch > 0 && Cin > 0 && Cout > 0, "mq_conv3x3_bf16: bad argument");
+extern "C" int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, void* Y_bf16, int64_t batch, int32_t Cin, int32_t Cout, int32_t flip,
+                               int32_t bn, void* stream) {
+    MQ_REQUIRE(X && Wk && (Y || Y_bf16) && batch > 0 && Cin > 0 && Cout > 0, "mq_conv3x3_bf16: bad argument");
     MQ_REQUIRE(Cin % 32 == 0, "mq_conv3x3_bf16: Cin must be a multiple of 32");
     cudaStream_t s = (cudaStream_t)stream;
     mq::tc::Epilogue ep{};
-    ep.out_f32 = Y; ep.ldc = Cout;
+    ep.out_f32 = Y; ep.out_bf16 = (__nv_bfloat16*)Y_bf16; ep.ldc = Cout;
     const __nv_bfloat16* x = (const __nv_bfloat16*)X;
     const __nv_bfloat16* w = (const __nv_bfloat16*)Wk;
     cudaError_t e;

@@ -139,8 +139,16 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, uint32_t tmem_
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (ep.bias) {
+            if (nb + 32 <= N) {         // nb is a multiple of 32: 16-byte aligned
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (nb + j < N) v[j] += __ldg(ep.bias + nb + j);
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
+                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (nb + j < N) v[j] += __ldg(ep.bias + nb + j);
+            }
         }
         if (ep.relu) {
 #pragma unroll
@@ -327,6 +335,91 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     pipe_fini(tmem_base, TMEM_COLS);
 }
 
+// ---- bf16 epilogue through shared memory + TMA store (persistent conv kernel) ----------------------------------------
+// Direct stores from the TMEM register layout (one row per thread) hit 32 different sectors per instruction with 16 bytes
+// each; the L2 write path, not the tensor pipe, then bounds the kernel.  Here a warp stages its 32 rows x 64 columns in a
+// 4 KB SWIZZLE_128B tile (conflict-free 16-byte shared stores) and one lane issues a bulk tensor store; rows >= 121 of the
+// sample fall outside the 3-D output map {Cout, 121, batch} and are clipped by TMA.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_tma(const Epilogue& ep, const CUtensorMap* tmap_out, uint32_t tmem_acc, int q, int lane,
+                                                  long long sample, unsigned char* stage) {
+    static_assert(BN % 64 == 0, "TMA-store epilogue works on 64-column groups");
+    const int r = q * 32 + lane;
+    const bool row_ok = r < PIXELS;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+        uint32_t ra[32], rb[32];
+        tmem_ld32_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, ra);
+        tmem_ld32_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 32), rb);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t packed[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(h ? rb[j] : ra[j]);
+            const int nb = c0 + 32 * h;
+            if (ep.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
+                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
+            }
+            if (ep.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (ep.mask_bf16 && row_ok) {
+                const uint4* mk = reinterpret_cast<const uint4*>(ep.mask_bf16 + ((size_t)sample * PIXELS + r) * BN + nb);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const uint4 w = __ldg(mk + j / 8);
+                    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ws[k]);
+                        if (!(__low2float(b2) > 0.f)) v[j + 2 * k] = 0.f;
+                        if (!(__high2float(b2) > 0.f)) v[j + 2 * k + 1] = 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                packed[16 * h + j / 2] = *reinterpret_cast<const uint32_t*>(&p2);
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous store has read the tile
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_3d(tmap_out, stage, c0, q * 32, (int)sample);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+}
+
 // =====================================================================================================================
 // Persistent implicit-GEMM convolution: the whole weight matrix Wk[BN][9*Cin] stays in shared memory (<= 147 KB for the
 // Q-network's layers), every CTA walks over samples (one 121-row tile each): the A ring streams the shifted boxes, the
@@ -338,8 +431,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 template <int BN, int BK, int STAGES>
 __global__ void __launch_bounds__(THREADS, 1)
-conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, long long batch, int nkb,
-                            ConvArgs cv, Epilogue ep) {
+conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                            const __grid_constant__ CUtensorMap tmap_out, long long batch, int nkb, int tma_store, ConvArgs cv, Epilogue ep) {
     extern __shared__ unsigned char smem_raw[];
     constexpr uint64_t LAYOUT = BK == 64 ? 2 : 4;
     constexpr uint32_t SBO = 8 * BK * 2;
@@ -347,7 +440,8 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     unsigned char* wtile = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = wtile + (size_t)nkb * W_BYTES;
-    uint64_t* full_bar = (uint64_t*)(ring + STAGES * A_BYTES);
+    unsigned char* stage = ring + STAGES * A_BYTES;            // 4 x 4 KB epilogue staging tiles (tma_store only)
+    uint64_t* full_bar = (uint64_t*)(stage + (tma_store ? 4 * 4096 : 0));
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;       // [2]
     uint64_t* tmem_empty = tmem_full + 2;           // [2]
@@ -425,11 +519,17 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             const int buf = it & 1;
             mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, r < PIXELS, sample * PIXELS + r, 0, batch * PIXELS, BN, 0);
+            if constexpr (BN % 64 == 0) {
+                if (tma_store) epilogue_tile_tma<BN>(ep, &tmap_out, tmem_base + (uint32_t)(buf * BN), q, lane, sample, stage + q * 4096);
+                else epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, r < PIXELS, sample * PIXELS + r, 0, batch * PIXELS, BN, 0);
+            } else {
+                epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, r < PIXELS, sample * PIXELS + r, 0, batch * PIXELS, BN, 0);
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         }
+        if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // stores complete before the CTA exits
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -662,7 +762,20 @@ inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfl
         !make_tmap(&tw, Wk, (uint64_t)Cout, (uint64_t)9 * Cin, (uint64_t)9 * Cin, BN, BK))
         return cudaErrorInvalidValue;
     const int nkb = 9 * Cin / BK;
-    const int smem = nkb * BN * BK * 2 + STAGES * BM * BK * 2 + 1024 + 256;
+    // bf16 output without per-element fp32 masks: epilogue through shared memory + TMA store
+    const int tma_store = (BN % 64 == 0 && ep.out_bf16 && !ep.out_f32 && !ep.mask_f32 && !ep.drop && ep.ldc == Cout) ? 1 : 0;
+    CUtensorMap to = ta;
+    if (tma_store) {
+        EncodeTiledFn fn = encode_fn();
+        cuuint64_t dims[3] = {(cuuint64_t)Cout, (cuuint64_t)PIXELS, (cuuint64_t)batch};
+        cuuint64_t strides[2] = {(cuuint64_t)Cout * 2, (cuuint64_t)PIXELS * Cout * 2};
+        cuuint32_t box[3] = {64, 32, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (!fn || fn(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ep.out_bf16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return cudaErrorInvalidValue;
+    }
+    const int smem = nkb * BN * BK * 2 + STAGES * BM * BK * 2 + (tma_store ? 4 * 4096 : 0) + 1024 + 256;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static int attr_bytes = 0;
     if (smem > attr_bytes) {
@@ -672,7 +785,7 @@ inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfl
     }
     ep.partial = nullptr;
     const int grid = (int)(batch < n_sms ? batch : n_sms);
-    conv_bf16_persistent_kernel<BN, BK, STAGES><<<grid, THREADS, smem, stream>>>(ta, tw, batch, nkb, ConvArgs{Cin / BK, flip}, ep);
+    conv_bf16_persistent_kernel<BN, BK, STAGES><<<grid, THREADS, smem, stream>>>(ta, tw, to, batch, nkb, tma_store, ConvArgs{Cin / BK, flip}, ep);
     return cudaGetLastError();
 }
 

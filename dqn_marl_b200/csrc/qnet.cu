@@ -149,6 +149,62 @@ colsum_partial_kernel(const float* __restrict__ X, long long M, int N, int rows_
         partial[(size_t)blockIdx.x * N + n] = acc;
     }
 }
+// streaming form (N % VEC == 0, N / VEC <= 256): a thread owns one 16-byte column vector and every RG-th row of the block's
+// row range, 4 rows in flight; the row groups are combined through shared memory in a fixed order (deterministic)
+template <typename T> struct ColVec;
+template <> struct ColVec<float> {
+    static constexpr int VEC = 4;
+    static __device__ __forceinline__ void add(float* a, const float* p) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        a[0] += v.x; a[1] += v.y; a[2] += v.z; a[3] += v.w;
+    }
+};
+template <> struct ColVec<bf::bf16> {
+    static constexpr int VEC = 8;
+    static __device__ __forceinline__ void add(float* a, const bf::bf16* p) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+            a[2 * k] += __low2float(b2); a[2 * k + 1] += __high2float(b2);
+        }
+    }
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_stream_kernel(const T* __restrict__ X, long long M, int N, long long rows_per_block, float* __restrict__ partial) {
+    constexpr int VEC = ColVec<T>::VEC;
+    __shared__ float red[256 * VEC];
+    const int cols_v = N / VEC, RG = 256 / cols_v;
+    const int cv = threadIdx.x % cols_v, rg = threadIdx.x / cols_v;
+    const long long m0 = (long long)blockIdx.x * rows_per_block;
+    const long long m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+    float acc[4][VEC];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[u][k] = 0.f;
+    if (rg < RG) {
+        long long m = m0 + rg;
+        for (; m + 3LL * RG < m1; m += 4LL * RG) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ColVec<T>::add(acc[u], X + (m + (long long)u * RG) * N + cv * VEC);
+        }
+        for (; m < m1; m += RG) ColVec<T>::add(acc[0], X + m * N + cv * VEC);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) red[threadIdx.x * VEC + k] = (acc[0][k] + acc[1][k]) + (acc[2][k] + acc[3][k]);
+    __syncthreads();
+    if (threadIdx.x < cols_v) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            float t = 0.f;
+            for (int g = 0; g < RG; ++g) t += red[(g * cols_v + threadIdx.x) * VEC + k];
+            partial[(size_t)blockIdx.x * N + threadIdx.x * VEC + k] = t;
+        }
+    }
+}
 // one warp per column: lanes stride over the partial rows, fixed shuffle tree: deterministic
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int blocks, int N, float* __restrict__ out) {
@@ -400,23 +456,30 @@ static int forward_net(mq_qnet* n, float* const* W, const float* obs, long long 
     return 0;
 }
 
-static void launch_colsum(mq_qnet* n, const float* X, long long M, int N, float* out, cudaStream_t s) {
+template <typename T>
+static void launch_colsum_t(mq_qnet* n, const T* X, long long M, int N, float* out, cudaStream_t s) {
+    constexpr int VEC = ColVec<T>::VEC;
+    if (N % VEC == 0 && N / VEC <= 256) {
+        int blocks = 4 * n->n_sms;
+        while (blocks > 1 && (size_t)blocks * N > n->partial_cap) blocks /= 2;
+        long long rows = (M + blocks - 1) / blocks;
+        if (rows < 64) rows = 64;
+        blocks = (int)((M + rows - 1) / rows);
+        colsum_stream_kernel<T><<<blocks, 256, 0, s>>>(X, M, N, rows, n->partial);
+        colsum_final_kernel<<<(N * 32 + 255) / 256, 256, 0, s>>>(n->partial, blocks, N, out);
+        n->launches += 2;
+        return;
+    }
     int rows = 256;
     int blocks = (int)((M + rows - 1) / rows);
     while ((size_t)blocks * N > n->partial_cap) { rows *= 2; blocks = (int)((M + rows - 1) / rows); }
-    colsum_partial_kernel<<<blocks, 256, 0, s>>>(X, M, N, rows, n->partial);
+    if (sizeof(T) == 4) colsum_partial_kernel<<<blocks, 256, 0, s>>>((const float*)X, M, N, rows, n->partial);
+    else bf::colsum_partial_bf16_kernel<<<blocks, 256, 0, s>>>((const bf::bf16*)X, M, N, rows, n->partial);
     colsum_final_kernel<<<(N * 32 + 255) / 256, 256, 0, s>>>(n->partial, blocks, N, out);
     n->launches += 2;
 }
-
-static void launch_colsum_bf16(mq_qnet* n, const bf::bf16* X, long long M, int N, float* out, cudaStream_t s) {
-    int rows = 256;
-    int blocks = (int)((M + rows - 1) / rows);
-    while ((size_t)blocks * N > n->partial_cap) { rows *= 2; blocks = (int)((M + rows - 1) / rows); }
-    bf::colsum_partial_bf16_kernel<<<blocks, 256, 0, s>>>(X, M, N, rows, n->partial);
-    colsum_final_kernel<<<(N * 32 + 255) / 256, 256, 0, s>>>(n->partial, blocks, N, out);
-    n->launches += 2;
-}
+static void launch_colsum(mq_qnet* n, const float* X, long long M, int N, float* out, cudaStream_t s) { launch_colsum_t<float>(n, X, M, N, out, s); }
+static void launch_colsum_bf16(mq_qnet* n, const bf::bf16* X, long long M, int N, float* out, cudaStream_t s) { launch_colsum_t<bf::bf16>(n, X, M, N, out, s); }
 
 // conv weight gradient on the tensor cores: split over samples so that ~one wave of CTAs runs, deterministic reduce
 template <int BN, int STAGES, int AW>
@@ -477,18 +540,20 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da3b; ep.ldc = FLAT; ep.mask_bf16 = n->a3b;
     if ((e = tc_gemm<128>(n, n->dh1b, H1, n->w1t, H1, (int)B, FLAT, H1, ep, false, s)) != cudaSuccess) return e;
-    // conv3: dWc3[(t,c)][n] = im2col(a2)^T dY (implicit, split over samples) ; db ; da2 = conv_flip(dY, Wd3) (masked by a2 > 0)
+    // conv3: dWc3[(t,c)][n] = im2col(a2)^T dY (implicit, split over samples) ; db ; da2 = conv_flip(dY, Wd3) (masked by a2 > 0).
+    // The data-gradient convolutions are L2-bandwidth bound (each sample's dY is read once per tap): two co-resident
+    // one-sample CTAs per SM keep more loads in flight than the persistent kernel and measure faster (profiles/README.md)
     launch_colsum_bf16(n, n->da3b, M, C3, G[P_C3B], s);
     if ((e = conv_wgrad<128, 3, 64>(n, n->a2b, n->da3b, B, C2, C3, G[P_C3W], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da2b; ep.ldc = C2; ep.mask_bf16 = n->a2b;
-    if ((e = tc::launch_conv_persistent<64, 64, 4>(n->da3b, n->w3d, B, C3, C2, 1, ep, n->n_sms, s)) != cudaSuccess) return e;
+    if ((e = tc::launch_conv<64, 4, 64>(n->da3b, n->w3d, B, C3, C2, 1, ep, s)) != cudaSuccess) return e;
     // conv2
     launch_colsum_bf16(n, n->da2b, M, C2, G[P_C2B], s);
     if ((e = conv_wgrad<64, 4, 32>(n, n->a1b, n->da2b, B, C1, C2, G[P_C2W], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_f32 = n->da1; ep.ldc = C1; ep.mask_f32 = n->a1;
-    if ((e = tc::launch_conv_persistent<32, 64, 4>(n->da2b, n->w2d, B, C2, C1, 1, ep, n->n_sms, s)) != cudaSuccess) return e;
+    if ((e = tc::launch_conv<32, 4, 64>(n->da2b, n->w2d, B, C2, C1, 1, ep, s)) != cudaSuccess) return e;
     n->launches += 2;
     // conv1 (fp32, 1 % of the flops)
     p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;

@@ -272,9 +272,11 @@ int mq_gemm_bf16_tn(const void* At, const void* Bt, float* C, int32_t M, int32_t
 /* 3x3 / padding 1 convolution over the 11x11 observation window as an implicit GEMM (nn.Conv2d(.., 3, padding=1) of
  * DQNNetwork, dqn_agent.py:22-24,48-50): Y[batch*121][Cout] f32 = im2col(X) * Wk^T with X [batch][11][11][Cin] bf16 (NHWC)
  * and Wk [Cout][9*Cin] bf16 (taps in (kh, kw, c) order).  The im2col matrix is never written: every tap is one shifted,
- * zero-filled 4-D TMA box.  flip = 1 mirrors the taps (the data-gradient convolution of loss.backward()). */
-int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, int64_t batch, int32_t Cin, int32_t Cout, int32_t flip, int32_t bn,
-                    void* stream);
+ * zero-filled 4-D TMA box.  flip = 1 mirrors the taps (the data-gradient convolution of loss.backward()).  Output in fp32
+ * (Y) and / or bf16 (Y_bf16).  bn = tile width 128 / 64 / 32, or 0 = the persistent kernel (weights resident in shared memory,
+ * double-buffered TMEM accumulators, TMA-store epilogue for a bf16-only output). */
+int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, void* Y_bf16, int64_t batch, int32_t Cin, int32_t Cout, int32_t flip,
+                    int32_t bn, void* stream);
 
 /* Weight gradient of that convolution: dW[9*Cin][Cout] f32 = im2col(X)^T * dY, dY [batch*121][Cout] bf16.  splits > 1
  * partitions the samples (workspace >= splits * 9*Cin*Cout floats). */

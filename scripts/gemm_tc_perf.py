@@ -52,10 +52,10 @@ for name, cin, cout, flip, bn in [("conv3 fwd", 64, 128, 0, 128), ("conv3 dgrad"
                                   ("conv2 dgrad", 64, 32, 1, 32)]:
     X = torch.randn((B, 11, 11, cin), device="cuda").to(torch.bfloat16)
     Wk = torch.randn((cout, 9 * cin), device="cuda").to(torch.bfloat16)
-    Y = torch.empty((M, cout), device="cuda")
+    Y = torch.empty((M, cout), device="cuda").to(torch.bfloat16)          # bf16 activations out, as in the Q-network
     fl = 2.0 * M * cout * 9 * cin
     for label, b in (("tile", bn), ("persistent", 0)):
-        ms = timeit(lambda: _lib.check(lib.mq_conv3x3_bf16(_lib.ptr(X), _lib.ptr(Wk), _lib.ptr(Y), B, cin, cout, flip, b, st), "conv"))
+        ms = timeit(lambda: _lib.check(lib.mq_conv3x3_bf16(_lib.ptr(X), _lib.ptr(Wk), None, _lib.ptr(Y), B, cin, cout, flip, b, st), "conv"))
         tf = fl / (ms * 1e-3) / 1e12
         print(f"{name:12s} {label:10s} Cin={cin:3d} Cout={cout:3d}  {ms:8.3f} ms  {tf:7.1f} TFLOP/s  {100*tf/peak:5.1f}% of {peak:.0f}")
 for name, cin, cout, splits in [("conv3 wgrad", 64, 128, 30), ("conv2 wgrad", 32, 64, 50)]:

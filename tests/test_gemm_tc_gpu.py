@@ -70,24 +70,32 @@ def _conv_ref(X, Wk, Cin, Cout, flip):
     return y.permute(0, 2, 3, 1).reshape(-1, Cout)
 
 
+@pytest.mark.parametrize("out", ["f32", "bf16"])
 @pytest.mark.parametrize("B,Cin,Cout,bn,flip", [(1, 64, 128, 128, 0), (5, 64, 128, 128, 0), (64, 64, 128, 128, 1), (37, 128, 64, 64, 1),
                                                 (16, 64, 32, 32, 1), (33, 32, 64, 64, 0), (300, 64, 128, 128, 0),
                                                 (1, 64, 128, 0, 0), (700, 64, 128, 0, 0), (333, 128, 64, 0, 1), (450, 64, 32, 0, 1),
                                                 (301, 32, 64, 0, 0)])
-def test_implicit_conv_matches_torch(B, Cin, Cout, bn, flip):
-    """3x3/pad-1 convolution as an implicit GEMM over shifted, zero-filled 4-D TMA boxes (no im2col buffer)."""
+def test_implicit_conv_matches_torch(B, Cin, Cout, bn, flip, out):
+    """3x3/pad-1 convolution as an implicit GEMM over shifted, zero-filled 4-D TMA boxes (no im2col buffer); bn = 0 is the
+    persistent kernel, whose bf16 output goes through the shared-memory + TMA-store epilogue."""
     from dqn_marl_b200 import _lib
     lib = _lib.load()
     g = torch.Generator(device="cuda:0"); g.manual_seed(B * 7 + Cin)
     X = torch.randn((B, 11, 11, Cin), generator=g, device="cuda:0").to(torch.bfloat16)
     Wk = (torch.randn((Cout, 9 * Cin), generator=g, device="cuda:0") / 8).to(torch.bfloat16)
-    Y = torch.full((B * 121, Cout), float("nan"), device="cuda:0")
-    _lib.check(lib.mq_conv3x3_bf16(_lib.ptr(X), _lib.ptr(Wk), _lib.ptr(Y), B, Cin, Cout, flip, bn, _stream()), "mq_conv3x3_bf16")
+    Y = torch.full((B * 121, Cout), float("nan"), device="cuda:0") if out == "f32" else None
+    Yb = torch.full((B * 121 + 7, Cout), 768.0, device="cuda:0").to(torch.bfloat16) if out == "bf16" else None    # 7 guard rows
+    _lib.check(lib.mq_conv3x3_bf16(_lib.ptr(X), _lib.ptr(Wk), _lib.ptr(Y), _lib.ptr(Yb), B, Cin, Cout, flip, bn, _stream()), "mq_conv3x3_bf16")
     torch.cuda.synchronize()
     ref = _conv_ref(X, Wk, Cin, Cout, flip)
-    err = (Y - ref).abs().max().item()
     scale = ref.abs().max().item()
-    assert err <= 2e-3 * scale + 1e-3, (B, Cin, Cout, bn, flip, err, scale)
+    if out == "f32":
+        err = (Y - ref).abs().max().item()
+        assert err <= 2e-3 * scale + 1e-3, (B, Cin, Cout, bn, flip, err, scale)
+    else:
+        assert torch.all(Yb[B * 121:].float() == 768.0), "rows past the last sample were written"
+        err = (Yb[:B * 121].float() - ref).abs().max().item()
+        assert err <= 1e-2 * scale + 1e-3, (B, Cin, Cout, bn, flip, err, scale)
 
 
 @pytest.mark.parametrize("B,Cin,Cout,splits", [(1, 64, 128, 1), (9, 64, 128, 1), (100, 64, 128, 7), (64, 128, 64, 4), (257, 64, 128, 29),
