@@ -127,7 +127,7 @@ fc3_wgrad_kernel(const float* __restrict__ dq, const float* __restrict__ h2, lon
 }
 __global__ void __launch_bounds__(256)
 fc3_dgrad_kernel(const float* __restrict__ dq, const float* __restrict__ w3, const float* __restrict__ h2, long long B,
-                 float* __restrict__ dh2) {
+                 float* __restrict__ dh2, __nv_bfloat16* __restrict__ dh2b) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * H2) return;
     const long long b = idx / H2;
@@ -135,7 +135,9 @@ fc3_dgrad_kernel(const float* __restrict__ dq, const float* __restrict__ w3, con
     float v = 0.f;
 #pragma unroll
     for (int a = 0; a < NA; ++a) v = fmaf(__ldg(dq + b * NA + a), __ldg(w3 + a * H2 + k), v);
-    dh2[idx] = h2[idx] > 0.f ? v : 0.f;
+    v = h2[idx] > 0.f ? v : 0.f;
+    dh2[idx] = v;
+    if (dh2b) dh2b[idx] = __float2bfloat16(v);
 }
 
 // ---- bias gradients: out[n] = sum_m X[m][n], two deterministic stages ---------------------------------------
@@ -333,7 +335,8 @@ struct mq_qnet {
     mq::bf::bf16 *w2f[2] = {nullptr, nullptr}, *w3f[2] = {nullptr, nullptr}, *w1f[2] = {nullptr, nullptr};   // forward operands
     mq::bf::bf16 *w2d = nullptr, *w3d = nullptr, *w1t = nullptr;                                              // dgrad operands (online)
     mq::bf::bf16 *a1b = nullptr, *a2b = nullptr, *a3b = nullptr;                     // NHWC activations (TMA operands)
-    mq::bf::bf16 *da3b = nullptr, *da2b = nullptr, *dh1b = nullptr;                  // activation grads
+    mq::bf::bf16 *da3b = nullptr, *da2b = nullptr, *dh1b = nullptr, *dh2b = nullptr; // activation grads
+    mq::bf::bf16 *h1b = nullptr, *wf2[2] = {nullptr, nullptr}, *wf2t = nullptr;      // fc2 operands: h1, W2 [256][512], W2^T [512][256]
 };
 
 namespace mq {
@@ -343,7 +346,7 @@ static void free_ws(mq_qnet* n) {
                      n->partial, n->norm_partial, n->gnorm};
     for (float* p : ptrs) cudaFree(p);
     bf::bf16* bptrs[] = {n->w2f[0], n->w2f[1], n->w3f[0], n->w3f[1], n->w1f[0], n->w1f[1], n->w2d, n->w3d, n->w1t, n->a1b, n->a2b,
-                         n->a3b, n->da3b, n->da2b, n->dh1b};
+                         n->a3b, n->da3b, n->da2b, n->dh1b, n->dh2b, n->h1b, n->wf2[0], n->wf2[1], n->wf2t};
     for (bf::bf16* p : bptrs) cudaFree(p);
 }
 
@@ -357,8 +360,9 @@ static cudaError_t alloc_bf16(mq_qnet* n) {
     auto alloc = [&](bf::bf16** p, size_t count) { if (ce == cudaSuccess) ce = cudaMalloc((void**)p, count * e); };
     for (int w = 0; w < 2; ++w) { alloc(&n->w2f[w], (size_t)C2 * 9 * C1); alloc(&n->w3f[w], (size_t)C3 * 9 * C2); alloc(&n->w1f[w], (size_t)H1 * FLAT); }
     alloc(&n->w2d, (size_t)C1 * 9 * C2); alloc(&n->w3d, (size_t)C2 * 9 * C3); alloc(&n->w1t, (size_t)FLAT * H1);
-    alloc(&n->a1b, M * C1); alloc(&n->a2b, M * C2); alloc(&n->a3b, M * C3);
-    if (n->tl.g[0]) { alloc(&n->da3b, M * C3); alloc(&n->da2b, M * C2); alloc(&n->dh1b, B * H1); }
+    alloc(&n->a1b, M * C1); alloc(&n->a2b, M * C2); alloc(&n->a3b, M * C3); alloc(&n->h1b, B * H1);
+    for (int w = 0; w < 2; ++w) alloc(&n->wf2[w], (size_t)H2 * H1);
+    if (n->tl.g[0]) { alloc(&n->da3b, M * C3); alloc(&n->da2b, M * C2); alloc(&n->dh1b, B * H1); alloc(&n->dh2b, B * H2); alloc(&n->wf2t, (size_t)H1 * H2); }
     return ce;
 }
 
@@ -370,7 +374,8 @@ static void refresh_weights(mq_qnet* n, int which, cudaStream_t s) {
     bf::conv_weight_bf16_kernel<<<ew_blocks(9 * C1 * C2), 256, 0, s>>>(W[P_C2W], n->w2f[which], bwd ? n->w2d : nullptr, C1, C2);
     bf::conv_weight_bf16_kernel<<<ew_blocks(9 * C2 * C3), 256, 0, s>>>(W[P_C3W], n->w3f[which], bwd ? n->w3d : nullptr, C2, C3);
     bf::cast_transpose_kernel<<<ew_blocks((long long)H1 * FLAT), 256, 0, s>>>(W[P_F1W], n->w1f[which], bwd ? n->w1t : nullptr, H1, FLAT);
-    n->launches += 3;
+    bf::cast_transpose_kernel<<<ew_blocks((long long)H2 * H1), 256, 0, s>>>(W[P_F2W], n->wf2[which], bwd ? n->wf2t : nullptr, H2, H1);
+    n->launches += 4;
     n->w_dirty[which] = false;
 }
 
@@ -389,7 +394,7 @@ static cudaError_t tc_gemm(mq_qnet* n, const bf::bf16* A, int lda, const bf::bf1
     n->launches += 1;
     if (e == cudaSuccess && splits > 1) {
         GemmParams p{};
-        p.M = M; p.N = N; p.C = final_out; p.ldc = ep.ldc; p.partial = n->partial; p.splits = splits;
+        p.M = M; p.N = N; p.C = final_out; p.Cb = ep.out_bf16; p.ldc = ep.ldc; p.partial = n->partial; p.splits = splits;
         p.bias = ep.bias; p.relu = ep.relu; p.drop = ep.drop; p.drop_scale = ep.drop_scale; p.mask_act = ep.mask_f32;
         size_t total = (size_t)M * N;
         int blocks = (int)((total + 255) / 256); if (blocks > 4 * n->n_sms) blocks = 4 * n->n_sms;
@@ -421,14 +426,14 @@ static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, lon
     e = tc::launch_conv_persistent<128, 64, 4>(n->a2b, n->w3f[which], B, C2, C3, 0, ep, n->n_sms, s);
     if (e != cudaSuccess) return e;
     ep = tc::Epilogue{};
-    ep.out_f32 = n->h1; ep.ldc = H1; ep.bias = W[P_F1B]; ep.relu = 1; ep.drop = drop_mask; ep.drop_scale = 1.f / (1.f - 0.2f);
+    ep.out_f32 = n->h1; ep.out_bf16 = n->h1b; ep.ldc = H1; ep.bias = W[P_F1B]; ep.relu = 1; ep.drop = drop_mask; ep.drop_scale = 1.f / (1.f - 0.2f);
     e = tc_gemm<128>(n, n->a3b, FLAT, n->w1f[which], FLAT, (int)B, H1, FLAT, ep, true, s);
     if (e != cudaSuccess) return e;
     n->launches += 2;
-    p = GemmParams{};
-    p.batch = (int)B; p.partial = n->partial; p.relu = 1;
-    p.M = (int)B; p.N = H2; p.K = H1; p.A = n->h1; p.lda = H1; p.B = W[P_F2W]; p.ldb = H1; p.C = n->h2; p.ldc = H2; p.bias = W[P_F2B];
-    n->launches += launch_gemm<A_ROW, B_COL, 64, 1>(p, n->partial_cap, n->n_sms, s);
+    ep = tc::Epilogue{};
+    ep.out_f32 = n->h2; ep.ldc = H2; ep.bias = W[P_F2B]; ep.relu = 1;
+    e = tc_gemm<128>(n, n->h1b, H1, n->wf2[which], H1, (int)B, H2, H1, ep, false, s);
+    if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }
 
@@ -517,20 +522,32 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
         colsum_final_kernel<<<(NA * 32 + 255) / 256, 256, 0, s>>>(pb, chunks, NA, G[P_F3B]);
         n->launches += 2;
     }
-    fc3_dgrad_kernel<<<(int)((B * H2 + 255) / 256), 256, 0, s>>>(n->dq, W[P_F3W], n->h2, B, n->dh2);
+    fc3_dgrad_kernel<<<(int)((B * H2 + 255) / 256), 256, 0, s>>>(n->dq, W[P_F3W], n->h2, B, n->dh2, n->dh2b);
     n->launches += 2;
     GemmParams p{};
-    p.batch = (int)B; p.partial = n->partial;
-    p.M = H2; p.N = H1; p.K = (int)B; p.A = n->dh2; p.lda = H2; p.B = n->h1; p.ldb = H1; p.C = G[P_F2W]; p.ldc = H1;
-    n->launches += launch_gemm<A_COL, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    // fc2 on the tensor cores: dW2[256][512] = dh2^T h1 (MN-major operands, split over the batch) ; db2 ; dh1 = dh2 W2 masked
+    // by relu(fc1) > 0 and the dropout mask
+    tc::Epilogue ep{};
+    {
+        int splits = 16;
+        while (splits > 1 && (size_t)splits * H2 * H1 > n->partial_cap) --splits;
+        ep.out_f32 = G[P_F2W]; ep.ldc = H1; ep.partial = n->partial;
+        if ((e = tc::launch_tn<128, 3>(n->dh2b, H2, n->h1b, H1, H2, H1, (int)B, ep, &splits, s)) != cudaSuccess) return e;
+        n->launches += 1;
+        if (splits > 1) {
+            p = GemmParams{};
+            p.M = H2; p.N = H1; p.C = G[P_F2W]; p.ldc = H1; p.partial = n->partial; p.splits = splits;
+            splitk_epilogue_kernel<<<(H2 * H1 + 255) / 256, 256, 0, s>>>(p);
+            n->launches += 1;
+        }
+    }
     launch_colsum(n, n->dh2, B, H2, G[P_F2B], s);
-    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
-    p.M = (int)B; p.N = H1; p.K = H2; p.A = n->dh2; p.lda = H2; p.B = W[P_F2W]; p.ldb = H1; p.C = n->dh1; p.ldc = H1;
-    p.mask_act = n->h1; p.drop = drop_online; p.drop_scale = 1.f / (1.f - 0.2f); p.Cb = n->dh1b;
-    n->launches += launch_gemm<A_ROW, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    ep = tc::Epilogue{};
+    ep.out_f32 = n->dh1; ep.out_bf16 = n->dh1b; ep.ldc = H1; ep.mask_f32 = n->h1; ep.drop = drop_online; ep.drop_scale = 1.f / (1.f - 0.2f);
+    if ((e = tc_gemm<128>(n, n->dh2b, H2, n->wf2t, H2, (int)B, H1, H2, ep, false, s)) != cudaSuccess) return e;
     launch_colsum(n, n->dh1, B, H1, G[P_F1B], s);
     // fc1 on the tensor cores: dW1 = dh1^T a3 (both operands MN-major: no transposes) ; da3 = dh1 W1 (masked by a3 > 0)
-    tc::Epilogue ep{};
+    ep = tc::Epilogue{};
     ep.out_f32 = G[P_F1W]; ep.ldc = FLAT;
     {
         int one = 1;
@@ -693,7 +710,7 @@ extern "C" int mq_qnet_td_backward(mq_qnet* n, const float* state, const int64_t
         colsum_final_kernel<<<(NA * 32 + 255) / 256, 256, 0, s>>>(pb, chunks, NA, G[P_F3B]);
         n->launches += 2;
     }
-    fc3_dgrad_kernel<<<(int)((B * H2 + 255) / 256), 256, 0, s>>>(n->dq, W[P_F3W], n->h2, B, n->dh2);
+    fc3_dgrad_kernel<<<(int)((B * H2 + 255) / 256), 256, 0, s>>>(n->dq, W[P_F3W], n->h2, B, n->dh2, nullptr);
     n->launches += 2;
     GemmParams p{};
     p.batch = (int)B; p.partial = n->partial;
