@@ -80,6 +80,7 @@ struct Smem {
     uint32_t* bm; uint32_t* pos;
     int* leaf_off; int* leaf_len;
     uint16_t* mov; uint32_t* mv;
+    uint16_t* hurt;      // per-warp lists of the people standing in danger this step (T + N entries, T = threads of the group)
     uint8_t* fl;
 };
 
@@ -89,7 +90,7 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 // occupancy bitmap and the pairwise-sum leaf tables stay in shared memory, the per-person arrays and the proposal
 // table live in a per-env global scratch area (returns the shared bytes; *gbytes receives the scratch bytes).
 __host__ __device__ inline size_t carve(Smem& s, unsigned char* base, unsigned char* gbase, int N, int cap, int words, int nleaf,
-                                        size_t* gbytes = nullptr) {
+                                        int T, size_t* gbytes = nullptr) {
     size_t o = 0, go = 0;
     unsigned char* pb = gbase ? gbase : base;          // where the per-person arrays go
     size_t& po = gbase ? go : o;
@@ -103,6 +104,7 @@ __host__ __device__ inline size_t carve(Smem& s, unsigned char* base, unsigned c
     s.pos = (uint32_t*)(pb + po); po += align_up(sizeof(uint32_t) * N, 16);
     s.mv = (uint32_t*)(pb + po); po += align_up(sizeof(uint32_t) * N, 16);
     s.mov = (uint16_t*)(pb + po); po += align_up(sizeof(uint16_t) * N, 16);
+    s.hurt = (uint16_t*)(pb + po); po += align_up(sizeof(uint16_t) * (N + T), 16);
     s.fl = (uint8_t*)(pb + po); po += align_up(N, 16);
     s.leaf_sum = (double*)(base + o); o += sizeof(double) * nleaf;
     o = align_up(o, 16);
@@ -263,7 +265,7 @@ env_reset_kernel(DevLayout lay, DevCfg cfg, DevState st, const uint8_t* env_mask
     if (env_mask && !env_mask[env]) return;
     Smem sm;
     carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
-          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
+          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE);
     int* sc = s_sc[g.gid];
     int(*rob)[2] = s_rob[g.gid];
     if (g.gtid < MQ_ENV_SCALARS) sc[g.gtid] = st.scalars[(size_t)env * MQ_ENV_SCALARS + g.gtid];
@@ -363,7 +365,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     if (env >= cfg.n_envs) return;              // whole group leaves together (GROUPS == 1 when WPE == CW)
     Smem sm;
     carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
-          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max);
+          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE);
     int* sc = s_sc[g.gid];
     int(*rob)[2] = s_rob[g.gid];
     int* s_cnt = s_cnt_all[g.gid];
@@ -411,7 +413,37 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     }
 
     // ---- phase 1 (people.py:203-220): health, speed, accumulator; movers are compacted.
-    //      State of PF persons per thread is fetched up front so the DRAM round trips overlap. ----
+    //      State of PF persons per thread is fetched up front so the DRAM round trips overlap.  The few people that stand
+    //      in danger are only LISTED here (per warp) and get their health update in a compact second pass: the keyed draw
+    //      and the loss arithmetic then run once per 32 of them instead of once per loop iteration. ----
+    uint16_t* const my_hurt = sm.hurt + (size_t)warp * (((N + T - 1) / T) * 32);
+    int n_hurt = 0;                              // warp-uniform
+    // Person.update_state speed (people.py:38-44), accumulator (people.py:216-220), shared-memory copies; returns "moves"
+    auto advance = [&](int i, uint32_t fl, double h, double a) -> bool {
+        bool mover = false;
+        if (!(fl & 2u)) {
+            const double speed = (h < 20.0) ? 0.4 : 1.0 * (0.3 + 0.7 * (h / 100.0));
+            a += speed * 0.5;
+            if (a >= 1.0) { a -= 1.0; mover = true; }
+            st.acc[base + i] = a;
+        }
+        sm.fl[i] = (uint8_t)fl;
+        sm.health[i] = (fl & 2u) ? 0.0 : h;          // summand of evacuation_env.py:245 (dead -> +0.0)
+        return mover;
+    };
+    auto push_movers = [&](bool mover, int i) {
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mover);
+        if (bal) {
+            int wbase = 0;
+            if (lane == 0) wbase = atomicAdd(&s_cnt[4], __popc(bal));
+            wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+            if (mover) {
+                const int mi = wbase + __popc(bal & ((1u << lane) - 1u));
+                sm.mov[mi] = (uint16_t)i;
+                sm.mv[mi] = 0xFFFFFFFFu;
+            }
+        }
+    };
     for (int i0 = 0; i0 < N; i0 += T * PF) {
         uint32_t p_[PF], fl_[PF];
         double h_[PF], a_[PF], dg_[PF];
@@ -428,52 +460,50 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         for (int k = 0; k < PF; ++k) {
             const int i = i0 + k * T + tid;
             if (i0 + k * T >= N) break;                       // uniform over the warp
-            bool mover = false;
+            bool mover = false, hurt = false;
             if (i < N) {
-                uint32_t fl = fl_[k];
-                double h = h_[k];
-                if (!(fl & 3u)) {
-                    double a = a_[k];
-                    const double danger = dg_[k];
-                    if (danger > 0.0) {                                   // Person.update_health (people.py:61-88)
-                        const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
-                        const double u = u53(w4.x, w4.y);
-                        double loss;
-                        if (danger >= 0.8) loss = danger * 50.0 + (1.0 + (3.0 - 1.0) * u);
-                        else if (danger >= 0.5) loss = danger * 40.0 + (0.8 + (2.0 - 0.8) * u);
-                        else if (danger >= 0.2) loss = danger * 30.0 + (0.5 + (1.5 - 0.5) * u);
-                        else loss = danger * 20.0 + (0.2 + (1.0 - 0.2) * u);
-                        if (h < 50.0) loss *= 1.2;
-                        h -= loss;
-                        if (h <= 0.0) { h = 0.0; fl |= 2u; } else if (h <= 8.0) fl |= 2u;
-                        h = fmax(0.0, fmin(h, 100.0));
-                        st.health[base + i] = h;
-                        if (fl & 2u) st.flags[base + i] = (uint8_t)fl;
-                    }
-                    if (!(fl & 2u)) {
-                        // Person.update_state speed (people.py:38-44), then accumulator (people.py:216-220)
-                        const double speed = (h < 20.0) ? 0.4 : 1.0 * (0.3 + 0.7 * (h / 100.0));
-                        a += speed * 0.5;
-                        if (a >= 1.0) { a -= 1.0; mover = true; }
-                        st.acc[base + i] = a;
-                    }
-                }
+                const uint32_t fl = fl_[k];
                 sm.pos[i] = p_[k];
-                sm.fl[i] = (uint8_t)fl;
-                sm.health[i] = (fl & 2u) ? 0.0 : h;          // summand of evacuation_env.py:245 (dead -> +0.0)
+                if (fl & 3u) { sm.fl[i] = (uint8_t)fl; sm.health[i] = (fl & 2u) ? 0.0 : h_[k]; }
+                else if (dg_[k] > 0.0) hurt = true;
+                else mover = advance(i, fl, h_[k], a_[k]);
             }
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, mover);
-            if (bal) {
-                int wbase = 0;
-                if (lane == 0) wbase = atomicAdd(&s_cnt[4], __popc(bal));
-                wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-                if (mover) {
-                    const int mi = wbase + __popc(bal & ((1u << lane) - 1u));
-                    sm.mov[mi] = (uint16_t)i;
-                    sm.mv[mi] = 0xFFFFFFFFu;
-                }
+            const uint32_t hb = __ballot_sync(0xFFFFFFFFu, hurt);
+            if (hb) {
+                if (hurt) my_hurt[n_hurt + __popc(hb & ((1u << lane) - 1u))] = (uint16_t)i;
+                n_hurt += __popc(hb);
             }
+            push_movers(mover, i);
         }
+    }
+    __syncwarp();
+    for (int e0 = 0; e0 < n_hurt; e0 += 32) {                 // Person.update_health (people.py:61-88), compact
+        const int e = e0 + lane;
+        bool mover = false;
+        int i = 0;
+        if (e < n_hurt) {
+            i = my_hurt[e];
+            const uint32_t p = sm.pos[i];
+            double h = st.health[base + i];
+            const double a = st.acc[base + i];
+            uint32_t fl = 0u;
+            const double danger = box_lookup(lay.ctr_box, lay.danger_ctr, fire_step, (int)(p & 0xFFFFu), (int)(p >> 16));
+            const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
+            const double u = u53(w4.x, w4.y);
+            double loss;
+            if (danger >= 0.8) loss = danger * 50.0 + (1.0 + (3.0 - 1.0) * u);
+            else if (danger >= 0.5) loss = danger * 40.0 + (0.8 + (2.0 - 0.8) * u);
+            else if (danger >= 0.2) loss = danger * 30.0 + (0.5 + (1.5 - 0.5) * u);
+            else loss = danger * 20.0 + (0.2 + (1.0 - 0.2) * u);
+            if (h < 50.0) loss *= 1.2;
+            h -= loss;
+            if (h <= 0.0) { h = 0.0; fl |= 2u; } else if (h <= 8.0) fl |= 2u;
+            h = fmax(0.0, fmin(h, 100.0));
+            st.health[base + i] = h;
+            if (fl & 2u) st.flags[base + i] = (uint8_t)fl;
+            mover = advance(i, fl, h, a);
+        }
+        push_movers(mover, i);
     }
     g.sync();
 
@@ -539,19 +569,33 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                     const int od = __shfl_xor_sync(0xFFFFFFFFu, best_dir, o);
                     if (os > best_score || (os == best_score && od < best_dir)) { best_score = os; best_dir = od; }
                 }
-                if (act && q == 0 && best_dir < 8) {
-                    const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
-                    const uint32_t t = (uint32_t)((x + move_dx(best_dir)) * stride + (y + move_dy(best_dir)));
-                    uint32_t hh = hash_cell(t, cfg.hash_shift);
-                    for (;;) {                                 // move_plan[(new_x,new_y)] (people.py:228-230)
-                        const uint32_t prev = atomicCAS(&sm.tab[hh].key, HEMPTY, t);
-                        if (prev == HEMPTY || prev == t) break;
-                        hh = (hh + 1) & hmask;
-                    }
-                    atomicMin(&sm.tab[hh].ml, (uint32_t)i);                      // leave half is still 0
-                    atomicMin(&sm.tab[hh].best, ((unsigned long long)w4.z << 32) | (unsigned long long)i);
-                    sm.mv[mi] = hh | ((uint32_t)best_dir << 20);
+                if (act && q == 0 && best_dir < 8) sm.mv[mi] = (uint32_t)best_dir << 20;
+            }
+            // proposals, one mover per lane: the movers this warp has just scored (8 per scoring iteration), so only a
+            // __syncwarp separates the two loops.  move_plan[(new_x,new_y)] (people.py:228-230) + shuffle priority (:239)
+            __syncwarp();
+            const int w0 = (wt & ~31);                            // first worker thread id of this warp
+            for (int itb = w0; itb < n_items; itb += 4 * TW) {
+                const int mi = ((itb + (lane >> 3) * TW) >> 2) + (lane & 7);
+                const bool in_iter = itb + (lane >> 3) * TW < n_items;
+                if (!in_iter || mi >= n_mov) continue;
+                const uint32_t mv = sm.mv[mi];
+                if (mv == 0xFFFFFFFFu) continue;
+                const int i = sm.mov[mi];
+                const int best_dir = (int)(mv >> 20);
+                const uint32_t p = sm.pos[i];
+                const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
+                const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
+                const uint32_t t = (uint32_t)((x + move_dx(best_dir)) * stride + (y + move_dy(best_dir)));
+                uint32_t hh = hash_cell(t, cfg.hash_shift);
+                for (;;) {
+                    const uint32_t prev = atomicCAS(&sm.tab[hh].key, HEMPTY, t);
+                    if (prev == HEMPTY || prev == t) break;
+                    hh = (hh + 1) & hmask;
                 }
+                atomicMin(&sm.tab[hh].ml, (uint32_t)i);                      // leave half is still 0
+                atomicMin(&sm.tab[hh].best, ((unsigned long long)w4.z << 32) | (unsigned long long)i);
+                sm.mv[mi] = hh | ((uint32_t)best_dir << 20);
             }
         }
         g.wsync();
@@ -865,16 +909,17 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
     c.scratch = nullptr; c.scratch_per_env = 0;
-    c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max);
+    c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 32);
     // one warp per env for small envs (no CTA barriers, 4 envs per CTA), one CTA per env otherwise; envs whose
     // person arrays do not fit shared memory keep only the occupancy bitmap there (BIG)
     e->wpe = (c.N <= 256 && (size_t)c.smem_per_env * SMALL_CW + 2048 <= (size_t)max_smem) ? 1 : 8;
+    if (e->wpe == 8) c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 256);
     e->big = e->wpe == 8 && (size_t)c.smem_per_env + 2048 > (size_t)max_smem;
     if (e->big) {
         e->wpe = BIG_WPE;                              // one CTA per SM (shared-memory bound): make it a wide one
         if (const char* v = getenv("MQ_BIG_WPE")) { int w = atoi(v); if (w == 8 || w == 16 || w == 32) e->wpe = w; }
         size_t gbytes = 0;
-        c.smem_per_env = (int)mq::carve(tmp, nullptr, (unsigned char*)16, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, &gbytes);
+        c.smem_per_env = (int)mq::carve(tmp, nullptr, (unsigned char*)16, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 32 * e->wpe, &gbytes);
         c.scratch_per_env = (long long)gbytes;
         if ((ce = cudaMalloc(&e->d_scratch, gbytes * (size_t)c.n_envs)) != cudaSuccess) {
             mq_env_destroy(e);

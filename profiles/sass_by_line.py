@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Aggregate an ncu SASS source page (`ncu -i X.ncu-rep --page source --csv --print-source sass`) per CUDA source
 line, using `nvdisasm -g -c <cubin>` output for the address -> line map.
-usage: sass_by_line.py sass.csv disasm.txt kernel_substring [launch_index]"""
+usage: sass_by_line.py sass.csv disasm.txt kernel_substring [launch_index] [top_n, 0 = all lines]"""
 import csv
 import re
 import sys
@@ -9,6 +9,7 @@ from collections import defaultdict
 
 sass_csv, disasm, kname = sys.argv[1:4]
 launch = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+top_n = int(sys.argv[5]) if len(sys.argv) > 5 else 60
 
 # 1. ordered list of source lines per instruction of the kernel from nvdisasm
 lines = open(disasm).read().split("\n")
@@ -42,5 +43,5 @@ for r, ln in zip(body, instr_lines):
         tot[k] += v[k]
 print(f"total warp-inst {tot[0]}  thread-inst {tot[1]}  samples {tot[2]}")
 print(f"{'file:line':28s} {'warp-inst':>10s} {'%':>6s} {'thr/inst':>8s} {'samples':>8s} {'%':>6s}")
-for ln, v in sorted(agg.items(), key=lambda kv: -kv[1][2])[:60]:
+for ln, v in sorted(agg.items(), key=lambda kv: -kv[1][2])[:(top_n if top_n > 0 else None)]:
     print(f"{str(ln[0]) + ':' + str(ln[1]):28s} {v[0]:10d} {100 * v[0] / tot[0]:6.2f} {v[1] / max(v[0], 1):8.1f} {v[2]:8d} {100 * v[2] / max(tot[2], 1):6.2f}")
