@@ -150,6 +150,36 @@ class VecEvacuationEnv:
         _lib.check(self.lib.mq_env_step(self._h, _lib.ptr(actions_i32), _lib.ptr(obs), None, _lib.ptr(reward), _lib.ptr(done),
                                         self._stream()), "mq_env_step")
 
+    # ---- host-buffer interface (gym-style step_async / step_wait) ------------------------------------------------
+    def step_async(self, actions_host: torch.Tensor):
+        """Enqueue one step driven from HOST memory on this env batch's own stream: H2D of the (pinned) int32 actions,
+        the fused step kernel, D2H of obs / reward / done into pinned host buffers.  Returns immediately; several env
+        batches can be in flight so that the PCIe copies of one overlap the kernel of another.  `step_wait()` returns the
+        host tensors.  (The reference's step() is synchronous and host-side: evacuation_env.py:122-172.)"""
+        if getattr(self, "_hs", None) is None:
+            self._hs = torch.cuda.Stream(device=self.device)
+            self._hev = torch.cuda.Event()
+            self._d_act = torch.empty((self.n_envs, self.n_robots), dtype=torch.int32, device=self.device)
+            self.h_obs = torch.empty(self.obs.shape, dtype=torch.float32).pin_memory()
+            self.h_reward = torch.empty((self.n_envs,), dtype=torch.float64).pin_memory()
+            self.h_done = torch.empty((self.n_envs,), dtype=torch.uint8).pin_memory()
+            self._hs.wait_stream(torch.cuda.current_stream(self.device))        # resets / earlier steps on the caller's stream
+        a = actions_host.reshape(self.n_envs, self.n_robots)
+        assert a.dtype == torch.int32 and a.device.type == "cpu"
+        with torch.cuda.stream(self._hs):
+            self._d_act.copy_(a, non_blocking=True)
+            _lib.check(self.lib.mq_env_step(self._h, _lib.ptr(self._d_act), _lib.ptr(self.obs), None, _lib.ptr(self.reward),
+                                            _lib.ptr(self.done), C.c_void_p(self._hs.cuda_stream)), "mq_env_step")
+            self.h_obs.copy_(self.obs, non_blocking=True)
+            self.h_reward.copy_(self.reward, non_blocking=True)
+            self.h_done.copy_(self.done, non_blocking=True)
+            self._hev.record(self._hs)
+
+    def step_wait(self):
+        """Block until the step enqueued by step_async() has landed in host memory -> (obs, reward, done) pinned host tensors."""
+        self._hev.synchronize()
+        return self.h_obs, self.h_reward, self.h_done
+
     def rmap_bytes(self) -> torch.Tensor:
         """People.rmap of every env as uint8 (E, L+2, W+2)."""
         out = torch.empty((self.n_envs, self.layout.L + 2, self.layout.W + 2), dtype=torch.uint8, device=self.device)

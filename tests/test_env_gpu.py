@@ -252,3 +252,25 @@ def test_c5_shape_matches_oracle():
     from dqn_marl_b200.layout import Layout
     lay = Layout.synthetic(1024, 1024, n_exits=8, wall_fill=0.15, seed=2024)
     _run_vs_oracle(lay, n_envs=2, N=20000, seed=5, steps=6, check_every=1)
+
+
+def test_host_buffer_step_async_equals_device_step():
+    """VecEvacuationEnv.step_async/step_wait (pinned host actions in, pinned host obs/reward/done out, own stream) gives
+    exactly the trajectory of the device-resident step()."""
+    from dqn_marl_b200.layout import Layout
+    lay = Layout.reference_room()
+    a = _vec(lay, 64, 150, seed=7)
+    b = _vec(lay, 64, 150, seed=7)
+    a.reset(); b.reset()
+    rng = np.random.default_rng(3)
+    for t in range(25):
+        acts = torch.from_numpy(rng.integers(0, 5, size=(64, 1)).astype(np.int32))
+        ha = acts.pin_memory()
+        b.step_async(ha)
+        obs, r, d = a.step(acts.cuda())
+        ho, hr, hd = b.step_wait()
+        assert torch.equal(obs.cpu(), ho) and torch.equal(r.cpu(), hr) and torch.equal(d.cpu(), hd), t
+    for k in (0, 63):
+        sa, sb = a.snapshot(k), b.snapshot(k)
+        for key in ("px", "py", "health", "acc", "flags", "rmap"):
+            assert np.array_equal(sa[key], sb[key]), (key, k)
