@@ -26,20 +26,48 @@ from . import qnet_params as qp
 from .qnet import QNet
 
 
+class _QFunction(torch.autograd.Function):
+    """Q = q_network(x) as an autograd node: forward = mq_qnet_forward, backward = mq_qnet_backward (the CUDA backward
+    kernels of csrc/qnet.cu fed with the incoming dL/dQ).  The parameter gradients land in the agent's flat gradient
+    buffer — the tensors `q_network.parameters()` expose as `.grad` — not in autograd's own accumulators; the observation
+    gets no gradient (neither does it in the reference: the batch tensors are leaves without requires_grad)."""
+
+    @staticmethod
+    def forward(ctx, x, token, view, mask):
+        ctx.view, ctx.mask = view, mask
+        ctx.save_for_backward(x)
+        return view._a.net.forward(x, "online", mask)
+
+    @staticmethod
+    def backward(ctx, dq):
+        (x,) = ctx.saved_tensors
+        ctx.view._a.net.backward(x, dq, ctx.mask)
+        return None, None, None, None
+
+
 class _NetworkView:
     """`agent.q_network` / `agent.target_network`: callable on a (B,11,11,6) tensor, state_dict()/load_state_dict()/
-    parameters() like the reference's nn.Module (used by train_dqn.py:75, train_qmix.py:92-100).  Forward only: it
-    does not record an autograd graph (the QMIX mixer of train_qmix.py is a later row of SURVEY.md §8f)."""
+    parameters() like the reference's nn.Module (used by train_dqn.py:75, train_qmix.py:92-100).  Under
+    torch.enable_grad() the online network's output carries an autograd node (`_QFunction`), so a loss a runner builds on
+    it — train_qmix.py mixes two agents' Q-values first — back-propagates into this agent's gradient buffer with one
+    `loss.backward()`; `optimizer.zero_grad()/step()` and `clip_grad_norm_(q_network.parameters(), ..)` then act on it.
+    One backward per zero_grad(): the kernels overwrite the gradient buffer instead of accumulating."""
 
     def __init__(self, agent: "DQNAgent", which: str):
         self._a, self._which = agent, which
         self.training = True
+        self._token = None
 
     def __call__(self, x):
         a = self._a
         if x.dim() == 3:
             x = x.unsqueeze(0)
         mask = a._mask(x.shape[0]) if (self.training and a.dropout_mode == "train") else None
+        if self._which == "online" and torch.is_grad_enabled() and a.net.trainable:
+            if self._token is None:       # a leaf that requires grad makes autograd call _QFunction.backward
+                self._token = torch.zeros((), device=a.net.device, requires_grad=True)
+            x = x.to(device=a.net.device, dtype=torch.float32).contiguous()
+            return _QFunction.apply(x, self._token, self, mask)
         return a.net.forward(x, self._which, mask)
 
     forward = __call__
@@ -59,8 +87,17 @@ class _NetworkView:
         self._a.net.load_state_dict(sd, self._which)
 
     def parameters(self):
-        flat = self._a.net.flat_p if self._which == "online" else self._a.net.flat_t
-        return [flat[qp.OFFSETS[k]:qp.OFFSETS[k] + qp.NUMEL[k]] for k in range(len(qp.NAMES))]
+        """The 12 parameter tensors as views of the flat buffer (kernel layouts); for the online network `.grad` is the
+        matching view of the flat gradient buffer, so torch.nn.utils.clip_grad_norm_ works on them."""
+        online = self._which == "online"
+        flat = self._a.net.flat_p if online else self._a.net.flat_t
+        out = []
+        for k in range(len(qp.NAMES)):
+            t = flat[qp.OFFSETS[k]:qp.OFFSETS[k] + qp.NUMEL[k]]
+            if online and self._a.net.trainable:
+                t.grad = self._a.net.flat_g[qp.OFFSETS[k]:qp.OFFSETS[k] + qp.NUMEL[k]]
+            out.append(t)
+        return out
 
     def to(self, *_a, **_k):
         return self

@@ -105,6 +105,15 @@ class QNet:
                    "mq_qnet_td_backward")
         return self._loss
 
+    def backward(self, obs: torch.Tensor, dq: torch.Tensor, drop_mask: Optional[torch.Tensor] = None):
+        """Gradients of the online parameters for an external dL/dQ (B,5) (mq_qnet_backward): fills flat_g."""
+        B = obs.shape[0]
+        obs = obs.to(device=self.device, dtype=torch.float32).contiguous()
+        dq = dq.to(device=self.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.mq_qnet_backward(self._h, _lib.ptr(obs), _lib.ptr(dq), B, _lib.ptr(drop_mask), self._stream()),
+                       "mq_qnet_backward")
+
     def clip_adam(self, hp: "_lib.MqHparams", grad_scale: float = 1.0) -> torch.Tensor:
         _lib.check(self.lib.mq_qnet_clip_adam(self._h, C.byref(hp), float(grad_scale), _lib.ptr(self._gnorm), self._stream()),
                    "mq_qnet_clip_adam")

@@ -670,37 +670,9 @@ extern "C" int mq_qnet_act(mq_qnet* n, const float* obs, int64_t B, float eps, u
     return MQ_OK;
 }
 
-extern "C" int mq_qnet_td_backward(mq_qnet* n, const float* state, const int64_t* action, const float* reward, const float* next_state,
-                                   const uint8_t* done, int64_t B, const mq_hparams* hp, const uint8_t* drop_online,
-                                   const uint8_t* drop_target, float* loss_out, void* stream) {
+// backward of the fp32 parity path from n->dq (loss.backward(), dqn_agent.py:154-155); the online activations are in the workspace
+static void backward_fp32(mq_qnet* n, const float* state, long long B, const uint8_t* drop_online, cudaStream_t s) {
     using namespace mq;
-    MQ_REQUIRE(n && state && action && reward && next_state && done && hp && loss_out, "mq_qnet_td_backward: null argument");
-    MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_td_backward: batch %lld outside 1..%lld", (long long)B, n->max_batch);
-    MQ_REQUIRE(n->tl.g[0] && n->da3, "mq_qnet_td_backward: handle was created without gradient buffers");
-    cudaStream_t s = (cudaStream_t)stream;
-    const int hb = (int)((B * 32 + 255) / 256);
-    // next_q = target_network(next_states).max(1)[0]   (dqn_agent.py:146-147)
-    const bool bf16 = n->precision == 1;
-    MQ_REQUIRE(!bf16 || B % 8 == 0, "mq_qnet_td_backward: the bf16 path needs a batch that is a multiple of 8 (got %lld)", (long long)B);
-    cudaError_t fe = cudaSuccess;
-    if (bf16) fe = forward_net_bf16(n, 1, next_state, B, drop_target, s);
-    else forward_net(n, n->tl.t, next_state, B, drop_target, s);
-    qhead_kernel<<<hb, 256, 0, s>>>(n->h2, n->tl.t[P_F3W], n->tl.t[P_F3B], B, 3, nullptr, nullptr, n->maxq, nullptr, 0.f, 0, 0, 0, 1);
-    // current_q = q_network(states).gather(1, actions)   (dqn_agent.py:143)
-    if (bf16 && fe == cudaSuccess) fe = forward_net_bf16(n, 0, state, B, drop_online, s);
-    else if (!bf16) forward_net(n, n->tl.p, state, B, drop_online, s);
-    if (fe != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_td_backward (bf16 forward): %s", cudaGetErrorString(fe));
-    qhead_kernel<<<hb, 256, 0, s>>>(n->h2, n->tl.p[P_F3W], n->tl.p[P_F3B], B, 2, nullptr, (const long long*)action, n->q_sa, nullptr, 0.f,
-                                    0, 0, 0, 1);
-    td_loss_kernel<<<1, 1024, 0, s>>>(n->q_sa, n->maxq, reward, done, (const long long*)action, B, hp->gamma, hp->huber, n->dq, loss_out);
-    n->launches += 3;
-
-    // ---- backward (loss.backward(), dqn_agent.py:154-155) ----
-    if (bf16) {
-        cudaError_t be = backward_bf16(n, state, B, drop_online, s);
-        if (be != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_td_backward (bf16 backward): %s", cudaGetErrorString(be));
-        return MQ_OK;
-    }
     float* const* W = n->tl.p; float* const* G = n->tl.g;
     {
         const int chunks = (int)((B + FC3_CHUNK - 1) / FC3_CHUNK);
@@ -752,6 +724,69 @@ extern "C" int mq_qnet_td_backward(mq_qnet* n, const float* state, const int64_t
     p.M = 9 * CIN; p.N = C1; p.K = M; p.A = state; p.B = n->da1; p.ldb = C1; p.C = G[P_C1W]; p.ldc = C1;
     n->launches += launch_gemm<A_IM2COL_T, B_ROW, 32, CIN>(p, n->partial_cap, n->n_sms, s);
     launch_colsum(n, n->da1, M, C1, G[P_C1B], s);
+}
+
+extern "C" int mq_qnet_td_backward(mq_qnet* n, const float* state, const int64_t* action, const float* reward, const float* next_state,
+                                   const uint8_t* done, int64_t B, const mq_hparams* hp, const uint8_t* drop_online,
+                                   const uint8_t* drop_target, float* loss_out, void* stream) {
+    using namespace mq;
+    MQ_REQUIRE(n && state && action && reward && next_state && done && hp && loss_out, "mq_qnet_td_backward: null argument");
+    MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_td_backward: batch %lld outside 1..%lld", (long long)B, n->max_batch);
+    MQ_REQUIRE(n->tl.g[0] && n->da3, "mq_qnet_td_backward: handle was created without gradient buffers");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int hb = (int)((B * 32 + 255) / 256);
+    // next_q = target_network(next_states).max(1)[0]   (dqn_agent.py:146-147)
+    const bool bf16 = n->precision == 1;
+    MQ_REQUIRE(!bf16 || B % 8 == 0, "mq_qnet_td_backward: the bf16 path needs a batch that is a multiple of 8 (got %lld)", (long long)B);
+    cudaError_t fe = cudaSuccess;
+    if (bf16) fe = forward_net_bf16(n, 1, next_state, B, drop_target, s);
+    else forward_net(n, n->tl.t, next_state, B, drop_target, s);
+    qhead_kernel<<<hb, 256, 0, s>>>(n->h2, n->tl.t[P_F3W], n->tl.t[P_F3B], B, 3, nullptr, nullptr, n->maxq, nullptr, 0.f, 0, 0, 0, 1);
+    // current_q = q_network(states).gather(1, actions)   (dqn_agent.py:143)
+    if (bf16 && fe == cudaSuccess) fe = forward_net_bf16(n, 0, state, B, drop_online, s);
+    else if (!bf16) forward_net(n, n->tl.p, state, B, drop_online, s);
+    if (fe != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_td_backward (bf16 forward): %s", cudaGetErrorString(fe));
+    qhead_kernel<<<hb, 256, 0, s>>>(n->h2, n->tl.p[P_F3W], n->tl.p[P_F3B], B, 2, nullptr, (const long long*)action, n->q_sa, nullptr, 0.f,
+                                    0, 0, 0, 1);
+    td_loss_kernel<<<1, 1024, 0, s>>>(n->q_sa, n->maxq, reward, done, (const long long*)action, B, hp->gamma, hp->huber, n->dq, loss_out);
+    n->launches += 3;
+
+    // ---- backward (loss.backward(), dqn_agent.py:154-155) ----
+    if (bf16) {
+        cudaError_t be = backward_bf16(n, state, B, drop_online, s);
+        if (be != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_td_backward (bf16 backward): %s", cudaGetErrorString(be));
+        return MQ_OK;
+    }
+    backward_fp32(n, state, B, drop_online, s);
+    MQ_CUDA(cudaGetLastError());
+    return MQ_OK;
+}
+
+// Backward of the online network from an EXTERNAL dL/dQ (B x 5): what autograd does when a runner builds its own loss on
+// agent.q_network(states) (train_qmix.py:92-110 mixes the Q-values of two agents before the loss).  The online forward is
+// recomputed here (the workspace holds one set of activations and the caller may have run the target network since),
+// then the same backward kernels as mq_qnet_td_backward fill the bound gradient buffers (overwriting them).
+extern "C" int mq_qnet_backward(mq_qnet* n, const float* state, const float* dq, int64_t B, const uint8_t* drop_online, void* stream) {
+    using namespace mq;
+    MQ_REQUIRE(n && state && dq, "mq_qnet_backward: null argument");
+    MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_backward: batch %lld outside 1..%lld", (long long)B, n->max_batch);
+    MQ_REQUIRE(n->tl.g[0] && n->da3, "mq_qnet_backward: handle was created without gradient buffers");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool bf16 = n->precision == 1;
+    MQ_REQUIRE(!bf16 || B % 8 == 0, "mq_qnet_backward: the bf16 path needs a batch that is a multiple of 8 (got %lld)", (long long)B);
+    if (bf16) {
+        cudaError_t fe = forward_net_bf16(n, 0, state, B, drop_online, s);
+        if (fe != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_backward (bf16 forward): %s", cudaGetErrorString(fe));
+    } else {
+        forward_net(n, n->tl.p, state, B, drop_online, s);
+    }
+    MQ_CUDA(cudaMemcpyAsync(n->dq, dq, sizeof(float) * (size_t)B * NA, cudaMemcpyDeviceToDevice, s));
+    if (bf16) {
+        cudaError_t be = backward_bf16(n, state, B, drop_online, s);
+        if (be != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_backward (bf16 backward): %s", cudaGetErrorString(be));
+    } else {
+        backward_fp32(n, state, B, drop_online, s);
+    }
     MQ_CUDA(cudaGetLastError());
     return MQ_OK;
 }

@@ -241,6 +241,10 @@ int mq_qnet_act(mq_qnet* net, const float* obs, int64_t B, float eps, uint64_t s
 int mq_qnet_td_backward(mq_qnet* net, const float* state, const int64_t* action, const float* reward,
                         const float* next_state, const uint8_t* done, int64_t B, const mq_hparams* hp,
                         const uint8_t* drop_online, const uint8_t* drop_target, float* loss_out, void* stream);
+/* Backward of the online network from an external dL/dQ (dev f32 [B][5]) — the autograd path a runner takes when it builds
+ * its own loss on agent.q_network(states) (train_qmix.py:92-110: two agents' Q-values go through a mixing network before
+ * the loss).  Recomputes the online forward on `state` with the same drop mask, then fills the bound gradient tensors. */
+int mq_qnet_backward(mq_qnet* net, const float* state, const float* dq, int64_t B, const uint8_t* drop_online, void* stream);
 /* clip_grad_norm_(params, clip_norm) + optimizer.step() (dqn_agent.py:158-160).  Gradients are multiplied by
  * grad_scale first (1/world_size after a summing all-reduce).  gnorm_out dev f32 [1] or NULL. */
 int mq_qnet_clip_adam(mq_qnet* net, const mq_hparams* hp, float grad_scale, float* gnorm_out, void* stream);

@@ -251,3 +251,77 @@ def test_bf16_tensor_core_path_tracks_fp32():
         assert cos > 0.995, (k, cos)
         assert abs(float(b.norm() / a.norm()) - 1.0) < 5e-2, (k, float(b.norm() / a.norm()))
     assert (p32 - p16).abs().max() <= 2.1e-4          # one Adam step moves a weight by at most lr = 1e-4 in either path
+
+
+def test_q_network_autograd_qmix_step_matches_torch():
+    """train_qmix.py:88-113 on the drop-in agents: Q-values of two agents go through a monotonic mixing network, ONE
+    loss.backward() fills both agents' gradient buffers through mq_qnet_backward, clip_grad_norm_ works on
+    q_network.parameters(), optimizer.step() applies Adam.  Compared with the same step on torch modules (fp32)."""
+    from dqn_marl_b200.agents import qnet_params as qp
+    from dqn_marl_b200.agents.dqn_agent import DQNAgent
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.allow_tf32 = False            # the torch side of this comparison must be real fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg = dict(gamma=0.99, learning_rate=1e-4, batch_size=16, warmup_steps=0, memory_size=100, dropout="eval")
+    agents = [DQNAgent((11, 11, 6), 5, dev, dict(cfg, seed=11 + k)) for k in range(2)]
+    refs = []
+    for k, ag in enumerate(agents):
+        torch.manual_seed(100 + k)
+        q, t = torch_ref.build_nets(100 + k)
+        ag.q_network.load_state_dict(q.state_dict()); ag.target_network.load_state_dict(t.state_dict())
+        refs.append((q.to(dev).eval(), t.to(dev).eval()))
+
+    class Mixer(torch.nn.Module):                      # MixingNetwork of train_qmix.py:39-54
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(9)
+            self.w1 = torch.nn.Parameter(torch.randn(2, 32, generator=g)); self.b1 = torch.nn.Parameter(torch.zeros(32))
+            self.w2 = torch.nn.Parameter(torch.randn(32, 1, generator=g)); self.b2 = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, q):
+            return (torch.relu(q @ self.w1.abs() + self.b1) @ self.w2.abs() + self.b2).squeeze(-1)
+
+    B = 16
+    g = torch.Generator().manual_seed(4)
+    s = [(torch.rand((B, 11, 11, 6), generator=g) < 0.3).float().to(dev) for _ in range(2)]
+    ns = [(torch.rand((B, 11, 11, 6), generator=g) < 0.3).float().to(dev) for _ in range(2)]
+    a = [torch.randint(0, 5, (B,), generator=g).to(dev) for _ in range(2)]
+    r = torch.randn(B, generator=g).to(dev)
+    d = (torch.rand(B, generator=g) < 0.2).to(dev)
+
+    def qmix_loss(qnets, tnets, mixer, tmixer):
+        q = torch.stack([qnets[k](s[k]).gather(1, a[k].unsqueeze(1)).squeeze(1) for k in range(2)], dim=1)
+        with torch.no_grad():
+            nq = torch.stack([tnets[k](ns[k]).max(1)[0] for k in range(2)], dim=1)
+            y = r + 0.99 * tmixer(nq) * (~d)
+        return torch.nn.functional.mse_loss(mixer(q), y)
+
+    mix_a, mix_b = Mixer().to(dev), Mixer().to(dev)
+    tmix = Mixer().to(dev)
+    # ours
+    for ag in agents:
+        ag.optimizer.zero_grad()
+    loss_a = qmix_loss([ag.q_network for ag in agents], [ag.target_network for ag in agents], mix_a, tmix)
+    loss_a.backward()
+    # torch reference
+    opts = [torch.optim.Adam(q.parameters(), lr=1e-4) for q, _ in refs]
+    loss_b = qmix_loss([lambda x, q=q: torch_ref.forward(q, x) for q, _ in refs], [lambda x, t=t: torch_ref.forward(t, x) for _, t in refs],
+                       mix_b, tmix)
+    loss_b.backward()
+    assert abs(loss_a.item() - loss_b.item()) <= 1e-5 * abs(loss_b.item())
+    for p_a, p_b in zip(mix_a.parameters(), mix_b.parameters()):
+        assert torch.allclose(p_a.grad, p_b.grad, rtol=1e-4, atol=1e-6)
+    for k, ag in enumerate(agents):
+        ours = qp.unpack(ag.net.flat_g)
+        gmax = max(p.grad.abs().max().item() for p in refs[k][0].parameters())
+        for name, p in refs[k][0].named_parameters():
+            assert (ours[name] - p.grad).abs().max().item() <= 3e-4 * gmax, (k, name)
+        n_a = torch.nn.utils.clip_grad_norm_(ag.q_network.parameters(), 1.0)
+        n_b = torch.nn.utils.clip_grad_norm_(refs[k][0].parameters(), 1.0)
+        assert abs(n_a.item() - n_b.item()) <= 1e-4 * n_b.item()
+        before = ag.net.flat_p.clone()
+        ag.optimizer.step(); opts[k].step()
+        assert not torch.equal(before, ag.net.flat_p)
+        after = qp.unpack(ag.net.flat_p)
+        for name, p in refs[k][0].named_parameters():
+            assert (after[name] - p.data).abs().max().item() <= 2e-5, (k, name)
