@@ -14,16 +14,18 @@ __global__ void __launch_bounds__(256) tc_splitk_reduce_kernel(const float* __re
 }
 }  // namespace mq
 
-// C[M][N] (fp32, row-major) = A[M][K] (bf16, K contiguous) * B[N][K]^T (bf16, K contiguous); fp32 accumulation in TMEM.
+// C[M][N] (fp32 in C and / or bf16 in C_bf16, row-major) = A[M][K] (bf16, K contiguous) * B[N][K]^T (bf16, K contiguous); fp32
+// accumulation in TMEM.  A bf16-only output with N a multiple of the tile width goes through the TMA-store epilogue.
 // bn = 128 / 64 / 32 selects the tile width; splits > 1 needs workspace >= splits*M*N floats.
-extern "C" int mq_gemm_bf16(const void* A, const void* B, float* C, int32_t M, int32_t N, int32_t K, int32_t bn, int32_t splits,
+extern "C" int mq_gemm_bf16(const void* A, const void* B, float* C, void* C_bf16, int32_t M, int32_t N, int32_t K, int32_t bn, int32_t splits,
                             float* workspace, void* stream) {
-    MQ_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0, "mq_gemm_bf16: bad argument");
+    MQ_REQUIRE(A && B && (C || C_bf16) && M > 0 && N > 0 && K > 0, "mq_gemm_bf16: bad argument");
+    MQ_REQUIRE(C || splits <= 1, "mq_gemm_bf16: split-K needs the fp32 output");
     MQ_REQUIRE(K % 8 == 0, "mq_gemm_bf16: K must be a multiple of 8 (TMA row pitch of 16 bytes)");
     MQ_REQUIRE(splits <= 1 || workspace, "mq_gemm_bf16: split-K needs a workspace");
     cudaStream_t s = (cudaStream_t)stream;
     mq::tc::Epilogue ep{};
-    ep.out_f32 = C; ep.ldc = N; ep.partial = splits > 1 ? workspace : nullptr;
+    ep.out_f32 = C; ep.out_bf16 = (__nv_bfloat16*)C_bf16; ep.ldc = N; ep.partial = splits > 1 ? workspace : nullptr;
     int sp = splits < 1 ? 1 : splits;
     cudaError_t e;
     const __nv_bfloat16* a = (const __nv_bfloat16*)A;

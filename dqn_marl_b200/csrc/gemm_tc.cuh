@@ -210,6 +210,97 @@ __device__ __forceinline__ void epilogue_tile(const Epilogue& ep, uint32_t tmem_
     }
 }
 
+// ---- bf16 epilogue through shared memory + TMA store ----------------------------------------------------------------
+// Direct stores from the TMEM register layout (one row per thread) hit 32 different sectors per instruction with 16 bytes
+// each; the L2 write path, not the tensor pipe, then bounds the kernel.  Here a warp stages its 32 rows x 64 columns in a
+// 4 KB SWIZZLE_128B tile (conflict-free 16-byte shared stores) and one lane issues a bulk tensor store.  Rows / columns
+// outside the output map are clipped by TMA (conv: the map is 3-D {Cout, 121, batch}, so rows >= 121 of a sample vanish).
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+// One 128 x BN accumulator: bias / relu / relu-mask, bf16, staged per warp, stored by TMA.
+//   mask_row  this thread's row of ep.mask_bf16 at column n0 (null: no mask or row out of range)
+//   (c_col, c_row, c_z)  coordinates of the warp's first element in the output map; c_z < 0: the map is 2-D
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_tma(const Epilogue& ep, const CUtensorMap* tmap_out, uint32_t tmem_acc, int q, int lane,
+                                                  const __nv_bfloat16* mask_row, int n0, int c_row, int c_z, unsigned char* stage) {
+    static_assert(BN % 64 == 0, "TMA-store epilogue works on 64-column groups");
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+        uint32_t ra[32], rb[32];
+        tmem_ld32_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, ra);
+        tmem_ld32_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 32), rb);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        uint32_t packed[32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(h ? rb[j] : ra[j]);
+            const int nb = c0 + 32 * h;
+            if (ep.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + nb + j));
+                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
+            }
+            if (ep.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (mask_row) {
+                const uint4* mk = reinterpret_cast<const uint4*>(mask_row + nb);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const uint4 w = __ldg(mk + j / 8);
+                    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ws[k]);
+                        if (!(__low2float(b2) > 0.f)) v[j + 2 * k] = 0.f;
+                        if (!(__high2float(b2) > 0.f)) v[j + 2 * k + 1] = 0.f;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j], v[j + 1]);
+                packed[16 * h + j / 2] = *reinterpret_cast<const uint32_t*>(&p2);
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous store has read the tile
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            if (c_z >= 0) tma_store_3d(tmap_out, stage, n0 + c0, c_row, c_z);
+            else tma_store_2d(tmap_out, stage, n0 + c0, c_row);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+}
+
 // common prologue: barriers, tensor-map prefetch, TMEM allocation
 struct Pipe {
     uint64_t *full_bar, *empty_bar, *tmem_full_bar;
@@ -259,8 +350,9 @@ struct SmemLayout {
 
 template <int BN, int STAGES, int BK, bool CONV>
 __global__ void __launch_bounds__(THREADS)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, long long M, int N, int K,
-                    int k_chunk, ConvArgs cv, Epilogue ep) {
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const __grid_constant__ CUtensorMap tmap_out, long long M, int N, int K, int k_chunk, int tma_store, ConvArgs cv,
+                    Epilogue ep) {
     extern __shared__ unsigned char smem_raw[];
     using L = SmemLayout<BN, STAGES, BK>;
     constexpr uint64_t LAYOUT = BK == 64 ? 2 : 4;
@@ -330,94 +422,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int r = q * 32 + lane;
         const long long row = CONV ? (long long)m_tile * PIXELS + r : (long long)m_tile * BM + r;
         const bool ok = (CONV ? r < PIXELS : true) && row < M && num_kb > 0;
-        epilogue_tile<BN>(ep, tmem_base, q, ok, row, n0, M, N, blockIdx.z);
+        bool done = false;
+        if constexpr (BN % 64 == 0) {
+            if (tma_store) {          // all MMAs have completed: the pipeline stages are free, stage 0 becomes the staging area
+                const __nv_bfloat16* mrow = (ep.mask_bf16 && ok) ? ep.mask_bf16 + (size_t)row * ep.ldc + n0 : nullptr;
+                epilogue_tile_tma<BN>(ep, &tmap_out, tmem_base, q, lane, mrow, n0, CONV ? q * 32 : m_tile * BM + q * 32, CONV ? m_tile : -1,
+                                      tiles + q * 4096);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                done = true;
+            }
+        }
+        if (!done) epilogue_tile<BN>(ep, tmem_base, q, ok, row, n0, M, N, blockIdx.z);
     }
     pipe_fini(tmem_base, TMEM_COLS);
-}
-
-// ---- bf16 epilogue through shared memory + TMA store (persistent conv kernel) ----------------------------------------
-// Direct stores from the TMEM register layout (one row per thread) hit 32 different sectors per instruction with 16 bytes
-// each; the L2 write path, not the tensor pipe, then bounds the kernel.  Here a warp stages its 32 rows x 64 columns in a
-// 4 KB SWIZZLE_128B tile (conflict-free 16-byte shared stores) and one lane issues a bulk tensor store; rows >= 121 of the
-// sample fall outside the 3-D output map {Cout, 121, batch} and are clipped by TMA.
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
-                 ::"l"(tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-template <int BN>
-__device__ __forceinline__ void epilogue_tile_tma(const Epilogue& ep, const CUtensorMap* tmap_out, uint32_t tmem_acc, int q, int lane,
-                                                  long long sample, unsigned char* stage) {
-    static_assert(BN % 64 == 0, "TMA-store epilogue works on 64-column groups");
-    const int r = q * 32 + lane;
-    const bool row_ok = r < PIXELS;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 64) {
-        uint32_t ra[32], rb[32];
-        tmem_ld32_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, ra);
-        tmem_ld32_nowait(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 32), rb);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        uint32_t packed[32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(h ? rb[j] : ra[j]);
-            const int nb = c0 + 32 * h;
-            if (ep.bias) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + nb + j));
-                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                }
-            }
-            if (ep.relu) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-            }
-            if (ep.mask_bf16 && row_ok) {
-                const uint4* mk = reinterpret_cast<const uint4*>(ep.mask_bf16 + ((size_t)sample * PIXELS + r) * BN + nb);
-#pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    const uint4 w = __ldg(mk + j / 8);
-                    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ws[k]);
-                        if (!(__low2float(b2) > 0.f)) v[j + 2 * k] = 0.f;
-                        if (!(__high2float(b2) > 0.f)) v[j + 2 * k + 1] = 0.f;
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j], v[j + 1]);
-                packed[16 * h + j / 2] = *reinterpret_cast<const uint32_t*>(&p2);
-            }
-        }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // the previous store has read the tile
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-            tma_store_3d(tmap_out, stage, c0, q * 32, (int)sample);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-    }
 }
 
 // =====================================================================================================================
@@ -520,7 +537,10 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if constexpr (BN % 64 == 0) {
-                if (tma_store) epilogue_tile_tma<BN>(ep, &tmap_out, tmem_base + (uint32_t)(buf * BN), q, lane, sample, stage + q * 4096);
+                if (tma_store) {
+                    const __nv_bfloat16* mrow = (ep.mask_bf16 && r < PIXELS) ? ep.mask_bf16 + ((size_t)sample * PIXELS + r) * BN : nullptr;
+                    epilogue_tile_tma<BN>(ep, &tmap_out, tmem_base + (uint32_t)(buf * BN), q, lane, mrow, 0, q * 32, (int)sample, stage + q * 4096);
+                }
                 else epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, r < PIXELS, sample * PIXELS + r, 0, batch * PIXELS, BN, 0);
             } else {
                 epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, r < PIXELS, sample * PIXELS + r, 0, batch * PIXELS, BN, 0);
@@ -694,6 +714,32 @@ inline bool make_tmap_act(CUtensorMap* out, const void* base, uint64_t batch, ui
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// bf16 output maps of the TMA-store epilogue, box = 32 rows x 64 columns (SWIZZLE_128B)
+inline bool make_tmap_out2d(CUtensorMap* out, void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+inline bool make_tmap_out_conv(CUtensorMap* out, void* base, uint64_t batch, uint64_t Cout) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {Cout, (cuuint64_t)PIXELS, batch};
+    cuuint64_t strides[2] = {Cout * 2, (cuuint64_t)PIXELS * Cout * 2};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// the TMA-store epilogue applies to a bf16-only output with at most bias / relu / a bf16 relu-mask
+inline bool tma_store_eligible(const Epilogue& ep, int N, int BN) {
+    return BN % 64 == 0 && N % BN == 0 && ep.out_bf16 && !ep.out_f32 && !ep.mask_f32 && !ep.drop && ep.ldc % 8 == 0;
+}
+
 template <typename KernelT>
 inline cudaError_t ensure_smem(KernelT kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -723,8 +769,11 @@ inline cudaError_t launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* 
     if (splits_inout) *splits_inout = splits;
     if (splits > 1 && !ep.partial) return cudaErrorInvalidValue;
     if (splits == 1) ep.partial = nullptr;
+    CUtensorMap to = ta;
+    const int tma_store = (splits == 1 && tma_store_eligible(ep, N, BN) && make_tmap_out2d(&to, ep.out_bf16, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldc)) ? 1 : 0;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
-    gemm_bf16_tc_kernel<BN, STAGES, BK, false><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, N, K, chunk_tiles * BK, ConvArgs{1, 0}, ep);
+    gemm_bf16_tc_kernel<BN, STAGES, BK, false><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, to, M, N, K, chunk_tiles * BK, tma_store,
+                                                                                   ConvArgs{1, 0}, ep);
     return cudaGetLastError();
 }
 
@@ -746,8 +795,10 @@ inline cudaError_t launch_conv(const __nv_bfloat16* X, const __nv_bfloat16* Wk, 
         attr_set = true;
     }
     ep.partial = nullptr;
+    CUtensorMap to = ta;
+    const int tma_store = (tma_store_eligible(ep, Cout, BN) && ep.ldc == Cout && make_tmap_out_conv(&to, ep.out_bf16, (uint64_t)batch, (uint64_t)Cout)) ? 1 : 0;
     dim3 grid((Cout + BN - 1) / BN, (unsigned)batch, 1);
-    gemm_bf16_tc_kernel<BN, STAGES, BK, true><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, batch * PIXELS, Cout, 9 * Cin, 9 * Cin,
+    gemm_bf16_tc_kernel<BN, STAGES, BK, true><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, to, batch * PIXELS, Cout, 9 * Cin, 9 * Cin, tma_store,
                                                                                  ConvArgs{Cin / BK, flip}, ep);
     return cudaGetLastError();
 }
@@ -763,18 +814,8 @@ inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfl
         return cudaErrorInvalidValue;
     const int nkb = 9 * Cin / BK;
     // bf16 output without per-element fp32 masks: epilogue through shared memory + TMA store
-    const int tma_store = (BN % 64 == 0 && ep.out_bf16 && !ep.out_f32 && !ep.mask_f32 && !ep.drop && ep.ldc == Cout) ? 1 : 0;
     CUtensorMap to = ta;
-    if (tma_store) {
-        EncodeTiledFn fn = encode_fn();
-        cuuint64_t dims[3] = {(cuuint64_t)Cout, (cuuint64_t)PIXELS, (cuuint64_t)batch};
-        cuuint64_t strides[2] = {(cuuint64_t)Cout * 2, (cuuint64_t)PIXELS * Cout * 2};
-        cuuint32_t box[3] = {64, 32, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        if (!fn || fn(&to, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, ep.out_bf16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return cudaErrorInvalidValue;
-    }
+    const int tma_store = (tma_store_eligible(ep, Cout, BN) && ep.ldc == Cout && make_tmap_out_conv(&to, ep.out_bf16, (uint64_t)batch, (uint64_t)Cout)) ? 1 : 0;
     const int smem = nkb * BN * BK * 2 + STAGES * BM * BK * 2 + (tma_store ? 4 * 4096 : 0) + 1024 + 256;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static int attr_bytes = 0;

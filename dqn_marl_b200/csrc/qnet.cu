@@ -491,7 +491,8 @@ template <int BN, int STAGES, int AW>
 static cudaError_t conv_wgrad(mq_qnet* n, const bf::bf16* X, const bf::bf16* dY, long long B, int Cin, int Cout, float* out, cudaStream_t s) {
     const int M = 9 * Cin;
     const int tiles = ((M + tc::BM - 1) / tc::BM) * ((Cout + BN - 1) / BN);
-    int splits = (n->n_sms + tiles - 1) / tiles;
+    int splits = n->n_sms / tiles;            // one CTA per SM (192 KB of shared memory each): never more CTAs than SMs
+    if (splits < 1) splits = 1;
     while (splits > 1 && (size_t)splits * M * Cout > n->partial_cap) --splits;
     tc::Epilogue ep{};
     ep.out_f32 = out; ep.ldc = Cout; ep.partial = n->partial;

@@ -262,10 +262,11 @@ int64_t mq_qnet_launch_count(const mq_qnet* net);
 
 /* ------------------------------------------------------------------------
  * Stand-alone bf16 tensor-core GEMM (tcgen05 + TMEM + TMA), the building block of the Q-network's throughput
- * path: C[M][N] f32 = A[M][K] bf16 * B[N][K]^T bf16 (both K-contiguous).  bn = tile width 128/64/32.
+ * path: C[M][N] = A[M][K] bf16 * B[N][K]^T bf16 (both K-contiguous), written as f32 (C) and / or bf16 (C_bf16).
+ * bn = tile width 128/64/32.
  * ---------------------------------------------------------------------- */
-int mq_gemm_bf16(const void* A, const void* B, float* C, int32_t M, int32_t N, int32_t K, int32_t bn, int32_t splits,
-                 float* workspace, void* stream);
+int mq_gemm_bf16(const void* A, const void* B, float* C, void* C_bf16, int32_t M, int32_t N, int32_t K, int32_t bn,
+                 int32_t splits, float* workspace, void* stream);
 
 /* C[M][N] f32 = At[K][M]^T * Bt[K][N]: both bf16 operands stored with K as the row index (MN-major UMMA descriptors).
  * The weight-gradient shapes of DQNAgent.learn (dqn_agent.py:153, loss.backward) reduce over the batch rows; this form

@@ -26,12 +26,12 @@ for name, m, n, k, bn, splits in shapes:
     C = torch.empty((m, n), device="cuda")
     ws = torch.empty((splits * m * n,), device="cuda") if splits > 1 else None
     for _ in range(3):
-        _lib.check(lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(C), m, n, k, bn, splits, _lib.ptr(ws), st), "gemm")
+        _lib.check(lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(C), None, m, n, k, bn, splits, _lib.ptr(ws), st), "gemm")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
     reps = 10
     for _ in range(reps):
-        lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(C), m, n, k, bn, splits, _lib.ptr(ws), st)
+        lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(C), None, m, n, k, bn, splits, _lib.ptr(ws), st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12
