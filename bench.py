@@ -212,11 +212,12 @@ def run_ours(args, wl):
             dist.barrier()
 
     step_no = 0
+    bound = [envs[b].bind_step(obs[b], rew[b], don[b]) for b in range(n_rot)]     # pointer conversions done once
+    act_rows = [actions[k] for k in range(n_act)]
 
     def one_step():
         nonlocal step_no
-        b = step_no % n_rot
-        envs[b].step_into(actions[step_no % n_act], obs[b], rew[b], don[b])
+        bound[step_no % n_rot](act_rows[step_no % n_act])
         step_no += 1
 
     for _ in range(max(args.warmup, 3)):

@@ -631,9 +631,9 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     for (int j = 0; j < L::B_SLABS; ++j) tma_load_2d(b_dst + j * L::B_SLAB, &tmap_b, &pp.full_bar[s], n0 + 64 * j, sample * PIXELS);
                 } else {
                     const int k = k_begin + kb * BKR;
-                    mbar_expect_tx(&pp.full_bar[s], L::STAGE_BYTES);
-#pragma unroll
-                    for (int j = 0; j < L::A_SLABS; ++j) tma_load_2d(a_dst + j * L::A_SLAB, &tmap_a, &pp.full_bar[s], m0 + AW * j, k);
+                    const int a_slabs = min(L::A_SLABS, (M - m0 + AW - 1) / AW);       // slabs past M are not loaded (their D rows are not stored)
+                    mbar_expect_tx(&pp.full_bar[s], a_slabs * L::A_SLAB + L::B_BYTES);
+                    for (int j = 0; j < a_slabs; ++j) tma_load_2d(a_dst + j * L::A_SLAB, &tmap_a, &pp.full_bar[s], m0 + AW * j, k);
 #pragma unroll
                     for (int j = 0; j < L::B_SLABS; ++j) tma_load_2d(b_dst + j * L::B_SLAB, &tmap_b, &pp.full_bar[s], n0 + 64 * j, k);
                 }
@@ -831,18 +831,18 @@ inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfl
 }
 
 // C[M][N] = At[K][M]^T Bt[K][N]   (M % 8 == 0 and N % 8 == 0: TMA row pitch)
-template <int BN, int STAGES>
+template <int BN, int STAGES, int AW = 64>
 inline cudaError_t launch_tn(const __nv_bfloat16* At, int lda, const __nv_bfloat16* Bt, int ldb, int M, int N, int K, Epilogue ep,
                              int* splits_inout, cudaStream_t stream) {
     constexpr int BKR = 64;
     int splits = splits_inout ? *splits_inout : 1;
     CUtensorMap ta, tb;
-    if (!make_tmap(&ta, At, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BKR) || !make_tmap(&tb, Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BKR))
+    if (!make_tmap(&ta, At, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BKR, AW) || !make_tmap(&tb, Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BKR))
         return cudaErrorInvalidValue;
-    using L = SmemLayoutTN<BN, STAGES, BKR, 64>;
+    using L = SmemLayoutTN<BN, STAGES, BKR, AW>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = ensure_smem(gemm_bf16_tn_kernel<BN, STAGES, BKR, false, 64>, L::TOTAL);
+        cudaError_t e = ensure_smem(gemm_bf16_tn_kernel<BN, STAGES, BKR, false, AW>, L::TOTAL);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -855,7 +855,7 @@ inline cudaError_t launch_tn(const __nv_bfloat16* At, int lda, const __nv_bfloat
     if (splits > 1 && !ep.partial) return cudaErrorInvalidValue;
     if (splits == 1) ep.partial = nullptr;
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
-    gemm_bf16_tn_kernel<BN, STAGES, BKR, false, 64><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, N, K, chunk_tiles * BKR, 0, ep);
+    gemm_bf16_tn_kernel<BN, STAGES, BKR, false, AW><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, N, K, chunk_tiles * BKR, 0, ep);
     return cudaGetLastError();
 }
 

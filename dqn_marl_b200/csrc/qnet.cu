@@ -337,6 +337,7 @@ struct mq_qnet {
     mq::bf::bf16 *a1b = nullptr, *a2b = nullptr, *a3b = nullptr;                     // NHWC activations (TMA operands)
     mq::bf::bf16 *da3b = nullptr, *da2b = nullptr, *dh1b = nullptr, *dh2b = nullptr; // activation grads
     mq::bf::bf16 *h1b = nullptr, *wf2[2] = {nullptr, nullptr}, *wf2t = nullptr;      // fc2 operands: h1, W2 [256][512], W2^T [512][256]
+    mq::bf::bf16 *A1 = nullptr, *w1c[2] = {nullptr, nullptr}, *da1b = nullptr;       // conv1: im2col rows [M][64], W [32][64], dY
 };
 
 namespace mq {
@@ -346,7 +347,7 @@ static void free_ws(mq_qnet* n) {
                      n->partial, n->norm_partial, n->gnorm};
     for (float* p : ptrs) cudaFree(p);
     bf::bf16* bptrs[] = {n->w2f[0], n->w2f[1], n->w3f[0], n->w3f[1], n->w1f[0], n->w1f[1], n->w2d, n->w3d, n->w1t, n->a1b, n->a2b,
-                         n->a3b, n->da3b, n->da2b, n->dh1b, n->dh2b, n->h1b, n->wf2[0], n->wf2[1], n->wf2t};
+                         n->a3b, n->da3b, n->da2b, n->dh1b, n->dh2b, n->h1b, n->wf2[0], n->wf2[1], n->wf2t, n->A1, n->w1c[0], n->w1c[1], n->da1b};
     for (bf::bf16* p : bptrs) cudaFree(p);
 }
 
@@ -361,8 +362,9 @@ static cudaError_t alloc_bf16(mq_qnet* n) {
     for (int w = 0; w < 2; ++w) { alloc(&n->w2f[w], (size_t)C2 * 9 * C1); alloc(&n->w3f[w], (size_t)C3 * 9 * C2); alloc(&n->w1f[w], (size_t)H1 * FLAT); }
     alloc(&n->w2d, (size_t)C1 * 9 * C2); alloc(&n->w3d, (size_t)C2 * 9 * C3); alloc(&n->w1t, (size_t)FLAT * H1);
     alloc(&n->a1b, M * C1); alloc(&n->a2b, M * C2); alloc(&n->a3b, M * C3); alloc(&n->h1b, B * H1);
-    for (int w = 0; w < 2; ++w) alloc(&n->wf2[w], (size_t)H2 * H1);
-    if (n->tl.g[0]) { alloc(&n->da3b, M * C3); alloc(&n->da2b, M * C2); alloc(&n->dh1b, B * H1); alloc(&n->dh2b, B * H2); alloc(&n->wf2t, (size_t)H1 * H2); }
+    for (int w = 0; w < 2; ++w) { alloc(&n->wf2[w], (size_t)H2 * H1); alloc(&n->w1c[w], (size_t)C1 * 64); }
+    alloc(&n->A1, M * 64);
+    if (n->tl.g[0]) { alloc(&n->da3b, M * C3); alloc(&n->da2b, M * C2); alloc(&n->dh1b, B * H1); alloc(&n->dh2b, B * H2); alloc(&n->wf2t, (size_t)H1 * H2); alloc(&n->da1b, M * C1); }
     return ce;
 }
 
@@ -373,9 +375,10 @@ static void refresh_weights(mq_qnet* n, int which, cudaStream_t s) {
     const bool bwd = which == 0 && n->tl.g[0];
     bf::conv_weight_bf16_kernel<<<ew_blocks(9 * C1 * C2), 256, 0, s>>>(W[P_C2W], n->w2f[which], bwd ? n->w2d : nullptr, C1, C2);
     bf::conv_weight_bf16_kernel<<<ew_blocks(9 * C2 * C3), 256, 0, s>>>(W[P_C3W], n->w3f[which], bwd ? n->w3d : nullptr, C2, C3);
-    bf::cast_transpose_kernel<<<ew_blocks((long long)H1 * FLAT), 256, 0, s>>>(W[P_F1W], n->w1f[which], bwd ? n->w1t : nullptr, H1, FLAT);
-    bf::cast_transpose_kernel<<<ew_blocks((long long)H2 * H1), 256, 0, s>>>(W[P_F2W], n->wf2[which], bwd ? n->wf2t : nullptr, H2, H1);
-    n->launches += 4;
+    bf::cast_transpose_kernel<<<(H1 / 32) * ((FLAT + 31) / 32), 256, 0, s>>>(W[P_F1W], n->w1f[which], bwd ? n->w1t : nullptr, H1, FLAT);
+    bf::cast_transpose_kernel<<<(H2 / 32) * ((H1 + 31) / 32), 256, 0, s>>>(W[P_F2W], n->wf2[which], bwd ? n->wf2t : nullptr, H2, H1);
+    bf::conv1_weight_bf16_kernel<<<ew_blocks(C1 * 64), 256, 0, s>>>(W[P_C1W], n->w1c[which]);
+    n->launches += 5;
     n->w_dirty[which] = false;
 }
 
@@ -406,20 +409,23 @@ static cudaError_t tc_gemm(mq_qnet* n, const bf::bf16* A, int lda, const bf::bf1
 
 static void launch_colsum_bf16(mq_qnet* n, const bf::bf16* X, long long M, int N, float* out, cudaStream_t s);
 
-// forward with conv2 / conv3 / fc1 on the tensor cores; conv1, fc2 and the head stay fp32 (1.7 % of the flops)
+// forward with every layer but the 5-output head on the tensor cores
 static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, long long B, const uint8_t* drop_mask, cudaStream_t s) {
     float* const* W = which ? n->tl.t : n->tl.p;
     const int M = (int)(B * PIX);
     refresh_weights(n, which, s);
-    GemmParams p{};
-    p.batch = (int)B; p.partial = n->partial;
-    p.M = M; p.N = C1; p.K = 9 * CIN; p.A = obs; p.B = W[P_C1W]; p.ldb = C1; p.C = n->a1; p.Cb = n->a1b; p.ldc = C1; p.bias = W[P_C1B]; p.relu = 1;
-    n->launches += launch_gemm<A_IM2COL, B_ROW, 32, CIN>(p, n->partial_cap, n->n_sms, s);
+    // conv1: im2col rows of the 6-channel observation (K = 54 padded to one 64-wide K-block), then a tcgen05 GEMM
+    bf::im2col_obs_bf16_kernel<<<(unsigned)((B + 1) / 2), 256, 0, s>>>(obs, n->A1, B);
+    n->launches += 1;
+    tc::Epilogue ep{};
+    ep.out_bf16 = n->a1b; ep.ldc = C1; ep.bias = W[P_C1B]; ep.relu = 1;
+    cudaError_t e = tc_gemm<32>(n, n->A1, 64, n->w1c[which], 64, M, C1, 64, ep, false, s);
+    if (e != cudaSuccess) return e;
     // conv2 / conv3: persistent implicit GEMMs (weights resident in shared memory), every tap a shifted zero-filled TMA box
     // of the NHWC activation (no im2col buffer)
-    tc::Epilogue ep{};
+    ep = tc::Epilogue{};
     ep.out_bf16 = n->a2b; ep.ldc = C2; ep.bias = W[P_C2B]; ep.relu = 1;
-    cudaError_t e = tc::launch_conv_persistent<64, 32, 6>(n->a1b, n->w2f[which], B, C1, C2, 0, ep, n->n_sms, s);
+    e = tc::launch_conv_persistent<64, 32, 6>(n->a1b, n->w2f[which], B, C1, C2, 0, ep, n->n_sms, s);
     if (e != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->a3b; ep.ldc = C3; ep.bias = W[P_C3B]; ep.relu = 1;
@@ -509,7 +515,7 @@ static cudaError_t conv_wgrad(mq_qnet* n, const bf::bf16* X, const bf::bf16* dY,
     return e;
 }
 
-// backward of the bf16 path.  Needs: forward_net_bf16(online) just ran (a1, a1b, a2b, a3b, h1, h2 hold the online
+// backward of the bf16 path.  Needs: forward_net_bf16(online) just ran (A1, a1b, a2b, a3b, h1, h2 hold the online
 // activations) and n->dq holds dL/dq.
 static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, const uint8_t* drop_online, cudaStream_t s) {
     float* const* W = n->tl.p; float* const* G = n->tl.g;
@@ -570,14 +576,22 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
     launch_colsum_bf16(n, n->da2b, M, C2, G[P_C2B], s);
     if ((e = conv_wgrad<64, 4, 32>(n, n->a1b, n->da2b, B, C1, C2, G[P_C2W], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
-    ep.out_f32 = n->da1; ep.ldc = C1; ep.mask_f32 = n->a1;
+    ep.out_bf16 = n->da1b; ep.ldc = C1; ep.mask_bf16 = n->a1b;
     if ((e = tc::launch_conv<32, 4, 64>(n->da2b, n->w2d, B, C2, C1, 1, ep, s)) != cudaSuccess) return e;
     n->launches += 2;
-    // conv1 (fp32, 1 % of the flops)
-    p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
-    p.M = 9 * CIN; p.N = C1; p.K = M; p.A = state; p.B = n->da1; p.ldb = C1; p.C = G[P_C1W]; p.ldc = C1;
-    n->launches += launch_gemm<A_IM2COL_T, B_ROW, 32, CIN>(p, n->partial_cap, n->n_sms, s);
-    launch_colsum(n, n->da1, M, C1, G[P_C1B], s);
+    // conv1: db = column sums of dY; dWc1^T [32][64] = dY^T A1 (MN-major operands, 32-wide A slabs, split over the rows),
+    // reduced and transposed into the [(tap, c)][32] layout.  The observation needs no gradient.
+    launch_colsum_bf16(n, n->da1b, M, C1, G[P_C1B], s);
+    {
+        int splits = n->n_sms;
+        while (splits > 1 && (size_t)splits * C1 * 64 > n->partial_cap) --splits;
+        ep = tc::Epilogue{};
+        ep.out_f32 = n->partial; ep.ldc = 64; ep.partial = n->partial;
+        if ((e = tc::launch_tn<64, 4, 32>(n->da1b, C1, n->A1, 64, C1, 64, M, ep, &splits, s)) != cudaSuccess) return e;
+        if (splits == 1) return cudaErrorInvalidValue;      // (never: M / 64 k-blocks >> 1) the reduce below expects partials
+        bf::conv1_wgrad_reduce_kernel<<<54, 256, 0, s>>>(n->partial, splits, G[P_C1W]);
+        n->launches += 2;
+    }
     return cudaGetLastError();
 }
 

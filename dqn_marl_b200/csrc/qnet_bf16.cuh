@@ -17,16 +17,90 @@ template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
 
+// conv1 on the tensor cores: the 6-channel observation is too narrow for a TMA box (12-byte pixels), so its im2col rows are
+// written once per forward: obs f32 [B][11][11][6] -> A1 bf16 [B*121][64], column k = tap*6 + c for k < 54, zero above.
+// One thread = 8 consecutive columns of one row (a 16-byte store).
+__global__ void __launch_bounds__(256)
+im2col_obs_bf16_kernel(const float* __restrict__ obs, bf16* __restrict__ A1, long long B) {
+    // two samples per CTA: the 2 x 726 floats are staged in shared memory (coalesced), then every thread emits 16-byte chunks
+    __shared__ float win[2][728];
+    const long long b0 = (long long)blockIdx.x * 2;
+    const int ns = (b0 + 1 < B) ? 2 : 1;
+    for (int t = threadIdx.x; t < ns * 726; t += 256) win[t / 726][t % 726] = __ldg(obs + b0 * 726 + t);
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < ns * 121 * 8; ch += 256) {
+        const int sidx = ch / (121 * 8), r = ch - sidx * (121 * 8);
+        const int q = r >> 3, k0 = (r & 7) * 8;
+        const int i = q / 11, j = q - i * 11;
+        __align__(16) bf16 v[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int k = k0 + t;
+            float x = 0.f;
+            if (k < 54) {
+                const int tap = k / 6, c = k - tap * 6;
+                const int ii = i + tap / 3 - 1, jj = j + tap % 3 - 1;
+                if ((unsigned)ii < 11u && (unsigned)jj < 11u) x = win[sidx][(ii * 11 + jj) * 6 + c];
+            }
+            v[t] = __float2bfloat16(x);
+        }
+        *reinterpret_cast<uint4*>(A1 + ((b0 + sidx) * 121 + q) * 64 + k0) = *reinterpret_cast<const uint4*>(v);
+    }
+}
+// conv1 weights Wc[(tap*6 + c)][32] f32 -> GEMM operand W1f[32][64] bf16 (K padded 54 -> 64 with zeros)
+__global__ void __launch_bounds__(256)
+conv1_weight_bf16_kernel(const float* __restrict__ wc, bf16* __restrict__ w1f) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 32 * 64) return;
+    const int n = idx >> 6, k = idx & 63;
+    w1f[idx] = __float2bfloat16(k < 54 ? wc[k * 32 + n] : 0.f);
+}
+// conv1 weight gradient: partial[split][n (32)][k (64)] (the TN GEMM computes dY^T A1) -> dWc[(tap*6 + c)][32], fixed order
+__global__ void __launch_bounds__(256)
+conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, float* __restrict__ dwc) {
+    // one CTA per k (54): thread = (n, split group of 8); the groups are combined through shared memory in a fixed order
+    __shared__ float red[8][32];
+    const int k = blockIdx.x, n = threadIdx.x & 31, sg = threadIdx.x >> 5;
+    float acc = 0.f;
+    for (int s = sg; s < splits; s += 8) acc += partial[((size_t)s * 32 + n) * 64 + k];
+    red[sg][n] = acc;
+    __syncthreads();
+    if (sg == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += red[g][n];
+        dwc[k * 32 + n] = t;
+    }
+}
+
 // f32 [R][C] -> bf16 [R][C] and (optionally) bf16 [C][R]
 __global__ void __launch_bounds__(256)
 cast_transpose_kernel(const float* __restrict__ src, bf16* __restrict__ dst, bf16* __restrict__ dst_t, long long R, int C) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= R * C) return;
-    const long long r = idx / C;
-    const int c = (int)(idx - r * C);
-    const bf16 v = __float2bfloat16(src[idx]);
-    if (dst) dst[idx] = v;
-    if (dst_t) dst_t[(long long)c * R + r] = v;
+    // 32 x 32 tiles through shared memory: both the row-major and the transposed copy are written coalesced
+    __shared__ float tile[32][33];
+    const int tiles_c = (C + 31) / 32;
+    const long long r0 = (long long)(blockIdx.x / tiles_c) * 32;
+    const int c0 = (blockIdx.x % tiles_c) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long long r = r0 + ty + 8 * k;
+        const int c = c0 + tx;
+        float v = 0.f;
+        if (r < R && c < C) {
+            v = src[r * C + c];
+            if (dst) dst[r * C + c] = __float2bfloat16(v);
+        }
+        tile[ty + 8 * k][tx] = v;
+    }
+    if (!dst_t) return;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k;
+        const long long r = r0 + tx;
+        if (r < R && c < C) dst_t[(long long)c * R + r] = __float2bfloat16(tile[tx][ty + 8 * k]);
+    }
 }
 
 // conv weight re-layouts from the fp32 kernel layout Wc[(tap*Cin + c)][Cout]:

@@ -146,9 +146,24 @@ class VecEvacuationEnv:
         return self.obs, self.reward, self.done
 
     def step_into(self, actions_i32: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor):
-        """Zero-overhead variant for benchmarks / trainers: caller-owned, correctly typed device tensors."""
+        """Low-overhead variant for benchmarks / trainers: caller-owned, correctly typed device tensors."""
         _lib.check(self.lib.mq_env_step(self._h, _lib.ptr(actions_i32), _lib.ptr(obs), None, _lib.ptr(reward), _lib.ptr(done),
                                         self._stream()), "mq_env_step")
+
+    def bind_step(self, obs: torch.Tensor, reward: torch.Tensor, done: torch.Tensor, stream: Optional[torch.cuda.Stream] = None):
+        """Pre-bound step for launch-rate-critical loops: returns fn(actions_i32) that enqueues one step into the given
+        output tensors on `stream` (default: the current stream at bind time) with the pointer conversions done once —
+        a 58 us kernel leaves ~15 us of Python per launch."""
+        fn, h = self.lib.mq_env_step, self._h
+        po, pr, pd = _lib.ptr(obs), _lib.ptr(reward), _lib.ptr(done)
+        st = C.c_void_p((stream or torch.cuda.current_stream(self.device)).cuda_stream)
+        keep = (obs, reward, done)
+
+        def step(actions_i32: torch.Tensor, _keep=keep):
+            rc = fn(h, C.c_void_p(actions_i32.data_ptr()), po, None, pr, pd, st)
+            if rc:
+                _lib.check(rc, "mq_env_step")
+        return step
 
     # ---- host-buffer interface (gym-style step_async / step_wait) ------------------------------------------------
     def step_async(self, actions_host: torch.Tensor):
