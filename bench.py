@@ -72,42 +72,61 @@ def load_traffic(workload):
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """SM clock / throttle-reason samples DURING the timed region (the profiling recipe's clocks line): an `nvidia-smi -lms 100`
+    subprocess started well before the region (its start-up takes longer than a short timed region); `mark()` brackets the
+    region and only samples whose timestamp falls inside it are used.  The period stays at 100 ms on purpose: polling at
+    20 ms (nvidia-smi) or 5 ms (an in-process NVML thread) slowed the 58 us env-step launches by 11 % (measured)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t0 = self.t1 = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def mark(self):
+        import datetime
+        if self.t0 is None:
+            self.t0 = datetime.datetime.now()
+        else:
+            self.t1 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = []
+        rows, all_rows = [], []
         with open(self.f.name) as f:
             for line in f:
                 c = [x.strip() for x in line.split(",")]
-                if len(c) >= 7:
+                if len(c) >= 8:
                     try:
-                        rows.append((float(c[0]), float(c[1]), float(c[2]), c[3:7]))
+                        ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
+                        row = (float(c[1]), float(c[2]), float(c[3]), c[4:8])
                     except ValueError:
-                        pass
+                        continue
+                    all_rows.append(row)
+                    if self.t0 and self.t1 and self.t0 <= ts <= self.t1 + datetime.timedelta(milliseconds=100):
+                        rows.append(row)
         os.unlink(self.f.name)
+        out["samples_in_region"] = len(rows)
+        if not rows:                       # region shorter than the sampling period: fall back to the samples under load
+            rows = [r for r in all_rows if r[2] > 250.0]
         if rows:
-            busy = [r for r in rows if r[2] > 250.0] or rows
-            sm = sorted(r[0] for r in busy)
+            sm = sorted(r[0] for r in rows)
             out["sm_mhz"] = sm[len(sm) // 2]
             out["sm_max_mhz"] = rows[0][1]
             names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -199,6 +218,7 @@ def run_ours(args, wl):
     rew = [torch.empty((E,), dtype=torch.float64, device=dev) for _ in range(n_rot)]
     don = [torch.empty((E,), dtype=torch.uint8, device=dev) for _ in range(n_rot)]
 
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get('MQ_BENCH_NO_SAMPLER')) else None      # started early: nvidia-smi needs ~100 ms before its first sample
     for b, env in enumerate(envs):
         env.reset()
     # prime: bring every batch to a desynchronised mid-episode mix (untimed)
@@ -223,15 +243,18 @@ def run_ours(args, wl):
     for _ in range(max(args.warmup, 3)):
         one_step()
     torch.cuda.synchronize(dev)
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = sum(e.launch_count for e in envs)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); torch.cuda.synchronize(dev)
+    if sampler:
+        sampler.mark()
     ev0.record()
     for _ in range(args.steps):
         one_step()
     ev1.record()
     torch.cuda.synchronize(dev); barrier()
+    if sampler:
+        sampler.mark()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = sum(e.launch_count for e in envs) - launches0
     clocks = sampler.stop() if sampler else None
@@ -440,7 +463,7 @@ def run_learner_loop(args, wl, layout, dev, rank, world, precision="bf16"):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--steps", type=int, default=6000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libmarl_b200.so")
+SO_PATH = os.environ.get("MARL_B200_SO") or os.path.join(HERE, "libmarl_b200.so")      # override: A/B timing of two builds
 
 MQ_MAX_ROBOTS = 4
 MQ_OBS_SIZE = 726

@@ -516,7 +516,10 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
 
         // ---- phase 2 (people.py:221-230, 255-297): 4 lanes score the 8 directions of one mover ----------------
         {
-            const int q = lane & 3, R = cfg.R;
+            int rbx[MAXR], rby[MAXR];
+#pragma unroll
+            for (int r = 0; r < MAXR; ++r) { rbx[r] = rob[r < cfg.R ? r : 0][0]; rby[r] = rob[r < cfg.R ? r : 0][1]; }
+            const int q = lane & 3;
             const int n_items = (n_mov * 4 + 31) & ~31;          // whole warps take part in the shuffles
             for (int it = wt; it < n_items; it += TW) {
                 const int mi = it >> 2;
@@ -538,24 +541,20 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                     }
                     if (adm[0] || adm[1]) {
                         const uint4 w = philox4x32(env_id, tick, (uint32_t)i, (uint32_t)q, cfg.seed);
-                        // the repulsion only reaches cells closer than 5 to a robot (people.py:95,282): a mover more than 6 cells
-                        // away from every robot in x or y has eff == 0 for all of its neighbours
-                        bool near = false;
-                        for (int r = 0; r < R; ++r) near = near || (abs(x - rob[r][0]) <= 6 && abs(y - rob[r][1]) <= 6);
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
                             if (!adm[k]) continue;
                             const int d = q * 2 + k;
-                            double eff = 0.0;
-                            if (near) {
-                                const int nx = x + move_dx(d), ny = y + move_dy(d);
-                                int d2 = 0x7FFFFFFF;
-                                for (int r = 0; r < R; ++r) {               // |ddx|, |ddy| <= 7 for the robots that matter
-                                    const int ddx = nx - rob[r][0], ddy = ny - rob[r][1];
-                                    if (abs(ddx) <= 8 && abs(ddy) <= 8) d2 = min(d2, ddx * ddx + ddy * ddy);
-                                }
-                                eff = d2 < 25 ? c_repel[d2] : 0.0;
+                            const int nx = x + move_dx(d), ny = y + move_dy(d);
+                            int d2 = 0x7FFFFFFF;
+#pragma unroll
+                            for (int r = 0; r < MAXR; ++r) {
+                                const int ddx = nx - rbx[r], ddy = ny - rby[r];
+                                // robots may sit far off-map (evaluate_strategies.py:83 sets [1000,1000])
+                                const int qq = (abs(ddx) > 30000 || abs(ddy) > 30000) ? 0x7FFFFFFF : ddx * ddx + ddy * ddy;
+                                d2 = min(d2, qq);               // r >= R repeats robot 0: harmless for the minimum
                             }
+                            const double eff = d2 < 25 ? c_repel[d2] : 0.0;
                             const double u = k ? u53(w.z, w.w) : u53(w.x, w.y);
                             const double noise = -0.1 + (0.1 - -0.1) * u;        // random.uniform(-0.1, 0.1)
                             const double score = (dpv[k] + eff) + noise;           // people.py:287-291
