@@ -124,7 +124,8 @@ template <bool BIG> __device__ __forceinline__ unsigned long long tab_ld(const u
 template <int WPE, int CW>
 struct Group {
     static constexpr int SIZE = 32 * WPE;
-    static constexpr int WORKERS = WPE == 1 ? 32 : SIZE - 32;
+    static constexpr bool CHAIN = WPE >= 8;            // a dedicated chain warp only pays for wide groups
+    static constexpr int WORKERS = CHAIN ? SIZE - 32 : SIZE;
     int gtid, gid;
     __device__ __forceinline__ Group() : gtid(threadIdx.x % SIZE), gid(threadIdx.x / SIZE) {}
     __device__ __forceinline__ void sync() const {          // all threads of the group
@@ -134,9 +135,10 @@ struct Group {
     }
     __device__ __forceinline__ void wsync() const {         // worker threads only
         if (WPE == 1) __syncwarp();
+        else if (!CHAIN && WPE == CW) __syncthreads();
         else asm volatile("bar.sync %0, %1;" ::"r"(2 * gid + 2), "r"(WORKERS) : "memory");
     }
-    __device__ __forceinline__ bool worker() const { return WPE == 1 || gtid < WORKERS; }
+    __device__ __forceinline__ bool worker() const { return !CHAIN || gtid < WORKERS; }
 };
 
 __device__ __forceinline__ uint32_t bm_get(const uint32_t* bm, int wpr, int x, int y) {
@@ -346,7 +348,7 @@ __device__ __forceinline__ double health_chain(const double* h, int N) {
 constexpr int PF = 4;     // persons per thread whose state is fetched before any of them is processed
 
 template <int WPE, int CW, bool BIG>
-__global__ void __launch_bounds__(32 * CW, WPE == 1 ? 7 : (BIG ? 1 : 3))      // 28 env-warps / 3 env-CTAs resident per SM (BIG: one)
+__global__ void __launch_bounds__(32 * CW, WPE < 8 ? 28 / CW : (BIG ? 1 : 3))      // 28 env-warps / 3 env-CTAs resident per SM (BIG: one)
 env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ actions, float* obs, double* obs64,
                 double* reward_out, uint8_t* done_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -507,7 +509,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     }
     g.sync();
 
-    if (WPE > 1 && !g.worker()) {
+    if (G::CHAIN && !g.worker()) {
         // chain warp: the left-to-right health sum only needs phase 1; it overlaps with everything the workers do
         if (lane == 0) s_sum[1] = health_chain(sm.health, N);
     } else {
@@ -716,7 +718,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
             __syncwarp();
             if (lane == 0) {
                 s_sum[0] = combine_leaves(n, sm.leaf_sum);
-                if (WPE == 1) s_sum[1] = health_chain(sm.health, N);
+                if (!G::CHAIN) s_sum[1] = health_chain(sm.health, N);
             }
         }
         // fire models step (evacuation_env.py:138-142; fire_model.py:63-67) — the observation uses the new step
@@ -814,7 +816,8 @@ struct mq_env {
 };
 
 static int round_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
-constexpr int SMALL_CW = 4;      // warps (= envs) per CTA in warp-per-env mode
+constexpr int SMALL_CW = 4;      // warps per CTA of the small-env variants (1, 2 or 4 warps per env)
+constexpr int SMALL_WPE = 1;     // default warps per env for small envs
 constexpr int BIG_WPE = 32;      // warps per env (= per CTA) of the BIG variant
 
 extern "C" int mq_env_state_sizes(const mq_env_cfg* cfg, const mq_layout* layout, int64_t* n_pad, int64_t* rmap_words) {
@@ -833,7 +836,7 @@ typedef void (*ResetFn)(mq::DevLayout, mq::DevCfg, mq::DevState, const uint8_t*,
 struct Variant { int wpe, cw; bool big; StepFn step; ResetFn reset; };
 #define MQ_VARIANT(WPE, CW, BIG) {WPE, CW, BIG, mq::env_step_kernel<WPE, CW, BIG>, mq::env_reset_kernel<WPE, CW, BIG>}
 static const Variant k_variants[] = {
-    MQ_VARIANT(1, SMALL_CW, false), MQ_VARIANT(8, 8, false), MQ_VARIANT(8, 8, true), MQ_VARIANT(16, 16, true), MQ_VARIANT(32, 32, true),
+    MQ_VARIANT(1, SMALL_CW, false), MQ_VARIANT(2, SMALL_CW, false), MQ_VARIANT(4, SMALL_CW, false), MQ_VARIANT(8, 8, false), MQ_VARIANT(8, 8, true), MQ_VARIANT(16, 16, true), MQ_VARIANT(32, 32, true),
 };
 static int find_variant(int wpe, bool big) {
     for (int i = 0; i < (int)(sizeof(k_variants) / sizeof(k_variants[0])); ++i)
@@ -912,7 +915,11 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 32);
     // one warp per env for small envs (no CTA barriers, 4 envs per CTA), one CTA per env otherwise; envs whose
     // person arrays do not fit shared memory keep only the occupancy bitmap there (BIG)
-    e->wpe = (c.N <= 256 && (size_t)c.smem_per_env * SMALL_CW + 2048 <= (size_t)max_smem) ? 1 : 8;
+    e->wpe = (c.N <= 256 && (size_t)c.smem_per_env * SMALL_CW + 2048 <= (size_t)max_smem) ? SMALL_WPE : 8;
+    if (e->wpe != 8) {
+        if (const char* v = getenv("MQ_SMALL_WPE")) { int w = atoi(v); if (w == 1 || w == 2 || w == 4) e->wpe = w; }
+        c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 32 * e->wpe);
+    }
     if (e->wpe == 8) c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 256);
     e->big = e->wpe == 8 && (size_t)c.smem_per_env + 2048 > (size_t)max_smem;
     if (e->big) {
@@ -929,7 +936,7 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
         c.scratch = (unsigned char*)e->d_scratch;
     }
     e->variant = find_variant(e->wpe, e->big);
-    const int groups = e->wpe == 1 ? SMALL_CW : 1;
+    const int groups = e->wpe < 8 ? SMALL_CW / e->wpe : 1;
     e->threads = 32 * k_variants[e->variant].cw;
     e->smem = (size_t)c.smem_per_env * groups;
     if ((int)e->smem + 2048 > max_smem) {
