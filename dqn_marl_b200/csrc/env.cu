@@ -346,6 +346,7 @@ __device__ __forceinline__ double health_chain(const double* h, int N) {
 // The fused step.
 // ---------------------------------------------------------------------------------------------
 constexpr int PF = 4;     // persons per thread whose state is fetched before any of them is processed
+constexpr int SCORE_UNROLL = 2;     // movers scored per lane and iteration of phase 2 (independent chains)
 
 template <int WPE, int CW, bool BIG>
 __global__ void __launch_bounds__(32 * CW, WPE < 8 ? 28 / CW : (BIG ? 1 : 3))      // 28 env-warps / 3 env-CTAs resident per SM (BIG: one)
@@ -521,57 +522,74 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
             int rbx[MAXR], rby[MAXR];
 #pragma unroll
             for (int r = 0; r < MAXR; ++r) { rbx[r] = rob[r < cfg.R ? r : 0][0]; rby[r] = rob[r < cfg.R ? r : 0][1]; }
-            const int q = lane & 3;
+            const int q = lane & 3, R = cfg.R;
             const int n_items = (n_mov * 4 + 31) & ~31;          // whole warps take part in the shuffles
-            for (int it = wt; it < n_items; it += TW) {
-                const int mi = it >> 2;
-                const bool act = mi < n_mov;
-                int i = 0, x = 0, y = 0;
-                double best_score = -INFINITY;
-                int best_dir = 8;
-                if (act) {
-                    i = sm.mov[mi];
-                    const uint32_t p = sm.pos[i];
-                    x = (int)(p & 0xFFFFu); y = (int)(p >> 16);
-                    const double2 dpv2 = __ldg(reinterpret_cast<const double2*>(lay.dp5 + (size_t)(x * stride + y) * 8) + q);
-                    const double dpv[2] = {dpv2.x, dpv2.y};
-                    bool adm[2];
+            // U items per lane and iteration, written stage by stage and branch-free so that the U independent Philox /
+            // scoring chains interleave: the loop is bound by the latency of one chain, not by issue slots
+            constexpr int U = SCORE_UNROLL;
+            for (int it0 = wt; it0 < n_items; it0 += U * TW) {
+                int mi[U], i[U], x[U], y[U];
+                bool act[U];
+                double dpv[U][2];
+                uint4 w[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int it = it0 + u * TW;
+                    mi[u] = it >> 2;
+                    act[u] = it < n_items && mi[u] < n_mov;
+                    i[u] = act[u] ? (int)sm.mov[mi[u]] : 0;
+                    const uint32_t p = act[u] ? sm.pos[i[u]] : 0x00010001u;       // (1,1): neighbours stay inside the bitmap
+                    x[u] = (int)(p & 0xFFFFu); y[u] = (int)(p >> 16);
+                    dpv[u][0] = -INFINITY; dpv[u][1] = -INFINITY;
+                    if (act[u]) {
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(lay.dp5 + (size_t)(x[u] * stride + y[u]) * 8) + q);
+                        dpv[u][0] = v.x; dpv[u][1] = v.y;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) w[u] = philox4x32(env_id, tick, (uint32_t)i[u], (uint32_t)q, cfg.seed);
+                double best_score[U];
+                int best_dir[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    best_score[u] = -INFINITY; best_dir[u] = 8;
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         const int d = q * 2 + k;
-                        adm[k] = (dpv[k] > -INFINITY) && !bm_get(sm.bm, wpr, x + move_dx(d), y + move_dy(d));
-                    }
-                    if (adm[0] || adm[1]) {
-                        const uint4 w = philox4x32(env_id, tick, (uint32_t)i, (uint32_t)q, cfg.seed);
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            if (!adm[k]) continue;
-                            const int d = q * 2 + k;
-                            const int nx = x + move_dx(d), ny = y + move_dy(d);
-                            int d2 = 0x7FFFFFFF;
-#pragma unroll
-                            for (int r = 0; r < MAXR; ++r) {
-                                const int ddx = nx - rbx[r], ddy = ny - rby[r];
-                                // robots may sit far off-map (evaluate_strategies.py:83 sets [1000,1000])
-                                const int qq = (abs(ddx) > 30000 || abs(ddy) > 30000) ? 0x7FFFFFFF : ddx * ddx + ddy * ddy;
-                                d2 = min(d2, qq);               // r >= R repeats robot 0: harmless for the minimum
-                            }
-                            const double eff = d2 < 25 ? c_repel[d2] : 0.0;
-                            const double u = k ? u53(w.z, w.w) : u53(w.x, w.y);
-                            const double noise = -0.1 + (0.1 - -0.1) * u;        // random.uniform(-0.1, 0.1)
-                            const double score = (dpv[k] + eff) + noise;           // people.py:287-291
-                            if (score > best_score) { best_score = score; best_dir = d; }
+                        const int nx = x[u] + move_dx(d), ny = y[u] + move_dy(d);
+                        const bool adm = (dpv[u][k] > -INFINITY) && !bm_get(sm.bm, wpr, nx, ny);
+                        // squared distance to the nearest robot, coordinates saturated at 30000 (robots may sit far off-map:
+                        // evaluate_strategies.py:83 sets [1000,1000]; anything >= 25 means "out of range")
+                        int d2;
+                        {
+                            const int ax = min(abs(nx - rbx[0]), 30000), ay = min(abs(ny - rby[0]), 30000);
+                            d2 = ax * ax + ay * ay;
                         }
+                        if (R > 1) {                         // warp-uniform
+#pragma unroll
+                            for (int r = 1; r < MAXR; ++r) {
+                                const int ax = min(abs(nx - rbx[r]), 30000), ay = min(abs(ny - rby[r]), 30000);
+                                d2 = min(d2, ax * ax + ay * ay);       // r >= R repeats robot 0: harmless for the minimum
+                            }
+                        }
+                        const double eff = d2 < 25 ? c_repel[d2] : 0.0;
+                        const double un = k ? u53(w[u].z, w[u].w) : u53(w[u].x, w[u].y);
+                        const double noise = -0.1 + (0.1 - -0.1) * un;       // random.uniform(-0.1, 0.1)
+                        const double score = (dpv[u][k] + eff) + noise;        // people.py:287-291
+                        if (adm && score > best_score[u]) { best_score[u] = score; best_dir[u] = d; }
                     }
                 }
                 // strict '>' in direction order (people.py:293): larger score wins, ties go to the lower direction
 #pragma unroll
-                for (int o = 1; o <= 2; o <<= 1) {
-                    const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score, o);
-                    const int od = __shfl_xor_sync(0xFFFFFFFFu, best_dir, o);
-                    if (os > best_score || (os == best_score && od < best_dir)) { best_score = os; best_dir = od; }
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int o = 1; o <= 2; o <<= 1) {
+                        const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score[u], o);
+                        const int od = __shfl_xor_sync(0xFFFFFFFFu, best_dir[u], o);
+                        if (os > best_score[u] || (os == best_score[u] && od < best_dir[u])) { best_score[u] = os; best_dir[u] = od; }
+                    }
+                    if (act[u] && q == 0 && best_dir[u] < 8) sm.mv[mi[u]] = (uint32_t)best_dir[u] << 20;
                 }
-                if (act && q == 0 && best_dir < 8) sm.mv[mi] = (uint32_t)best_dir << 20;
             }
             // proposals, one mover per lane: the movers this warp has just scored (8 per scoring iteration), so only a
             // __syncwarp separates the two loops.  move_plan[(new_x,new_y)] (people.py:228-230) + shuffle priority (:239)
