@@ -50,6 +50,7 @@ struct DevLayout {
 struct DevCfg {
     int n_envs, N, n_pad, R;
     unsigned long long seed;
+    PhiloxKeys pk;                     // round keys of `seed`
     int env_id_base, max_steps, reset_robots, reset_fire, auto_reset;
     int hash_cap, hash_shift, n_leaf_max;
     int smem_per_env;
@@ -220,7 +221,7 @@ __device__ void reset_env(const Group<WPE, CW>& g, const DevLayout& lay, const D
             y = inject[((size_t)env * N + i) * 2 + 1];
         } else {
             for (uint32_t attempt = 0;; ++attempt) {   // randint(1, L-2), randint(1, W-2) until Check_Valid
-                uint4 w = philox4x32(env_id, episode, (uint32_t)i, STREAM_SPAWN + (attempt >> 1), cfg.seed);
+                uint4 w = philox4x32(env_id, episode, (uint32_t)i, STREAM_SPAWN + (attempt >> 1), cfg.pk);
                 uint32_t wx = (attempt & 1) ? w.z : w.x, wy = (attempt & 1) ? w.w : w.y;
                 x = 1 + (int)__umulhi(wx, (uint32_t)(lay.L - 2));
                 y = 1 + (int)__umulhi(wy, (uint32_t)(lay.W - 2));
@@ -491,7 +492,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
             const double a = st.acc[base + i];
             uint32_t fl = 0u;
             const double danger = box_lookup(lay.ctr_box, lay.danger_ctr, fire_step, (int)(p & 0xFFFFu), (int)(p >> 16));
-            const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
+            const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.pk);
             const double u = u53(w4.x, w4.y);
             double loss;
             if (danger >= 0.8) loss = danger * 50.0 + (1.0 + (3.0 - 1.0) * u);
@@ -547,7 +548,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u) w[u] = philox4x32(env_id, tick, (uint32_t)i[u], (uint32_t)q, cfg.seed);
+                for (int u = 0; u < U; ++u) w[u] = philox4x32(env_id, tick, (uint32_t)i[u], (uint32_t)q, cfg.pk);
                 double best_score[U];
                 int best_dir[U];
 #pragma unroll
@@ -605,7 +606,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                 const int best_dir = (int)(mv >> 20);
                 const uint32_t p = sm.pos[i];
                 const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
-                const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.seed);
+                const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.pk);
                 const uint32_t t = (uint32_t)((x + move_dx(best_dir)) * stride + (y + move_dy(best_dir)));
                 uint32_t hh = hash_cell(t, cfg.hash_shift);
                 for (;;) {
@@ -915,7 +916,7 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
 
     mq::DevCfg& c = e->cfg;
     c.n_envs = cfg->n_envs; c.N = cfg->n_people; c.n_pad = (cfg->n_people + 15) / 16 * 16; c.R = cfg->n_robots;
-    c.seed = cfg->seed; c.env_id_base = cfg->env_id_base; c.max_steps = cfg->max_steps;
+    c.seed = cfg->seed; c.pk = mq::philox_keys(cfg->seed); c.env_id_base = cfg->env_id_base; c.max_steps = cfg->max_steps;
     c.reset_robots = cfg->reset_robots; c.reset_fire = cfg->reset_fire; c.auto_reset = cfg->auto_reset;
     int want = c.N + c.N / 3 + 8;                      // load factor <= 0.75 even if everybody proposes a distinct cell
     c.hash_cap = round_pow2(want < 64 ? 64 : want);    // < 2^20 (20-bit slot ids in Smem::mv)

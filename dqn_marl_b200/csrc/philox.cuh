@@ -35,6 +35,26 @@ __host__ __device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, u
     return make_uint4(c0, c1, c2, c3);
 }
 
+// Same function with the ten round keys precomputed (k_r = seed words + r * Weyl constants): the env kernels keep them in the
+// kernel-parameter constant bank, which turns the key schedule (20 integer adds per call) into constant operands of the xors.
+struct PhiloxKeys { uint32_t k[20]; };
+__host__ __device__ inline PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys pk;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { pk.k[2 * r] = k0; pk.k[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+    return pk;
+}
+__device__ __forceinline__ uint4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& pk) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = h1 ^ c1 ^ pk.k[2 * r], n2 = h0 ^ c3 ^ pk.k[2 * r + 1];
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // CPython random.random() / NumPy legacy random_sample: ((a>>5)*2^26 + (b>>6)) / 2^53, exact.
 __host__ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
     return (double)(((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6)) * (1.0 / 9007199254740992.0);
