@@ -346,7 +346,7 @@ __device__ __forceinline__ double health_chain(const double* h, int N) {
 // ---------------------------------------------------------------------------------------------
 // The fused step.
 // ---------------------------------------------------------------------------------------------
-constexpr int PF = 4;     // persons per thread whose state is fetched before any of them is processed
+constexpr int PF_MAX = 5;  // persons per thread whose state is fetched before any of them is processed (5 x 32 >= 150: one pass at C2)
 constexpr int SCORE_UNROLL = 2;     // movers scored per lane and iteration of phase 2 (independent chains)
 
 template <int WPE, int CW, bool BIG>
@@ -426,7 +426,9 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     auto advance = [&](int i, uint32_t fl, double h, double a) -> bool {
         bool mover = false;
         if (!(fl & 2u)) {
-            const double speed = (h < 20.0) ? 0.4 : 1.0 * (0.3 + 0.7 * (h / 100.0));
+            double hr = 1.0;                              // 100.0 / 100.0; most people are unhurt: skip the fp64 division
+            if (h != 100.0) hr = h / 100.0;
+            const double speed = (h < 20.0) ? 0.4 : 1.0 * (0.3 + 0.7 * hr);
             a += speed * 0.5;
             if (a >= 1.0) { a -= 1.0; mover = true; }
             st.acc[base + i] = a;
@@ -448,6 +450,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
             }
         }
     };
+    constexpr int PF = WPE == 1 ? PF_MAX : 4;
     for (int i0 = 0; i0 < N; i0 += T * PF) {
         uint32_t p_[PF], fl_[PF];
         double h_[PF], a_[PF], dg_[PF];
