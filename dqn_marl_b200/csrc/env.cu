@@ -363,6 +363,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     __shared__ int s_cnt_all[GROUPS][6];        // evacuated, dead, guidance in halves, live, movers, reset flag
     __shared__ int s_wtot_all[GROUPS][WPE];
     __shared__ double s_sum_all[GROUPS][2];     // sum of distances, total health
+    __shared__ int s_pre[GROUPS + 1];           // COOP: exclusive prefix of the envs' scoring chunks
 
     const G g;
     const int env = blockIdx.x * GROUPS + g.gid;
@@ -522,7 +523,106 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         const int n_mov = s_cnt[4];
 
         // ---- phase 2 (people.py:221-230, 255-297): 4 lanes score the 8 directions of one mover ----------------
-        {
+        // Warp-per-env CTAs with many envs (COOP): the cost of this phase differs by 10x between envs (everybody moves /
+        // nobody moves) and the launch is one wave, so the slowest env of the whole grid sets the kernel time.  The warps of
+        // a CTA therefore score the movers of ALL its envs together: the envs' 32-item chunks are numbered through an
+        // exclusive prefix and dealt to the warps round-robin, between two CTA barriers.
+        constexpr bool COOP = WPE == 1 && CW >= 8;
+        const bool coop = COOP && (blockIdx.x + 1) * GROUPS <= cfg.n_envs;       // CTA-uniform; a partial last CTA works per warp
+        if (coop) {
+            __syncthreads();                       // every env of the CTA has its mover list and its robots
+            if (g.gid == 0) {
+                const int nch = lane < GROUPS ? (s_cnt_all[lane][4] * 4 + 31) >> 5 : 0;
+                int incl = nch;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += v; }
+                if (lane < GROUPS) s_pre[lane] = incl - nch;
+                if (lane == GROUPS - 1) s_pre[GROUPS] = incl;
+            }
+            __syncthreads();
+            const int total = s_pre[GROUPS];
+            const int q = lane & 3, R = cfg.R;
+            constexpr int U = SCORE_UNROLL;
+            for (int c0 = g.gid; c0 < total; c0 += U * GROUPS) {
+                int mi[U], i[U], x[U], y[U], rx0[U], ry0[U], eo[U];
+                bool act[U];
+                double dpv[U][2];
+                uint4 w[U];
+                const uint16_t* movp[U]; const uint32_t* posp[U]; const uint32_t* bmp[U]; uint32_t* mvp[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int c = c0 + u * GROUPS;
+                    int e = 0;
+                    if (c < total) {                // owner env of chunk c: last e with s_pre[e] <= c (<= 32 entries, warp-uniform)
+                        int lo = 0, hi = GROUPS - 1;
+                        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (s_pre[mid] <= c) lo = mid; else hi = mid - 1; }
+                        e = lo;
+                    }
+                    eo[u] = e;
+                    const long long delta = (long long)(e - g.gid) * cfg.smem_per_env;
+                    movp[u] = reinterpret_cast<const uint16_t*>(reinterpret_cast<const unsigned char*>(sm.mov) + delta);
+                    posp[u] = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(sm.pos) + delta);
+                    bmp[u] = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(sm.bm) + delta);
+                    mvp[u] = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(sm.mv) + delta);
+                    rx0[u] = s_rob[e][0][0]; ry0[u] = s_rob[e][0][1];
+                    const int it = (c - s_pre[e]) * 32 + lane;
+                    mi[u] = it >> 2;
+                    act[u] = c < total && mi[u] < s_cnt_all[e][4];
+                    i[u] = act[u] ? (int)movp[u][mi[u]] : 0;
+                    const uint32_t p = act[u] ? posp[u][i[u]] : 0x00010001u;
+                    x[u] = (int)(p & 0xFFFFu); y[u] = (int)(p >> 16);
+                    dpv[u][0] = -INFINITY; dpv[u][1] = -INFINITY;
+                    if (act[u]) {
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(lay.dp5 + (size_t)(x[u] * stride + y[u]) * 8) + q);
+                        dpv[u][0] = v.x; dpv[u][1] = v.y;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    w[u] = philox4x32((uint32_t)(cfg.env_id_base + blockIdx.x * GROUPS + eo[u]), (uint32_t)s_sc[eo[u]][MQ_S_TICK], (uint32_t)i[u],
+                                      (uint32_t)q, cfg.pk);
+                double best_score[U];
+                int best_dir[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    best_score[u] = -INFINITY; best_dir[u] = 8;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int d = q * 2 + k;
+                        const int nx = x[u] + move_dx(d), ny = y[u] + move_dy(d);
+                        const bool adm = (dpv[u][k] > -INFINITY) && !bm_get(bmp[u], wpr, nx, ny);
+                        int d2;
+                        {
+                            const int ax = min(abs(nx - rx0[u]), 30000), ay = min(abs(ny - ry0[u]), 30000);
+                            d2 = ax * ax + ay * ay;
+                        }
+                        if (R > 1) {                         // warp-uniform
+                            for (int r = 1; r < R; ++r) {
+                                const int ax = min(abs(nx - s_rob[eo[u]][r][0]), 30000), ay = min(abs(ny - s_rob[eo[u]][r][1]), 30000);
+                                d2 = min(d2, ax * ax + ay * ay);
+                            }
+                        }
+                        const double eff = d2 < 25 ? c_repel[d2] : 0.0;
+                        const double un = k ? u53(w[u].z, w[u].w) : u53(w[u].x, w[u].y);
+                        const double noise = -0.1 + (0.1 - -0.1) * un;       // random.uniform(-0.1, 0.1)
+                        const double score = (dpv[u][k] + eff) + noise;        // people.py:287-291
+                        if (adm && score > best_score[u]) { best_score[u] = score; best_dir[u] = d; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int o = 1; o <= 2; o <<= 1) {
+                        const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score[u], o);
+                        const int od = __shfl_xor_sync(0xFFFFFFFFu, best_dir[u], o);
+                        if (os > best_score[u] || (os == best_score[u] && od < best_dir[u])) { best_score[u] = os; best_dir[u] = od; }
+                    }
+                    if (act[u] && q == 0 && best_dir[u] < 8) mvp[u][mi[u]] = (uint32_t)best_dir[u] << 20;
+                }
+            }
+            __syncthreads();
+        }
+        if (!coop) {
             int rbx[MAXR], rby[MAXR];
 #pragma unroll
             for (int r = 0; r < MAXR; ++r) { rbx[r] = rob[r < cfg.R ? r : 0][0]; rby[r] = rob[r < cfg.R ? r : 0][1]; }
@@ -595,6 +695,9 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                     if (act[u] && q == 0 && best_dir[u] < 8) sm.mv[mi[u]] = (uint32_t)best_dir[u] << 20;
                 }
             }
+        }
+        {
+            const int n_items = (n_mov * 4 + 31) & ~31;
             // proposals, one mover per lane: the movers this warp has just scored (8 per scoring iteration), so only a
             // __syncwarp separates the two loops.  move_plan[(new_x,new_y)] (people.py:228-230) + shuffle priority (:239)
             __syncwarp();
@@ -858,11 +961,11 @@ typedef void (*ResetFn)(mq::DevLayout, mq::DevCfg, mq::DevState, const uint8_t*,
 struct Variant { int wpe, cw; bool big; StepFn step; ResetFn reset; };
 #define MQ_VARIANT(WPE, CW, BIG) {WPE, CW, BIG, mq::env_step_kernel<WPE, CW, BIG>, mq::env_reset_kernel<WPE, CW, BIG>}
 static const Variant k_variants[] = {
-    MQ_VARIANT(1, SMALL_CW, false), MQ_VARIANT(2, SMALL_CW, false), MQ_VARIANT(4, SMALL_CW, false), MQ_VARIANT(8, 8, false), MQ_VARIANT(8, 8, true), MQ_VARIANT(16, 16, true), MQ_VARIANT(32, 32, true),
+    MQ_VARIANT(1, SMALL_CW, false), MQ_VARIANT(1, 14, false), MQ_VARIANT(1, 28, false), MQ_VARIANT(2, SMALL_CW, false), MQ_VARIANT(4, SMALL_CW, false), MQ_VARIANT(8, 8, false), MQ_VARIANT(8, 8, true), MQ_VARIANT(16, 16, true), MQ_VARIANT(32, 32, true),
 };
-static int find_variant(int wpe, bool big) {
+static int find_variant(int wpe, bool big, int cw = 0) {
     for (int i = 0; i < (int)(sizeof(k_variants) / sizeof(k_variants[0])); ++i)
-        if (k_variants[i].wpe == wpe && k_variants[i].big == big) return i;
+        if (k_variants[i].wpe == wpe && k_variants[i].big == big && (cw == 0 || k_variants[i].cw == cw)) return i;
     return -1;
 }
 
@@ -957,8 +1060,17 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
         }
         c.scratch = (unsigned char*)e->d_scratch;
     }
-    e->variant = find_variant(e->wpe, e->big);
-    const int groups = e->wpe < 8 ? SMALL_CW / e->wpe : 1;
+    // warp-per-env: as many envs per CTA as fit one SM (28 = one 896-thread CTA per SM, 14 = two), so that the cooperative
+    // scoring phase averages over many envs; 4 envs per CTA (no cooperation) when the envs' shared memory is too large
+    int small_cw = SMALL_CW;
+    if (e->wpe == 1) {
+        const size_t fixed = 8192;                        // static shared memory of the widest variant + driver reserve
+        if ((size_t)c.smem_per_env * 28 + fixed <= (size_t)max_smem) small_cw = 28;
+        else if (((size_t)c.smem_per_env * 14 + fixed) * 2 <= (size_t)max_smem + 4096) small_cw = 14;
+        if (const char* v = getenv("MQ_SMALL_CW")) { int w = atoi(v); if (w == 4 || w == 14 || w == 28) small_cw = w; }
+    }
+    e->variant = find_variant(e->wpe, e->big, e->wpe == 1 ? small_cw : 0);
+    const int groups = e->wpe < 8 ? small_cw / e->wpe : 1;
     e->threads = 32 * k_variants[e->variant].cw;
     e->smem = (size_t)c.smem_per_env * groups;
     if ((int)e->smem + 2048 > max_smem) {
