@@ -97,8 +97,16 @@ class QNet:
                                         int(n_robots), _lib.ptr(drop_mask), _lib.ptr(out), _lib.ptr(q_out), self._stream()), "mq_qnet_act")
         return out
 
-    def td_backward(self, batch: dict, hp: "_lib.MqHparams", drop_online=None, drop_target=None) -> torch.Tensor:
+    def td_backward(self, batch: dict, hp: "_lib.MqHparams", drop_online=None, drop_target=None, part: int = 0) -> torch.Tensor:
+        """part 0 = the whole differentiable half of learn(); 1 / 2 = its two halves (mq_qnet_td_backward_part): after part 1
+        the gradients of fc1/fc2/fc3 (flat_g[HEAD_OFFSET:]) are final, part 2 adds the convolution layers."""
         B = batch["actions"].shape[0]
+        if part:
+            _lib.check(self.lib.mq_qnet_td_backward_part(self._h, _lib.ptr(batch["states"]), _lib.ptr(batch["actions"]), _lib.ptr(batch["rewards"]),
+                                                         _lib.ptr(batch["next_states"]), _lib.ptr(batch["dones"]), B, C.byref(hp),
+                                                         _lib.ptr(drop_online), _lib.ptr(drop_target), _lib.ptr(self._loss), int(part),
+                                                         self._stream()), "mq_qnet_td_backward_part")
+            return self._loss
         _lib.check(self.lib.mq_qnet_td_backward(self._h, _lib.ptr(batch["states"]), _lib.ptr(batch["actions"]), _lib.ptr(batch["rewards"]),
                                                 _lib.ptr(batch["next_states"]), _lib.ptr(batch["dones"]), B, C.byref(hp),
                                                 _lib.ptr(drop_online), _lib.ptr(drop_target), _lib.ptr(self._loss), self._stream()),

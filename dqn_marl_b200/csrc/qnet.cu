@@ -517,10 +517,15 @@ static cudaError_t conv_wgrad(mq_qnet* n, const bf::bf16* X, const bf::bf16* dY,
 
 // backward of the bf16 path.  Needs: forward_net_bf16(online) just ran (A1, a1b, a2b, a3b, h1, h2 hold the online
 // activations) and n->dq holds dL/dq.
-static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, const uint8_t* drop_online, cudaStream_t s) {
+// part: 0 = everything; 1 = head only (fc3, fc2, fc1: the last ~99 % of the flat gradient, so that its all-reduce can
+// overlap the convolution backward); 2 = the convolution layers only (after a part-1 call)
+static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, const uint8_t* drop_online, cudaStream_t s, int part = 0) {
     float* const* W = n->tl.p; float* const* G = n->tl.g;
     const int M = (int)(B * PIX);
     cudaError_t e;
+    tc::Epilogue ep{};
+    GemmParams p{};
+    if (part != 2) {
     {
         const int chunks = (int)((B + FC3_CHUNK - 1) / FC3_CHUNK);
         float* pw = n->partial; float* pb = n->partial + (size_t)chunks * NA * H2;
@@ -531,10 +536,8 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
     }
     fc3_dgrad_kernel<<<(int)((B * H2 + 255) / 256), 256, 0, s>>>(n->dq, W[P_F3W], n->h2, B, n->dh2, n->dh2b);
     n->launches += 2;
-    GemmParams p{};
     // fc2 on the tensor cores: dW2[256][512] = dh2^T h1 (MN-major operands, split over the batch) ; db2 ; dh1 = dh2 W2 masked
     // by relu(fc1) > 0 and the dropout mask
-    tc::Epilogue ep{};
     {
         int splits = 16;
         while (splits > 1 && (size_t)splits * H2 * H1 > n->partial_cap) --splits;
@@ -564,6 +567,8 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da3b; ep.ldc = FLAT; ep.mask_bf16 = n->a3b;
     if ((e = tc_gemm<128>(n, n->dh1b, H1, n->w1t, H1, (int)B, FLAT, H1, ep, false, s)) != cudaSuccess) return e;
+    }
+    if (part == 1) return cudaGetLastError();
     // conv3: dWc3[(t,c)][n] = im2col(a2)^T dY (implicit, split over samples) ; db ; da2 = conv_flip(dY, Wd3) (masked by a2 > 0).
     // The data-gradient convolutions are L2-bandwidth bound (each sample's dY is read once per tap): two co-resident
     // one-sample CTAs per SM keep more loads in flight than the persistent kernel and measure faster (profiles/README.md)
@@ -686,9 +691,11 @@ extern "C" int mq_qnet_act(mq_qnet* n, const float* obs, int64_t B, float eps, u
 }
 
 // backward of the fp32 parity path from n->dq (loss.backward(), dqn_agent.py:154-155); the online activations are in the workspace
-static void backward_fp32(mq_qnet* n, const float* state, long long B, const uint8_t* drop_online, cudaStream_t s) {
+static void backward_fp32(mq_qnet* n, const float* state, long long B, const uint8_t* drop_online, cudaStream_t s, int part = 0) {
     using namespace mq;
     float* const* W = n->tl.p; float* const* G = n->tl.g;
+    GemmParams p{};
+    if (part != 2) {
     {
         const int chunks = (int)((B + FC3_CHUNK - 1) / FC3_CHUNK);
         float* pw = n->partial; float* pb = n->partial + (size_t)chunks * NA * H2;
@@ -699,7 +706,6 @@ static void backward_fp32(mq_qnet* n, const float* state, long long B, const uin
     }
     fc3_dgrad_kernel<<<(int)((B * H2 + 255) / 256), 256, 0, s>>>(n->dq, W[P_F3W], n->h2, B, n->dh2, nullptr);
     n->launches += 2;
-    GemmParams p{};
     p.batch = (int)B; p.partial = n->partial;
     // fc2: dW2[256][512] = dh2^T h1 ; db2 ; dh1 = dh2 W2, masked by relu(fc1) > 0 and the dropout mask
     p.M = H2; p.N = H1; p.K = (int)B; p.A = n->dh2; p.lda = H2; p.B = n->h1; p.ldb = H1; p.C = G[P_F2W]; p.ldc = H1;
@@ -717,6 +723,8 @@ static void backward_fp32(mq_qnet* n, const float* state, long long B, const uin
     p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
     p.M = (int)B; p.N = FLAT; p.K = H1; p.A = n->dh1; p.lda = H1; p.B = W[P_F1W]; p.ldb = FLAT; p.C = n->da3; p.ldc = FLAT; p.mask_act = n->a3;
     n->launches += launch_gemm<A_ROW, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    }
+    if (part == 1) return;
     // conv3: dWc3[(tap,c)][n] = im2col(a2)^T da3 ; db ; da2 = dgrad masked by a2 > 0
     const int M = (int)(B * PIX);
     p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
@@ -741,9 +749,9 @@ static void backward_fp32(mq_qnet* n, const float* state, long long B, const uin
     launch_colsum(n, n->da1, M, C1, G[P_C1B], s);
 }
 
-extern "C" int mq_qnet_td_backward(mq_qnet* n, const float* state, const int64_t* action, const float* reward, const float* next_state,
-                                   const uint8_t* done, int64_t B, const mq_hparams* hp, const uint8_t* drop_online,
-                                   const uint8_t* drop_target, float* loss_out, void* stream) {
+static int td_backward_impl(mq_qnet* n, const float* state, const int64_t* action, const float* reward, const float* next_state,
+                            const uint8_t* done, int64_t B, const mq_hparams* hp, const uint8_t* drop_online,
+                            const uint8_t* drop_target, float* loss_out, void* stream, int part) {
     using namespace mq;
     MQ_REQUIRE(n && state && action && reward && next_state && done && hp && loss_out, "mq_qnet_td_backward: null argument");
     MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_td_backward: batch %lld outside 1..%lld", (long long)B, n->max_batch);
@@ -753,6 +761,16 @@ extern "C" int mq_qnet_td_backward(mq_qnet* n, const float* state, const int64_t
     // next_q = target_network(next_states).max(1)[0]   (dqn_agent.py:146-147)
     const bool bf16 = n->precision == 1;
     MQ_REQUIRE(!bf16 || B % 8 == 0, "mq_qnet_td_backward: the bf16 path needs a batch that is a multiple of 8 (got %lld)", (long long)B);
+    if (part == 2) {                  // convolution layers of the backward only; part 1 has just run on the same batch
+        if (bf16) {
+            cudaError_t be = backward_bf16(n, state, B, drop_online, s, 2);
+            if (be != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_td_backward (bf16 backward, part 2): %s", cudaGetErrorString(be));
+        } else {
+            backward_fp32(n, state, B, drop_online, s, 2);
+        }
+        MQ_CUDA(cudaGetLastError());
+        return MQ_OK;
+    }
     cudaError_t fe = cudaSuccess;
     if (bf16) fe = forward_net_bf16(n, 1, next_state, B, drop_target, s);
     else forward_net(n, n->tl.t, next_state, B, drop_target, s);
@@ -768,13 +786,29 @@ extern "C" int mq_qnet_td_backward(mq_qnet* n, const float* state, const int64_t
 
     // ---- backward (loss.backward(), dqn_agent.py:154-155) ----
     if (bf16) {
-        cudaError_t be = backward_bf16(n, state, B, drop_online, s);
+        cudaError_t be = backward_bf16(n, state, B, drop_online, s, part);
         if (be != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_td_backward (bf16 backward): %s", cudaGetErrorString(be));
         return MQ_OK;
     }
-    backward_fp32(n, state, B, drop_online, s);
+    backward_fp32(n, state, B, drop_online, s, part);
     MQ_CUDA(cudaGetLastError());
     return MQ_OK;
+}
+
+extern "C" int mq_qnet_td_backward(mq_qnet* n, const float* state, const int64_t* action, const float* reward, const float* next_state,
+                                   const uint8_t* done, int64_t B, const mq_hparams* hp, const uint8_t* drop_online,
+                                   const uint8_t* drop_target, float* loss_out, void* stream) {
+    return td_backward_impl(n, state, action, reward, next_state, done, B, hp, drop_online, drop_target, loss_out, stream, 0);
+}
+
+// The same step in two calls so that a data-parallel caller can overlap the gradient exchange with the backward: part 1 =
+// both forwards, loss, backward of fc3 / fc2 / fc1 (99 % of the gradient: tensors 6..11 of the flat buffer are final when it
+// returns); part 2 = backward of the three convolutions (tensors 0..5).  Same arguments for both parts.
+extern "C" int mq_qnet_td_backward_part(mq_qnet* n, const float* state, const int64_t* action, const float* reward, const float* next_state,
+                                        const uint8_t* done, int64_t B, const mq_hparams* hp, const uint8_t* drop_online,
+                                        const uint8_t* drop_target, float* loss_out, int32_t part, void* stream) {
+    MQ_REQUIRE(part == 1 || part == 2, "mq_qnet_td_backward_part: part must be 1 or 2");
+    return td_backward_impl(n, state, action, reward, next_state, done, B, hp, drop_online, drop_target, loss_out, stream, part);
 }
 
 // Backward of the online network from an EXTERNAL dL/dQ (B x 5): what autograd does when a runner builds its own loss on

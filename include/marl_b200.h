@@ -241,6 +241,12 @@ int mq_qnet_act(mq_qnet* net, const float* obs, int64_t B, float eps, uint64_t s
 int mq_qnet_td_backward(mq_qnet* net, const float* state, const int64_t* action, const float* reward,
                         const float* next_state, const uint8_t* done, int64_t B, const mq_hparams* hp,
                         const uint8_t* drop_online, const uint8_t* drop_target, float* loss_out, void* stream);
+/* mq_qnet_td_backward in two calls (same arguments) so that a data-parallel caller overlaps the gradient exchange with the
+ * backward: part 1 = both forwards, loss, backward of fc3 / fc2 / fc1 — gradient tensors 6..11 (99 % of the 8,157,093 floats)
+ * are final when its work completes; part 2 = backward of the three convolutions (tensors 0..5). */
+int mq_qnet_td_backward_part(mq_qnet* net, const float* state, const int64_t* action, const float* reward,
+                             const float* next_state, const uint8_t* done, int64_t B, const mq_hparams* hp,
+                             const uint8_t* drop_online, const uint8_t* drop_target, float* loss_out, int32_t part, void* stream);
 /* Backward of the online network from an external dL/dQ (dev f32 [B][5]) — the autograd path a runner takes when it builds
  * its own loss on agent.q_network(states) (train_qmix.py:92-110: two agents' Q-values go through a mixing network before
  * the loss).  Recomputes the online forward on `state` with the same drop mask, then fills the bound gradient tensors. */

@@ -325,3 +325,30 @@ def test_q_network_autograd_qmix_step_matches_torch():
         after = qp.unpack(ag.net.flat_p)
         for name, p in refs[k][0].named_parameters():
             assert (after[name] - p.data).abs().max().item() <= 2e-5, (k, name)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_td_backward_in_two_parts_equals_one_call(precision):
+    """mq_qnet_td_backward_part: part 1 (forwards, loss, fc backward) + part 2 (conv backward) == mq_qnet_td_backward, and the
+    fc gradients are already final after part 1 (what the overlapped all-reduce of VecDQNAgent relies on)."""
+    from dqn_marl_b200.agents import qnet_params as qp
+    q, t = torch_ref.build_nets(21, target_perturb_seed=5)
+    net = _qnet(q, t, max_batch=64)
+    net.set_precision(precision)
+    g = torch.Generator().manual_seed(8)
+    B = 64
+    batch = dict(states=(torch.rand((B, 11, 11, 6), generator=g) < 0.3).float().cuda(), actions=torch.randint(0, 5, (B,), generator=g).cuda(),
+                 rewards=torch.randn(B, generator=g).cuda(), next_states=(torch.rand((B, 11, 11, 6), generator=g) < 0.3).float().cuda(),
+                 dones=(torch.rand(B, generator=g) < 0.2).to(torch.uint8).cuda())
+    hp = _hp(1)
+    mask = net.dropout_mask(B, 3, 1)
+    loss0 = net.td_backward(batch, hp, mask, mask).clone()
+    g0 = net.flat_g.clone()
+    head = qp.OFFSETS[6]
+    net.flat_g.fill_(float("nan"))
+    loss1 = net.td_backward(batch, hp, mask, mask, part=1).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(net.flat_g[head:], g0[head:]) and torch.isnan(net.flat_g[:head]).all()
+    net.td_backward(batch, hp, mask, mask, part=2)
+    torch.cuda.synchronize()
+    assert torch.equal(net.flat_g, g0) and torch.equal(loss0, loss1)
