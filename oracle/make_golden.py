@@ -95,6 +95,9 @@ def main():
     record("multi", 36, 30, None, 150, 99, 120, "traj_room_multi.npz")
     record("single", 36, 30, [36, 15], 20, 5, 200, "traj_room_small.npz")
     record("single", 40, 24, [1, 12], 60, 77, 120, "traj_room_westexit.npz")
+    # six people, all of them reach the exit at step 50: the completion bonus branch of _calculate_reward
+    # (evacuation_env.py:253-265), done by evacuation, reset, and a second episode
+    record("single", 36, 30, None, 6, 100, 90, "traj_room_allevac.npz")
     ref = record("single", 256, 256, [256, 128], 1000, 2024, 24, "traj_big256.npz")
     layout_file(ref, "layout_big256.npz", steps=[0, 5, 24, 90, 180], box=(-6, -6, 50, 46))
 
