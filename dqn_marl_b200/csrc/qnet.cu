@@ -281,14 +281,27 @@ clip_adam_kernel(TensorList tl, const float* __restrict__ gnorm, float grad_scal
     const float gs = grad_scale * coef;
     float* __restrict__ P = tl.p[k]; float* __restrict__ M = tl.m[k]; float* __restrict__ V = tl.v[k];
     const float* __restrict__ G = tl.g[k];
-    for (long long i = base + threadIdx.x; i < end; i += blockDim.x) {
-        const float g = G[i] * gs;
-        float m = M[i], v = V[i];
+    auto upd = [&](float g, float& p, float& m, float& v) {
+        g *= gs;
         m = m + (g - m) * (1.f - beta1);
         v = v * beta2 + (1.f - beta2) * g * g;
         const float denom = sqrtf(v) / bc2_sqrt + eps;
-        P[i] = P[i] - step_size * (m / denom);
-        M[i] = m; V[i] = v;
+        p = p - step_size * (m / denom);
+    };
+    // 16-byte accesses on the aligned body of the chunk (every tensor of the flat buffer starts on a multiple of 4 floats)
+    const bool vec = ((reinterpret_cast<uintptr_t>(P + base) | reinterpret_cast<uintptr_t>(M + base) | reinterpret_cast<uintptr_t>(V + base) |
+                       reinterpret_cast<uintptr_t>(G + base)) & 15) == 0;
+    const long long body = vec ? base + ((end - base) & ~3LL) : base;
+    for (long long i = base + 4LL * threadIdx.x; i < body; i += 4LL * blockDim.x) {
+        const float4 g4 = *reinterpret_cast<const float4*>(G + i);
+        float4 p4 = *reinterpret_cast<float4*>(P + i), m4 = *reinterpret_cast<float4*>(M + i), v4 = *reinterpret_cast<float4*>(V + i);
+        upd(g4.x, p4.x, m4.x, v4.x); upd(g4.y, p4.y, m4.y, v4.y); upd(g4.z, p4.z, m4.z, v4.z); upd(g4.w, p4.w, m4.w, v4.w);
+        *reinterpret_cast<float4*>(P + i) = p4; *reinterpret_cast<float4*>(M + i) = m4; *reinterpret_cast<float4*>(V + i) = v4;
+    }
+    for (long long i = body + threadIdx.x; i < end; i += blockDim.x) {
+        float p = P[i], m = M[i], v = V[i];
+        upd(G[i], p, m, v);
+        P[i] = p; M[i] = m; V[i] = v;
     }
 }
 __global__ void __launch_bounds__(256)
