@@ -1,4 +1,9 @@
-"""Host-side cost of one env-step launch (Python + ctypes + cudaLaunchKernel) vs its device time, C2 shape."""
+"""Host-side cost of one env-step launch (Python + ctypes + cudaLaunchKernel) vs its device time, C2 shape.
+
+Reading the output: the "host" figure of the env-step loops is NOT the launch cost — 3000 launches of a ~50 us kernel
+fill the 1024-entry launch queue, after which every launch call blocks until a slot frees, so the loop returns after
+(3000 - 1024) kernel times.  The true cost of a launch through ctypes is the 3-4 us of the tiny-kernel loops below: the
+device-resident bench loop is never host-bound."""
 import os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
