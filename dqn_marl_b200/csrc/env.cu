@@ -330,8 +330,27 @@ __device__ __forceinline__ double leaf_sum8(const double* a, int n, int g, uint3
     if (g == 0) for (int i = main_end; i < n; ++i) res += a[i];
     return res;
 }
-// sum(p.health for p in list if not p.dead) (evacuation_env.py:245): strictly left to right; dead entries hold +0.0
-__device__ __forceinline__ double health_chain(const double* h, int N) {
+// sum(p.health for p in list if not p.dead) (evacuation_env.py:245): strictly left to right; dead entries hold +0.0.
+// A literal chain costs ~20 cycles per person (dependent fp64 adds).  Most people are unhurt, i.e. exactly 100.0, and a run
+// of k additions of 100.0 to S is EXACT as long as S stays inside its binade (100 k is a multiple of S's ulp for S < 2^54):
+// the rounded left-to-right result of such a run is S + 100 j for the j additions that stay below the next power of two,
+// one real (rounding) addition across it, and so on — O(binades) instead of O(k).  Hurt people are added one by one.
+__device__ __forceinline__ double add_hundreds(double S, int k) {
+    while (k > 0) {
+        if (S == 0.0) { S = 100.0; --k; continue; }
+        const int e = (__double2hiint(S) >> 20) & 0x7FF;                // biased exponent (S > 0, finite)
+        const double P = __hiloint2double((e + 1) << 20, 0);             // the next power of two above S
+        const double d = P - S;                                          // exact
+        long long j = (long long)(d / 100.0);
+        while ((double)j * 100.0 >= d) --j;
+        while ((double)(j + 1) * 100.0 < d) ++j;                         // now 100 j < P - S <= 100 (j + 1)
+        if (j >= k) { S = S + (double)k * 100.0; k = 0; }
+        else { S = S + (double)j * 100.0; S = S + 100.0; k -= (int)j + 1; }
+    }
+    return S;
+}
+// the literal chain (one lane): cheapest for the small warp-per-env shapes, where crossing ~8 binades costs more than 150 adds
+__device__ __forceinline__ double health_chain_literal(const double* h, int N) {
     double tot = 0.0;
     int i = 0;
     for (; i + 4 <= N; i += 4) {
@@ -341,6 +360,36 @@ __device__ __forceinline__ double health_chain(const double* h, int N) {
     }
     for (; i < N; ++i) tot += h[i];
     return tot;
+}
+// run-based chain, executed by a whole warp; every lane returns the sum
+__device__ __noinline__ double health_chain_runs(const double* h, int N, int lane) {
+    double S = 0.0;
+    int pend = 0;                                   // 100.0's seen since the last hurt person
+    for (int b = 0; b < N; b += 32) {
+        const int i = b + lane;
+        const double v = i < N ? h[i] : 0.0;
+        const uint32_t m100 = __ballot_sync(0xFFFFFFFFu, v == 100.0);
+        uint32_t hard = __ballot_sync(0xFFFFFFFFu, v != 100.0 && v != 0.0);      // + 0.0 (dead) is a no-op
+        if (__popc(hard) > 4) {                     // mostly hurt people: the plain chain over the batch is cheaper
+            S = add_hundreds(S, pend);
+            pend = 0;
+            const int cnt = min(32, N - b);
+            for (int k = 0; k < cnt; ++k) S = S + __shfl_sync(0xFFFFFFFFu, v, k);
+            continue;
+        }
+        uint32_t done = 0;
+        while (hard) {
+            const int hp = __ffs(hard) - 1;
+            const uint32_t below = (1u << hp) - 1u;
+            S = add_hundreds(S, pend + __popc(m100 & below & ~done));
+            pend = 0;
+            S = S + __shfl_sync(0xFFFFFFFFu, v, hp);
+            done |= below | (1u << hp);
+            hard &= hard - 1;
+        }
+        pend += __popc(m100 & ~done);
+    }
+    return add_hundreds(S, pend);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -517,7 +566,8 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
 
     if (G::CHAIN && !g.worker()) {
         // chain warp: the left-to-right health sum only needs phase 1; it overlaps with everything the workers do
-        if (lane == 0) s_sum[1] = health_chain(sm.health, N);
+        const double th = health_chain_runs(sm.health, N, lane);
+        if (lane == 0) s_sum[1] = th;
     } else {
         const int wt = tid;                 // worker thread id (workers are the first TW threads of the group)
         const int n_mov = s_cnt[4];
@@ -841,9 +891,10 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                 }
             }
             __syncwarp();
-            if (lane == 0) {
-                s_sum[0] = combine_leaves(n, sm.leaf_sum);
-                if (!G::CHAIN) s_sum[1] = health_chain(sm.health, N);
+            if (lane == 0) s_sum[0] = combine_leaves(n, sm.leaf_sum);
+            if (!G::CHAIN) {
+                if (WPE == 1) { if (lane == 0) s_sum[1] = health_chain_literal(sm.health, N); }
+                else { const double th = health_chain_runs(sm.health, N, lane); if (lane == 0) s_sum[1] = th; }
             }
         }
         // fire models step (evacuation_env.py:138-142; fire_model.py:63-67) — the observation uses the new step
