@@ -80,6 +80,8 @@ struct Smem {
     double* health; double* dist; double* leaf_sum;
     uint32_t* bm; uint32_t* pos;
     int* leaf_off; int* leaf_len;
+    int* nchild;         // parallel np.mean tree (wide groups): 2 * nleaf nodes in level order; leaf_sum / leaf_off / leaf_len double as
+                         // the node arrays (value, offset, length)
     uint16_t* mov; uint32_t* mv;
     uint16_t* hurt;      // per-warp lists of the people standing in danger this step (T + N entries, T = threads of the group)
     uint8_t* fl;
@@ -107,11 +109,12 @@ __host__ __device__ inline size_t carve(Smem& s, unsigned char* base, unsigned c
     s.mov = (uint16_t*)(pb + po); po += align_up(sizeof(uint16_t) * N, 16);
     s.hurt = (uint16_t*)(pb + po); po += align_up(sizeof(uint16_t) * (N + T), 16);
     s.fl = (uint8_t*)(pb + po); po += align_up(N, 16);
-    s.leaf_sum = (double*)(base + o); o += sizeof(double) * nleaf;
+    s.leaf_sum = (double*)(base + o); o += sizeof(double) * 2 * nleaf;
     o = align_up(o, 16);
     s.bm = (uint32_t*)(base + o); o += sizeof(uint32_t) * align_up(words, 4);
-    s.leaf_off = (int*)(base + o); o += sizeof(int) * nleaf;
-    s.leaf_len = (int*)(base + o); o += sizeof(int) * nleaf;
+    s.leaf_off = (int*)(base + o); o += sizeof(int) * 2 * nleaf;
+    s.leaf_len = (int*)(base + o); o += sizeof(int) * 2 * nleaf;
+    s.nchild = (int*)(base + o); o += sizeof(int) * 2 * nleaf;
     if (gbytes) *gbytes = align_up(go, 256);
     return align_up(o, 16);
 }
@@ -413,6 +416,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     __shared__ int s_wtot_all[GROUPS][WPE];
     __shared__ double s_sum_all[GROUPS][2];     // sum of distances, total health
     __shared__ int s_pre[GROUPS + 1];           // COOP: exclusive prefix of the envs' scoring chunks
+    __shared__ int s_lvl_all[WPE >= 8 ? GROUPS : 1][20];   // wide groups: first node of every level of the np.mean tree, [19] = levels
 
     const G g;
     const int env = blockIdx.x * GROUPS + g.gid;
@@ -874,7 +878,72 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         }
         g.wsync();
 
-        // ---- np.mean tree (warp 0); the other workers start on the outputs --------------------------------
+        // ---- np.mean tree (numpy pairwise summation, evacuation_env.py:228) --------------------------------------------
+        if (WPE >= 8) {
+            // Wide groups: the serial enumerate / combine of the leaves cost 160 us per step at 20,000 people.  Warp 0 builds the
+            // tree level by level (node arrays in level order, children found with a ballot scan) while the other workers
+            // write the outputs; every 8-lane group of the group then sums leaves; warp 0 adds the levels bottom-up.
+            int* lvl = s_lvl_all[WPE >= 8 ? g.gid : 0];
+            const int fs_new = min(sc[MQ_S_FIRE_STEP] + 1, lay.n_fire_steps - 1);
+            if (warp == 0) {
+                const int n = s_cnt[3];
+                if (lane == 0) { sm.leaf_off[0] = 0; sm.leaf_len[0] = n; }
+                __syncwarp();
+                int lo = 0, hi = 1, nlev = 0;
+                for (;;) {
+                    if (lane == 0) lvl[nlev] = lo;
+                    ++nlev;
+                    int next = hi;
+                    for (int b0 = lo; b0 < hi; b0 += 32) {
+                        const int i = b0 + lane;
+                        const int len = i < hi ? sm.leaf_len[i] : 0;
+                        const bool split = len > 128;
+                        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, split);
+                        const int c = next + 2 * __popc(bal & ((1u << lane) - 1u));
+                        if (i < hi) sm.nchild[i] = split ? c : -1;
+                        if (split) {
+                            const int off = sm.leaf_off[i];
+                            int n2 = len / 2; n2 -= n2 % 8;
+                            sm.leaf_off[c] = off; sm.leaf_len[c] = n2;
+                            sm.leaf_off[c + 1] = off + n2; sm.leaf_len[c + 1] = len - n2;
+                        }
+                        next += 2 * __popc(bal);
+                    }
+                    __syncwarp();
+                    if (next == hi) break;          // nothing split: [lo, hi) is the last level
+                    lo = hi; hi = next;
+                }
+                if (lane == 0) { lvl[nlev] = hi; lvl[19] = nlev; }
+            } else {
+                store_bitmap(wt - 32, TW - 32, lay, sm, st.rmap, env);
+                gather_obs(wt - 32, TW - 32, lay, cfg, sm, rob, rpx, rpy, fs_new, obs, obs64, env);
+            }
+            g.wsync();
+            {
+                const int nlev = lvl[19], n_nodes = lvl[nlev];
+                const int gl = lane & 7;
+                const uint32_t gmask = 0xFFu << ((lane >> 3) * 8);
+                for (int nd = wt >> 3; nd < n_nodes; nd += TW >> 3) {         // one 8-lane group per node
+                    if (sm.nchild[nd] < 0) {
+                        const double sv = leaf_sum8(sm.dist + sm.leaf_off[nd], sm.leaf_len[nd], gl, gmask);
+                        if (gl == 0) sm.leaf_sum[nd] = sv;
+                    }
+                }
+            }
+            g.wsync();
+            if (warp == 0) {
+                const int nlev = lvl[19];
+                for (int L = nlev - 2; L >= 0; --L) {                          // the last level holds leaves only
+                    for (int i = lvl[L] + lane; i < lvl[L + 1]; i += 32) {
+                        const int c = sm.nchild[i];
+                        if (c >= 0) sm.leaf_sum[i] = sm.leaf_sum[c] + sm.leaf_sum[c + 1];      // pairwise(left) + pairwise(right)
+                    }
+                    __syncwarp();
+                }
+                if (lane == 0) s_sum[0] = sm.leaf_sum[0];
+                if (!G::CHAIN) { const double th = health_chain_runs(sm.health, N, lane); if (lane == 0) s_sum[1] = th; }
+            }
+        } else {
         if (warp == 0) {
             const int n = s_cnt[3];
             int nl = 0;
@@ -900,6 +969,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         // fire models step (evacuation_env.py:138-142; fire_model.py:63-67) — the observation uses the new step
         store_bitmap(wt, TW, lay, sm, st.rmap, env);
         gather_obs(wt, TW, lay, cfg, sm, rob, rpx, rpy, min(sc[MQ_S_FIRE_STEP] + 1, lay.n_fire_steps - 1), obs, obs64, env);
+        }
     }
     g.sync();
 
