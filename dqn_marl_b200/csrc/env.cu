@@ -365,32 +365,40 @@ __device__ __forceinline__ double health_chain_literal(const double* h, int N) {
     return tot;
 }
 // run-based chain, executed by a whole warp; every lane returns the sum
+template <int DEPTH>      // batches of 32 fetched before any is consumed: 8 when the list lives in global scratch (BIG), else 1
 __device__ __noinline__ double health_chain_runs(const double* h, int N, int lane) {
     double S = 0.0;
     int pend = 0;                                   // 100.0's seen since the last hurt person
-    for (int b = 0; b < N; b += 32) {
-        const int i = b + lane;
-        const double v = i < N ? h[i] : 0.0;
-        const uint32_t m100 = __ballot_sync(0xFFFFFFFFu, v == 100.0);
-        uint32_t hard = __ballot_sync(0xFFFFFFFFu, v != 100.0 && v != 0.0);      // + 0.0 (dead) is a no-op
-        if (__popc(hard) > 4) {                     // mostly hurt people: the plain chain over the batch is cheaper
-            S = add_hundreds(S, pend);
-            pend = 0;
-            const int cnt = min(32, N - b);
-            for (int k = 0; k < cnt; ++k) S = S + __shfl_sync(0xFFFFFFFFu, v, k);
-            continue;
+    for (int b0 = 0; b0 < N; b0 += 32 * DEPTH) {
+        double vv[DEPTH];
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u) { const int i = b0 + 32 * u + lane; vv[u] = i < N ? h[i] : 0.0; }
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u) {
+            const int b = b0 + 32 * u;
+            if (b >= N) break;
+            const double v = vv[u];
+            const uint32_t m100 = __ballot_sync(0xFFFFFFFFu, v == 100.0);
+            uint32_t hard = __ballot_sync(0xFFFFFFFFu, v != 100.0 && v != 0.0);      // + 0.0 (dead) is a no-op
+            if (__popc(hard) > 4) {                     // mostly hurt people: the plain chain over the batch is cheaper
+                S = add_hundreds(S, pend);
+                pend = 0;
+                const int cnt = min(32, N - b);
+                for (int k = 0; k < cnt; ++k) S = S + __shfl_sync(0xFFFFFFFFu, v, k);
+                continue;
+            }
+            uint32_t done = 0;
+            while (hard) {
+                const int hp = __ffs(hard) - 1;
+                const uint32_t below = (1u << hp) - 1u;
+                S = add_hundreds(S, pend + __popc(m100 & below & ~done));
+                pend = 0;
+                S = S + __shfl_sync(0xFFFFFFFFu, v, hp);
+                done |= below | (1u << hp);
+                hard &= hard - 1;
+            }
+            pend += __popc(m100 & ~done);
         }
-        uint32_t done = 0;
-        while (hard) {
-            const int hp = __ffs(hard) - 1;
-            const uint32_t below = (1u << hp) - 1u;
-            S = add_hundreds(S, pend + __popc(m100 & below & ~done));
-            pend = 0;
-            S = S + __shfl_sync(0xFFFFFFFFu, v, hp);
-            done |= below | (1u << hp);
-            hard &= hard - 1;
-        }
-        pend += __popc(m100 & ~done);
     }
     return add_hundreds(S, pend);
 }
@@ -570,7 +578,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
 
     if (G::CHAIN && !g.worker()) {
         // chain warp: the left-to-right health sum only needs phase 1; it overlaps with everything the workers do
-        const double th = health_chain_runs(sm.health, N, lane);
+        const double th = health_chain_runs<BIG ? 8 : 1>(sm.health, N, lane);
         if (lane == 0) s_sum[1] = th;
     } else {
         const int wt = tid;                 // worker thread id (workers are the first TW threads of the group)
@@ -941,7 +949,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                     __syncwarp();
                 }
                 if (lane == 0) s_sum[0] = sm.leaf_sum[0];
-                if (!G::CHAIN) { const double th = health_chain_runs(sm.health, N, lane); if (lane == 0) s_sum[1] = th; }
+                if (!G::CHAIN) { const double th = health_chain_runs<BIG ? 8 : 1>(sm.health, N, lane); if (lane == 0) s_sum[1] = th; }
             }
         } else {
         if (warp == 0) {
@@ -963,7 +971,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
             if (lane == 0) s_sum[0] = combine_leaves(n, sm.leaf_sum);
             if (!G::CHAIN) {
                 if (WPE == 1) { if (lane == 0) s_sum[1] = health_chain_literal(sm.health, N); }
-                else { const double th = health_chain_runs(sm.health, N, lane); if (lane == 0) s_sum[1] = th; }
+                else { const double th = health_chain_runs<BIG ? 8 : 1>(sm.health, N, lane); if (lane == 0) s_sum[1] = th; }
             }
         }
         // fire models step (evacuation_env.py:138-142; fire_model.py:63-67) — the observation uses the new step
