@@ -373,13 +373,23 @@ __device__ __noinline__ double health_chain_runs(const double* h, int N, int lan
         double vv[DEPTH];
 #pragma unroll
         for (int u = 0; u < DEPTH; ++u) { const int i = b0 + 32 * u + lane; vv[u] = i < N ? h[i] : 0.0; }
+        uint32_t m100_[DEPTH], hard_[DEPTH], any_hard = 0;
+        int n100 = 0;
+#pragma unroll
+        for (int u = 0; u < DEPTH; ++u) {           // classify all fetched batches first (independent ballots)
+            m100_[u] = __ballot_sync(0xFFFFFFFFu, vv[u] == 100.0);
+            hard_[u] = __ballot_sync(0xFFFFFFFFu, vv[u] != 100.0 && vv[u] != 0.0);      // + 0.0 (dead / past the end) is a no-op
+            any_hard |= hard_[u];
+            n100 += __popc(m100_[u]);
+        }
+        if (!any_hard) { pend += n100; continue; }  // nobody hurt in these 32 * DEPTH people
 #pragma unroll
         for (int u = 0; u < DEPTH; ++u) {
             const int b = b0 + 32 * u;
             if (b >= N) break;
             const double v = vv[u];
-            const uint32_t m100 = __ballot_sync(0xFFFFFFFFu, v == 100.0);
-            uint32_t hard = __ballot_sync(0xFFFFFFFFu, v != 100.0 && v != 0.0);      // + 0.0 (dead) is a no-op
+            const uint32_t m100 = m100_[u];
+            uint32_t hard = hard_[u];
             if (__popc(hard) > 4) {                     // mostly hurt people: the plain chain over the batch is cheaper
                 S = add_hundreds(S, pend);
                 pend = 0;
