@@ -401,7 +401,8 @@ static cudaError_t tc_gemm(mq_qnet* n, const bf::bf16* A, int lda, const bf::bf1
     int splits = 1;
     const long long tiles = (long long)((M + tc::BM - 1) / tc::BM) * ((N + BN - 1) / BN);
     if (allow_split && tiles < n->n_sms) {
-        splits = (int)((2LL * n->n_sms + tiles - 1) / tiles);
+        splits = (int)((2LL * n->n_sms) / tiles);          // two CTAs per SM are co-resident: fill one wave, never spill into a second
+        if (splits < 1) splits = 1;
         while (splits > 1 && (size_t)splits * M * N > n->partial_cap) --splits;
     }
     float* final_out = ep.out_f32;
