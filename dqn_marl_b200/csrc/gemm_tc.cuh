@@ -446,8 +446,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(THREADS, 1)
+// EPI = number of epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, each taking half of the columns —
+// the epilogue, not the MMAs, bounds the forward convolutions: ~3 us per 121 x 128 sample with four warps vs 1.2 us of MMAs)
+template <int BN, int BK, int STAGES, int EPI>
+__global__ void __launch_bounds__(64 + 32 * EPI, 1)
 conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                             const __grid_constant__ CUtensorMap tmap_out, long long batch, int nkb, int tma_store, ConvArgs cv, Epilogue ep) {
     extern __shared__ unsigned char smem_raw[];
@@ -457,8 +459,8 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     unsigned char* wtile = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = wtile + (size_t)nkb * W_BYTES;
-    unsigned char* stage = ring + STAGES * A_BYTES;            // 4 x 4 KB epilogue staging tiles (tma_store only)
-    uint64_t* full_bar = (uint64_t*)(stage + (tma_store ? 4 * 4096 : 0));
+    unsigned char* stage = ring + STAGES * A_BYTES;            // EPI x 4 KB epilogue staging tiles (tma_store only)
+    uint64_t* full_bar = (uint64_t*)(stage + (tma_store ? EPI * 4096 : 0));
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;       // [2]
     uint64_t* tmem_empty = tmem_full + 2;           // [2]
@@ -468,7 +470,7 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI); }
         mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -531,20 +533,23 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     } else {
         const int q = warp & 3;
         const int r = q * 32 + lane;
+        constexpr int HW = BN / (EPI / 4);              // columns per epilogue warp
+        const int n0 = ((warp - 2) >> 2) * HW;          // 0, or HW for the second warp of a quadrant
         int it = 0;
         for (long long sample = blockIdx.x; sample < batch; sample += gridDim.x, ++it) {
             const int buf = it & 1;
             mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if constexpr (BN % 64 == 0) {
+            const uint32_t acc = tmem_base + (uint32_t)(buf * BN + n0);
+            bool done = false;
+            if constexpr (HW % 64 == 0) {
                 if (tma_store) {
-                    const __nv_bfloat16* mrow = (ep.mask_bf16 && r < PIXELS) ? ep.mask_bf16 + ((size_t)sample * PIXELS + r) * BN : nullptr;
-                    epilogue_tile_tma<BN>(ep, &tmap_out, tmem_base + (uint32_t)(buf * BN), q, lane, mrow, 0, q * 32, (int)sample, stage + q * 4096);
+                    const __nv_bfloat16* mrow = (ep.mask_bf16 && r < PIXELS) ? ep.mask_bf16 + ((size_t)sample * PIXELS + r) * BN + n0 : nullptr;
+                    epilogue_tile_tma<HW>(ep, &tmap_out, acc, q, lane, mrow, n0, q * 32, (int)sample, stage + (warp - 2) * 4096);
+                    done = true;
                 }
-                else epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, r < PIXELS, sample * PIXELS + r, 0, batch * PIXELS, BN, 0);
-            } else {
-                epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, r < PIXELS, sample * PIXELS + r, 0, batch * PIXELS, BN, 0);
             }
+            if (!done) epilogue_tile<HW>(ep, acc, q, r < PIXELS, sample * PIXELS + r, n0, batch * PIXELS, BN, 0);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -804,7 +809,7 @@ inline cudaError_t launch_conv(const __nv_bfloat16* X, const __nv_bfloat16* Wk, 
 }
 
 // Persistent form of launch_conv (Cout == BN): weights resident in shared memory, one CTA per SM walking over the samples.
-template <int BN, int BK, int STAGES>
+template <int BN, int BK, int STAGES, int EPI = 4>
 inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfloat16* Wk, long long batch, int Cin, int Cout, int flip,
                                           Epilogue ep, int n_sms, cudaStream_t stream) {
     if (Cin % BK != 0 || batch <= 0 || Cout != BN) return cudaErrorInvalidValue;
@@ -814,19 +819,22 @@ inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfl
         return cudaErrorInvalidValue;
     const int nkb = 9 * Cin / BK;
     // bf16 output without per-element fp32 masks: epilogue through shared memory + TMA store
+    static_assert(EPI == 4 || EPI == 8, "4 or 8 epilogue warps");
+    constexpr int HWE = BN / (EPI / 4);
+    static_assert(HWE >= 32, "an epilogue warp handles at least 32 columns");
     CUtensorMap to = ta;
-    const int tma_store = (tma_store_eligible(ep, Cout, BN) && ep.ldc == Cout && make_tmap_out_conv(&to, ep.out_bf16, (uint64_t)batch, (uint64_t)Cout)) ? 1 : 0;
-    const int smem = nkb * BN * BK * 2 + STAGES * BM * BK * 2 + (tma_store ? 4 * 4096 : 0) + 1024 + 256;
+    const int tma_store = (HWE % 64 == 0 && tma_store_eligible(ep, Cout, BN) && ep.ldc == Cout && make_tmap_out_conv(&to, ep.out_bf16, (uint64_t)batch, (uint64_t)Cout)) ? 1 : 0;
+    const int smem = nkb * BN * BK * 2 + STAGES * BM * BK * 2 + (tma_store ? EPI * 4096 : 0) + 1024 + 256;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static int attr_bytes = 0;
     if (smem > attr_bytes) {
-        cudaError_t e = ensure_smem(conv_bf16_persistent_kernel<BN, BK, STAGES>, smem);
+        cudaError_t e = ensure_smem(conv_bf16_persistent_kernel<BN, BK, STAGES, EPI>, smem);
         if (e != cudaSuccess) return e;
         attr_bytes = smem;
     }
     ep.partial = nullptr;
     const int grid = (int)(batch < n_sms ? batch : n_sms);
-    conv_bf16_persistent_kernel<BN, BK, STAGES><<<grid, THREADS, smem, stream>>>(ta, tw, to, batch, nkb, tma_store, ConvArgs{Cin / BK, flip}, ep);
+    conv_bf16_persistent_kernel<BN, BK, STAGES, EPI><<<grid, 64 + 32 * EPI, smem, stream>>>(ta, tw, to, batch, nkb, tma_store, ConvArgs{Cin / BK, flip}, ep);
     return cudaGetLastError();
 }
 
