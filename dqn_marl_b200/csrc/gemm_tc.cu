@@ -1,6 +1,7 @@
 // C-ABI entry of the stand-alone tensor-core GEMM (used by tests and by bench.py's tensor-pipe roofline leg);
 // the Q-network's bf16 path calls mq::tc::launch directly.
 #include <new>
+#include <cstdlib>
 #include "common.h"
 #include "gemm_tc.cuh"
 

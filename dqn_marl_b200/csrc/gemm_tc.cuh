@@ -451,12 +451,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 template <int BN, int BK, int STAGES, int EPI>
 __global__ void __launch_bounds__(64 + 32 * EPI, 1)
 conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                            const __grid_constant__ CUtensorMap tmap_out, long long batch, int nkb, int tma_store, ConvArgs cv, Epilogue ep) {
+                            const __grid_constant__ CUtensorMap tmap_out, long long batch, int nkb, int tma_store, int n_total, ConvArgs cv,
+                            Epilogue ep) {
     extern __shared__ unsigned char smem_raw[];
     constexpr uint64_t LAYOUT = BK == 64 ? 2 : 4;
     constexpr uint32_t SBO = 8 * BK * 2;
     constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
     constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    const int n_base = blockIdx.y * BN;             // output-channel slice of this CTA (gridDim.y = Cout / BN)
     unsigned char* wtile = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = wtile + (size_t)nkb * W_BYTES;
     unsigned char* stage = ring + STAGES * A_BYTES;            // EPI x 4 KB epilogue staging tiles (tma_store only)
@@ -488,7 +490,7 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     if (warp == 0) {
         if (lane == 0) {
             mbar_expect_tx(w_full, (uint32_t)nkb * W_BYTES);
-            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(wtile + (size_t)kb * W_BYTES, &tmap_w, w_full, kb * BK, 0);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(wtile + (size_t)kb * W_BYTES, &tmap_w, w_full, kb * BK, n_base);
             long long g = 0;
             for (long long sample = blockIdx.x; sample < batch; sample += gridDim.x) {
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
@@ -534,22 +536,22 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
         const int q = warp & 3;
         const int r = q * 32 + lane;
         constexpr int HW = BN / (EPI / 4);              // columns per epilogue warp
-        const int n0 = ((warp - 2) >> 2) * HW;          // 0, or HW for the second warp of a quadrant
+        const int n0 = n_base + ((warp - 2) >> 2) * HW; // first output column of this warp
         int it = 0;
         for (long long sample = blockIdx.x; sample < batch; sample += gridDim.x, ++it) {
             const int buf = it & 1;
             mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t acc = tmem_base + (uint32_t)(buf * BN + n0);
+            const uint32_t acc = tmem_base + (uint32_t)(buf * BN + (n0 - n_base));
             bool done = false;
             if constexpr (HW % 64 == 0) {
                 if (tma_store) {
-                    const __nv_bfloat16* mrow = (ep.mask_bf16 && r < PIXELS) ? ep.mask_bf16 + ((size_t)sample * PIXELS + r) * BN + n0 : nullptr;
+                    const __nv_bfloat16* mrow = (ep.mask_bf16 && r < PIXELS) ? ep.mask_bf16 + ((size_t)sample * PIXELS + r) * n_total + n0 : nullptr;
                     epilogue_tile_tma<HW>(ep, &tmap_out, acc, q, lane, mrow, n0, q * 32, (int)sample, stage + (warp - 2) * 4096);
                     done = true;
                 }
             }
-            if (!done) epilogue_tile<HW>(ep, acc, q, r < PIXELS, sample * PIXELS + r, n0, batch * PIXELS, BN, 0);
+            if (!done) epilogue_tile<HW>(ep, acc, q, r < PIXELS, sample * PIXELS + r, n0, batch * PIXELS, n_total, 0);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -812,7 +814,7 @@ inline cudaError_t launch_conv(const __nv_bfloat16* X, const __nv_bfloat16* Wk, 
 template <int BN, int BK, int STAGES, int EPI = 4>
 inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfloat16* Wk, long long batch, int Cin, int Cout, int flip,
                                           Epilogue ep, int n_sms, cudaStream_t stream) {
-    if (Cin % BK != 0 || batch <= 0 || Cout != BN) return cudaErrorInvalidValue;
+    if (Cin % BK != 0 || batch <= 0 || Cout % BN != 0) return cudaErrorInvalidValue;
     CUtensorMap ta, tw;
     if (!make_tmap_act(&ta, X, (uint64_t)batch, (uint64_t)Cin, BK) ||
         !make_tmap(&tw, Wk, (uint64_t)Cout, (uint64_t)9 * Cin, (uint64_t)9 * Cin, BN, BK))
@@ -833,8 +835,11 @@ inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfl
         attr_bytes = smem;
     }
     ep.partial = nullptr;
-    const int grid = (int)(batch < n_sms ? batch : n_sms);
-    conv_bf16_persistent_kernel<BN, BK, STAGES, EPI><<<grid, 64 + 32 * EPI, smem, stream>>>(ta, tw, to, batch, nkb, tma_store, ConvArgs{Cin / BK, flip}, ep);
+    const int slices = Cout / BN;                       // CTAs of different output-channel slices walk over the same samples
+    const int per_slice = n_sms / slices < 1 ? 1 : n_sms / slices;
+    dim3 grid((unsigned)(batch < per_slice ? batch : per_slice), (unsigned)slices, 1);
+    conv_bf16_persistent_kernel<BN, BK, STAGES, EPI><<<grid, 64 + 32 * EPI, smem, stream>>>(ta, tw, to, batch, nkb, tma_store, Cout,
+                                                                                          ConvArgs{Cin / BK, flip}, ep);
     return cudaGetLastError();
 }
 
