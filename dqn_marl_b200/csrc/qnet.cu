@@ -429,7 +429,7 @@ static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, lon
     const int M = (int)(B * PIX);
     refresh_weights(n, which, s);
     // conv1: im2col rows of the 6-channel observation (K = 54 padded to one 64-wide K-block), then a tcgen05 GEMM
-    bf::im2col_obs_bf16_kernel<<<(unsigned)(B < 8LL * n->n_sms ? B : 8LL * n->n_sms), 256, 0, s>>>(obs, n->A1, B);
+    bf::im2col_obs_bf16_kernel<<<(unsigned)((B + 1) / 2), 256, 0, s>>>(obs, n->A1, B);
     n->launches += 1;
     tc::Epilogue ep{};
     ep.out_bf16 = n->a1b; ep.ldc = C1; ep.bias = W[P_C1B]; ep.relu = 1;

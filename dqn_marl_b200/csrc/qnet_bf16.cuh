@@ -22,42 +22,29 @@ template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloa
 // One thread = 8 consecutive columns of one row (a 16-byte store).
 __global__ void __launch_bounds__(256)
 im2col_obs_bf16_kernel(const float* __restrict__ obs, bf16* __restrict__ A1, long long B) {
-    // Persistent CTAs walk over samples.  A thread owns up to four fixed 8-column chunks (pixel q, columns k0..k0+7) of the
-    // 121 x 64 im2col tile: the tap / channel / padding arithmetic is done once, the per-sample work is 8 shared loads and
-    // one 16-byte store per chunk.  The sample's 726 floats are staged in shared memory (coalesced), slot 726 holds 0.
+    // two samples per CTA: the 2 x 726 floats are staged in shared memory (coalesced), then every thread emits 16-byte chunks
     __shared__ float win[2][728];
-    constexpr int CHUNKS = 121 * 8, PER = (CHUNKS + 255) / 256;
-    short src[PER][8];
-#pragma unroll
-    for (int c = 0; c < PER; ++c) {
-        const int ch = threadIdx.x + c * 256;
-        const int q = ch >> 3, k0 = (ch & 7) * 8, i = q / 11, j = q - i * 11;
+    const long long b0 = (long long)blockIdx.x * 2;
+    const int ns = (b0 + 1 < B) ? 2 : 1;
+    for (int t = threadIdx.x; t < ns * 726; t += 256) win[t / 726][t % 726] = __ldg(obs + b0 * 726 + t);
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < ns * 121 * 8; ch += 256) {
+        const int sidx = ch / (121 * 8), r = ch - sidx * (121 * 8);
+        const int q = r >> 3, k0 = (r & 7) * 8;
+        const int i = q / 11, j = q - i * 11;
+        __align__(16) bf16 v[8];
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
             const int k = k0 + t;
-            int o = 726;                                     // zero slot: padding or k >= 54
-            if (ch < CHUNKS && k < 54) {
-                const int tap = k / 6, cc = k - tap * 6;
+            float x = 0.f;
+            if (k < 54) {
+                const int tap = k / 6, c = k - tap * 6;
                 const int ii = i + tap / 3 - 1, jj = j + tap % 3 - 1;
-                if ((unsigned)ii < 11u && (unsigned)jj < 11u) o = (ii * 11 + jj) * 6 + cc;
+                if ((unsigned)ii < 11u && (unsigned)jj < 11u) x = win[sidx][(ii * 11 + jj) * 6 + c];
             }
-            src[c][t] = (short)o;
+            v[t] = __float2bfloat16(x);
         }
-    }
-    if (threadIdx.x < 2) { win[threadIdx.x][726] = 0.f; win[threadIdx.x][727] = 0.f; }
-    int buf = 0;
-    for (long long b = blockIdx.x; b < B; b += gridDim.x, buf ^= 1) {
-        for (int t = threadIdx.x; t < 726; t += 256) win[buf][t] = __ldg(obs + b * 726 + t);
-        __syncthreads();                                     // the other buffer is free again after the next barrier
-#pragma unroll
-        for (int c = 0; c < PER; ++c) {
-            const int ch = threadIdx.x + c * 256;
-            if (ch >= CHUNKS) break;
-            __align__(16) bf16 v[8];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) v[t] = __float2bfloat16(win[buf][src[c][t]]);
-            *reinterpret_cast<uint4*>(A1 + (b * 121 + (ch >> 3)) * 64 + (ch & 7) * 8) = *reinterpret_cast<const uint4*>(v);
-        }
+        *reinterpret_cast<uint4*>(A1 + ((b0 + sidx) * 121 + q) * 64 + k0) = *reinterpret_cast<const uint4*>(v);
     }
 }
 // conv1 weights Wc[(tap*6 + c)][32] f32 -> GEMM operand W1f[32][64] bf16 (K padded 54 -> 64 with zeros)
