@@ -116,6 +116,27 @@ def test_two_robots_matches_oracle():
     _run_vs_oracle(Layout.reference_room(n_robots=2), n_envs=12, N=150, seed=3, steps=70)
 
 
+def test_cooperative_scoring_full_ctas_match_oracle():
+    """Warp-per-env variant with 28 envs per CTA: in a FULL CTA the warps score the movers of all 28 envs together (chunk
+    prefix + round-robin); 60 envs = two cooperative CTAs + a partial one that works per warp.  Single robot, two robots
+    (the R > 1 branch reads the other envs' robots from shared memory) and auto-reset (envs of one CTA in different episodes)."""
+    from dqn_marl_b200.layout import Layout
+    _run_vs_oracle(Layout.reference_room(), n_envs=60, N=150, seed=21, steps=60, check_every=4)
+    _run_vs_oracle(Layout.reference_room(n_robots=2), n_envs=31, N=150, seed=22, steps=40, check_every=4)
+    _run_vs_oracle(Layout.reference_room(), n_envs=58, N=40, seed=23, steps=150, auto_reset=True, check_every=5)
+
+
+def test_wide_group_serial_sums_with_many_hurt_people():
+    """CTA-per-env variant (N > 256) in the small burning room: most people get hurt or die, so the run-based health sum takes
+    every path (pure runs of 100.0, sparse hurt people, mostly-hurt batches, dead = +0.0) and the parallel pairwise tree sees
+    shrinking n with several leaves; rewards are compared as f64 bits every other step."""
+    from dqn_marl_b200.layout import Layout
+    _run_vs_oracle(Layout.reference_room(), n_envs=5, N=400, seed=31, steps=160, check_every=2)
+    _run_vs_oracle(Layout.reference_room(), n_envs=3, N=700, seed=32, steps=120, auto_reset=True, check_every=3)
+    # 3000 people in the same room: the 1024-thread variant with the person arrays in global scratch (prefetching chain)
+    _run_vs_oracle(Layout.reference_room(), n_envs=2, N=3000, seed=33, steps=90, check_every=3)
+
+
 def test_synthetic_multi_exit_matches_oracle():
     from dqn_marl_b200.layout import Layout
     lay = Layout.synthetic(96, 80, n_exits=3, seed=5)
