@@ -454,7 +454,7 @@ def run_learner_loop(args, wl, layout, dev, rank, world, precision="bf16"):
             "unit": "transitions/s", "batch_per_gpu": B, "loop_steps": K, "ms_per_loop_step": total_ms / K,
             "env_agent_steps_per_s_in_loop": world * E * N * K / (total_ms * 1e-3),
             "segments_ms": {"act": seg[0] / K, "env_step": seg[1] / K, "replay_push": seg[2] / K, "sample+learn": learn_ms},
-            "qnet_dtype": "bf16 tcgen05 tensor cores (conv2/conv3/fc1), fp32 accumulate + master weights" if precision == "bf16"
+            "qnet_dtype": "bf16 tcgen05 tensor cores (conv1-3, fc1, fc2), fp32 accumulate + master weights" if precision == "bf16"
             else "f32 (parity path, CUDA-core FFMA)", "learn_tflops": 155.4e6 * B / (learn_ms * 1e-3) / 1e12,
             "act_tflops": 38.85e6 * E / (seg[0] / K * 1e-3) / 1e12, "gpu_launches": int(launches),
             "allreduce": "nccl all-reduce of the flat 8,157,093-float gradient per learn step" if world > 1 else None}

@@ -219,7 +219,7 @@ def test_dqn_agent_facade_reference_surface(tmp_path):
 
 
 def test_bf16_tensor_core_path_tracks_fp32():
-    """The tcgen05 bf16 path (conv2/conv3/fc1 on tensor cores, fp32 accumulate / master weights) against the fp32
+    """The tcgen05 bf16 path (every layer but the 5-output head on tensor cores, fp32 accumulate / master weights) against the fp32
     parity path on the same weights and batch: Q within 2e-2 of the Q scale, loss within 1e-2, gradients aligned."""
     from dqn_marl_b200.agents import qnet_params as qp
     q, t = torch_ref.build_nets(21, 22)
