@@ -88,8 +88,8 @@ extern "C" int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, void* Y_
         int dev = 0, n_sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (Cin % 64 == 0 && Cout == 128) e = mq::tc::launch_conv_persistent<128, 64, 4>(x, w, batch, Cin, Cout, flip, ep, n_sms, s);
-        else if (Cin % 64 == 0 && Cout == 64) e = mq::tc::launch_conv_persistent<64, 64, 4>(x, w, batch, Cin, Cout, flip, ep, n_sms, s);
+        if (Cin % 64 == 0 && Cout == 128) e = mq::tc::launch_conv_persistent<128, 64, 3>(x, w, batch, Cin, Cout, flip, ep, n_sms, s);
+        else if (Cin % 64 == 0 && Cout == 64) e = mq::tc::launch_conv_persistent<64, 64, 3>(x, w, batch, Cin, Cout, flip, ep, n_sms, s);
         else if (Cin % 64 == 0 && Cout == 32) e = mq::tc::launch_conv_persistent<32, 64, 4>(x, w, batch, Cin, Cout, flip, ep, n_sms, s);
         else if (Cout == 64) e = mq::tc::launch_conv_persistent<64, 32, 6>(x, w, batch, Cin, Cout, flip, ep, n_sms, s);
         else return mq::fail(MQ_ERR_ARG, "mq_conv3x3_bf16: the persistent kernel (bn = 0) supports Cout = 128/64/32 (Cin %% 64 == 0) or Cout = 64");

@@ -456,7 +456,11 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     extern __shared__ unsigned char smem_raw[];
     constexpr uint64_t LAYOUT = BK == 64 ? 2 : 4;
     constexpr uint32_t SBO = 8 * BK * 2;
-    constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
+    // One A stage = the three vertical taps of one column offset dj: a {BK, 11, 13, 1} box whose origin is (dj, -1) holds image
+    // rows -1 .. 11 (143 tile rows, zero outside the image); tap di starts at tile row (di + 1) * 11, a row offset of the
+    // shared-memory descriptor (the hardware swizzle works on absolute addresses: scripts/probes/tc_desc_probe.cu).  Three
+    // boxes per sample and channel block instead of nine: TMA's per-row rate was the limit of the nine-box form.
+    constexpr int A_ROWS = 13 * 11, ROW_BYTES = BK * 2, A_BYTES = 160 * ROW_BYTES, W_BYTES = BN * BK * 2;
     constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     const int n_base = blockIdx.y * BN;             // output-channel slice of this CTA (gridDim.y = Cout / BN)
     unsigned char* wtile = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -493,14 +497,13 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             for (int kb = 0; kb < nkb; ++kb) tma_load_2d(wtile + (size_t)kb * W_BYTES, &tmap_w, w_full, kb * BK, n_base);
             long long g = 0;
             for (long long sample = blockIdx.x; sample < batch; sample += gridDim.x) {
-                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                for (int grp = 0; grp < 3 * cv.cblocks; ++grp, ++g) {          // (column offset, channel block)
                     const int s = (int)(g % STAGES);
                     mbar_wait(&empty_bar[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
-                    mbar_expect_tx(&full_bar[s], PIXELS * BK * 2);
-                    const int tap = kb / cv.cblocks, cb = kb - tap * cv.cblocks;
-                    int di = tap / 3 - 1, dj = tap % 3 - 1;
-                    if (cv.flip) { di = -di; dj = -dj; }
-                    tma_load_4d(ring + s * A_BYTES, &tmap_a, &full_bar[s], cb * BK, dj, di, (int)sample);
+                    mbar_expect_tx(&full_bar[s], A_ROWS * ROW_BYTES);
+                    const int u = grp / cv.cblocks, cb = grp - u * cv.cblocks;
+                    const int dj = cv.flip ? 1 - u : u - 1;
+                    tma_load_4d(ring + s * A_BYTES, &tmap_a, &full_bar[s], cb * BK, dj, -1, (int)sample);
                 }
             }
         }
@@ -515,17 +518,23 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                 mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));       // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                for (int grp = 0; grp < 3 * cv.cblocks; ++grp, ++g) {
                     const int s = (int)(g % STAGES);
                     mbar_wait(&full_bar[s], (uint32_t)((g / STAGES) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = smem_u32(ring + s * A_BYTES);
-                    const uint32_t b_addr = smem_u32(wtile + (size_t)kb * W_BYTES);
+                    const int u = grp / cv.cblocks, cb = grp - u * cv.cblocks;
+                    const uint32_t a_base = smem_u32(ring + s * A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
-                        const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
-                        umma_bf16(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    for (int t = 0; t < 3; ++t) {                  // vertical tap di = t - 1 (mirrored when flip)
+                        const int kb = (t * 3 + u) * cv.cblocks + cb;
+                        const uint32_t a_addr = a_base + (uint32_t)((cv.flip ? 2 - t : t) * 11) * ROW_BYTES;
+                        const uint32_t b_addr = smem_u32(wtile + (size_t)kb * W_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
+                            const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
+                            umma_bf16(d_tmem, adesc, bdesc, idesc, (grp > 0 || t > 0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     umma_commit(&empty_bar[s]);
                 }
@@ -709,12 +718,12 @@ inline bool make_tmap(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 }
 // NHWC activation [B][11][11][C] bf16 as a 4-D tensor (C, x, y, b); box = {box_c channels, 11, 11, 1}: one sample's window,
 // shifted by the tap through the box origin, zero-filled outside the 11 x 11 image
-inline bool make_tmap_act(CUtensorMap* out, const void* base, uint64_t batch, uint64_t C, uint32_t box_c) {
+inline bool make_tmap_act(CUtensorMap* out, const void* base, uint64_t batch, uint64_t C, uint32_t box_c, uint32_t box_y = 11) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[4] = {C, 11, 11, batch};
     cuuint64_t strides[3] = {C * 2, 11 * C * 2, 121 * C * 2};
-    cuuint32_t box[4] = {box_c, 11, 11, 1};
+    cuuint32_t box[4] = {box_c, 11, box_y, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -816,7 +825,7 @@ inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfl
                                           Epilogue ep, int n_sms, cudaStream_t stream) {
     if (Cin % BK != 0 || batch <= 0 || Cout % BN != 0) return cudaErrorInvalidValue;
     CUtensorMap ta, tw;
-    if (!make_tmap_act(&ta, X, (uint64_t)batch, (uint64_t)Cin, BK) ||
+    if (!make_tmap_act(&ta, X, (uint64_t)batch, (uint64_t)Cin, BK, 13) ||
         !make_tmap(&tw, Wk, (uint64_t)Cout, (uint64_t)9 * Cin, (uint64_t)9 * Cin, BN, BK))
         return cudaErrorInvalidValue;
     const int nkb = 9 * Cin / BK;
@@ -826,7 +835,7 @@ inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfl
     static_assert(HWE >= 32, "an epilogue warp handles at least 32 columns");
     CUtensorMap to = ta;
     const int tma_store = (HWE % 64 == 0 && tma_store_eligible(ep, Cout, BN) && ep.ldc == Cout && make_tmap_out_conv(&to, ep.out_bf16, (uint64_t)batch, (uint64_t)Cout)) ? 1 : 0;
-    const int smem = nkb * BN * BK * 2 + STAGES * BM * BK * 2 + (tma_store ? EPI * 4096 : 0) + 1024 + 256;
+    const int smem = nkb * BN * BK * 2 + STAGES * 160 * BK * 2 + (tma_store ? EPI * 4096 : 0) + 1024 + 256;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static int attr_bytes = 0;
     if (smem > attr_bytes) {

@@ -443,7 +443,7 @@ static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, lon
     if (e != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->a3b; ep.ldc = C3; ep.bias = W[P_C3B]; ep.relu = 1;
-    e = tc::launch_conv_persistent<128, 64, 4>(n->a2b, n->w3f[which], B, C2, C3, 0, ep, n->n_sms, s);
+    e = tc::launch_conv_persistent<128, 64, 3>(n->a2b, n->w3f[which], B, C2, C3, 0, ep, n->n_sms, s);
     if (e != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_f32 = n->h1; ep.out_bf16 = n->h1b; ep.ldc = H1; ep.bias = W[P_F1B]; ep.relu = 1; ep.drop = drop_mask; ep.drop_scale = 1.f / (1.f - 0.2f);
@@ -584,19 +584,17 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
     }
     if (part == 1) return cudaGetLastError();
     // conv3: dWc3[(t,c)][n] = im2col(a2)^T dY (implicit, split over samples) ; db ; da2 = conv_flip(dY, Wd3) (masked by a2 > 0).
-    // The data-gradient convolutions are L2-bandwidth bound (each sample's dY is read once per tap): two co-resident
-    // one-sample CTAs per SM keep more loads in flight than the persistent kernel and measure faster (profiles/README.md)
     launch_colsum_bf16(n, n->da3b, M, C3, G[P_C3B], s);
     if ((e = conv_wgrad<128, 3, 64>(n, n->a2b, n->da3b, B, C2, C3, G[P_C3W], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da2b; ep.ldc = C2; ep.mask_bf16 = n->a2b;
-    if ((e = tc::launch_conv<64, 4, 64>(n->da3b, n->w3d, B, C3, C2, 1, ep, s)) != cudaSuccess) return e;
+    if ((e = tc::launch_conv_persistent<64, 64, 3>(n->da3b, n->w3d, B, C3, C2, 1, ep, n->n_sms, s)) != cudaSuccess) return e;
     // conv2
     launch_colsum_bf16(n, n->da2b, M, C2, G[P_C2B], s);
     if ((e = conv_wgrad<64, 4, 32>(n, n->a1b, n->da2b, B, C1, C2, G[P_C2W], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da1b; ep.ldc = C1; ep.mask_bf16 = n->a1b;
-    if ((e = tc::launch_conv<32, 4, 64>(n->da2b, n->w2d, B, C2, C1, 1, ep, s)) != cudaSuccess) return e;
+    if ((e = tc::launch_conv_persistent<32, 64, 4>(n->da2b, n->w2d, B, C2, C1, 1, ep, n->n_sms, s)) != cudaSuccess) return e;
     n->launches += 2;
     // conv1: db = column sums of dY; dWc1^T [32][64] = dY^T A1 (MN-major operands, 32-wide A slabs, split over the rows),
     // reduced and transposed into the [(tap, c)][32] layout.  The observation needs no gradient.
