@@ -510,6 +510,9 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BN);
+            const uint64_t a_desc0 = make_smem_desc(smem_u32(ring), SBO, 0, LAYOUT);
+            const uint64_t b_desc0 = make_smem_desc(smem_u32(wtile), SBO, 0, LAYOUT);
+            constexpr uint32_t tap_off[3] = {0u, (11u * ROW_BYTES) >> 4, (22u * ROW_BYTES) >> 4};
             mbar_wait(w_full, 0);
             long long g = 0;
             int it = 0;
@@ -523,18 +526,18 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                     mbar_wait(&full_bar[s], (uint32_t)((g / STAGES) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const int u = grp / cv.cblocks, cb = grp - u * cv.cblocks;
-                    const uint32_t a_base = smem_u32(ring + s * A_BYTES);
+                    // The single issuing thread must not spend more than the ~64 cycles an MMA takes on preparing the next
+                    // one: descriptors are advanced by adding (byte offset >> 4) to their address field, nothing is rebuilt.
+                    const uint64_t a_desc = a_desc0 + (uint64_t)((uint32_t)(s * A_BYTES) >> 4);
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {                  // vertical tap di = t - 1 (mirrored when flip)
                         const int kb = (t * 3 + u) * cv.cblocks + cb;
-                        const uint32_t a_addr = a_base + (uint32_t)((cv.flip ? 2 - t : t) * 11) * ROW_BYTES;
-                        const uint32_t b_addr = smem_u32(wtile + (size_t)kb * W_BYTES);
+                        const uint64_t a_t = a_desc + (uint64_t)(cv.flip ? tap_off[2 - t] : tap_off[t]);
+                        const uint64_t b_t = b_desc0 + (uint64_t)((uint32_t)(kb * W_BYTES) >> 4);
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
-                            const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
-                            umma_bf16(d_tmem, adesc, bdesc, idesc, (grp > 0 || t > 0 || k > 0) ? 1u : 0u);
-                        }
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16(d_tmem, a_t + (uint64_t)((k * UMMA_K * 2) >> 4), b_t + (uint64_t)((k * UMMA_K * 2) >> 4), idesc,
+                                      (grp > 0 || t > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[s]);
                 }
