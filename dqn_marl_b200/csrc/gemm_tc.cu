@@ -31,10 +31,13 @@ extern "C" int mq_gemm_bf16(const void* A, const void* B, float* C, void* C_bf16
     cudaError_t e;
     const __nv_bfloat16* a = (const __nv_bfloat16*)A;
     const __nv_bfloat16* b = (const __nv_bfloat16*)B;
-    if (bn == 128) e = mq::tc::launch<128, 3>(a, K, b, K, M, N, K, ep, &sp, s);
+    if (bn == 512) e = mq::tc::launch<256, 3, 2>(a, K, b, K, M, N, K, ep, &sp, s);         // 256 x 256 outputs per CTA
+    else if (bn == 384) e = mq::tc::launch<128, 4, 2>(a, K, b, K, M, N, K, ep, &sp, s);    // 256 x 128
+    else if (bn == 256) e = mq::tc::launch<256, 4>(a, K, b, K, M, N, K, ep, &sp, s);
+    else if (bn == 128) e = mq::tc::launch<128, 3>(a, K, b, K, M, N, K, ep, &sp, s);
     else if (bn == 64) e = mq::tc::launch<64, 4>(a, K, b, K, M, N, K, ep, &sp, s);
     else if (bn == 32) e = mq::tc::launch<32, 4>(a, K, b, K, M, N, K, ep, &sp, s);
-    else return mq::fail(MQ_ERR_ARG, "mq_gemm_bf16: bn must be 128, 64 or 32");
+    else return mq::fail(MQ_ERR_ARG, "mq_gemm_bf16: bn must be 32, 64, 128, 256 (128-row tiles) or 384, 512 (256 x 128 / 256 x 256 tiles)");
     if (e != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     if (sp > 1) {
         size_t total = (size_t)M * N;
@@ -128,3 +131,10 @@ extern "C" int mq_conv3x3_wgrad_bf16(const void* X, const void* dY, float* dW, i
     if (e != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_conv3x3_wgrad_bf16: launch failed: %s", cudaGetErrorString(e));
     return finish_split(workspace, sp, (size_t)9 * Cin * Cout, dW, s);
 }
+
+#ifdef MQ_CONV_TRACE
+extern "C" int mq_debug_conv_trace(long long* host_out, int reset) {
+    if (reset) { static long long z[256 * 8]; return (int)cudaMemcpyToSymbol(mq::tc::g_conv_trace, z, sizeof(z)); }
+    return (int)cudaMemcpyFromSymbol(host_out, mq::tc::g_conv_trace, sizeof(long long) * 256 * 8);
+}
+#endif

@@ -341,24 +341,27 @@ __device__ __forceinline__ void pipe_fini(uint32_t tmem_base, uint32_t tmem_cols
 // =====================================================================================================================
 struct ConvArgs { int cblocks; int flip; };     // K-blocks per tap (= Cin / BK); mirrored taps
 
-template <int BN, int STAGES, int BK>
+template <int BN, int STAGES, int BK, int MT = 1>
 struct SmemLayout {
-    static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+    static constexpr int A_BYTES = MT * BM * BK * 2, B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int STAGES, int BK, bool CONV>
+// MT = 128-row tiles of A per CTA (1 or 2): with MT = 2 one B tile feeds two accumulators, 256 x BN outputs per CTA — the
+// operand bytes pulled from L2 per flop drop from 1/64 (128 x 128) to 1/128 (256 x 256), which is what bounds the fc1 GEMMs.
+template <int BN, int STAGES, int BK, bool CONV, int MT = 1>
 __global__ void __launch_bounds__(THREADS)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const __grid_constant__ CUtensorMap tmap_out, long long M, int N, int K, int k_chunk, int tma_store, ConvArgs cv,
                     Epilogue ep) {
     extern __shared__ unsigned char smem_raw[];
-    using L = SmemLayout<BN, STAGES, BK>;
+    using L = SmemLayout<BN, STAGES, BK, MT>;
+    static_assert(MT == 1 || (!CONV && MT * BN <= 512), "two row tiles: plain GEMM, accumulators within the 512 TMEM columns");
     constexpr uint64_t LAYOUT = BK == 64 ? 2 : 4;
     constexpr uint32_t SBO = 8 * BK * 2;
     unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // swizzle atoms: 1024 B alignment
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TMEM_COLS = MT * BN < 32 ? 32 : MT * BN;
     Pipe pp;
     const uint32_t tmem_base = pipe_init<STAGES>(pp, tiles + STAGES * L::STAGE_BYTES, &tmap_a, &tmap_b, TMEM_COLS);
 
@@ -386,7 +389,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     tma_load_4d(a_dst, &tmap_a, &pp.full_bar[s], cb * BK, dj, di, m_tile);
                 } else {
                     mbar_expect_tx(&pp.full_bar[s], L::STAGE_BYTES);
-                    tma_load_2d(a_dst, &tmap_a, &pp.full_bar[s], k, m_tile * BM);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) tma_load_2d(a_dst + mt * (BM * BK * 2), &tmap_a, &pp.full_bar[s], k, (m_tile * MT + mt) * BM);
                 }
                 tma_load_2d(b_dst, &tmap_b, &pp.full_bar[s], k, n0);
                 if (s == STAGES - 1) phase ^= 1;
@@ -396,19 +400,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===== MMA issuer (single thread) =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BN);
+            const uint64_t desc0 = make_smem_desc(smem_u32(tiles), SBO, 0, LAYOUT);       // advanced by (byte offset >> 4), never rebuilt
             uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait(&pp.full_bar[s], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
-                const uint32_t b_addr = a_addr + L::A_BYTES;
+                const uint64_t adesc = desc0 + (uint64_t)((uint32_t)(s * L::STAGE_BYTES) >> 4);
+                const uint64_t bdesc = adesc + (uint64_t)(L::A_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
-                    const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 2, SBO, 0, LAYOUT);
-                    umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                }
+                for (int k = 0; k < BK / UMMA_K; ++k)
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt)
+                        umma_bf16(tmem_base + (uint32_t)(mt * BN), adesc + (uint64_t)((mt * BM * BK * 2 + k * UMMA_K * 2) >> 4),
+                                  bdesc + (uint64_t)((k * UMMA_K * 2) >> 4), idesc, (kb > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&pp.empty_bar[s]);          // frees the stage once these MMAs have read it
                 if (s == STAGES - 1) phase ^= 1;
             }
@@ -420,19 +425,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         mbar_wait(pp.tmem_full_bar, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int r = q * 32 + lane;
-        const long long row = CONV ? (long long)m_tile * PIXELS + r : (long long)m_tile * BM + r;
-        const bool ok = (CONV ? r < PIXELS : true) && row < M && num_kb > 0;
-        bool done = false;
-        if constexpr (BN % 64 == 0) {
-            if (tma_store) {          // all MMAs have completed: the pipeline stages are free, stage 0 becomes the staging area
-                const __nv_bfloat16* mrow = (ep.mask_bf16 && ok) ? ep.mask_bf16 + (size_t)row * ep.ldc + n0 : nullptr;
-                epilogue_tile_tma<BN>(ep, &tmap_out, tmem_base, q, lane, mrow, n0, CONV ? q * 32 : m_tile * BM + q * 32, CONV ? m_tile : -1,
-                                      tiles + q * 4096);
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                done = true;
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+            const int mtile = m_tile * MT + mt;
+            const uint32_t acc = tmem_base + (uint32_t)(mt * BN);
+            const long long row = CONV ? (long long)m_tile * PIXELS + r : (long long)mtile * BM + r;
+            const bool ok = (CONV ? r < PIXELS : true) && row < M && num_kb > 0;
+            bool done = false;
+            if constexpr (BN % 64 == 0) {
+                if (tma_store) {      // all MMAs have completed: the pipeline stages are free, stage 0 becomes the staging area
+                    const __nv_bfloat16* mrow = (ep.mask_bf16 && ok) ? ep.mask_bf16 + (size_t)row * ep.ldc + n0 : nullptr;
+                    epilogue_tile_tma<BN>(ep, &tmap_out, acc, q, lane, mrow, n0, CONV ? q * 32 : mtile * BM + q * 32, CONV ? m_tile : -1,
+                                          tiles + q * 4096);
+                    done = true;
+                }
             }
+            if (!done) epilogue_tile<BN>(ep, acc, q, ok, row, n0, M, N, blockIdx.z);
         }
-        if (!done) epilogue_tile<BN>(ep, tmem_base, q, ok, row, n0, M, N, blockIdx.z);
+        if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     pipe_fini(tmem_base, TMEM_COLS);
 }
@@ -446,8 +456,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// EPI = number of epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two per quadrant, each taking half of the columns —
-// the epilogue, not the MMAs, bounds the forward convolutions: ~3 us per 121 x 128 sample with four warps vs 1.2 us of MMAs)
+// EPI = number of epilogue warps: 4 (one per TMEM lane quadrant) or 8 (two sets of four; set 0 drains accumulator buffer 0 =
+// the even samples of this CTA, set 1 buffer 1 = the odd ones, so two epilogues are in flight — the epilogue's latency per
+// sample (TMEM load, pack, staging, TMA store: 1.4 - 2.3 us) and not the MMAs (0.3 - 1.2 us) bounds these kernels)
+#ifdef MQ_CONV_TRACE
+__device__ long long g_conv_trace[256 * 8];
+#define TRACE_T0() const long long _t0 = clock64()
+#define TRACE_ADD(slot) g_conv_trace[blockIdx.x * 8 + (slot)] += clock64() - _t0
+#else
+#define TRACE_T0()
+#define TRACE_ADD(slot)
+#endif
 template <int BN, int BK, int STAGES, int EPI>
 __global__ void __launch_bounds__(64 + 32 * EPI, 1)
 conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -476,7 +495,7 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -499,7 +518,7 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             for (long long sample = blockIdx.x; sample < batch; sample += gridDim.x) {
                 for (int grp = 0; grp < 3 * cv.cblocks; ++grp, ++g) {          // (column offset, channel block)
                     const int s = (int)(g % STAGES);
-                    mbar_wait(&empty_bar[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
+                    { TRACE_T0(); mbar_wait(&empty_bar[s], (uint32_t)(((g / STAGES) & 1) ^ 1)); TRACE_ADD(0); }
                     mbar_expect_tx(&full_bar[s], A_ROWS * ROW_BYTES);
                     const int u = grp / cv.cblocks, cb = grp - u * cv.cblocks;
                     const int dj = cv.flip ? 1 - u : u - 1;
@@ -518,12 +537,12 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             int it = 0;
             for (long long sample = blockIdx.x; sample < batch; sample += gridDim.x, ++it) {
                 const int buf = it & 1;
-                mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));       // epilogue has drained this accumulator
+                { TRACE_T0(); mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1)); TRACE_ADD(1); }   // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
                 for (int grp = 0; grp < 3 * cv.cblocks; ++grp, ++g) {
                     const int s = (int)(g % STAGES);
-                    mbar_wait(&full_bar[s], (uint32_t)((g / STAGES) & 1));
+                    { TRACE_T0(); mbar_wait(&full_bar[s], (uint32_t)((g / STAGES) & 1)); TRACE_ADD(2); }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const int u = grp / cv.cblocks, cb = grp - u * cv.cblocks;
                     // The single issuing thread must not spend more than the ~64 cycles an MMA takes on preparing the next
@@ -547,12 +566,26 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     } else {
         const int q = warp & 3;
         const int r = q * 32 + lane;
-        constexpr int HW = BN / (EPI / 4);              // columns per epilogue warp
-        const int n0 = n_base + ((warp - 2) >> 2) * HW; // first output column of this warp
+        constexpr int HW = BN;                          // columns per epilogue warp
+        const int n0 = n_base;                          // first output column of this warp
+        const int eset = (warp - 2) >> 2;               // EPI == 8: warps 2-5 take the even samples of this CTA, 6-9 the odd ones
         int it = 0;
         for (long long sample = blockIdx.x; sample < batch; sample += gridDim.x, ++it) {
             const int buf = it & 1;
+            if (EPI == 8 && buf != eset) continue;
+            if (ep.mask_bf16 && r < PIXELS) {               // pull this row of the relu mask towards the SM while the MMAs run
+                const __nv_bfloat16* mp = ep.mask_bf16 + ((size_t)sample * PIXELS + r) * n_total + n0;
+#pragma unroll
+                for (int b = 0; b < HW * 2; b += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"((const char*)mp + b));
+            }
+#ifdef MQ_CONV_TRACE
+            const long long _e0 = clock64();
+#endif
             mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
+#ifdef MQ_CONV_TRACE
+            const long long _e1 = clock64();
+            if (warp == 2 && lane == 0) g_conv_trace[blockIdx.x * 8 + 3] += _e1 - _e0;
+#endif
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc = tmem_base + (uint32_t)(buf * BN + (n0 - n_base));
             bool done = false;
@@ -567,6 +600,9 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+#ifdef MQ_CONV_TRACE
+            if (warp == 2 && lane == 0) { g_conv_trace[blockIdx.x * 8 + 4] += clock64() - _e1; g_conv_trace[blockIdx.x * 8 + 5] += 1; }
+#endif
         }
         if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // stores complete before the CTA exits
     }
@@ -662,19 +698,18 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BN, true);
+            const uint64_t a_desc0 = make_smem_desc(smem_u32(tiles), 8 * A_ROW, (uint32_t)L::A_SLAB, A_LAYOUT);      // advanced, never rebuilt
+            const uint64_t b_desc0 = make_smem_desc(smem_u32(tiles) + L::A_BYTES, 1024u, (uint32_t)L::B_SLAB, 2);
             uint32_t phase = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % STAGES;
                 mbar_wait(&pp.full_bar[s], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_addr = smem_u32(tiles + s * L::STAGE_BYTES);
-                const uint32_t b_addr = a_addr + L::A_BYTES;
+                const uint64_t st_off = (uint64_t)((uint32_t)(s * L::STAGE_BYTES) >> 4);
 #pragma unroll
-                for (int k = 0; k < BKR / UMMA_K; ++k) {
-                    const uint64_t adesc = make_smem_desc(a_addr + k * UMMA_K * A_ROW, 8 * A_ROW, (uint32_t)L::A_SLAB, A_LAYOUT);
-                    const uint64_t bdesc = make_smem_desc(b_addr + k * UMMA_K * 128, 1024u, (uint32_t)L::B_SLAB, 2);
-                    umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                }
+                for (int k = 0; k < BKR / UMMA_K; ++k)
+                    umma_bf16(tmem_base, a_desc0 + st_off + (uint64_t)((k * UMMA_K * A_ROW) >> 4), b_desc0 + st_off + (uint64_t)((k * UMMA_K * 128) >> 4),
+                              idesc, (kb > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&pp.empty_bar[s]);
                 if (s == STAGES - 1) phase ^= 1;
             }
@@ -765,7 +800,7 @@ inline cudaError_t ensure_smem(KernelT kernel, int bytes) {
 }
 
 // C[M][N] = A[M][K] B[N][K]^T
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT = 1>
 inline cudaError_t launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K, Epilogue ep,
                           int* splits_inout, cudaStream_t stream) {
     constexpr int BK = 64;
@@ -773,10 +808,10 @@ inline cudaError_t launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* 
     CUtensorMap ta, tb;
     if (!make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM) || !make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN))
         return cudaErrorInvalidValue;
-    using L = SmemLayout<BN, STAGES, BK>;
+    using L = SmemLayout<BN, STAGES, BK, MT>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = ensure_smem(gemm_bf16_tc_kernel<BN, STAGES, BK, false>, L::TOTAL);
+        cudaError_t e = ensure_smem(gemm_bf16_tc_kernel<BN, STAGES, BK, false, MT>, L::TOTAL);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -790,8 +825,8 @@ inline cudaError_t launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* 
     if (splits == 1) ep.partial = nullptr;
     CUtensorMap to = ta;
     const int tma_store = (splits == 1 && tma_store_eligible(ep, N, BN) && make_tmap_out2d(&to, ep.out_bf16, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldc)) ? 1 : 0;
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
-    gemm_bf16_tc_kernel<BN, STAGES, BK, false><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, to, M, N, K, chunk_tiles * BK, tma_store,
+    dim3 grid((N + BN - 1) / BN, (M + MT * BM - 1) / (MT * BM), splits);
+    gemm_bf16_tc_kernel<BN, STAGES, BK, false, MT><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, to, M, N, K, chunk_tiles * BK, tma_store,
                                                                                    ConvArgs{1, 0}, ep);
     return cudaGetLastError();
 }
@@ -834,7 +869,7 @@ inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfl
     const int nkb = 9 * Cin / BK;
     // bf16 output without per-element fp32 masks: epilogue through shared memory + TMA store
     static_assert(EPI == 4 || EPI == 8, "4 or 8 epilogue warps");
-    constexpr int HWE = BN / (EPI / 4);
+    constexpr int HWE = BN;
     static_assert(HWE >= 32, "an epilogue warp handles at least 32 columns");
     CUtensorMap to = ta;
     const int tma_store = (HWE % 64 == 0 && tma_store_eligible(ep, Cout, BN) && ep.ldc == Cout && make_tmap_out_conv(&to, ep.out_bf16, (uint64_t)batch, (uint64_t)Cout)) ? 1 : 0;
