@@ -183,6 +183,29 @@ gemm_f32_kernel(GemmParams p) {
 
 __global__ void __launch_bounds__(256) splitk_epilogue_kernel(GemmParams p) {
     const size_t total = (size_t)p.M * p.N;
+    if (p.N % 4 == 0 && p.ldc % 4 == 0 && (((uintptr_t)p.C | (uintptr_t)p.partial) & 15) == 0 && ((uintptr_t)p.Cb & 7) == 0) {
+        // four columns per thread: 16-byte loads of the partials, one pass
+        const size_t total4 = total / 4;
+        for (size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (size_t)gridDim.x * blockDim.x) {
+            const size_t idx = i4 * 4;
+            const int m = (int)(idx / p.N), n = (int)(idx - (size_t)m * p.N);
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int s = 0; s < p.splits; ++s) {                                          // fixed order: deterministic
+                const float4 w = *reinterpret_cast<const float4*>(p.partial + (size_t)s * total + idx);
+                a.x += w.x; a.y += w.y; a.z += w.z; a.w += w.w;
+            }
+            float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = epilogue_value(p, v[j], m, n + j);
+            const size_t o = (size_t)m * p.ldc + n;
+            if (p.C) *reinterpret_cast<float4*>(p.C + o) = make_float4(v[0], v[1], v[2], v[3]);
+            if (p.Cb) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+                *reinterpret_cast<uint2*>(p.Cb + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+            }
+        }
+        return;
+    }
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int m = (int)(idx / p.N), n = (int)(idx - (size_t)m * p.N);
         float v = 0.f;
