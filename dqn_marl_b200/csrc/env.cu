@@ -1220,9 +1220,15 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
                         layout->L, layout->W, need, max_smem);
     }
     e->blocks = (c.n_envs + groups - 1) / groups;
-    ce = cudaFuncSetAttribute((const void*)k_variants[e->variant].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem);
-    if (ce == cudaSuccess)
-        ce = cudaFuncSetAttribute((const void*)k_variants[e->variant].reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem);
+    // The limit is an attribute of the FUNCTION (per device), shared by every env handle that uses this variant: raise it to
+    // the device's opt-in maximum once instead of to this env's size (a later, smaller env must not lower it under a live one).
+    // (the dynamic part may be at most the opt-in maximum minus the kernel's static shared memory)
+    for (const void* fn : {(const void*)k_variants[e->variant].step, (const void*)k_variants[e->variant].reset}) {
+        cudaFuncAttributes fa{};
+        ce = cudaFuncGetAttributes(&fa, fn);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - (int)fa.sharedSizeBytes);
+        if (ce != cudaSuccess) break;
+    }
     if (ce != cudaSuccess) {
         mq_env_destroy(e);
         return mq::fail(MQ_ERR_CUDA, "mq_env_create: cudaFuncSetAttribute: %s", cudaGetErrorString(ce));

@@ -794,9 +794,19 @@ inline bool tma_store_eligible(const Epilogue& ep, int N, int BN) {
     return BN % 64 == 0 && N % BN == 0 && ep.out_bf16 && !ep.out_f32 && !ep.mask_f32 && !ep.drop && ep.ldc % 8 == 0;
 }
 
+// The dynamic shared-memory limit is a per-device function attribute: remember per device what has been raised already
+// (one process normally drives one GPU, but nothing here may depend on that).
+struct SmemMemo { int bytes[64]; };
 template <typename KernelT>
-inline cudaError_t ensure_smem(KernelT kernel, int bytes) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+inline cudaError_t ensure_smem(SmemMemo& memo, KernelT kernel, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const bool tracked = dev >= 0 && dev < 64;
+    if (tracked && bytes <= memo.bytes[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && tracked) memo.bytes[dev] = bytes;
+    return e;
 }
 
 // C[M][N] = A[M][K] B[N][K]^T
@@ -809,12 +819,8 @@ inline cudaError_t launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* 
     if (!make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM) || !make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN))
         return cudaErrorInvalidValue;
     using L = SmemLayout<BN, STAGES, BK, MT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = ensure_smem(gemm_bf16_tc_kernel<BN, STAGES, BK, false, MT>, L::TOTAL);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static SmemMemo memo{};
+    if (cudaError_t e = ensure_smem(memo, gemm_bf16_tc_kernel<BN, STAGES, BK, false, MT>, L::TOTAL); e != cudaSuccess) return e;
     const int k_tiles = (K + BK - 1) / BK;
     if (splits < 1) splits = 1;
     if (splits > k_tiles) splits = k_tiles;
@@ -842,12 +848,8 @@ inline cudaError_t launch_conv(const __nv_bfloat16* X, const __nv_bfloat16* Wk, 
         !make_tmap(&tb, Wk, (uint64_t)Cout, (uint64_t)9 * Cin, (uint64_t)9 * Cin, BN, BK))
         return cudaErrorInvalidValue;
     using L = SmemLayout<BN, STAGES, BK>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = ensure_smem(gemm_bf16_tc_kernel<BN, STAGES, BK, true>, L::TOTAL);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static SmemMemo memo{};
+    if (cudaError_t e = ensure_smem(memo, gemm_bf16_tc_kernel<BN, STAGES, BK, true>, L::TOTAL); e != cudaSuccess) return e;
     ep.partial = nullptr;
     CUtensorMap to = ta;
     const int tma_store = (tma_store_eligible(ep, Cout, BN) && ep.ldc == Cout && make_tmap_out_conv(&to, ep.out_bf16, (uint64_t)batch, (uint64_t)Cout)) ? 1 : 0;
@@ -875,12 +877,8 @@ inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfl
     const int tma_store = (HWE % 64 == 0 && tma_store_eligible(ep, Cout, BN) && ep.ldc == Cout && make_tmap_out_conv(&to, ep.out_bf16, (uint64_t)batch, (uint64_t)Cout)) ? 1 : 0;
     const int smem = nkb * BN * BK * 2 + STAGES * 160 * BK * 2 + (tma_store ? EPI * 4096 : 0) + 1024 + 256;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static int attr_bytes = 0;
-    if (smem > attr_bytes) {
-        cudaError_t e = ensure_smem(conv_bf16_persistent_kernel<BN, BK, STAGES, EPI>, smem);
-        if (e != cudaSuccess) return e;
-        attr_bytes = smem;
-    }
+    static SmemMemo memo{};
+    if (cudaError_t e = ensure_smem(memo, conv_bf16_persistent_kernel<BN, BK, STAGES, EPI>, smem); e != cudaSuccess) return e;
     ep.partial = nullptr;
     const int slices = Cout / BN;                       // CTAs of different output-channel slices walk over the same samples
     const int per_slice = n_sms / slices < 1 ? 1 : n_sms / slices;
@@ -900,12 +898,8 @@ inline cudaError_t launch_tn(const __nv_bfloat16* At, int lda, const __nv_bfloat
     if (!make_tmap(&ta, At, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BKR, AW) || !make_tmap(&tb, Bt, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BKR))
         return cudaErrorInvalidValue;
     using L = SmemLayoutTN<BN, STAGES, BKR, AW>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = ensure_smem(gemm_bf16_tn_kernel<BN, STAGES, BKR, false, AW>, L::TOTAL);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static SmemMemo memo{};
+    if (cudaError_t e = ensure_smem(memo, gemm_bf16_tn_kernel<BN, STAGES, BKR, false, AW>, L::TOTAL); e != cudaSuccess) return e;
     const int k_tiles = (K + BKR - 1) / BKR;
     if (splits < 1) splits = 1;
     if (splits > k_tiles) splits = k_tiles;
@@ -932,12 +926,8 @@ inline cudaError_t launch_conv_wgrad(const __nv_bfloat16* X, const __nv_bfloat16
         !make_tmap(&tb, dY, (uint64_t)batch * PIXELS, (uint64_t)Cout, (uint64_t)Cout, PIXELS))
         return cudaErrorInvalidValue;
     using L = SmemLayoutTN<BN, STAGES, BKR, AW>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = ensure_smem(gemm_bf16_tn_kernel<BN, STAGES, BKR, true, AW>, L::TOTAL);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static SmemMemo memo{};
+    if (cudaError_t e = ensure_smem(memo, gemm_bf16_tn_kernel<BN, STAGES, BKR, true, AW>, L::TOTAL); e != cudaSuccess) return e;
     const int M = 9 * Cin;
     if (splits < 1) splits = 1;
     if (splits > batch) splits = (int)batch;

@@ -269,7 +269,7 @@ int64_t mq_qnet_launch_count(const mq_qnet* net);
 /* ------------------------------------------------------------------------
  * Stand-alone bf16 tensor-core GEMM (tcgen05 + TMEM + TMA), the building block of the Q-network's throughput
  * path: C[M][N] = A[M][K] bf16 * B[N][K]^T bf16 (both K-contiguous), written as f32 (C) and / or bf16 (C_bf16).
- * bn = tile width 128/64/32.
+ * bn = tile selector: 32 / 64 / 128 / 256 = 128 x bn outputs per CTA; 384 = 256 x 128, 512 = 256 x 256 (two row tiles per CTA).
  * ---------------------------------------------------------------------- */
 int mq_gemm_bf16(const void* A, const void* B, float* C, void* C_bf16, int32_t M, int32_t N, int32_t K, int32_t bn,
                  int32_t splits, float* workspace, void* stream);

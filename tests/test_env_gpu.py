@@ -295,3 +295,27 @@ def test_host_buffer_step_async_equals_device_step():
         sa, sb = a.snapshot(k), b.snapshot(k)
         for key in ("px", "py", "health", "acc", "flags", "rmap"):
             assert np.array_equal(sa[key], sb[key]), (key, k)
+
+
+@pytest.mark.gpu
+def test_two_live_env_handles_of_one_kernel_variant():
+    """The dynamic shared-memory limit is an attribute of the kernel function, not of the env handle: creating a second,
+    smaller env of the same variant must not lower it under the first one.  Two handles stepped alternately, both bit-exact."""
+    from dqn_marl_b200.envs import VecEvacuationEnv
+    from dqn_marl_b200.layout import Layout
+    from oracle import LayoutTables, OracleEnv
+    lay = Layout.reference_room()
+    tabs = LayoutTables.from_layout(lay)
+    big = VecEvacuationEnv(lay, 30, 150, device="cuda:0", seed=5, env_id_base=0)
+    small = VecEvacuationEnv(lay, 30, 12, device="cuda:0", seed=6, env_id_base=0)
+    o_big, o_small = OracleEnv(tabs, 150, 1, seed=5, env_id=3), OracleEnv(tabs, 12, 1, seed=6, env_id=3)
+    big.reset(); small.reset(); o_big.reset(); o_small.reset()
+    rng = np.random.default_rng(0)
+    for t in range(12):
+        for env, orc in ((big, o_big), (small, o_small)):
+            acts = rng.integers(0, 5, size=(30, 1)).astype(np.int32)
+            _, r, d = env.step(torch.tensor(acts, device="cuda:0"))
+            _, rr, dd = orc.step(acts[3])
+            assert r[3].item() == rr and bool(d[3].item()) == bool(dd), (t, r[3].item(), rr)
+            a, b = env.snapshot(3), orc.snapshot()
+            assert np.array_equal(a["px"], b["px"]) and np.array_equal(a["health"].view(np.uint64), b["health"].view(np.uint64))
