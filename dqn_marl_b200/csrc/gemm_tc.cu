@@ -111,25 +111,37 @@ extern "C" int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, void* Y_
 
 // dW[9*Cin][Cout] (fp32) = im2col(X)^T * dY: X [B][11][11][Cin] bf16, dY [B*121][Cout] bf16; Cin % 32 == 0, Cout % 8 == 0.
 // splits > 1 partitions the samples; workspace >= splits * 9*Cin * Cout floats.
-extern "C" int mq_conv3x3_wgrad_bf16(const void* X, const void* dY, float* dW, int64_t batch, int32_t Cin, int32_t Cout, int32_t splits,
-                                     float* workspace, void* stream) {
+// dBias (optional): [Cout] column sums of dY (the bias gradient), produced by the same kernel through a spare A row of ones;
+// needs 9*Cin not to be a multiple of 128 (MQ_ERR_UNSUPPORTED otherwise) and splits * Cout more workspace floats.
+extern "C" int mq_conv3x3_wgrad_bf16(const void* X, const void* dY, float* dW, float* dBias, int64_t batch, int32_t Cin, int32_t Cout,
+                                     int32_t splits, float* workspace, void* stream) {
     MQ_REQUIRE(X && dY && dW && batch > 0, "mq_conv3x3_wgrad_bf16: bad argument");
     MQ_REQUIRE(Cin % 32 == 0 && Cout % 8 == 0, "mq_conv3x3_wgrad_bf16: Cin must be a multiple of 32 and Cout of 8");
     MQ_REQUIRE(splits <= 1 || workspace, "mq_conv3x3_wgrad_bf16: split needs a workspace");
+    MQ_REQUIRE(!dBias || workspace, "mq_conv3x3_wgrad_bf16: the bias gradient needs a workspace");
     cudaStream_t s = (cudaStream_t)stream;
     mq::tc::Epilogue ep{};
-    ep.out_f32 = dW; ep.ldc = Cout; ep.partial = splits > 1 ? workspace : nullptr;
     int sp = splits < 1 ? 1 : splits;
+    if (sp > batch) sp = (int)batch;
+    const size_t wtotal = (size_t)9 * Cin * Cout;
+    ep.out_f32 = dW; ep.ldc = Cout; ep.partial = sp > 1 ? workspace : nullptr;
+    ep.colsum_partial = dBias ? workspace + (sp > 1 ? (size_t)sp * wtotal : 0) : nullptr;       // behind the (at most sp) weight partials
+    bool fused = false;
     cudaError_t e;
     const __nv_bfloat16* x = (const __nv_bfloat16*)X;
     const __nv_bfloat16* dy = (const __nv_bfloat16*)dY;
     if (Cin % 64 != 0) {
         MQ_REQUIRE(Cout <= 64, "mq_conv3x3_wgrad_bf16: Cin = 32 (mod 64) supports Cout <= 64 only");
-        e = mq::tc::launch_conv_wgrad<64, 4, 32>(x, dy, batch, Cin, Cout, ep, &sp, s);
-    } else if (Cout > 64) e = mq::tc::launch_conv_wgrad<128, 3, 64>(x, dy, batch, Cin, Cout, ep, &sp, s);
-    else e = mq::tc::launch_conv_wgrad<64, 4, 64>(x, dy, batch, Cin, Cout, ep, &sp, s);
+        e = mq::tc::launch_conv_wgrad<64, 4, 32>(x, dy, batch, Cin, Cout, ep, &sp, s, &fused);
+    } else if (Cout > 64) e = mq::tc::launch_conv_wgrad<128, 3, 64>(x, dy, batch, Cin, Cout, ep, &sp, s, &fused);
+    else e = mq::tc::launch_conv_wgrad<64, 4, 64>(x, dy, batch, Cin, Cout, ep, &sp, s, &fused);
     if (e != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_conv3x3_wgrad_bf16: launch failed: %s", cudaGetErrorString(e));
-    return finish_split(workspace, sp, (size_t)9 * Cin * Cout, dW, s);
+    if (dBias) {
+        if (!fused) return mq::fail(MQ_ERR_UNSUPPORTED, "mq_conv3x3_wgrad_bf16: no spare operand row for the bias gradient (9*Cin %% 128 == 0)");
+        mq::tc_splitk_reduce_kernel<<<1, 256, 0, s>>>(ep.colsum_partial, sp, (size_t)Cout, dBias);      // sp >= 1 rows of [Cout]
+        MQ_CUDA(cudaGetLastError());
+    }
+    return finish_split(workspace, sp, wtotal, dW, s);
 }
 
 #ifdef MQ_CONV_TRACE

@@ -39,6 +39,7 @@ struct Epilogue {
     const uint8_t* drop;         // [M][N] keep mask or null
     float drop_scale;
     float* partial;              // split-K: [splits][M][N] fp32 (then no other epilogue op is applied)
+    float* colsum_partial;       // conv weight gradient only: [splits][N] column sums of dY (= the bias gradient), or null
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -656,11 +657,27 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    // Bias gradient for free: when the last row tile has an A slab that starts exactly at row M (9 Cin is not a multiple of
+    // 128), that slab is never loaded; filled once with ones in its first column (all 121 pixel rows), its first D row
+    // becomes sum_k dY[k][n], the column sums of the B operand.
+    const int slabs_here = min(L::A_SLABS, (M - m0 + AW - 1) / AW);
+    const bool ones_row = CONV && ep.colsum_partial != nullptr && slabs_here < L::A_SLABS && m0 + slabs_here * AW == M;
+    if (ones_row) {
+        constexpr int CHUNKS_PER_ROW = (int)A_ROW / 16;
+        for (int i = threadIdx.x; i < STAGES * BKR * CHUNKS_PER_ROW; i += THREADS) {
+            const int st = i / (BKR * CHUNKS_PER_ROW), o = i - st * (BKR * CHUNKS_PER_ROW);
+            const int k = o / CHUNKS_PER_ROW, pc = o - k * CHUNKS_PER_ROW;
+            const int logical = pc ^ (AW == 64 ? (k & 7) : ((k >> 1) & 3));          // TMA's swizzle: chunk index xor row bits
+            unsigned char* dst = tiles + (size_t)st * L::STAGE_BYTES + slabs_here * L::A_SLAB + k * A_ROW + pc * 16;
+            *reinterpret_cast<uint4*>(dst) = make_uint4((logical == 0 && k < PIXELS) ? 0x00003F80u : 0u, 0, 0, 0);     // bf16 1.0 in element 0
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     Pipe pp;
     const uint32_t tmem_base = pipe_init<STAGES>(pp, tiles + STAGES * L::STAGE_BYTES, &tmap_a, &tmap_b, TMEM_COLS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     // K is counted in rows (2-D) or samples (CONV)
     const int k_begin = blockIdx.z * k_chunk;
     const int k_end = min(K, k_begin + k_chunk);
@@ -721,6 +738,19 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const long long row = m0 + q * 32 + lane;
         epilogue_tile<BN>(ep, tmem_base, q, row < M && num_kb > 0, row, n0, M, N, blockIdx.z);
+        if (ones_row && q == (slabs_here * AW) / 32) {          // the warp that owns the ones row stores it (warp-uniform branch)
+            const bool mine = lane == (slabs_here * AW) % 32;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                if (mine) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + c0 + j < N) ep.colsum_partial[(size_t)blockIdx.z * N + n0 + c0 + j] = num_kb > 0 ? __uint_as_float(r[j]) : 0.f;
+                }
+            }
+        }
     }
     pipe_fini(tmem_base, TMEM_COLS);
 }
@@ -916,8 +946,10 @@ inline cudaError_t launch_tn(const __nv_bfloat16* At, int lda, const __nv_bfloat
 // weight gradient of the 3x3 convolution: dW[9*Cin][Cout] = im2col(X)^T dY, X [B][11][11][Cin], dY [B*121][Cout]; split over samples.
 // AW = width of an A slab: 64 (Cin % 64 == 0) or 32 (Cin % 32 == 0, 64-byte swizzle)
 template <int BN, int STAGES, int AW>
+// ep.colsum_partial != null asks for the column sums of dY as well ([splits][Cout], to be summed over the splits by the caller);
+// *colsum_fused tells whether the shape allowed it (a spare A slab starting at row 9 Cin).
 inline cudaError_t launch_conv_wgrad(const __nv_bfloat16* X, const __nv_bfloat16* dY, long long batch, int Cin, int Cout, Epilogue ep,
-                                     int* splits_inout, cudaStream_t stream) {
+                                     int* splits_inout, cudaStream_t stream, bool* colsum_fused = nullptr) {
     constexpr int BKR = 128;
     if (Cin % AW != 0 || Cout % 8 != 0 || batch <= 0) return cudaErrorInvalidValue;
     int splits = splits_inout ? *splits_inout : 1;
@@ -936,6 +968,9 @@ inline cudaError_t launch_conv_wgrad(const __nv_bfloat16* X, const __nv_bfloat16
     if (splits_inout) *splits_inout = splits;
     if (splits > 1 && !ep.partial) return cudaErrorInvalidValue;
     if (splits == 1) ep.partial = nullptr;
+    const bool spare_slab = (M % BM) != 0 && (M % BM) % AW == 0;
+    if (!spare_slab) ep.colsum_partial = nullptr;
+    if (colsum_fused) *colsum_fused = ep.colsum_partial != nullptr;
     dim3 grid((Cout + BN - 1) / BN, (M + BM - 1) / BM, splits);
     gemm_bf16_tn_kernel<BN, STAGES, BKR, true, AW><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, M, Cout, (int)batch, chunk, Cin, ep);
     return cudaGetLastError();

@@ -509,17 +509,28 @@ static void launch_colsum_bf16(mq_qnet* n, const bf::bf16* X, long long M, int N
 
 // conv weight gradient on the tensor cores: split over samples so that ~one wave of CTAs runs, deterministic reduce
 template <int BN, int STAGES, int AW>
-static cudaError_t conv_wgrad(mq_qnet* n, const bf::bf16* X, const bf::bf16* dY, long long B, int Cin, int Cout, float* out, cudaStream_t s) {
+static cudaError_t conv_wgrad(mq_qnet* n, const bf::bf16* X, const bf::bf16* dY, long long B, int Cin, int Cout, float* out, float* bias_out,
+                              cudaStream_t s) {
     const int M = 9 * Cin;
     const int tiles = ((M + tc::BM - 1) / tc::BM) * ((Cout + BN - 1) / BN);
     int splits = n->n_sms / tiles;            // one CTA per SM (192 KB of shared memory each): never more CTAs than SMs
     if (splits < 1) splits = 1;
-    while (splits > 1 && (size_t)splits * M * Cout > n->partial_cap) --splits;
+    // the last COLSUM_RESERVE floats of the partial buffer hold the per-split column sums of dY (the bias gradient), which
+    // the kernel produces through a spare A row of ones when the shape has one
+    constexpr size_t COLSUM_RESERVE = (size_t)1024 * 256;
+    while (splits > 1 && ((size_t)splits * M * Cout > n->partial_cap - COLSUM_RESERVE || (size_t)splits * Cout > COLSUM_RESERVE)) --splits;
     tc::Epilogue ep{};
     ep.out_f32 = out; ep.ldc = Cout; ep.partial = n->partial;
-    cudaError_t e = tc::launch_conv_wgrad<BN, STAGES, AW>(X, dY, B, Cin, Cout, ep, &splits, s);
+    ep.colsum_partial = n->partial + (n->partial_cap - COLSUM_RESERVE);
+    bool fused = false;
+    cudaError_t e = tc::launch_conv_wgrad<BN, STAGES, AW>(X, dY, B, Cin, Cout, ep, &splits, s, &fused);
     n->launches += 1;
-    if (e == cudaSuccess && splits > 1) {
+    if (e != cudaSuccess) return e;
+    if (fused) {
+        colsum_final_kernel<<<(Cout * 32 + 255) / 256, 256, 0, s>>>(ep.colsum_partial, splits, Cout, bias_out);
+        n->launches += 1;
+    }
+    if (splits > 1) {
         GemmParams p{};
         p.M = M; p.N = Cout; p.C = out; p.ldc = Cout; p.partial = n->partial; p.splits = splits;
         size_t total = (size_t)M * Cout;
@@ -527,6 +538,7 @@ static cudaError_t conv_wgrad(mq_qnet* n, const bf::bf16* X, const bf::bf16* dY,
         splitk_epilogue_kernel<<<blocks, 256, 0, s>>>(p);
         n->launches += 1;
     }
+    if (!fused) launch_colsum_bf16(n, dY, B * PIX, Cout, bias_out, s);      // after the split reduce: it reuses the partial buffer
     return e;
 }
 
@@ -585,21 +597,19 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
     }
     if (part == 1) return cudaGetLastError();
     // conv3: dWc3[(t,c)][n] = im2col(a2)^T dY (implicit, split over samples) ; db ; da2 = conv_flip(dY, Wd3) (masked by a2 > 0).
-    launch_colsum_bf16(n, n->da3b, M, C3, G[P_C3B], s);
-    if ((e = conv_wgrad<128, 3, 64>(n, n->a2b, n->da3b, B, C2, C3, G[P_C3W], s)) != cudaSuccess) return e;
+    if ((e = conv_wgrad<128, 3, 64>(n, n->a2b, n->da3b, B, C2, C3, G[P_C3W], G[P_C3B], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da2b; ep.ldc = C2; ep.mask_bf16 = n->a2b;
     if ((e = tc::launch_conv_persistent<64, 64, 3>(n->da3b, n->w3d, B, C3, C2, 1, ep, n->n_sms, s)) != cudaSuccess) return e;
     // conv2
-    launch_colsum_bf16(n, n->da2b, M, C2, G[P_C2B], s);
-    if ((e = conv_wgrad<64, 4, 32>(n, n->a1b, n->da2b, B, C1, C2, G[P_C2W], s)) != cudaSuccess) return e;
+    if ((e = conv_wgrad<64, 4, 32>(n, n->a1b, n->da2b, B, C1, C2, G[P_C2W], G[P_C2B], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da1b; ep.ldc = C1; ep.mask_bf16 = n->a1b;
     if ((e = tc::launch_conv_persistent<32, 64, 4>(n->da2b, n->w2d, B, C2, C1, 1, ep, n->n_sms, s)) != cudaSuccess) return e;
     n->launches += 2;
-    // conv1: db = column sums of dY; dWc1^T [32][64] = dY^T A1 (MN-major operands, 32-wide A slabs, split over the rows),
-    // reduced and transposed into the [(tap, c)][32] layout.  The observation needs no gradient.
-    launch_colsum_bf16(n, n->da1b, M, C1, G[P_C1B], s);
+    // conv1: dWc1^T [32][64] = dY^T A1 (MN-major operands, 32-wide A slabs, split over the rows), reduced and transposed into
+    // the [(tap, c)][32] layout; column 54 of A1 is all ones, so row 54 of the product is db = the column sums of dY.
+    // The observation needs no gradient.
     {
         int splits = n->n_sms;
         while (splits > 1 && (size_t)splits * C1 * 64 > n->partial_cap) --splits;
@@ -607,7 +617,7 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
         ep.out_f32 = n->partial; ep.ldc = 64; ep.partial = n->partial;
         if ((e = tc::launch_tn<64, 4, 32>(n->da1b, C1, n->A1, 64, C1, 64, M, ep, &splits, s)) != cudaSuccess) return e;
         if (splits == 1) return cudaErrorInvalidValue;      // (never: M / 64 k-blocks >> 1) the reduce below expects partials
-        bf::conv1_wgrad_reduce_kernel<<<54, 256, 0, s>>>(n->partial, splits, G[P_C1W]);
+        bf::conv1_wgrad_reduce_kernel<<<55, 256, 0, s>>>(n->partial, splits, G[P_C1W], G[P_C1B]);
         n->launches += 2;
     }
     return cudaGetLastError();

@@ -18,7 +18,8 @@ template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
 
 // conv1 on the tensor cores: the 6-channel observation is too narrow for a TMA box (12-byte pixels), so its im2col rows are
-// written once per forward: obs f32 [B][11][11][6] -> A1 bf16 [B*121][64], column k = tap*6 + c for k < 54, zero above.
+// written once per forward: obs f32 [B][11][11][6] -> A1 bf16 [B*121][64], column k = tap*6 + c for k < 54, 1.0 in column 54
+// (a ones column: the weight gradient GEMM then yields the bias gradient as row 54), zero above.
 // One thread = 8 consecutive columns of one row (a 16-byte store).
 __global__ void __launch_bounds__(256)
 im2col_obs_bf16_kernel(const float* __restrict__ obs, bf16* __restrict__ A1, long long B) {
@@ -41,6 +42,8 @@ im2col_obs_bf16_kernel(const float* __restrict__ obs, bf16* __restrict__ A1, lon
                 const int tap = k / 6, c = k - tap * 6;
                 const int ii = i + tap / 3 - 1, jj = j + tap % 3 - 1;
                 if ((unsigned)ii < 11u && (unsigned)jj < 11u) x = win[sidx][(ii * 11 + jj) * 6 + c];
+            } else if (k == 54) {
+                x = 1.f;          // the weight operand is zero here (forward unaffected); dY^T A1 gets the bias gradient in this row
             }
             v[t] = __float2bfloat16(x);
         }
@@ -57,8 +60,9 @@ conv1_weight_bf16_kernel(const float* __restrict__ wc, bf16* __restrict__ w1f) {
 }
 // conv1 weight gradient: partial[split][n (32)][k (64)] (the TN GEMM computes dY^T A1) -> dWc[(tap*6 + c)][32], fixed order
 __global__ void __launch_bounds__(256)
-conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, float* __restrict__ dwc) {
-    // one CTA per k (54): thread = (n, split group of 8); the groups are combined through shared memory in a fixed order
+conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, float* __restrict__ dwc, float* __restrict__ dbias) {
+    // one CTA per k (54 weight rows + the ones column k = 54 -> bias gradient): thread = (n, split group of 8); the groups are
+    // combined through shared memory in a fixed order
     __shared__ float red[8][32];
     const int k = blockIdx.x, n = threadIdx.x & 31, sg = threadIdx.x >> 5;
     float acc = 0.f;
@@ -69,7 +73,8 @@ conv1_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, float* 
         float t = 0.f;
 #pragma unroll
         for (int g = 0; g < 8; ++g) t += red[g][n];
-        dwc[k * 32 + n] = t;
+        if (k < 54) dwc[k * 32 + n] = t;
+        else dbias[n] = t;
     }
 }
 

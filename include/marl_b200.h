@@ -290,9 +290,10 @@ int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, void* Y_bf16, int64
                     int32_t bn, void* stream);
 
 /* Weight gradient of that convolution: dW[9*Cin][Cout] f32 = im2col(X)^T * dY, dY [batch*121][Cout] bf16.  splits > 1
- * partitions the samples (workspace >= splits * 9*Cin*Cout floats). */
-int mq_conv3x3_wgrad_bf16(const void* X, const void* dY, float* dW, int64_t batch, int32_t Cin, int32_t Cout, int32_t splits,
-                          float* workspace, void* stream);
+ * partitions the samples (workspace >= splits * 9*Cin*Cout floats).  dBias (optional, [Cout]) = column sums of dY, computed
+ * by the same kernel through a spare operand row of ones (needs 9*Cin % 128 != 0 and splits*Cout more workspace floats). */
+int mq_conv3x3_wgrad_bf16(const void* X, const void* dY, float* dW, float* dBias, int64_t batch, int32_t Cin, int32_t Cout,
+                          int32_t splits, float* workspace, void* stream);
 
 #ifdef __cplusplus
 }

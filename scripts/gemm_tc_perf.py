@@ -63,7 +63,7 @@ for name, cin, cout, splits in [("conv3 wgrad", 64, 128, 30), ("conv2 wgrad", 32
     dY = torch.randn((M, cout), device="cuda").to(torch.bfloat16)
     dW = torch.empty((9 * cin, cout), device="cuda")
     ws = torch.empty((splits * 9 * cin * cout,), device="cuda")
-    ms = timeit(lambda: _lib.check(lib.mq_conv3x3_wgrad_bf16(_lib.ptr(X), _lib.ptr(dY), _lib.ptr(dW), B, cin, cout, splits, _lib.ptr(ws), st), "wgrad"))
+    ms = timeit(lambda: _lib.check(lib.mq_conv3x3_wgrad_bf16(_lib.ptr(X), _lib.ptr(dY), _lib.ptr(dW), None, B, cin, cout, splits, _lib.ptr(ws), st), "wgrad"))
     tf = 2.0 * M * cout * 9 * cin / (ms * 1e-3) / 1e12
     print(f"{name:12s} implicit TN splits={splits:3d}  {ms:8.3f} ms  {tf:7.1f} TFLOP/s  {100*tf/peak:5.1f}% of {peak:.0f}")
 At = torch.randn((B, 512), device="cuda").to(torch.bfloat16)

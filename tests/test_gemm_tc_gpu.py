@@ -117,10 +117,20 @@ def test_conv_wgrad_matches_torch(B, Cin, Cout, splits):
     X = torch.randn((B, 11, 11, Cin), generator=g, device="cuda:0").to(torch.bfloat16)
     dY = torch.randn((B * 121, Cout), generator=g, device="cuda:0").to(torch.bfloat16)
     dW = torch.full((9 * Cin, Cout), float("nan"), device="cuda:0")
-    ws = torch.empty((splits * 9 * Cin * Cout,), device="cuda:0") if splits > 1 else None
-    _lib.check(lib.mq_conv3x3_wgrad_bf16(_lib.ptr(X), _lib.ptr(dY), _lib.ptr(dW), B, Cin, Cout, splits, _lib.ptr(ws), _stream()),
+    ws = torch.empty((splits * (9 * Cin + 1) * Cout,), device="cuda:0")
+    has_spare_row = (9 * Cin) % 128 != 0
+    db = torch.full((Cout,), float("nan"), device="cuda:0")
+    if not has_spare_row:      # 9 Cin is a multiple of 128: no spare operand row, the bias gradient must be refused, not made up
+        with pytest.raises(_lib.MqError, match="spare"):
+            _lib.check(lib.mq_conv3x3_wgrad_bf16(_lib.ptr(X), _lib.ptr(dY), _lib.ptr(dW), _lib.ptr(db), B, Cin, Cout, splits, _lib.ptr(ws),
+                                                 _stream()), "mq_conv3x3_wgrad_bf16")
+        db = None
+    _lib.check(lib.mq_conv3x3_wgrad_bf16(_lib.ptr(X), _lib.ptr(dY), _lib.ptr(dW), _lib.ptr(db), B, Cin, Cout, splits, _lib.ptr(ws), _stream()),
                "mq_conv3x3_wgrad_bf16")
     torch.cuda.synchronize()
+    if has_spare_row:          # bias gradient = column sums of dY, from the spare operand row of ones
+        ref_b = dY.float().sum(0)
+        assert (db - ref_b).abs().max().item() <= 2e-3 * ref_b.abs().max().item() + 1e-3
     cols = torch.nn.functional.unfold(X.float().permute(0, 3, 1, 2), 3, padding=1)         # [B][Cin*9][121], (c, kh, kw) order
     cols = cols.reshape(B, Cin, 9, 121).permute(0, 3, 2, 1).reshape(B * 121, 9 * Cin)      # rows (b, pixel), cols (tap, c)
     ref = cols.t() @ dY.float()
