@@ -335,9 +335,11 @@ def run_ours(args, wl):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "value_sync_each_step": e2e_sync_value,
+                    "d2h_GBs_per_gpu": e2e_value / world / (E * N) * d2h / 1e9,
                     "note": f"VecEvacuationEnv.step_async/step_wait: pinned host actions in (H2D), obs+reward+done out (D2H) every "
                             f"step; {n_rot} independent env batches in flight on their own streams (copies overlap kernels); "
-                            f"value_sync_each_step = one batch at a time with a host sync per step"},
+                            f"value_sync_each_step = one batch at a time with a host sync per step; d2h_GBs_per_gpu = the PCIe "
+                            f"device-to-host rate this e2e value corresponds to (the bound of this leg)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
