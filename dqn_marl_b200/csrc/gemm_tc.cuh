@@ -840,13 +840,12 @@ inline cudaError_t ensure_smem(SmemMemo& memo, KernelT kernel, int bytes) {
 }
 
 // C[M][N] = A[M][K] B[N][K]^T
-template <int BN, int STAGES, int MT = 1>
+template <int BN, int STAGES, int MT = 1, int BK = 64>
 inline cudaError_t launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K, Epilogue ep,
                           int* splits_inout, cudaStream_t stream) {
-    constexpr int BK = 64;
     int splits = splits_inout ? *splits_inout : 1;
     CUtensorMap ta, tb;
-    if (!make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM) || !make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN))
+    if (!make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK) || !make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, BK))
         return cudaErrorInvalidValue;
     using L = SmemLayout<BN, STAGES, BK, MT>;
     static SmemMemo memo{};
