@@ -17,6 +17,7 @@
 // warp 1 = TMEM allocator + MMA issuer (one lane), warps 2..5 = epilogue (each owns 32 TMEM lanes).
 // One 128 x BN output tile per CTA, optional split-K over gridDim.z (fp32 partials).
 #pragma once
+#include <cstdio>
 #include <cstdint>
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -449,6 +450,131 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 // =====================================================================================================================
+// CTA-pair kernel (cta_group::2): two CTAs of a cluster (consecutive 128-row tiles) compute a 256 x BN tile with ONE MMA
+// stream issued by the leader.  Each CTA loads its own 128 rows of A and only HALF of the B tile (BN / 2 rows); the tensor
+// cores of the pair exchange the halves, so every SM reads 4 KB + BN/2 * 32 B of operands per MMA instead of 4 KB + BN * 32 B
+// and pulls half of the B bytes from L2.  The peer's TMA loads complete on the LEADER's full barrier (barrier address with
+// the CTA-rank bit cleared), tcgen05.commit multicasts to the empty / accumulator barriers of both CTAs, each CTA drains its
+// own 128 rows of D from its own TMEM.  Mechanics established by scripts/probes/cta_pair_probe.cu.
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c_inner, int c_outer) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c_inner), "r"(c_outer) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {      // arrives on this barrier in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(THREADS)
+gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const __grid_constant__ CUtensorMap tmap_out, long long M, int N, int K, int k_chunk, int tma_store, Epilogue ep) {
+    extern __shared__ unsigned char smem_raw[];
+    constexpr int BK = 64;
+    constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    static_assert(BN % 32 == 0 && BN <= 256, "pair tile: N a multiple of 32 (16 per CTA half would do for the MMA, 32 for the loads)");
+    unsigned char* tiles = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = (uint64_t*)(tiles + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint32_t* tmem_ptr = (uint32_t*)(tmem_full + 1);
+    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                 // the peer's barriers exist before anything is signalled on them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int m_tile = blockIdx.x, n0 = blockIdx.y * BN;      // the pair = two consecutive row tiles = cluster (2, 1, 1) along x
+    const int k_begin = blockIdx.z * k_chunk;
+    const int k_end = min(K, k_begin + k_chunk);
+    const int num_kb = (k_end - k_begin + BK - 1) / BK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t phase = 1;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&empty_bar[s], phase);                                   // own copy: the commit arrives in both CTAs
+                if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);      // the leader's barrier counts the bytes of both
+                unsigned char* a_dst = tiles + s * STAGE_BYTES;
+                const int k = k_begin + kb * BK;
+                tma_load_2d_pair(a_dst, &tmap_a, &full_bar[s], k, m_tile * BM);
+                tma_load_2d_pair(a_dst + A_BYTES, &tmap_b, &full_bar[s], k, n0 + (int)rank * (BN / 2));
+                if (s == STAGES - 1) phase ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // instruction descriptor of the pair: M = 256, N = BN
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            const uint64_t desc0 = make_smem_desc(smem_u32(tiles), 1024u, 0, 2);
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                mbar_wait(&full_bar[s], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t adesc = desc0 + (uint64_t)((uint32_t)(s * STAGE_BYTES) >> 4);
+                const uint64_t bdesc = adesc + (uint64_t)(A_BYTES >> 4);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma_bf16_pair(tmem_base, adesc + (uint64_t)((k * UMMA_K * 2) >> 4), bdesc + (uint64_t)((k * UMMA_K * 2) >> 4), idesc,
+                                   (kb > 0 || k > 0) ? 1u : 0u);
+                umma_commit_pair(&empty_bar[s]);
+                if (s == STAGES - 1) phase ^= 1;
+            }
+            umma_commit_pair(tmem_full);
+        }
+    } else {
+        const int q = warp & 3;
+        if (num_kb > 0) mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int r = q * 32 + lane;
+        const long long row = (long long)m_tile * BM + r;
+        const bool ok = row < M && num_kb > 0;
+        bool done = false;
+        if constexpr (BN % 64 == 0) {
+            if (tma_store && num_kb > 0) {
+                const __nv_bfloat16* mrow = (ep.mask_bf16 && ok) ? ep.mask_bf16 + (size_t)row * ep.ldc + n0 : nullptr;
+                epilogue_tile_tma<BN>(ep, &tmap_out, tmem_base, q, lane, mrow, n0, m_tile * BM + q * 32, -1, tiles + q * 4096);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                done = true;
+            }
+        }
+        if (!done) epilogue_tile<BN>(ep, tmem_base, q, ok, row, n0, M, N, blockIdx.z);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();                 // nobody leaves (or frees TMEM) while the pair's MMAs may still read its shared memory
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+// =====================================================================================================================
 // Persistent implicit-GEMM convolution: the whole weight matrix Wk[BN][9*Cin] stays in shared memory (<= 147 KB for the
 // Q-network's layers), every CTA walks over samples (one 121-row tile each): the A ring streams the shifted boxes, the
 // accumulator is double-buffered in TMEM so the epilogue of sample t overlaps the MMAs of sample t+1.
@@ -864,6 +990,42 @@ inline cudaError_t launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* 
     gemm_bf16_tc_kernel<BN, STAGES, BK, false, MT><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, to, M, N, K, chunk_tiles * BK, tma_store,
                                                                                    ConvArgs{1, 0}, ep);
     return cudaGetLastError();
+}
+
+// CTA-pair form of launch(): 256 x BN outputs per pair of CTAs (cluster 2 x 1 x 1; grid.x walks over the row tiles)
+template <int BN, int STAGES>
+inline cudaError_t launch_pair(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, int M, int N, int K, Epilogue ep,
+                               int* splits_inout, cudaStream_t stream) {
+    constexpr int BK = 64;
+    int splits = splits_inout ? *splits_inout : 1;
+    CUtensorMap ta, tb;
+    if (!make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM) || !make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN / 2))
+        return cudaErrorInvalidValue;
+    constexpr int SMEM = STAGES * (BM * BK * 2 + (BN / 2) * BK * 2) + 1024 + 256;
+    static SmemMemo memo{};
+    if (cudaError_t e = ensure_smem(memo, gemm_bf16_pair_kernel<BN, STAGES>, SMEM); e != cudaSuccess) return e;
+    const int k_tiles = (K + BK - 1) / BK;
+    if (splits < 1) splits = 1;
+    if (splits > k_tiles) splits = k_tiles;
+    const int chunk_tiles = (k_tiles + splits - 1) / splits;
+    splits = (k_tiles + chunk_tiles - 1) / chunk_tiles;
+    if (splits_inout) *splits_inout = splits;
+    if (splits > 1 && !ep.partial) return cudaErrorInvalidValue;
+    if (splits == 1) ep.partial = nullptr;
+    CUtensorMap to = ta;
+    const int tma_store = (splits == 1 && tma_store_eligible(ep, N, BN) && make_tmap_out2d(&to, ep.out_bf16, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ldc)) ? 1 : 0;
+    const int m_tiles = (M + BM - 1) / BM;
+    dim3 grid((m_tiles + 1) & ~1, (N + BN - 1) / BN, splits);       // an even number of row tiles: the odd one out pairs with an empty tile
+    // the pair is a cluster of two CTAs along the row tiles (launch attribute, so that the pairing is visible at the call site)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;      // cta_group::2 pairs are adjacent in x
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const int k_chunk = chunk_tiles * BK;
+    const long long Mll = M;
+    return cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<BN, STAGES>, ta, tb, to, Mll, N, K, k_chunk, tma_store, ep);
 }
 
 // 3x3 / pad 1 convolution over 11 x 11 windows as an implicit GEMM: Y[B*121][Cout] = im2col(X [B][11][11][Cin]) * Wk[Cout][9*Cin]^T

@@ -408,7 +408,9 @@ static cudaError_t tc_gemm(mq_qnet* n, const bf::bf16* A, int lda, const bf::bf1
     }
     float* final_out = ep.out_f32;
     if (splits > 1) ep.partial = n->partial;
-    cudaError_t e = tc::launch<BN, (BN == 128 ? 3 : 4)>(A, lda, Bm, ldb, M, N, K, ep, &splits, s);
+    cudaError_t e;
+    if constexpr (BN == 256) e = tc::launch_pair<256, 6>(A, lda, Bm, ldb, M, N, K, ep, &splits, s);     // CTA pairs: 256 x 256 per cluster
+    else e = tc::launch<BN, (BN == 128 ? 3 : 4)>(A, lda, Bm, ldb, M, N, K, ep, &splits, s);
     n->launches += 1;
     if (e == cudaSuccess && splits > 1) {
         GemmParams p{};
@@ -448,7 +450,7 @@ static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, lon
     if (e != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_f32 = n->h1; ep.out_bf16 = n->h1b; ep.ldc = H1; ep.bias = W[P_F1B]; ep.relu = 1; ep.drop = drop_mask; ep.drop_scale = 1.f / (1.f - 0.2f);
-    e = tc_gemm<256>(n, n->a3b, FLAT, n->w1f[which], FLAT, (int)B, H1, FLAT, ep, true, s);      // 128 x 256 tiles: 979 vs 881 TFLOP/s
+    e = tc_gemm<256>(n, n->a3b, FLAT, n->w1f[which], FLAT, (int)B, H1, FLAT, ep, true, s);      // cta_group::2 pairs, 256 x 256: 1071 TFLOP/s (128 x 128: 881)
     if (e != cudaSuccess) return e;
     n->launches += 2;
     ep = tc::Epilogue{};

@@ -36,12 +36,15 @@ def _run(M, N, K, bn, splits=1, seed=0):
                                       (495, 64, 288, 64), (4096, 64, 1152, 64), (777, 32, 576, 32), (512, 15488, 512, 128),
                                       (128, 512, 15488, 128), (256, 512, 1024, 256), (300, 700, 576, 256), (512, 15488, 512, 256),
                                       (256, 256, 64, 512), (512, 512, 1024, 512), (300, 700, 576, 512), (640, 15488, 512, 512),
-                                      (900, 384, 576, 384), (128, 128, 256, 384)])
+                                      (900, 384, 576, 384), (128, 128, 256, 384),
+                                      (256, 256, 64, 1256), (512, 512, 1024, 1256), (300, 700, 576, 1256), (640, 15488, 512, 1256),
+                                      (128, 128, 256, 1128), (1000, 384, 576, 1128), (4096, 512, 15488, 1256)])
 def test_gemm_matches_torch(M, N, K, bn):
     _run(M, N, K, bn)
 
 
-@pytest.mark.parametrize("M,N,K,bn,splits", [(576, 128, 8192, 128, 8), (288, 64, 4000, 64, 5), (512, 1024, 4096, 128, 3), (384, 512, 15488, 256, 2), (512, 512, 15488, 512, 4), (384, 640, 4096, 384, 3)])
+@pytest.mark.parametrize("M,N,K,bn,splits", [(576, 128, 8192, 128, 8), (288, 64, 4000, 64, 5), (512, 1024, 4096, 128, 3), (384, 512, 15488, 256, 2), (512, 512, 15488, 512, 4), (384, 640, 4096, 384, 3),
+                                             (512, 512, 15488, 1256, 4), (384, 640, 4096, 1128, 3)])
 def test_gemm_split_k(M, N, K, bn, splits):
     _run(M, N, K, bn, splits)
 
