@@ -417,6 +417,12 @@ __device__ __noinline__ double health_chain_runs(const double* h, int N, int lan
 // The fused step.
 // ---------------------------------------------------------------------------------------------
 constexpr int PF_MAX = 5;  // persons per thread whose state is fetched before any of them is processed (5 x 32 >= 150: one pass at C2)
+#ifdef MQ_ENV_TRACE
+__device__ long long g_env_trace[16];
+#define ENV_MARK(k) do { if (tid == 0) { const long long _t = clock64(); atomicAdd((unsigned long long*)&g_env_trace[k], (unsigned long long)(_t - _tprev)); _tprev = _t; } } while (0)
+#else
+#define ENV_MARK(k) do { } while (0)
+#endif
 constexpr int SCORE_UNROLL = 2;     // movers scored per lane and iteration of phase 2 (independent chains)
 
 template <int WPE, int CW, bool BIG>
@@ -439,6 +445,9 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     const G g;
     const int env = blockIdx.x * GROUPS + g.gid;
     if (env >= cfg.n_envs) return;              // whole group leaves together (GROUPS == 1 when WPE == CW)
+#ifdef MQ_ENV_TRACE
+    long long _tprev = clock64();
+#endif
     Smem sm;
     carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
           cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE);
@@ -468,6 +477,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     }
     g.sync();
 
+    ENV_MARK(0);      // stage
     const uint32_t env_id = (uint32_t)(cfg.env_id_base + env);
     const uint32_t tick = (uint32_t)sc[MQ_S_TICK];
     const int fire_step = min(sc[MQ_S_FIRE_STEP], lay.n_fire_steps - 1);
@@ -586,6 +596,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     }
     g.sync();
 
+    ENV_MARK(1);      // phase 1
     if (G::CHAIN && !g.worker()) {
         // chain warp: the left-to-right health sum only needs phase 1; it overlaps with everything the workers do
         const double th = health_chain_runs<BIG ? 8 : 1>(sm.health, N, lane);
@@ -768,6 +779,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                 }
             }
         }
+        ENV_MARK(2);      // scoring
         {
             const int n_items = (n_mov * 4 + 31) & ~31;
             // proposals, one mover per lane: the movers this warp has just scored (8 per scoring iteration), so only a
@@ -799,6 +811,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         }
         g.wsync();
 
+        ENV_MARK(3);      // proposals
         // ---- phase 4a: winners leave their old cell (people.py:239-246,301) ---------------------------------
         for (int mi = wt; mi < n_mov; mi += TW) {
             const uint32_t mv = sm.mv[mi];
@@ -844,6 +857,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         }
         g.wsync();      // the proposal table is dead from here on: sm.dist may overwrite it
 
+        ENV_MARK(4);      // moves
         // ---- reward inputs (evacuation_env.py:174-233): counts, guidance, ordered list of distances --------
         const int rpx = sc[MQ_S_ROBOT_POS_X], rpy = sc[MQ_S_ROBOT_POS_Y];
         {
@@ -896,6 +910,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         }
         g.wsync();
 
+        ENV_MARK(5);      // reward inputs
         // ---- np.mean tree (numpy pairwise summation, evacuation_env.py:228) --------------------------------------------
         if (WPE >= 8) {
             // Wide groups: the serial enumerate / combine of the leaves cost 160 us per step at 20,000 people.  Warp 0 builds the
@@ -984,6 +999,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                 else { const double th = health_chain_runs<BIG ? 8 : 1>(sm.health, N, lane); if (lane == 0) s_sum[1] = th; }
             }
         }
+        ENV_MARK(6);      // tree + chain
         // fire models step (evacuation_env.py:138-142; fire_model.py:63-67) — the observation uses the new step
         store_bitmap(wt, TW, lay, sm, st.rmap, env);
         gather_obs(wt, TW, lay, cfg, sm, rob, rpx, rpy, min(sc[MQ_S_FIRE_STEP] + 1, lay.n_fire_steps - 1), obs, obs64, env);
@@ -991,6 +1007,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     }
     g.sync();
 
+    ENV_MARK(7);      // bitmap + obs
     // ---- _calculate_reward (evacuation_env.py:174-288), done (:150-157), scalars -----------------------
     if (tid == 0) {
         const int cur_evac = s_cnt[0], cur_dead = s_cnt[1], n_rem = s_cnt[3];
@@ -1042,6 +1059,7 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
         s_cnt[5] = done && cfg.auto_reset;
     }
     g.sync();
+    ENV_MARK(8);      // reward
     if (s_cnt[5]) {
         reset_env<WPE, CW>(g, lay, cfg, st, sm, sc, rob, nullptr, obs, obs64, env);
     } else {
@@ -1272,6 +1290,12 @@ extern "C" int mq_env_step(mq_env* e, const int32_t* actions, float* obs_out, do
     return MQ_OK;
 }
 
+#ifdef MQ_ENV_TRACE
+extern "C" int mq_debug_env_trace(long long* host_out, int reset) {
+    if (reset) { static long long z[16]; return (int)cudaMemcpyToSymbol(mq::g_env_trace, z, sizeof(z)); }
+    return (int)cudaMemcpyFromSymbol(host_out, mq::g_env_trace, sizeof(long long) * 16);
+}
+#endif
 extern "C" int mq_env_unpack_rmap(mq_env* e, uint8_t* rmap_out, void* stream) {
     MQ_REQUIRE(e && rmap_out, "mq_env_unpack_rmap: null argument");
     long long total = (long long)e->cfg.n_envs * e->lay.G;
