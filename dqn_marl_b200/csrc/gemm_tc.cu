@@ -31,7 +31,13 @@ extern "C" int mq_gemm_bf16(const void* A, const void* B, float* C, void* C_bf16
     cudaError_t e;
     const __nv_bfloat16* a = (const __nv_bfloat16*)A;
     const __nv_bfloat16* b = (const __nv_bfloat16*)B;
-    if (bn == 1256) e = mq::tc::launch_pair<256, 6>(a, K, b, K, M, N, K, ep, &sp, s);       // 1000 + bn: CTA pairs (cta_group::2), 256 x bn per pair
+    if (bn == 2032) {                  // 2000 + bn: persistent kernel with the B operand resident (N == bn, K a few 64-blocks)
+        MQ_REQUIRE(N == 32 && K % 64 == 0 && sp == 1, "mq_gemm_bf16: the resident-B form needs N == 32, K %% 64 == 0, no split");
+        int dev = 0, n_sms = 0;
+        MQ_CUDA(cudaGetDevice(&dev));
+        MQ_CUDA(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+        e = mq::tc::launch_resident<32, 8>(a, K, b, K, M, N, K, ep, n_sms, s);
+    } else if (bn == 1256) e = mq::tc::launch_pair<256, 6>(a, K, b, K, M, N, K, ep, &sp, s);       // 1000 + bn: CTA pairs (cta_group::2), 256 x bn per pair
     else if (bn == 1128) e = mq::tc::launch_pair<128, 8>(a, K, b, K, M, N, K, ep, &sp, s);
     else if (bn == 512) e = mq::tc::launch<256, 3, 2>(a, K, b, K, M, N, K, ep, &sp, s);         // 256 x 256 outputs per CTA
     else if (bn == 384) e = mq::tc::launch<128, 4, 2>(a, K, b, K, M, N, K, ep, &sp, s);    // 256 x 128
@@ -39,7 +45,7 @@ extern "C" int mq_gemm_bf16(const void* A, const void* B, float* C, void* C_bf16
     else if (bn == 128) e = mq::tc::launch<128, 3>(a, K, b, K, M, N, K, ep, &sp, s);
     else if (bn == 64) e = mq::tc::launch<64, 4>(a, K, b, K, M, N, K, ep, &sp, s);
     else if (bn == 32) e = mq::tc::launch<32, 4>(a, K, b, K, M, N, K, ep, &sp, s);
-    else return mq::fail(MQ_ERR_ARG, "mq_gemm_bf16: bn must be 32, 64, 128, 256 (128-row tiles), 384, 512 (256 x 128 / 256 x 256 tiles) or 1128, 1256 (CTA pairs)");
+    else return mq::fail(MQ_ERR_ARG, "mq_gemm_bf16: bn must be 32, 64, 128, 256 (128-row tiles), 384, 512 (256 x 128 / 256 x 256 tiles) 1128, 1256 (CTA pairs) or 2032 (resident B)");
     if (e != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_gemm_bf16: launch failed: %s", cudaGetErrorString(e));
     if (sp > 1) {
         size_t total = (size_t)M * N;

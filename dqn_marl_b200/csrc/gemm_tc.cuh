@@ -739,6 +739,107 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
 }
 
 // =====================================================================================================================
+// Persistent GEMM with a RESIDENT B operand (N == BN, K <= a few 64-wide blocks): for tall, skinny products such as conv1
+// (495,616 x 32 x 64) a 128-row tile is 4 MMAs of work, and a CTA per tile spends its life in prologue and epilogue.  Here
+// one CTA per SM keeps B in shared memory, streams the A tiles through a deep ring (the kernel is an HBM stream) and
+// double-buffers the accumulator so that the epilogue of tile t overlaps the loads and MMAs of tile t+1.
+// =====================================================================================================================
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_bf16_resident_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, long long M, int N,
+                          int nkb, Epilogue ep) {
+    extern __shared__ unsigned char smem_raw[];
+    constexpr int BK = 64;
+    constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
+    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    unsigned char* wtile = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = wtile + (((size_t)nkb * W_BYTES + 1023) & ~(size_t)1023);
+    uint64_t* full_bar = (uint64_t*)(ring + STAGES * A_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;           // [2]
+    uint64_t* w_full = tmem_empty + 2;
+    uint32_t* tmem_ptr = (uint32_t*)(w_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        mbar_init(w_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+    const long long m_tiles = (M + BM - 1) / BM;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(w_full, (uint32_t)nkb * W_BYTES);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(wtile + (size_t)kb * W_BYTES, &tmap_w, w_full, kb * BK, 0);
+            long long g = 0;
+            for (long long tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % STAGES);
+                    mbar_wait(&empty_bar[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
+                    mbar_expect_tx(&full_bar[s], A_BYTES);
+                    tma_load_2d(ring + s * A_BYTES, &tmap_a, &full_bar[s], kb * BK, (int)(tile * BM));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            const uint64_t a_desc0 = make_smem_desc(smem_u32(ring), 1024u, 0, 2);
+            const uint64_t b_desc0 = make_smem_desc(smem_u32(wtile), 1024u, 0, 2);
+            mbar_wait(w_full, 0);
+            long long g = 0;
+            int it = 0;
+            for (long long tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % STAGES);
+                    mbar_wait(&full_bar[s], (uint32_t)((g / STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t a_d = a_desc0 + (uint64_t)((uint32_t)(s * A_BYTES) >> 4);
+                    const uint64_t b_d = b_desc0 + (uint64_t)((uint32_t)(kb * W_BYTES) >> 4);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(d_tmem, a_d + (uint64_t)((k * UMMA_K * 2) >> 4), b_d + (uint64_t)((k * UMMA_K * 2) >> 4), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long row = tile * BM + q * 32 + lane;
+            epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, row < M, row, 0, M, N, 0);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+// =====================================================================================================================
 // MN-major ("TN") kernel: C[M][N] = sum_k At[k][m] * Bt[k][n].  A stage holds BKR k-rows: 2 A slabs and BN/64 B slabs of
 // [BKR][64] bf16 (128-byte rows, SWIZZLE_128B).  CONV: one stage = one sample (121 of the 128 rows are loaded, the rest
 // stay zero); the A slab of output rows m0 + 64 j is tap (m / Cin), channels (m % Cin) .. +64 of the shifted activation.
@@ -989,6 +1090,27 @@ inline cudaError_t launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* 
     dim3 grid((N + BN - 1) / BN, (M + MT * BM - 1) / (MT * BM), splits);
     gemm_bf16_tc_kernel<BN, STAGES, BK, false, MT><<<grid, THREADS, L::TOTAL, stream>>>(ta, tb, to, M, N, K, chunk_tiles * BK, tma_store,
                                                                                    ConvArgs{1, 0}, ep);
+    return cudaGetLastError();
+}
+
+// C[M][N] = A[M][K] B[N][K]^T for N == BN and K a small multiple of 64: persistent kernel with B resident in shared memory
+template <int BN, int STAGES>
+inline cudaError_t launch_resident(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, long long M, int N, int K, Epilogue ep,
+                                   int n_sms, cudaStream_t stream) {
+    constexpr int BK = 64;
+    if (N != BN || K % BK != 0 || M <= 0) return cudaErrorInvalidValue;
+    const int nkb = K / BK;
+    CUtensorMap ta, tw;
+    if (!make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM) || !make_tmap(&tw, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN))
+        return cudaErrorInvalidValue;
+    const int smem = ((nkb * BN * BK * 2 + 1023) & ~1023) + STAGES * BM * BK * 2 + 1024 + 256;
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    static SmemMemo memo{};
+    if (cudaError_t e = ensure_smem(memo, gemm_bf16_resident_kernel<BN, STAGES>, smem); e != cudaSuccess) return e;
+    ep.partial = nullptr;
+    const long long m_tiles = (M + BM - 1) / BM;
+    const unsigned grid = (unsigned)(m_tiles < n_sms ? m_tiles : n_sms);
+    gemm_bf16_resident_kernel<BN, STAGES><<<grid, THREADS, smem, stream>>>(ta, tw, M, N, nkb, ep);
     return cudaGetLastError();
 }
 

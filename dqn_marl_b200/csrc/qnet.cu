@@ -436,7 +436,9 @@ static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, lon
     n->launches += 1;
     tc::Epilogue ep{};
     ep.out_bf16 = n->a1b; ep.ldc = C1; ep.bias = W[P_C1B]; ep.relu = 1;
-    cudaError_t e = tc_gemm<32>(n, n->A1, 64, n->w1c[which], 64, M, C1, 64, ep, false, s);
+    // 495,616 x 32 x 64 at B = 4096: an HBM stream, not a GEMM — persistent kernel with the 4 KB weight tile resident
+    cudaError_t e = tc::launch_resident<32, 8>(n->A1, 64, n->w1c[which], 64, M, C1, 64, ep, n->n_sms, s);
+    n->launches += 1;
     if (e != cudaSuccess) return e;
     // conv2 / conv3: persistent implicit GEMMs (weights resident in shared memory), every tap a shifted zero-filled TMA box
     // of the NHWC activation (no im2col buffer)

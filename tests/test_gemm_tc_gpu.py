@@ -38,7 +38,8 @@ def _run(M, N, K, bn, splits=1, seed=0):
                                       (256, 256, 64, 512), (512, 512, 1024, 512), (300, 700, 576, 512), (640, 15488, 512, 512),
                                       (900, 384, 576, 384), (128, 128, 256, 384),
                                       (256, 256, 64, 1256), (512, 512, 1024, 1256), (300, 700, 576, 1256), (640, 15488, 512, 1256),
-                                      (128, 128, 256, 1128), (1000, 384, 576, 1128), (4096, 512, 15488, 1256)])
+                                      (128, 128, 256, 1128), (1000, 384, 576, 1128), (4096, 512, 15488, 1256),
+                                      (128, 32, 64, 2032), (777, 32, 64, 2032), (60000, 32, 128, 2032), (495616, 32, 64, 2032)])
 def test_gemm_matches_torch(M, N, K, bn):
     _run(M, N, K, bn)
 
