@@ -839,6 +839,157 @@ gemm_bf16_resident_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
+// OBS variant (conv1 without an im2col buffer): the A tile is not loaded but BUILT in shared memory by eight extra warps, one
+// thread per tile row, straight from the fp32 observation [B][11][11][6]: row = (sample, pixel), column k = tap * 6 + c for
+// k < 54, 1.0 at k = 54 (the ones column of qnet_bf16.cuh), zero above; 16-byte chunk c of row r goes to chunk c ^ (r & 7)
+// (the SWIZZLE_128B pattern the K-major descriptors expect).  Generic-proxy writes, then fence.proxy.async before the arrive.
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(THREADS + 256, 1)
+conv1_obs_resident_kernel(const float* __restrict__ obs, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a1,
+                          int store_a1, long long M, int N, Epilogue ep) {
+    constexpr int nkb = 1;
+    extern __shared__ unsigned char smem_raw[];
+    constexpr int BK = 64;
+    constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
+    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    unsigned char* wtile = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring = wtile + (((size_t)nkb * W_BYTES + 1023) & ~(size_t)1023);
+    uint64_t* full_bar = (uint64_t*)(ring + STAGES * A_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;           // [2]
+    uint64_t* w_full = tmem_empty + 2;
+    uint32_t* tmem_ptr = (uint32_t*)(w_full + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }      // four builder warps fill a stage
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        mbar_init(w_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+    const long long m_tiles = (M + BM - 1) / BM;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(w_full, (uint32_t)nkb * W_BYTES);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(wtile + (size_t)kb * W_BYTES, &tmap_w, w_full, kb * BK, 0);
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN);
+            const uint64_t a_desc0 = make_smem_desc(smem_u32(ring), 1024u, 0, 2);
+            const uint64_t b_desc0 = make_smem_desc(smem_u32(wtile), 1024u, 0, 2);
+            mbar_wait(w_full, 0);
+            long long g = 0;
+            int it = 0;
+            for (long long tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+                for (int kb = 0; kb < nkb; ++kb, ++g) {
+                    const int s = (int)(g % STAGES);
+                    mbar_wait(&full_bar[s], (uint32_t)((g / STAGES) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t a_d = a_desc0 + (uint64_t)((uint32_t)(s * A_BYTES) >> 4);
+                    const uint64_t b_d = b_desc0 + (uint64_t)((uint32_t)(kb * W_BYTES) >> 4);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_bf16(d_tmem, a_d + (uint64_t)((k * UMMA_K * 2) >> 4), b_d + (uint64_t)((k * UMMA_K * 2) >> 4), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full[buf]);
+            }
+        }
+    } else if (warp >= 6) {
+        // ===== builders: warps 6..9, thread j builds row j of the tile =====
+        // two groups of four warps take alternate tiles: building a tile is a latency chain (loads, convert, swizzled stores,
+        // proxy fence), two in flight keep the MMAs and the epilogue fed
+        const int j = ((warp - 6) & 3) * 32 + lane, bgrp = (warp - 6) >> 2;
+        long long g = 0;
+        for (long long tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++g) {
+            if ((int)(g & 1) != bgrp) continue;
+            const int s = (int)(g % STAGES);
+            mbar_wait(&empty_bar[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
+            const long long r = tile * BM + j;
+            float v[64];
+#pragma unroll
+            for (int k = 0; k < 64; ++k) v[k] = 0.f;
+            if (r < M) {
+                const long long b = r / PIXELS;
+                const int q = (int)(r - b * PIXELS), i = q / 11, jx = q - i * 11;
+                const float* src = obs + b * (PIXELS * 6);
+                // all 27 loads are issued unconditionally (clamped coordinates) so that they are in flight together; taps
+                // outside the image are zeroed afterwards — a branch per tap serialised nine round trips
+                float2 x[9][3];
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int ii = min(max(i + t / 3 - 1, 0), 10), jj = min(max(jx + t % 3 - 1, 0), 10);
+                    const float2* p2 = reinterpret_cast<const float2*>(src + (ii * 11 + jj) * 6);
+                    x[t][0] = __ldg(p2); x[t][1] = __ldg(p2 + 1); x[t][2] = __ldg(p2 + 2);
+                }
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int ii = i + t / 3 - 1, jj = jx + t % 3 - 1;
+                    const bool in = (unsigned)ii < 11u && (unsigned)jj < 11u;
+                    v[t * 6] = in ? x[t][0].x : 0.f; v[t * 6 + 1] = in ? x[t][0].y : 0.f; v[t * 6 + 2] = in ? x[t][1].x : 0.f;
+                    v[t * 6 + 3] = in ? x[t][1].y : 0.f; v[t * 6 + 4] = in ? x[t][2].x : 0.f; v[t * 6 + 5] = in ? x[t][2].y : 0.f;
+                }
+                v[54] = 1.f;
+            }
+            unsigned char* rowp = ring + s * A_BYTES + j * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * c], v[8 * c + 1]), p1 = __floats2bfloat162_rn(v[8 * c + 2], v[8 * c + 3]);
+                const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * c + 4], v[8 * c + 5]), p3 = __floats2bfloat162_rn(v[8 * c + 6], v[8 * c + 7]);
+                *reinterpret_cast<uint4*>(rowp + ((c ^ (j & 7)) << 4)) =
+                    make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
+                               *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[s]);
+            if (store_a1) {
+                // The tile just built IS a 128 x 64 block of the im2col matrix A1 in the layout TMA writes: when the weight
+                // gradient will need A1, the group's first lane sends the stage out as one bulk tensor store (rows >= M are
+                // clipped).  The stage is only overwritten STAGES tiles later, and not before this store has read it.
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + bgrp) : "memory");                 // all four warps of the group have written
+                if (j == 0) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");            // (previous store of this group)
+                    tma_store_2d(&tmap_a1, ring + s * A_BYTES, 0, (int)(tile * BM));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+        }
+        if (store_a1 && j == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else {
+        const int q = warp & 3;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const long long row = tile * BM + q * 32 + lane;
+            epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, row < M, row, 0, M, N, 0);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
 // =====================================================================================================================
 // MN-major ("TN") kernel: C[M][N] = sum_k At[k][m] * Bt[k][n].  A stage holds BKR k-rows: 2 A slabs and BN/64 B slabs of
 // [BKR][64] bf16 (128-byte rows, SWIZZLE_128B).  CONV: one stage = one sample (121 of the 128 rows are loaded, the rest
@@ -1111,6 +1262,27 @@ inline cudaError_t launch_resident(const __nv_bfloat16* A, int lda, const __nv_b
     const long long m_tiles = (M + BM - 1) / BM;
     const unsigned grid = (unsigned)(m_tiles < n_sms ? m_tiles : n_sms);
     gemm_bf16_resident_kernel<BN, STAGES><<<grid, THREADS, smem, stream>>>(ta, tw, M, N, nkb, ep);
+    return cudaGetLastError();
+}
+
+// conv1 forward straight from the fp32 observation (no im2col buffer): Y[B*121][32] = relu(im2col(obs) W1c^T + b)
+template <int STAGES>
+// a1_out (optional): also write the im2col rows A1 [batch*121][64] bf16 (the conv1 weight gradient reads them)
+inline cudaError_t launch_conv1_obs(const float* obs, const __nv_bfloat16* W1c, long long batch, Epilogue ep, int n_sms, cudaStream_t stream,
+                                    __nv_bfloat16* a1_out = nullptr) {
+    constexpr int BN = 32, BK = 64;
+    if (batch <= 0) return cudaErrorInvalidValue;
+    CUtensorMap tw, ta1;
+    if (!make_tmap(&tw, W1c, (uint64_t)BN, (uint64_t)BK, (uint64_t)BK, BN)) return cudaErrorInvalidValue;
+    ta1 = tw;
+    if (a1_out && !make_tmap(&ta1, a1_out, (uint64_t)batch * PIXELS, (uint64_t)BK, (uint64_t)BK, BM)) return cudaErrorInvalidValue;
+    const int smem = ((BN * BK * 2 + 1023) & ~1023) + STAGES * BM * BK * 2 + 1024 + 256;
+    static SmemMemo memo{};
+    if (cudaError_t e = ensure_smem(memo, conv1_obs_resident_kernel<BN, STAGES>, smem); e != cudaSuccess) return e;
+    ep.partial = nullptr;
+    const long long M = batch * PIXELS, m_tiles = (M + BM - 1) / BM;
+    const unsigned grid = (unsigned)(m_tiles < n_sms ? m_tiles : n_sms);
+    conv1_obs_resident_kernel<BN, STAGES><<<grid, THREADS + 256, smem, stream>>>(obs, tw, ta1, a1_out ? 1 : 0, M, BN, ep);
     return cudaGetLastError();
 }
 

@@ -427,17 +427,20 @@ static cudaError_t tc_gemm(mq_qnet* n, const bf::bf16* A, int lda, const bf::bf1
 static void launch_colsum_bf16(mq_qnet* n, const bf::bf16* X, long long M, int N, float* out, cudaStream_t s);
 
 // forward with every layer but the 5-output head on the tensor cores
-static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, long long B, const uint8_t* drop_mask, cudaStream_t s) {
+// keep_im2col: the weight gradient of conv1 needs the im2col rows A1 afterwards (the online forward of a learn step); every
+// other forward (target network, act, plain forward) builds the conv1 operand tile in shared memory and never writes A1
+static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, long long B, const uint8_t* drop_mask, cudaStream_t s,
+                                    bool keep_im2col = false) {
     float* const* W = which ? n->tl.t : n->tl.p;
     const int M = (int)(B * PIX);
     refresh_weights(n, which, s);
-    // conv1: im2col rows of the 6-channel observation (K = 54 padded to one 64-wide K-block), then a tcgen05 GEMM
-    bf::im2col_obs_bf16_kernel<<<(unsigned)((B + 1) / 2), 256, 0, s>>>(obs, n->A1, B);
-    n->launches += 1;
+    // conv1 (K = 54 padded to one 64-wide K-block; 495,616 x 32 x 64 at B = 4096 is an HBM stream, not a GEMM): persistent
+    // kernel with the 4 KB weight tile resident; the operand rows are built in shared memory straight from the observation and,
+    // when the backward pass will need them, also sent out to the im2col buffer A1 by a bulk tensor store of the same tile.
     tc::Epilogue ep{};
     ep.out_bf16 = n->a1b; ep.ldc = C1; ep.bias = W[P_C1B]; ep.relu = 1;
-    // 495,616 x 32 x 64 at B = 4096: an HBM stream, not a GEMM — persistent kernel with the 4 KB weight tile resident
-    cudaError_t e = tc::launch_resident<32, 8>(n->A1, 64, n->w1c[which], 64, M, C1, 64, ep, n->n_sms, s);
+    cudaError_t e;
+    e = tc::launch_conv1_obs<8>(obs, n->w1c[which], B, ep, n->n_sms, s, keep_im2col ? n->A1 : nullptr);
     n->launches += 1;
     if (e != cudaSuccess) return e;
     // conv2 / conv3: persistent implicit GEMMs (weights resident in shared memory), every tap a shifted zero-filled TMA box
@@ -803,7 +806,7 @@ static int td_backward_impl(mq_qnet* n, const float* state, const int64_t* actio
     else forward_net(n, n->tl.t, next_state, B, drop_target, s);
     qhead_kernel<<<hb, 256, 0, s>>>(n->h2, n->tl.t[P_F3W], n->tl.t[P_F3B], B, 3, nullptr, nullptr, n->maxq, nullptr, 0.f, 0, 0, 0, 1);
     // current_q = q_network(states).gather(1, actions)   (dqn_agent.py:143)
-    if (bf16 && fe == cudaSuccess) fe = forward_net_bf16(n, 0, state, B, drop_online, s);
+    if (bf16 && fe == cudaSuccess) fe = forward_net_bf16(n, 0, state, B, drop_online, s, true);
     else if (!bf16) forward_net(n, n->tl.p, state, B, drop_online, s);
     if (fe != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_td_backward (bf16 forward): %s", cudaGetErrorString(fe));
     qhead_kernel<<<hb, 256, 0, s>>>(n->h2, n->tl.p[P_F3W], n->tl.p[P_F3B], B, 2, nullptr, (const long long*)action, n->q_sa, nullptr, 0.f,
@@ -851,7 +854,7 @@ extern "C" int mq_qnet_backward(mq_qnet* n, const float* state, const float* dq,
     const bool bf16 = n->precision == 1;
     MQ_REQUIRE(!bf16 || B % 8 == 0, "mq_qnet_backward: the bf16 path needs a batch that is a multiple of 8 (got %lld)", (long long)B);
     if (bf16) {
-        cudaError_t fe = forward_net_bf16(n, 0, state, B, drop_online, s);
+        cudaError_t fe = forward_net_bf16(n, 0, state, B, drop_online, s, true);
         if (fe != cudaSuccess) return mq::fail(MQ_ERR_CUDA, "mq_qnet_backward (bf16 forward): %s", cudaGetErrorString(fe));
     } else {
         forward_net(n, n->tl.p, state, B, drop_online, s);

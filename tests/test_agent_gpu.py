@@ -218,12 +218,13 @@ def test_dqn_agent_facade_reference_surface(tmp_path):
     assert agent3.learn() is None
 
 
-def test_bf16_tensor_core_path_tracks_fp32():
+@pytest.mark.parametrize("B", [256, 200])
+def test_bf16_tensor_core_path_tracks_fp32(B):
     """The tcgen05 bf16 path (every layer but the 5-output head on tensor cores, fp32 accumulate / master weights) against the fp32
-    parity path on the same weights and batch: Q within 2e-2 of the Q scale, loss within 1e-2, gradients aligned."""
+    parity path on the same weights and batch: Q within 2e-2 of the Q scale, loss within 1e-2, gradients aligned.  B = 200 ends
+    in a partial 128-row tile (the im2col rows the conv1 weight gradient reads are stored by clipped bulk tensor stores)."""
     from dqn_marl_b200.agents import qnet_params as qp
     q, t = torch_ref.build_nets(21, 22)
-    B = 256
     gen = torch.Generator().manual_seed(4)
     states = (torch.rand((B, 11, 11, 6), generator=gen) < 0.3).float() * torch.rand((B, 11, 11, 6), generator=gen)
     nstates = (torch.rand((B, 11, 11, 6), generator=gen) < 0.3).float()
@@ -352,3 +353,29 @@ def test_td_backward_in_two_parts_equals_one_call(precision):
     net.td_backward(batch, hp, mask, mask, part=2)
     torch.cuda.synchronize()
     assert torch.equal(net.flat_g, g0) and torch.equal(loss0, loss1)
+
+
+@pytest.mark.gpu
+def test_conv1_built_from_observation_equals_im2col_path():
+    """bf16 path: forward() builds the conv1 operand tiles in shared memory straight from the observation, the online forward
+    inside td_backward() goes through the im2col buffer (its weight gradient needs it).  Same bf16 operands, same MMAs: the TD
+    loss recomputed from forward()'s Q-values must equal the loss td_backward() reports, up to the fp32 rounding of the mean.
+    Ragged batch sizes exercise the partial last 128-row tile."""
+    q, t = torch_ref.build_nets(31, 32)
+    for B in (8, 136, 1000):
+        gen = torch.Generator().manual_seed(B)
+        d = "cuda:0"
+        states = ((torch.rand((B, 11, 11, 6), generator=gen) < 0.3).float() * torch.rand((B, 11, 11, 6), generator=gen)).to(d)
+        nstates = (torch.rand((B, 11, 11, 6), generator=gen) < 0.3).float().to(d)
+        batch = dict(states=states, actions=torch.randint(0, 5, (B,), generator=gen).to(d), rewards=(torch.randn(B, generator=gen) * 0.1).to(d),
+                     next_states=nstates, dones=(torch.rand(B, generator=gen) < 0.1).to(torch.uint8).to(d))
+        mask = (torch.rand((B, 512), generator=gen) >= 0.2).to(torch.uint8).to(d)
+        net = _qnet(q, t, max_batch=B)
+        net.set_precision("bf16")
+        hp = _hp(1)
+        q_on = net.forward(states, "online", mask)
+        q_tg = net.forward(nstates, "target", mask)
+        y = batch["rewards"] + hp.gamma * q_tg.max(dim=1).values * (1.0 - batch["dones"].float())
+        ref = ((q_on.gather(1, batch["actions"].view(-1, 1)).squeeze(1) - y) ** 2).mean().item()
+        loss = net.td_backward(batch, hp, mask, mask).item()
+        assert abs(loss - ref) <= 1e-5 * abs(ref) + 1e-9, (B, loss, ref)
