@@ -17,39 +17,9 @@ template <typename T> __device__ __forceinline__ float to_f(T v);
 template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
 
-// conv1 on the tensor cores: the 6-channel observation is too narrow for a TMA box (12-byte pixels), so its im2col rows are
-// written once per forward: obs f32 [B][11][11][6] -> A1 bf16 [B*121][64], column k = tap*6 + c for k < 54, 1.0 in column 54
-// (a ones column: the weight gradient GEMM then yields the bias gradient as row 54), zero above.
-// One thread = 8 consecutive columns of one row (a 16-byte store).
-__global__ void __launch_bounds__(256)
-im2col_obs_bf16_kernel(const float* __restrict__ obs, bf16* __restrict__ A1, long long B) {
-    // two samples per CTA: the 2 x 726 floats are staged in shared memory (coalesced), then every thread emits 16-byte chunks
-    __shared__ float win[2][728];
-    const long long b0 = (long long)blockIdx.x * 2;
-    const int ns = (b0 + 1 < B) ? 2 : 1;
-    for (int t = threadIdx.x; t < ns * 726; t += 256) win[t / 726][t % 726] = __ldg(obs + b0 * 726 + t);
-    __syncthreads();
-    for (int ch = threadIdx.x; ch < ns * 121 * 8; ch += 256) {
-        const int sidx = ch / (121 * 8), r = ch - sidx * (121 * 8);
-        const int q = r >> 3, k0 = (r & 7) * 8;
-        const int i = q / 11, j = q - i * 11;
-        __align__(16) bf16 v[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int k = k0 + t;
-            float x = 0.f;
-            if (k < 54) {
-                const int tap = k / 6, c = k - tap * 6;
-                const int ii = i + tap / 3 - 1, jj = j + tap % 3 - 1;
-                if ((unsigned)ii < 11u && (unsigned)jj < 11u) x = win[sidx][(ii * 11 + jj) * 6 + c];
-            } else if (k == 54) {
-                x = 1.f;          // the weight operand is zero here (forward unaffected); dY^T A1 gets the bias gradient in this row
-            }
-            v[t] = __float2bfloat16(x);
-        }
-        *reinterpret_cast<uint4*>(A1 + ((b0 + sidx) * 121 + q) * 64 + k0) = *reinterpret_cast<const uint4*>(v);
-    }
-}
+// conv1 on the tensor cores: the 6-channel observation is too narrow for a TMA box (12-byte pixels), so its im2col rows
+// A1 bf16 [B*121][64] — column k = tap*6 + c for k < 54, 1.0 in column 54 so that the weight-gradient GEMM yields the bias
+// gradient as row 54, zero above — are built in shared memory by tc::conv1_obs_resident_kernel (gemm_tc.cuh).
 // conv1 weights Wc[(tap*6 + c)][32] f32 -> GEMM operand W1f[32][64] bf16 (K padded 54 -> 64 with zeros)
 __global__ void __launch_bounds__(256)
 conv1_weight_bf16_kernel(const float* __restrict__ wc, bf16* __restrict__ w1f) {
