@@ -12,7 +12,7 @@ from dqn_marl_b200 import _lib
 lib = _lib.load()
 B = 4096
 M = B * 121
-shapes = [("conv1 fwd", M, 32, 64, 32, 1), ("conv1 fwd", M, 32, 64, 2032, 1), ("fc1 fwd", B, 512, 15488, 1256, 2), ("fc1 fwd", B, 512, 15488, 1256, 4), ("fc1 fwd", B, 512, 15488, 1128, 2), ("fc1 fwd", B, 512, 15488, 1128, 4), ("fc1 dgrad", B, 15488, 512, 1256, 1), ("fc1 dgrad", B, 15488, 512, 1128, 1), ("fc1 fwd", B, 512, 15488, 128, 2), ("fc1 fwd", B, 512, 15488, 256, 2), ("fc1 fwd", B, 512, 15488, 256, 4), ("fc1 fwd", B, 512, 15488, 512, 4), ("fc1 fwd", B, 512, 15488, 384, 2), ("fc1 fwd", B, 512, 15488, 384, 3), ("fc1 dgrad", B, 15488, 512, 256, 1), ("fc1 dgrad", B, 15488, 512, 512, 1), ("fc1 dgrad", B, 15488, 512, 384, 1), ("fc1 fwd", B, 512, 15488, 128, 1), ("conv3 fwd", M, 128, 576, 128, 1), ("conv2 fwd", M, 64, 288, 64, 1),
+shapes = [("fc1 dgrad bf16", B, 15488, 512, 128, 1), ("conv1 fwd", M, 32, 64, 32, 1), ("conv1 fwd", M, 32, 64, 2032, 1), ("fc1 fwd", B, 512, 15488, 1256, 2), ("fc1 fwd", B, 512, 15488, 1256, 4), ("fc1 fwd", B, 512, 15488, 1128, 2), ("fc1 fwd", B, 512, 15488, 1128, 4), ("fc1 dgrad", B, 15488, 512, 1256, 1), ("fc1 dgrad", B, 15488, 512, 1128, 1), ("fc1 fwd", B, 512, 15488, 128, 2), ("fc1 fwd", B, 512, 15488, 256, 2), ("fc1 fwd", B, 512, 15488, 256, 4), ("fc1 fwd", B, 512, 15488, 512, 4), ("fc1 fwd", B, 512, 15488, 384, 2), ("fc1 fwd", B, 512, 15488, 384, 3), ("fc1 dgrad", B, 15488, 512, 256, 1), ("fc1 dgrad", B, 15488, 512, 512, 1), ("fc1 dgrad", B, 15488, 512, 384, 1), ("fc1 fwd", B, 512, 15488, 128, 1), ("conv3 fwd", M, 128, 576, 128, 1), ("conv2 fwd", M, 64, 288, 64, 1),
           ("fc1 dgrad", B, 15488, 512, 128, 1), ("fc1 wgrad", 512, 15488, B, 128, 1), ("conv3 dgrad", M, 64, 1152, 64, 1),
           ("conv3 wgrad", 576, 128, M, 128, 96), ("conv2 wgrad", 288, 64, M, 64, 148), ("conv2 dgrad", M, 32, 576, 32, 1)]
 peak = 1629.4
@@ -23,15 +23,17 @@ st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
 for name, m, n, k, bn, splits in shapes:
     A = torch.randn((m, k), device="cuda").to(torch.bfloat16)
     Bm = torch.randn((n, k), device="cuda").to(torch.bfloat16)
-    C = torch.empty((m, n), device="cuda")
+    bf16_out = name.endswith("bf16")          # bf16-only output (TMA-store epilogue), as the learner uses these shapes
+    C = torch.empty((m, n), device="cuda", dtype=torch.bfloat16 if bf16_out else torch.float32)
+    cf, cb = (None, _lib.ptr(C)) if bf16_out else (_lib.ptr(C), None)
     ws = torch.empty((splits * m * n,), device="cuda") if splits > 1 else None
     for _ in range(3):
-        _lib.check(lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(C), None, m, n, k, bn, splits, _lib.ptr(ws), st), "gemm")
+        _lib.check(lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(Bm), cf, cb, m, n, k, bn, splits, _lib.ptr(ws), st), "gemm")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(); e0.record()
     reps = 10
     for _ in range(reps):
-        lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(Bm), _lib.ptr(C), None, m, n, k, bn, splits, _lib.ptr(ws), st)
+        lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(Bm), cf, cb, m, n, k, bn, splits, _lib.ptr(ws), st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     tf = 2.0 * m * n * k / (ms * 1e-3) / 1e12

@@ -17,12 +17,13 @@ def _run(M, N, K, bn, splits=1, seed=0):
     ws = torch.empty((max(splits, 1) * M * N,), device="cuda:0") if splits > 1 else None
     import ctypes as Ct
     st = Ct.c_void_p(torch.cuda.current_stream().cuda_stream)
-    _lib.check(lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), None, M, N, K, bn, splits, _lib.ptr(ws), st), "mq_gemm_bf16")
-    torch.cuda.synchronize()
     ref = A.float() @ B.float().t()
-    err = (C - ref).abs().max().item()
     scale = ref.abs().max().item()
-    assert err <= 2e-3 * scale + 1e-3, (M, N, K, bn, splits, err, scale)
+    if True:
+        _lib.check(lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(B), _lib.ptr(C), None, M, N, K, bn, splits, _lib.ptr(ws), st), "mq_gemm_bf16")
+        torch.cuda.synchronize()
+        err = (C - ref).abs().max().item()
+        assert err <= 2e-3 * scale + 1e-3, (M, N, K, bn, splits, err, scale)
     if splits == 1:          # bf16-only output: TMA-store epilogue when N is a multiple of the tile width
         Cb = torch.full((M + 3, N), 768.0, device="cuda:0").to(torch.bfloat16)
         _lib.check(lib.mq_gemm_bf16(_lib.ptr(A), _lib.ptr(B), None, _lib.ptr(Cb), M, N, K, bn, 1, None, st), "mq_gemm_bf16")
