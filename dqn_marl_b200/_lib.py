@@ -65,6 +65,7 @@ SIGNATURES = {
     "mq_last_error": (C.c_char_p, []),
     "mq_abi_version": (C.c_int, []),
     "mq_floor_field": (C.c_int, [_i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "mq_floor_field_device": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mq_env_state_sizes": (C.c_int, [C.POINTER(MqEnvCfg), C.POINTER(MqLayout), C.POINTER(_i64), C.POINTER(_i64)]),
     "mq_env_create": (C.c_int, [C.POINTER(_vp), C.POINTER(MqEnvCfg), C.POINTER(MqLayout), C.POINTER(MqEnvState)]),
     "mq_env_destroy": (C.c_int, [_vp]),
@@ -146,3 +147,24 @@ def floor_field(L, W, wall, exits, add_term):
     out = np.empty((L + 2, W + 2), dtype=np.float64)
     check(lib.mq_floor_field(L, W, ptr(wall), ptr(exits), len(exits), ptr(add), ptr(out)), "mq_floor_field")
     return out
+
+
+def floor_field_device(L, W, wall, exits, n_exits, add_term=None, stream=None):
+    """mq_floor_field_device: floor fields of a batch of layouts on the GPU (reference map.py:127-148 per layout).
+    wall (n, L+2, W+2) uint8 CUDA tensor, exits (n, max_exits, 2) int32, n_exits (n,) int32, add_term (n, L+2, W+2) float64 or None
+    -> (space (n, L+2, W+2) float64 CUDA tensor, number of relaxation sweeps)."""
+    import torch
+    lib = load()
+    n = wall.shape[0]
+    wall = wall.to(torch.uint8).contiguous()
+    exits = exits.to(torch.int32).contiguous()
+    n_exits = n_exits.to(torch.int32).contiguous()
+    if add_term is not None:
+        add_term = add_term.to(torch.float64).contiguous()
+    out = torch.empty((n, L + 2, W + 2), dtype=torch.float64, device=wall.device)
+    sweeps = C.c_int32(0)
+    st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(wall.device).cuda_stream)
+    with torch.cuda.device(wall.device):
+        check(lib.mq_floor_field_device(L, W, n, ptr(wall), ptr(exits), exits.shape[1], ptr(n_exits), ptr(add_term), ptr(out),
+                                        C.cast(C.pointer(sweeps), C.c_void_p), st), "mq_floor_field_device")
+    return out, sweeps.value

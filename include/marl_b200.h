@@ -62,6 +62,15 @@ int mq_abi_version(void);
 int mq_floor_field(int32_t L, int32_t W, const uint8_t* wall, const int32_t* exits, int32_t n_exits,
                    const double* add_term, double* space_out);
 
+/* The same field for a batch of layouts, on the device (device pointers; init-time: synchronises `stream` while it
+ * waits for the relaxation sweeps to reach their fixed point).  Bit-identical to mq_floor_field per layout.
+ *   wall      dev u8  [n_layouts][(L+2)*(W+2)]
+ *   exits     dev i32 [n_layouts][max_exits][2],  n_exits dev i32 [n_layouts]
+ *   add_term  dev f64 [n_layouts][(L+2)*(W+2)] or NULL
+ *   space_out dev f64 [n_layouts][(L+2)*(W+2)];  sweeps_out (host, optional) = relaxation sweeps that were run */
+int mq_floor_field_device(int32_t L, int32_t W, int32_t n_layouts, const uint8_t* wall, const int32_t* exits, int32_t max_exits,
+                          const int32_t* n_exits, const double* add_term, double* space_out, int32_t* sweeps_out, void* stream);
+
 /* ------------------------------------------------------------------------
  * Layout tables (host pointers; copied to the device by mq_env_create).
  * Cell index = x*(W+2)+y, the reference indexes space[x][y] (map.py:44).
