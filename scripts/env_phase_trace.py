@@ -31,4 +31,5 @@ def window(t0, t1, label):
     print(f"{label}: {e0.elapsed_time(e1) / (t1 - t0) * 1e3:.1f} us per launch; cycles per env-step by phase: " +
           ", ".join(f"{n} {c:.0f}" for n, c in zip(names, per)) + f"; total {per.sum():.0f}")
 window(0, 1, "step 0 (nobody moves)"); window(1, 2, "step 1 (everybody moves)"); window(2, 3, "step 2"); window(3, 4, "step 3")
-window(4, 150, "steps 4-149"); window(150, steps, f"steps 150-{steps - 1}")
+window(4, min(150, steps), "steps 4-149")
+if steps > 150: window(150, steps, f"steps 150-{steps - 1}")
