@@ -319,3 +319,15 @@ def test_two_live_env_handles_of_one_kernel_variant():
             assert r[3].item() == rr and bool(d[3].item()) == bool(dd), (t, r[3].item(), rr)
             a, b = env.snapshot(3), orc.snapshot()
             assert np.array_equal(a["px"], b["px"]) and np.array_equal(a["health"].view(np.uint64), b["health"].view(np.uint64))
+
+
+@pytest.mark.gpu
+def test_long_runs_with_auto_reset_match_oracle():
+    """Several consecutive episodes per env (auto-reset inside the step kernel, envs of one CTA in different episodes and fire
+    steps) for every kernel variant: warp-per-env with cooperative scoring, CTA-per-env, global-scratch envs."""
+    from dqn_marl_b200.layout import Layout
+    _run_vs_oracle(Layout.reference_room(), n_envs=140, N=150, seed=99, steps=900, auto_reset=True, check_every=30)
+    _run_vs_oracle(Layout.reference_room(n_robots=2), n_envs=84, N=150, seed=98, steps=700, auto_reset=True, strict=False, check_every=35)
+    _run_vs_oracle(Layout.synthetic(256, 256, n_exits=1, seed=2024), n_envs=10, N=1000, seed=77, steps=400, auto_reset=True, check_every=20)
+    _run_vs_oracle(Layout.synthetic(96, 80, n_exits=3, seed=5), n_envs=20, N=400, seed=78, steps=500, auto_reset=True, strict=False, check_every=25)
+    _run_vs_oracle(Layout.synthetic(160, 160, n_exits=4, seed=11), n_envs=3, N=6000, seed=79, steps=120, check_every=10)
