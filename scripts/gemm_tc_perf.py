@@ -12,7 +12,7 @@ from dqn_marl_b200 import _lib
 lib = _lib.load()
 B = 4096
 M = B * 121
-shapes = [("fc1 dgrad bf16", B, 15488, 512, 128, 1), ("fc1 dgrad bf16", B, 15488, 512, 256, 1), ("fc1 dgrad bf16", B, 15488, 512, 384, 1), ("fc1 dgrad bf16", B, 15488, 512, 512, 1), ("fc1 dgrad bf16", B, 15488, 512, 1256, 1), ("fc1 dgrad bf16", B, 15488, 512, 1128, 1), ("fc2 fwd bf16", B, 256, 512, 128, 1), ("fc2 dgrad bf16", B, 512, 256, 128, 1), ("conv1 fwd", M, 32, 64, 32, 1), ("conv1 fwd", M, 32, 64, 2032, 1), ("fc1 fwd", B, 512, 15488, 1256, 2), ("fc1 fwd", B, 512, 15488, 1256, 4), ("fc1 fwd", B, 512, 15488, 1128, 2), ("fc1 fwd", B, 512, 15488, 1128, 4), ("fc1 dgrad", B, 15488, 512, 1256, 1), ("fc1 dgrad", B, 15488, 512, 1128, 1), ("fc1 fwd", B, 512, 15488, 128, 2), ("fc1 fwd", B, 512, 15488, 256, 2), ("fc1 fwd", B, 512, 15488, 256, 4), ("fc1 fwd", B, 512, 15488, 512, 4), ("fc1 fwd", B, 512, 15488, 384, 2), ("fc1 fwd", B, 512, 15488, 384, 3), ("fc1 dgrad", B, 15488, 512, 256, 1), ("fc1 dgrad", B, 15488, 512, 512, 1), ("fc1 dgrad", B, 15488, 512, 384, 1), ("fc1 fwd", B, 512, 15488, 128, 1), ("conv3 fwd", M, 128, 576, 128, 1), ("conv2 fwd", M, 64, 288, 64, 1),
+shapes = [("fc1 fwd", B, 512, 15488, 1128, 1), ("fc1 fwd", B, 512, 15488, 1256, 1), ("fc1 fwd bf16", B, 512, 15488, 1128, 1), ("fc1 fwd", B, 512, 15488, 1256, 2), ("fc1 dgrad bf16", B, 15488, 512, 128, 1), ("fc1 dgrad bf16", B, 15488, 512, 256, 1), ("fc1 dgrad bf16", B, 15488, 512, 384, 1), ("fc1 dgrad bf16", B, 15488, 512, 512, 1), ("fc1 dgrad bf16", B, 15488, 512, 1256, 1), ("fc1 dgrad bf16", B, 15488, 512, 1128, 1), ("fc2 fwd bf16", B, 256, 512, 128, 1), ("fc2 dgrad bf16", B, 512, 256, 128, 1), ("conv1 fwd", M, 32, 64, 32, 1), ("conv1 fwd", M, 32, 64, 2032, 1), ("fc1 fwd", B, 512, 15488, 1256, 2), ("fc1 fwd", B, 512, 15488, 1256, 4), ("fc1 fwd", B, 512, 15488, 1128, 2), ("fc1 fwd", B, 512, 15488, 1128, 4), ("fc1 dgrad", B, 15488, 512, 1256, 1), ("fc1 dgrad", B, 15488, 512, 1128, 1), ("fc1 fwd", B, 512, 15488, 128, 2), ("fc1 fwd", B, 512, 15488, 256, 2), ("fc1 fwd", B, 512, 15488, 256, 4), ("fc1 fwd", B, 512, 15488, 512, 4), ("fc1 fwd", B, 512, 15488, 384, 2), ("fc1 fwd", B, 512, 15488, 384, 3), ("fc1 dgrad", B, 15488, 512, 256, 1), ("fc1 dgrad", B, 15488, 512, 512, 1), ("fc1 dgrad", B, 15488, 512, 384, 1), ("fc1 fwd", B, 512, 15488, 128, 1), ("conv3 fwd", M, 128, 576, 128, 1), ("conv2 fwd", M, 64, 288, 64, 1),
           ("fc1 dgrad", B, 15488, 512, 128, 1), ("fc1 wgrad", 512, 15488, B, 128, 1), ("conv3 dgrad", M, 64, 1152, 64, 1),
           ("conv3 wgrad", 576, 128, M, 128, 96), ("conv2 wgrad", 288, 64, M, 64, 148), ("conv2 dgrad", M, 32, 576, 32, 1)]
 peak = 1629.4
