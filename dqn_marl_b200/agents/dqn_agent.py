@@ -261,9 +261,10 @@ class DQNAgent:
             "steps": self.steps,
         }, filepath)
 
-    def load(self, filepath):
-        """dqn_agent.py:184-191"""
-        ck = torch.load(filepath, map_location="cpu", weights_only=False)
+    def load(self, filepath, allow_pickle: bool = False):
+        """dqn_agent.py:184-191.  Reference-format checkpoints hold only tensors, dicts and primitives, so they load with
+        `weights_only=True`; `allow_pickle=True` is the explicit opt-in for files that need the unsafe unpickler."""
+        ck = torch.load(filepath, map_location="cpu", weights_only=not allow_pickle)
         self.q_network.load_state_dict(ck["q_network"])
         self.target_network.load_state_dict(ck["target_network"])
         self.optimizer.load_state_dict(ck["optimizer"])
@@ -287,7 +288,16 @@ class VecDQNAgent(DQNAgent):
         if self.world > 1:       # identical replicas: rank 0's initial weights everywhere
             torch.distributed.broadcast(self.net.flat_p, src=torch.distributed.get_global_rank(self.pg, 0) if self.pg else 0,
                                         group=self.pg)
+            self.net.params_changed()          # flat_p was written behind the library's back: refresh the bf16 operand copies
             self.update_target_network()
+        # transitions every rank is guaranteed to have pushed per remember_batch(): env shards may differ by one env
+        # (parallel.env_shard), and the learn gate must open on the SAME step everywhere because learn_device() is a collective
+        self.min_push = n_envs * n_robots
+        if self.world > 1:
+            t = torch.tensor([self.min_push], dtype=torch.int64, device=self.net.device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.pg)
+            self.min_push = int(t.item())
+        self._pushes = 0
         self._actions = torch.zeros((n_envs * n_robots,), dtype=torch.int32, device=self.net.device)
         self._tick = 0
 
@@ -308,6 +318,15 @@ class VecDQNAgent(DQNAgent):
             reward = reward.repeat_interleave(R)
             done = done.repeat_interleave(R)
         self.memory.push(obs.reshape(-1, 726), actions.reshape(-1), reward, next_obs.reshape(-1, 726), done)
+        self._pushes += 1
+
+    def ready_to_learn(self) -> bool:
+        """The gate of train_dqn.py:117-118 / dqn_agent.py:128 (`len(memory) > batch_size`, warm-up) evaluated on quantities
+        every rank agrees on — the number of remember_batch() calls times the smallest shard's push size and the replicated
+        step counter — so that all ranks enter the collective learn step together (a rank-local len(memory) opens one step
+        apart when n_envs % world != 0 and the run hangs in NCCL)."""
+        filled = min(self._pushes * self.min_push, self.memory.capacity)
+        return filled > self.batch_size and self.steps >= self.warmup_steps
 
     def _allreduce_grads(self):
         if self.world > 1:
@@ -317,7 +336,10 @@ class VecDQNAgent(DQNAgent):
         return 1.0 / self.world
 
     def learn_device(self) -> torch.Tensor:
-        """learn() without the host sync of loss.item(): returns the device loss tensor."""
+        """learn() without the host sync of loss.item(): returns the device loss tensor, or None while the (rank-consistent)
+        gate of ready_to_learn() is closed."""
+        if not self.ready_to_learn():
+            return None
         B = self.batch_size
         batch = self.memory.sample(B, out=getattr(self, "_batch", None))
         self._batch = batch

@@ -40,6 +40,7 @@ class QNet:
         self.precision = "fp32"
         self._loss = torch.zeros(1, dtype=torch.float32, device=dev)
         self._gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._seen = [self.flat_p._version, self.flat_t._version]
 
     def close(self):
         if getattr(self, "_h", None):
@@ -67,6 +68,14 @@ class QNet:
     def params_changed(self):
         """Call after writing flat_p / flat_t directly (the bf16 operand copies are refreshed lazily)."""
         _lib.check(self.lib.mq_qnet_params_changed(self._h), "mq_qnet_params_changed")
+        self._seen = [self.flat_p._version, self.flat_t._version]
+
+    def _track_writes(self):
+        """Torch-side in-place writes to the parameter buffers or to any view of them (`q_network.parameters()`, a broadcast,
+        an external optimizer, a soft update) bump the tensors' version counters: refresh the library's bf16 operand copies
+        when that happened since the last call.  The library's own kernels (Adam, target sync) mark their writes themselves."""
+        if self.flat_p._version != self._seen[0] or self.flat_t._version != self._seen[1]:
+            self.params_changed()
 
     def set_precision(self, precision: str):
         """'fp32' = CUDA-core parity path, 'bf16' = tcgen05 tensor-core path (conv2/conv3/fc1)."""
@@ -81,6 +90,7 @@ class QNet:
     def forward(self, obs: torch.Tensor, which: str = "online", drop_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
         """DQNNetwork.forward (dqn_agent.py:35-61): obs (B,11,11,6) f32 on device -> Q (B,5) f32."""
         B = obs.shape[0]
+        self._track_writes()
         obs = obs.to(device=self.device, dtype=torch.float32).contiguous()
         q = torch.empty((B, 5), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
@@ -91,6 +101,7 @@ class QNet:
     def act(self, obs: torch.Tensor, eps: float, seed: int, env_id_base: int, tick: int, n_robots: int = 1,
             drop_mask: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, q_out: Optional[torch.Tensor] = None):
         B = obs.shape[0]
+        self._track_writes()
         if out is None:
             out = torch.empty((B,), dtype=torch.int32, device=self.device)
         _lib.check(self.lib.mq_qnet_act(self._h, _lib.ptr(obs), B, float(eps), int(seed), int(env_id_base), int(tick) & 0xFFFFFFFF,
@@ -101,6 +112,7 @@ class QNet:
         """part 0 = the whole differentiable half of learn(); 1 / 2 = its two halves (mq_qnet_td_backward_part): after part 1
         the gradients of fc1/fc2/fc3 (flat_g[HEAD_OFFSET:]) are final, part 2 adds the convolution layers."""
         B = batch["actions"].shape[0]
+        self._track_writes()
         if part:
             _lib.check(self.lib.mq_qnet_td_backward_part(self._h, _lib.ptr(batch["states"]), _lib.ptr(batch["actions"]), _lib.ptr(batch["rewards"]),
                                                          _lib.ptr(batch["next_states"]), _lib.ptr(batch["dones"]), B, C.byref(hp),
@@ -116,6 +128,7 @@ class QNet:
     def backward(self, obs: torch.Tensor, dq: torch.Tensor, drop_mask: Optional[torch.Tensor] = None):
         """Gradients of the online parameters for an external dL/dQ (B,5) (mq_qnet_backward): fills flat_g."""
         B = obs.shape[0]
+        self._track_writes()
         obs = obs.to(device=self.device, dtype=torch.float32).contiguous()
         dq = dq.to(device=self.device, dtype=torch.float32).contiguous()
         with torch.cuda.device(self.device):

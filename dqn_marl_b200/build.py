@@ -57,14 +57,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return OUT
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
-    objs = []
-    logs = []
-    for src in sources():
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(OBJ, src + ".o")
         cmd = [nvcc, *ARCH, *COMMON, *EXTRA.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         p = subprocess.run(cmd, capture_output=True, text=True)
+        return src, obj, p
+
+    objs = []
+    logs = []
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:      # translation units are independent
+        results = list(pool.map(compile_one, sources()))
+    for src, obj, p in results:
         logs.append(f"== {src}\n{p.stdout}{p.stderr}")
         if p.returncode != 0:
             sys.stderr.write(logs[-1])

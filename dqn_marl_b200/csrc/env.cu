@@ -1088,6 +1088,7 @@ struct mq_env {
     mq::DevCfg cfg;
     mq::DevState st;
     void* d_dp5 = nullptr; void* d_cellinfo = nullptr; void* d_ctr = nullptr; void* d_int = nullptr;
+    int device = 0;
     int wpe = 8;            // warps per env: 1 (4 envs per 128-thread CTA), 8 (one 256-thread CTA per env), 16 / 32 (BIG)
     bool big = false;       // per-person arrays + proposal table in global scratch (envs too large for shared memory)
     int variant = 0;        // index into the kernel variant table
@@ -1138,10 +1139,12 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return mq::fail(MQ_ERR_CUDA, "mq_env_create: no CUDA device (this build has no CPU fallback)");
-    MQ_CUDA(cudaSetDevice(cfg->device));
+    MQ_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "mq_env_create: device %d outside 0..%d", cfg->device, ndev - 1);
+    MQ_ON_DEVICE(cfg->device);
 
     mq_env* e = new (std::nothrow) mq_env();
     if (!e) return mq::fail(MQ_ERR_ALLOC, "mq_env_create: out of host memory");
+    e->device = cfg->device;
     mq::DevLayout& l = e->lay;
     l.L = layout->L; l.W = layout->W; l.stride = layout->W + 2; l.G = (layout->L + 2) * (layout->W + 2);
     l.wpr = (layout->W + 2 + 31) / 32;
@@ -1257,6 +1260,7 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
 
 extern "C" int mq_env_destroy(mq_env* e) {
     if (!e) return MQ_OK;
+    MQ_ON_DEVICE(e->device);
     cudaFree(e->d_dp5); cudaFree(e->d_cellinfo); cudaFree(e->d_ctr); cudaFree(e->d_int); cudaFree(e->d_scratch);
     delete e;
     return MQ_OK;
@@ -1273,6 +1277,7 @@ extern "C" int mq_env_set_reward_coefs(mq_env* e, double evac_reward, double dea
 extern "C" int mq_env_reset(mq_env* e, const uint8_t* env_mask, const int16_t* inject_spawn, float* obs_out,
                             double* obs64_out, void* stream) {
     MQ_REQUIRE(e, "mq_env_reset: null handle");
+    MQ_ON_DEVICE(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     k_variants[e->variant].reset<<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, env_mask, inject_spawn, obs_out, obs64_out);
     MQ_CUDA(cudaGetLastError());
@@ -1283,6 +1288,7 @@ extern "C" int mq_env_reset(mq_env* e, const uint8_t* env_mask, const int16_t* i
 extern "C" int mq_env_step(mq_env* e, const int32_t* actions, float* obs_out, double* obs64_out, double* reward_out,
                            uint8_t* done_out, void* stream) {
     MQ_REQUIRE(e && actions && reward_out && done_out, "mq_env_step: null argument");
+    MQ_ON_DEVICE(e->device);
     cudaStream_t s = (cudaStream_t)stream;
     k_variants[e->variant].step<<<e->blocks, e->threads, e->smem, s>>>(e->lay, e->cfg, e->st, actions, obs_out, obs64_out, reward_out, done_out);
     MQ_CUDA(cudaGetLastError());
@@ -1298,6 +1304,7 @@ extern "C" int mq_debug_env_trace(long long* host_out, int reset) {
 #endif
 extern "C" int mq_env_unpack_rmap(mq_env* e, uint8_t* rmap_out, void* stream) {
     MQ_REQUIRE(e && rmap_out, "mq_env_unpack_rmap: null argument");
+    MQ_ON_DEVICE(e->device);
     long long total = (long long)e->cfg.n_envs * e->lay.G;
     int blocks = (int)((total + 255) / 256);
     mq::unpack_rmap_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(e->lay, e->st.rmap, rmap_out, total);

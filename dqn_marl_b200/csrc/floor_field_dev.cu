@@ -61,6 +61,7 @@ __global__ void ff_add_kernel(long long total, const double* __restrict__ add_te
 extern "C" int mq_floor_field_device(int32_t L, int32_t W, int32_t n_layouts, const uint8_t* wall, const int32_t* exits, int32_t max_exits,
                                      const int32_t* n_exits, const double* add_term, double* space_out, int32_t* sweeps_out, void* stream) {
     MQ_REQUIRE(L > 0 && W > 0 && n_layouts > 0 && wall && exits && max_exits > 0 && n_exits && space_out, "mq_floor_field_device: bad argument");
+    MQ_ON_DEVICE_OF(wall);
     cudaStream_t s = (cudaStream_t)stream;
     const int stride = W + 2, G = (L + 2) * stride;
     const long long total = (long long)G * n_layouts;

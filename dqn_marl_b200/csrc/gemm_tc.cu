@@ -24,6 +24,7 @@ extern "C" int mq_gemm_bf16(const void* A, const void* B, float* C, void* C_bf16
     MQ_REQUIRE(C || splits <= 1, "mq_gemm_bf16: split-K needs the fp32 output");
     MQ_REQUIRE(K % 8 == 0, "mq_gemm_bf16: K must be a multiple of 8 (TMA row pitch of 16 bytes)");
     MQ_REQUIRE(splits <= 1 || workspace, "mq_gemm_bf16: split-K needs a workspace");
+    MQ_ON_DEVICE_OF(A);
     cudaStream_t s = (cudaStream_t)stream;
     mq::tc::Epilogue ep{};
     ep.out_f32 = C; ep.out_bf16 = (__nv_bfloat16*)C_bf16; ep.ldc = N; ep.partial = splits > 1 ? workspace : nullptr;
@@ -72,6 +73,7 @@ extern "C" int mq_gemm_bf16_tn(const void* At, const void* Bt, float* C, int32_t
     MQ_REQUIRE(At && Bt && C && M > 0 && N > 0 && K > 0, "mq_gemm_bf16_tn: bad argument");
     MQ_REQUIRE(M % 8 == 0 && N % 8 == 0, "mq_gemm_bf16_tn: M and N must be multiples of 8 (TMA row pitch of 16 bytes)");
     MQ_REQUIRE(splits <= 1 || workspace, "mq_gemm_bf16_tn: split-K needs a workspace");
+    MQ_ON_DEVICE_OF(At);
     cudaStream_t s = (cudaStream_t)stream;
     mq::tc::Epilogue ep{};
     ep.out_f32 = C; ep.ldc = N; ep.partial = splits > 1 ? workspace : nullptr;
@@ -89,6 +91,7 @@ extern "C" int mq_conv3x3_bf16(const void* X, const void* Wk, float* Y, void* Y_
                                int32_t bn, void* stream) {
     MQ_REQUIRE(X && Wk && (Y || Y_bf16) && batch > 0 && Cin > 0 && Cout > 0, "mq_conv3x3_bf16: bad argument");
     MQ_REQUIRE(Cin % 32 == 0, "mq_conv3x3_bf16: Cin must be a multiple of 32");
+    MQ_ON_DEVICE_OF(X);
     cudaStream_t s = (cudaStream_t)stream;
     mq::tc::Epilogue ep{};
     ep.out_f32 = Y; ep.out_bf16 = (__nv_bfloat16*)Y_bf16; ep.ldc = Cout;
@@ -127,6 +130,7 @@ extern "C" int mq_conv3x3_wgrad_bf16(const void* X, const void* dY, float* dW, f
     MQ_REQUIRE(Cin % 32 == 0 && Cout % 8 == 0, "mq_conv3x3_wgrad_bf16: Cin must be a multiple of 32 and Cout of 8");
     MQ_REQUIRE(splits <= 1 || workspace, "mq_conv3x3_wgrad_bf16: split needs a workspace");
     MQ_REQUIRE(!dBias || workspace, "mq_conv3x3_wgrad_bf16: the bias gradient needs a workspace");
+    MQ_ON_DEVICE_OF(X);
     cudaStream_t s = (cudaStream_t)stream;
     mq::tc::Epilogue ep{};
     int sp = splits < 1 ? 1 : splits;

@@ -637,7 +637,8 @@ extern "C" int mq_qnet_create(mq_qnet** out, int32_t device, int64_t max_batch, 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return mq::fail(MQ_ERR_CUDA, "mq_qnet_create: no CUDA device (this build has no CPU fallback)");
-    MQ_CUDA(cudaSetDevice(device));
+    MQ_REQUIRE(device >= 0 && device < ndev, "mq_qnet_create: device %d outside 0..%d", device, ndev - 1);
+    MQ_ON_DEVICE(device);
     mq_qnet* n = new (std::nothrow) mq_qnet();
     if (!n) return mq::fail(MQ_ERR_ALLOC, "mq_qnet_create: out of host memory");
     n->device = device; n->max_batch = max_batch;
@@ -676,6 +677,7 @@ extern "C" int mq_qnet_create(mq_qnet** out, int32_t device, int64_t max_batch, 
 
 extern "C" int mq_qnet_destroy(mq_qnet* n) {
     if (!n) return MQ_OK;
+    MQ_ON_DEVICE(n->device);
     mq::free_ws(n);
     delete n;
     return MQ_OK;
@@ -686,6 +688,7 @@ extern "C" int mq_qnet_forward(mq_qnet* n, int32_t which, const float* obs, int6
                                void* stream) {
     MQ_REQUIRE(n && obs && q_out, "mq_qnet_forward: null argument");
     MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_forward: batch %lld outside 1..%lld", (long long)B, n->max_batch);
+    MQ_ON_DEVICE(n->device);
     cudaStream_t s = (cudaStream_t)stream;
     float* const* W = which ? n->tl.t : n->tl.p;
     if (n->precision == 1) {
@@ -705,6 +708,7 @@ extern "C" int mq_qnet_act(mq_qnet* n, const float* obs, int64_t B, float eps, u
                            int32_t n_robots, const uint8_t* drop_mask, int32_t* action_out, float* q_out, void* stream) {
     MQ_REQUIRE(n && obs && action_out && n_robots >= 1, "mq_qnet_act: bad argument");
     MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_act: batch %lld outside 1..%lld", (long long)B, n->max_batch);
+    MQ_ON_DEVICE(n->device);
     cudaStream_t s = (cudaStream_t)stream;
     if (n->precision == 1) {
         cudaError_t e = mq::forward_net_bf16(n, 0, obs, B, drop_mask, s);
@@ -786,6 +790,7 @@ static int td_backward_impl(mq_qnet* n, const float* state, const int64_t* actio
     MQ_REQUIRE(n && state && action && reward && next_state && done && hp && loss_out, "mq_qnet_td_backward: null argument");
     MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_td_backward: batch %lld outside 1..%lld", (long long)B, n->max_batch);
     MQ_REQUIRE(n->tl.g[0] && n->da3, "mq_qnet_td_backward: handle was created without gradient buffers");
+    MQ_ON_DEVICE(n->device);
     cudaStream_t s = (cudaStream_t)stream;
     const int hb = (int)((B * 32 + 255) / 256);
     // next_q = target_network(next_states).max(1)[0]   (dqn_agent.py:146-147)
@@ -850,6 +855,7 @@ extern "C" int mq_qnet_backward(mq_qnet* n, const float* state, const float* dq,
     MQ_REQUIRE(n && state && dq, "mq_qnet_backward: null argument");
     MQ_REQUIRE(B > 0 && B <= n->max_batch, "mq_qnet_backward: batch %lld outside 1..%lld", (long long)B, n->max_batch);
     MQ_REQUIRE(n->tl.g[0] && n->da3, "mq_qnet_backward: handle was created without gradient buffers");
+    MQ_ON_DEVICE(n->device);
     cudaStream_t s = (cudaStream_t)stream;
     const bool bf16 = n->precision == 1;
     MQ_REQUIRE(!bf16 || B % 8 == 0, "mq_qnet_backward: the bf16 path needs a batch that is a multiple of 8 (got %lld)", (long long)B);
@@ -874,6 +880,7 @@ extern "C" int mq_qnet_clip_adam(mq_qnet* n, const mq_hparams* hp, float grad_sc
     using namespace mq;
     MQ_REQUIRE(n && hp && hp->adam_step >= 1, "mq_qnet_clip_adam: bad argument");
     MQ_REQUIRE(n->tl.g[0] && n->tl.m[0] && n->tl.v[0], "mq_qnet_clip_adam: gradient / Adam buffers not bound");
+    MQ_ON_DEVICE(n->device);
     cudaStream_t s = (cudaStream_t)stream;
     sqnorm_partial_kernel<<<(int)n->total_chunks, 256, 0, s>>>(n->tl, grad_scale, n->norm_partial);
     sqnorm_final_kernel<<<1, 1024, 0, s>>>(n->norm_partial, (int)n->total_chunks, n->gnorm);
@@ -893,6 +900,7 @@ extern "C" int mq_qnet_clip_adam(mq_qnet* n, const mq_hparams* hp, float grad_sc
 
 extern "C" int mq_qnet_sync_target(mq_qnet* n, float tau, void* stream) {
     MQ_REQUIRE(n, "mq_qnet_sync_target: null handle");
+    MQ_ON_DEVICE(n->device);
     mq::sync_target_kernel<<<(int)n->total_chunks, 256, 0, (cudaStream_t)stream>>>(n->tl, tau);
     n->launches += 1;
     n->w_dirty[1] = true;
@@ -902,6 +910,7 @@ extern "C" int mq_qnet_sync_target(mq_qnet* n, float tau, void* stream) {
 
 extern "C" int mq_qnet_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t seed, uint64_t counter, void* stream) {
     MQ_REQUIRE(mask && n > 0 && p >= 0.f && p < 1.f, "mq_qnet_dropout_mask: bad argument");
+    MQ_ON_DEVICE_OF(mask);
     const unsigned threshold = (unsigned)((double)p * 4294967296.0);
     const long long groups = (n + 3) / 4;
     mq::dropout_mask_kernel<<<(int)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(mask, n, threshold, seed, counter);
@@ -911,8 +920,8 @@ extern "C" int mq_qnet_dropout_mask(uint8_t* mask, int64_t n, float p, uint64_t 
 
 extern "C" int mq_qnet_set_precision(mq_qnet* n, int32_t precision) {
     MQ_REQUIRE(n && (precision == 0 || precision == 1), "mq_qnet_set_precision: precision must be 0 (fp32) or 1 (bf16 tensor cores)");
+    MQ_ON_DEVICE(n->device);
     if (precision == 1) {
-        MQ_CUDA(cudaSetDevice(n->device));
         cudaError_t e = mq::alloc_bf16(n);
         if (e != cudaSuccess) return mq::fail(MQ_ERR_ALLOC, "mq_qnet_set_precision: bf16 workspace allocation failed: %s", cudaGetErrorString(e));
         if (!mq::tc::encode_fn()) return mq::fail(MQ_ERR_UNSUPPORTED, "mq_qnet_set_precision: cuTensorMapEncodeTiled is not available in this driver");

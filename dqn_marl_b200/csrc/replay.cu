@@ -105,6 +105,7 @@ extern "C" int mq_replay_create(mq_replay** out, int64_t capacity, int32_t devic
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return mq::fail(MQ_ERR_CUDA, "mq_replay_create: no CUDA device (this build has no CPU fallback)");
+    MQ_REQUIRE(device >= 0 && device < ndev, "mq_replay_create: device %d outside 0..%d", device, ndev - 1);
     mq_replay* rb = new (std::nothrow) mq_replay();
     if (!rb) return mq::fail(MQ_ERR_ALLOC, "mq_replay_create: out of host memory");
     rb->ring = {store->state, store->next_state, store->action, store->reward, store->done, (long long)capacity};
@@ -123,6 +124,7 @@ extern "C" int mq_replay_push(mq_replay* rb, const float* state, const int32_t* 
     MQ_REQUIRE(rb && state && action && reward && next_state && done, "mq_replay_push: null argument");
     MQ_REQUIRE(n >= 0 && n <= rb->ring.capacity, "mq_replay_push: n=%lld exceeds the capacity %lld", (long long)n, rb->ring.capacity);
     if (n == 0) return MQ_OK;
+    MQ_ON_DEVICE(rb->device);
     const long long warps = 2 * n;
     const int blocks = (int)((warps * 32 + 255) / 256);
     mq::replay_push_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rb->ring, rb->cursor, state, action, reward, next_state,
@@ -141,6 +143,7 @@ extern "C" int mq_replay_sample(mq_replay* rb, int64_t B, uint64_t seed, uint64_
     // random.sample raises ValueError when the population is smaller than the sample (dqn_agent.py:132)
     MQ_REQUIRE(B > 0 && B <= rb->size, "mq_replay_sample: sample larger than population (B=%lld, size=%lld)", (long long)B,
                rb->size);
+    MQ_ON_DEVICE(rb->device);
     const uint4 rk = mq::philox4x32(0u, (uint32_t)draw_id, 0u, mq::STREAM_SAMPLE, seed);
     const long long oldest = rb->size < rb->ring.capacity ? 0 : rb->cursor;
     const long long warps = 2 * B;

@@ -115,7 +115,10 @@ class VecEvacuationEnv:
             pass
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        cur = torch.cuda.current_stream(self.device)
+        if getattr(self, "_hs", None) is not None:        # an asynchronous host-buffer step may still be in flight on its own stream
+            cur.wait_stream(self._hs)
+        return C.c_void_p(cur.cuda_stream)
 
     def set_reward_coefs(self, evac_reward, death_penalty, death_acc_penalty, alive_bonus):
         """EvacuationEnv.EVAC_REWARD etc. are class attributes mutated at runtime (overnight_experiments.py:69-70)."""
@@ -178,7 +181,9 @@ class VecEvacuationEnv:
             self.h_obs = torch.empty(self.obs.shape, dtype=torch.float32).pin_memory()
             self.h_reward = torch.empty((self.n_envs,), dtype=torch.float64).pin_memory()
             self.h_done = torch.empty((self.n_envs,), dtype=torch.uint8).pin_memory()
-            self._hs.wait_stream(torch.cuda.current_stream(self.device))        # resets / earlier steps on the caller's stream
+        # everything the caller has enqueued so far on its own stream (reset(), step(), writes to the state tensors such as the
+        # facade's robot_position setter) happens before this step
+        self._hs.wait_stream(torch.cuda.current_stream(self.device))
         a = actions_host.reshape(self.n_envs, self.n_robots)
         assert a.dtype == torch.int32 and a.device.type == "cpu"
         with torch.cuda.stream(self._hs):

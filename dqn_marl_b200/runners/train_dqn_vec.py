@@ -56,7 +56,7 @@ class VecTrainer:
         self.cur ^= 1
         self.stats.env_steps += 1
         loss = None
-        if learn and len(a.memory) > a.batch_size:                                # train_dqn.py:117-118
+        if learn and a.ready_to_learn():                                          # train_dqn.py:117-118, rank-consistent
             loss = a.learn_device()
             self.stats.learn_steps += 1
             if self.stats.learn_steps % self.target_sync_every == 0:

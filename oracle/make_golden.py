@@ -39,9 +39,9 @@ def actions_for(seed, t, R, n_act=6):
     return [int((w[r] * n_act) >> 32) for r in range(R)]
 
 
-def record(kind, W, H, exit_loc, N, seed, n_steps, name, extra_resets=()):
+def record(kind, W, H, exit_loc, N, seed, n_steps, name, extra_resets=(), layout=None):
     R = 2 if kind == "multi" else 1
-    ref = RefEnv(kind, W, H, exit_loc, N, seed=seed)
+    ref = RefEnv(kind, W, H, exit_loc, N, seed=seed, layout=layout)
     frames = []
 
     def grab(op, act, obs, reward, done):
@@ -61,8 +61,11 @@ def record(kind, W, H, exit_loc, N, seed, n_steps, name, extra_resets=()):
             obs = ref.reset()
             grab(OP_RESET, [0] * R, obs, 0.0, 0)
     out = {k: np.stack([f[k] for f in frames]) for k in frames[0]}
+    extra = {} if layout is None else dict(layout=dict(exits=[list(map(int, e)) for e in layout["exits"]],
+                                                       barriers=[[list(map(int, A)), list(map(int, B))] for (A, B) in layout["barriers"]],
+                                                       fire_first_only=bool(layout.get("fire_first_only", False))))
     out["meta"] = meta(kind=kind, width=W, height=H, exit=list(exit_loc) if exit_loc else [36, 15], n_people=N,
-                       seed=seed, n_robots=R)
+                       seed=seed, n_robots=R, **extra)
     path = os.path.join(OUT, name)
     np.savez_compressed(path, **out)
     print(name, "frames", len(frames), "resets", int((out["op"][1:] == OP_RESET).sum()),
@@ -88,8 +91,33 @@ def layout_file(ref, name, steps, box=None):
     print(name, "kB", os.path.getsize(path) // 1024)
 
 
+def synthetic_specs():
+    """Multi-exit / multi-barrier layouts run through the reference's own Map + People:
+    (a) the geometry dqn_marl_b200.layout.Layout.synthetic generates (exits, barrier rectangles; only barrier 0 burns), so the
+        benchmark layouts' generator is pinned to the reference's floor field, spawn rule, conflict logic and reward;
+    (b) a hand-written hall with three exits and four barriers, EVERY barrier burning (map.py:58-65 as is)."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from dqn_marl_b200.layout import Layout
+    lay = Layout.synthetic(96, 80, n_exits=3, wall_fill=0.10, seed=7)
+    a = dict(exits=[tuple(e) for e in lay.exits], barriers=[(tuple(A), tuple(B)) for (A, B) in lay.barriers], fire_first_only=True)
+    b = dict(exits=[(64, 32), (1, 20), (30, 1)],
+             barriers=[((18, 14), (20, 16)), ((24, 30), (27, 33)), ((40, 10), (44, 12)), ((8, 40), (12, 44))],
+             fire_first_only=False)
+    return a, b
+
+
+def main_synthetic():
+    a, b = synthetic_specs()
+    ref = record("single", 96, 80, list(a["exits"][0]), 300, 31, 70, "traj_synth_gallery.npz", extra_resets=(40,), layout=a)
+    layout_file(ref, "layout_synth_gallery.npz", steps=[0, 3, 40, 180], box=(-6, -6, 50, 46))
+    ref = record("single", 64, 48, list(b["exits"][0]), 200, 32, 90, "traj_synth_hall.npz", extra_resets=(55,), layout=b)
+    layout_file(ref, "layout_synth_hall.npz", steps=[0, 10, 60, 180])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--synthetic-only" in sys.argv:
+        return main_synthetic()
     ref = record("single", 36, 30, None, 150, 1234, 260, "traj_room_single.npz", extra_resets=(7,))
     layout_file(ref, "layout_room.npz", steps=range(0, 181))
     record("multi", 36, 30, None, 150, 99, 120, "traj_room_multi.npz")
@@ -100,6 +128,7 @@ def main():
     record("single", 36, 30, None, 6, 100, 90, "traj_room_allevac.npz")
     ref = record("single", 256, 256, [256, 128], 1000, 2024, 24, "traj_big256.npz")
     layout_file(ref, "layout_big256.npz", steps=[0, 5, 24, 90, 180], box=(-6, -6, 50, 46))
+    main_synthetic()
 
 
 if __name__ == "__main__":

@@ -123,7 +123,12 @@ class RefEnv:
     """
 
     def __init__(self, kind="single", width=36, height=30, exit_location=None, num_people=150,
-                 seed=0, env_id=0):
+                 seed=0, env_id=0, layout=None):
+        """layout = dict(exits=[(x, y), ...], barriers=[((x0, y0), (x1, y1)), ...], fire_first_only=bool) replaces the
+        room hard-wired in EvacuationEnv.__init__ (evacuation_env.py:42-53) by the reference's own
+        ``Map(L, W, exits, [Init_Barrier(A, B), ...])`` (map.py:38-79: multi-exit Dijkstra, one fire source per
+        barrier) — SURVEY.md §8(c).  fire_first_only keeps only the first barrier's source (what
+        dqn_marl_b200.layout.Layout.synthetic builds) by overriding map.fire_model and re-running Init_Potential."""
         import random as _random
         people_mod, map_mod, fire_mod, env_mod, envm_mod = _import_reference()
         self.mods = (people_mod, map_mod, fire_mod, env_mod, envm_mod)
@@ -142,6 +147,21 @@ class RefEnv:
             self.draws.episode = 0
             self._rp.new_episode()
             self.env = cls(width, height, None, exit_location, num_people)   # ctor spawns episode 0
+            if layout is not None:
+                assert kind == "single"
+                exits = [list(map(int, e)) for e in layout["exits"]]
+                bars = [map_mod.Init_Barrier(tuple(A), tuple(B)) for (A, B) in layout["barriers"]]
+                m = map_mod.Map(width, height, exits, bars)
+                if layout.get("fire_first_only"):
+                    (A, B) = bars[0]
+                    m.fire_model = fire_mod.FireSpreadModel([fire_mod.FireSource(
+                        center=((A[0] + B[0]) / 2, (A[1] + B[1]) / 2), size=(2, 2), temp_max=900, co_max=1800)])
+                    m.Init_Potential()
+                self.env.map = m
+                self.env.exit_location = exits[0]
+                self.draws.episode = 0
+                self._rp.new_episode()
+                self.env.reset()                                             # episode 0 again, on the new map
         finally:
             self._uninstall()
         self.last_obs = None

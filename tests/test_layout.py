@@ -57,6 +57,45 @@ def test_big256_tables():
         _check_danger(mine, ref, exact)
 
 
+def _check_synth(layout_name, traj_name, boxed):
+    """Multi-exit / multi-barrier tables against the reference's own Map(L, W, exits, barriers) (map.py:38-79,127-148) and its
+    fire models evaluated on that map (oracle/make_golden.py main_synthetic)."""
+    from dqn_marl_b200.layout import CELL_VALID
+    from util import layout_for
+    g = load_golden(layout_name)
+    lay = layout_for(load_golden(traj_name)["meta"])
+    assert np.array_equal(lay.space.view(np.uint64), g["space"].view(np.uint64))          # multi-source Dijkstra + fire term
+    assert np.array_equal(lay.barrier_mask, g["barrier"])
+    valid = (lay.cellinfo & CELL_VALID) != 0
+    ref_valid = np.isfinite(g["space"]); ref_valid[[0, -1], :] = False; ref_valid[:, [0, -1]] = False
+    assert np.array_equal(valid, ref_valid)
+    exact = _np_exp_matches(g)
+    pad = int(g["pad"])
+    L, W = lay.L, lay.W
+    x0, y0, w, h = lay.ctr_box
+    ix0, iy0, iw, ih = lay.int_box
+    for k, s in enumerate(g["steps"]):
+        full = np.zeros((L + 2, W + 2)); full[x0:x0 + w, y0:y0 + h] = lay.danger_ctr[s]
+        full_int = np.zeros((L + 2 + 2 * pad, W + 2 + 2 * pad))
+        sx0, sx1 = max(ix0, -pad), min(ix0 + iw, L + 2 + pad)
+        sy0, sy1 = max(iy0, -pad), min(iy0 + ih, W + 2 + pad)
+        full_int[sx0 + pad:sx1 + pad, sy0 + pad:sy1 + pad] = lay.danger_int[s, sx0 - ix0:sx1 - ix0, sy0 - iy0:sy1 - iy0]
+        if boxed:
+            bx0, by0, bx1, by1 = g["box"]
+            full = full[max(0, bx0):bx1, max(0, by0):by1]
+            full_int = full_int[bx0 + pad:bx1 + pad, by0 + pad:by1 + pad]
+        _check_danger(full, g["danger_ctr"][k], exact)
+        _check_danger(full_int, g["danger_int"][k], exact)
+
+
+def test_synthetic_gallery_tables_match_reference_map():
+    _check_synth("layout_synth_gallery.npz", "traj_synth_gallery.npz", boxed=True)
+
+
+def test_multi_fire_hall_tables_match_reference_map():
+    _check_synth("layout_synth_hall.npz", "traj_synth_hall.npz", boxed=False)
+
+
 def test_dp5_and_cellinfo_semantics():
     """dp5 = (space[c]-space[n])*5.0 for valid pairs, -inf otherwise; exit neighbourhood evacuates."""
     from dqn_marl_b200.layout import CELL_EVACUATES, CELL_OBS_EXIT, MOVE_TO, Layout

@@ -18,11 +18,28 @@ def load_golden(name):
     return d
 
 
+def layout_from_spec(L, W, spec):
+    """Product Layout of a multi-exit / multi-barrier geometry recorded in a golden's meta (oracle/make_golden.py
+    synthetic_specs): the reference's Map(L, W, exits, barriers) burns every barrier (map.py:58-65) unless fire_first_only."""
+    from dqn_marl_b200.fire import FireSchedule
+    from dqn_marl_b200.layout import Layout, init_barrier
+    exits = [tuple(e) for e in spec["exits"]]
+    bars = [init_barrier(tuple(A), tuple(B)) for (A, B) in spec["barriers"]]
+    lay = Layout(L=L, W=W, exits=exits, barriers=bars, obs_exit=exits[0])
+    if spec.get("fire_first_only"):
+        (A, B) = bars[0]
+        lay.fire = FireSchedule([(((A[0] + B[0]) / 2, (A[1] + B[1]) / 2), (2, 2), 0.4)])
+    return lay.build()
+
+
 def layout_for(meta):
     from dqn_marl_b200.layout import Layout
-    key = (meta["width"], meta["height"], tuple(meta["exit"]), meta["n_robots"])
+    key = (meta["width"], meta["height"], tuple(meta["exit"]), meta["n_robots"], json.dumps(meta.get("layout"), sort_keys=True))
     if key not in _layout_cache:
-        _layout_cache[key] = Layout.reference_room(meta["width"], meta["height"], meta["exit"], n_robots=meta["n_robots"])
+        if meta.get("layout"):
+            _layout_cache[key] = layout_from_spec(meta["width"], meta["height"], meta["layout"])
+        else:
+            _layout_cache[key] = Layout.reference_room(meta["width"], meta["height"], meta["exit"], n_robots=meta["n_robots"])
     return _layout_cache[key]
 
 
