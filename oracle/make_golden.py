@@ -111,7 +111,7 @@ def main_synthetic():
     ref = record("single", 96, 80, list(a["exits"][0]), 300, 31, 70, "traj_synth_gallery.npz", extra_resets=(40,), layout=a)
     layout_file(ref, "layout_synth_gallery.npz", steps=[0, 3, 40, 180], box=(-6, -6, 50, 46))
     ref = record("single", 64, 48, list(b["exits"][0]), 200, 32, 90, "traj_synth_hall.npz", extra_resets=(55,), layout=b)
-    layout_file(ref, "layout_synth_hall.npz", steps=[0, 10, 60, 180])
+    layout_file(ref, "layout_synth_hall.npz", steps=range(0, 101))        # every fire step the trajectory visits
 
 
 def main():

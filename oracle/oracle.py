@@ -78,6 +78,20 @@ class LayoutTables:
         self.reset_obs_center = np.asarray(reset_obs_center, dtype=np.int32)
 
     @classmethod
+    def from_golden(cls, g, meta):
+        """Tables EVALUATED BY THE REFERENCE (tests/golden/layout_*.npz written by oracle/make_golden.py layout_file: Map.space,
+        barrier_list, both fire models per fire step) — nothing of the product's table builders is involved.  Needs a fixture
+        whose ``steps`` are 0..S-1 on the full grid (no box)."""
+        L, W = int(meta["width"]), int(meta["height"])
+        steps = [int(s) for s in g["steps"]]
+        assert steps == list(range(len(steps))) and "box" not in g, "from_golden needs contiguous fire steps on the full grid"
+        pad = int(g["pad"])
+        spec = meta.get("layout")
+        exits = spec["exits"] if spec else [meta["exit"]]
+        return cls(L, W, g["space"], g["barrier"], exits, exits[0], (0, 0, L + 2, W + 2), g["danger_ctr"],
+                   (-pad, -pad, L + 2 + 2 * pad, W + 2 + 2 * pad), g["danger_int"])
+
+    @classmethod
     def from_layout(cls, lay):
         return cls(lay.L, lay.W, lay.space, lay.barrier_mask, lay.exits, lay.obs_exit, lay.ctr_box, lay.danger_ctr,
                    lay.int_box, lay.danger_int, lay.robot_range, lay.robot_starts, lay.reset_obs_center)

@@ -29,6 +29,29 @@ def test_oracle_replays_reference(name):
             assert_frame_equal(g, f, env.snapshot(), obs, None, None, lay.L, lay.W, name)
 
 
+@pytest.mark.parametrize("traj,layout", [("traj_room_single.npz", "layout_room.npz"), ("traj_synth_hall.npz", "layout_synth_hall.npz")])
+def test_oracle_replays_reference_on_reference_tables(traj, layout):
+    """Same replay with the static tables taken from the reference's own evaluation (Map.space, barrier_list, both fire
+    models) instead of the product's Layout: the oracle's parity does not lean on the product's table builders."""
+    from oracle import LayoutTables, OracleEnv
+    g = load_golden(traj)
+    m = g["meta"]
+    tabs = LayoutTables.from_golden(load_golden(layout), m)
+    env = OracleEnv(tabs, m["n_people"], m["n_robots"], seed=m["seed"])
+    L, W = m["width"], m["height"]
+    obs = env.reset()
+    assert_frame_equal(g, 0, env.snapshot(), obs, None, None, L, W, traj)
+    for f in range(1, len(g["op"])):
+        if g["op"][f] == OP_STEP:
+            if tabs.danger_ctr.shape[0] < 181 and env.snapshot()["fire_step"] + 1 >= tabs.danger_ctr.shape[0]:
+                break                      # beyond the fire steps the fixture tabulates
+            obs, r, d = env.step(g["actions"][f])
+            assert_frame_equal(g, f, env.snapshot(), obs, r, d, L, W, traj)
+        else:
+            obs = env.reset()
+            assert_frame_equal(g, f, env.snapshot(), obs, None, None, L, W, traj)
+
+
 def test_pairwise_sum_matches_numpy():
     """np.mean at evacuation_env.py:228 is numpy's pairwise add.reduce (third party, numpy 2.3.x)."""
     from oracle import pairwise_sum
