@@ -1,27 +1,36 @@
 #!/usr/bin/env python3
 """bench.py — headline benchmark of the DQN-MARL hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c5]
 
-Metric (BASELINE.json): env agent-steps/s.  Workload at N=1 = BASELINE.json configs[1] ("CA-dqn1
-single-room cellular-automaton evacuation, 4096 batched envs, env-step-only throughput on 1 B200"):
-36x30 room, 150 people per env, 4096 envs, uniform random robot actions, auto-reset.  One "step" = one
-fused env-step launch over the whole batch = 4096*150 agent-steps (every person counted every step,
-SURVEY.md §8d).
+Metrics (BASELINE.json): env agent-steps/s (headline line) and learner transitions/s (first-class `learner` block of the
+same line).  Workload at N=1 = the largest single-GPU configuration, BASELINE.json configs[2] ("C3": synthetic Louvre
+layout 256x256, 1000 pedestrians/env, 16384 batched envs, full DQN act/learn loop on 1 B200); `--workload c2` is
+configs[1] (36x30 room, 150 people, 4096 envs, env-step only; a short C2 run rides along as `secondary_c2`), `--workload c5`
+the stress shape of configs[4].  One env "step" = one fused env-step launch over the whole batch = envs x people agent-steps
+(every person counted every step); one learner "step" = act -> env step -> replay push -> sample + learn
+(runners/train_dqn.py:98-125 batched) and learns B transitions.
 
-  value     device-resident throughput: K back-to-back steps, inputs already in HBM, CUDA events.
-            The whole state of one batch (27 MB) would sit in the 126 MB L2, so the timed loop ROTATES over
-            enough independent batches that the state touched between two visits of the same batch exceeds
-            L2 (config.l2 says how many) — every step reads its state from HBM.
-  e2e       same metric through the host-facing call: actions from pinned host memory (H2D), step, and
-            obs/reward/done read back to pinned host memory (D2H) inside the timed region, every step.
-  roofline  env_step_kernel: algorithmic bytes (2*N*24 + 2*G + R*2904 + 9 per env-step)
-            / measured launch duration vs MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline  the oracle port (oracle/env_oracle.c, the reference's algorithm restated in C) on the
-            host cores, bounded sample.  `--impl reference` times the same port on all host threads as
-            its own arm (the reference is pure Python; there is no compiled reference to build).
+  value     device-resident env throughput: K back-to-back steps, inputs already in HBM, CUDA events.  The timed loop
+            ROTATES over independent env batches whose state together exceeds the 126 MB L2 (config.l2), so every step
+            reads its state from HBM.
+  e2e       same metric through the host-facing call (VecEvacuationEnv.step_async / step_wait): actions from pinned host
+            memory (H2D), step, obs/reward/done back to pinned host memory (D2H) inside the timed region, every step.
+  roofline  env_step_kernel: algorithmic bytes (2*N*24 + 2*G + R*2904 + 9 per env-step) / measured launch
+            duration vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the oracle port (oracle/env_oracle.c, the reference's algorithm restated in C) on the host cores, bounded
+            sample.
+  learner   {value (transitions/s of the full loop), segments, roofline (tensor: 155.4 MFLOP x B / learn ms vs the
+            sustained bf16 peak), e2e (the learn step fed from pinned HOST batches, loss read back), cpu_baseline (the torch
+            fp32 restatement of DQNAgent.learn(), oracle/qnet_oracle.py, on the host cores at B = 32 and B = batch),
+            param_checksum / replicas_identical (data-parallel replicas hold the same weights after the loop)}.
+  learner_fp32  the same loop on the 1e-5 parity path (CUDA-core FFMA), fewer steps.
 
-N > 1 (torchrun): every rank owns its own env batches (weak scaling, no data-path collective).
+`--impl reference` times the reference's CPU implementation of the path (the oracle ports; the reference itself is pure
+Python and cannot travel to the GPU box) on all host threads, without loading libmarl_b200.so.
+
+N > 1 (torchrun): every rank owns its env batches and replay (weak scaling, no data-path collective); the learner's
+gradient is all-reduced over NCCL.
 """
 from __future__ import annotations
 
@@ -38,14 +47,16 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (L, W, people, envs, synthetic layout?)
-    "c2": dict(L=36, W=30, people=150, envs=4096, synthetic=False,
+    "c2": dict(L=36, W=30, people=150, envs=4096, synthetic=False, learner_batch=4096,
                desc="CA-dqn1 single room 36x30, 150 people/env, 4096 envs, env-step only (BASELINE.json configs[1])"),
-    "c3": dict(L=256, W=256, people=1000, envs=16384, synthetic=True,
-               desc="synthetic Louvre layout 256x256, 1000 people/env, 16384 envs, env-step only (BASELINE.json configs[2] env part)"),
-    "c5": dict(L=1024, W=1024, people=20000, envs=512, synthetic=True, exits=8, wall_fill=0.15,
-               desc="stress: synthetic 1024x1024 multi-exit museum grid, 20000 people/env, 512 envs per GPU, env-step only (BASELINE.json configs[4] env part)"),
+    "c3": dict(L=256, W=256, people=1000, envs=16384, synthetic=True, learner_batch=4096,
+               desc="synthetic Louvre layout 256x256, 1000 people/env, 16384 envs per GPU, full DQN act/learn loop (BASELINE.json configs[2]; configs[3] when sharded over N GPUs)"),
+    "c5": dict(L=1024, W=1024, people=20000, envs=512, synthetic=True, exits=8, wall_fill=0.15, learner_batch=8192,
+               desc="stress: synthetic 1024x1024 multi-exit museum grid, 20000 people/env, 512 envs per GPU, replay sample 8192 per GPU (65536 over 8 GPUs) (BASELINE.json configs[4])"),
 }
 L2_BYTES = 126e6
+LEARN_FLOP = 155.4e6        # per learned transition
+ACT_FLOP = 38.85e6          # per forward sample
 
 
 def algorithmic_bytes_per_env_step(L, W, N, R=1):
@@ -59,7 +70,7 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f), "measured (MEASURED_PEAKS.json)"
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1590.0}, "fallback (B200_PROFILING.md)"
 
 
 def load_traffic(workload):
@@ -135,13 +146,16 @@ class ClockSampler:
         return out
 
 
-def make_layout(wl):
+def make_layout(wl, floor_field=None):
     from dqn_marl_b200.layout import Layout
     if wl["synthetic"]:
-        return Layout.synthetic(wl["L"], wl["W"], n_exits=wl.get("exits", 1), wall_fill=wl.get("wall_fill", 0.10), seed=2024)
-    return Layout.reference_room(wl["L"], wl["W"])
+        return Layout.synthetic(wl["L"], wl["W"], n_exits=wl.get("exits", 1), wall_fill=wl.get("wall_fill", 0.10), seed=2024,
+                                floor_field=floor_field)
+    return Layout.reference_room(wl["L"], wl["W"], floor_field=floor_field)
 
 
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (the checker timed as a baseline: the only places bench.py executes oracle/)
 # ---------------------------------------------------------------------------------------------------
 def cpu_port_throughput(layout, wl, n_envs, steps, warm, threads, seed=2026):
     """agent-steps/s of the oracle port on `threads` host threads (same layout, people, reset policy)."""
@@ -162,14 +176,59 @@ def cpu_port_throughput(layout, wl, n_envs, steps, warm, threads, seed=2026):
     return n_envs * wl["people"] * steps / dt, dt
 
 
+def cpu_env_baseline(layout, wl, threads, budget_s=12.0):
+    N = wl["people"]
+    n_cpu_envs = max(threads * 2, min(wl["envs"], max(64, int(150 * 1024 / N))))
+    v0, _ = cpu_port_throughput(layout, wl, n_cpu_envs, 3, 1, threads)
+    cpu_steps = int(max(6, min(5000, budget_s * v0 / (n_cpu_envs * N))))
+    v, dt = cpu_port_throughput(layout, wl, n_cpu_envs, cpu_steps, 2, threads)
+    return {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{n_cpu_envs} envs x {N} people x {cpu_steps} steps of the same workload, oracle/env_oracle.c on {threads} threads ({dt:.1f} s)"}
+
+
+def cpu_learner_baseline(batch, budget_s=10.0, seed=0):
+    """DQNAgent.learn() (dqn_agent.py:126-168) as restated in torch fp32 (oracle/qnet_oracle.py, pinned to the reference's
+    golden numbers by tests/test_agent_ref.py) on the host cores: transitions/s at B = 32 (configs/dqn.yaml) and B = batch."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import qnet_oracle
+    threads = torch.get_num_threads()
+    out = {}
+    for B in (32, batch):
+        q, t = qnet_oracle.build_nets(seed)
+        opt = torch.optim.Adam(q.parameters(), lr=1e-4)
+        g = torch.Generator().manual_seed(seed + B)
+        b = (torch.rand((B, 11, 11, 6), generator=g), torch.randint(0, 5, (B,), generator=g), torch.rand((B,), generator=g),
+             torch.rand((B, 11, 11, 6), generator=g), torch.rand((B,), generator=g) < 0.05)
+        keep = (torch.rand((B, 512), generator=g) >= 0.2)
+        qnet_oracle.learn_step(q, t, opt, b, drop_online=keep, drop_target=keep)            # warm-up (allocations, oneDNN primitives)
+        n, t0 = 0, time.perf_counter()
+        while True:
+            qnet_oracle.learn_step(q, t, opt, b, drop_online=keep, drop_target=keep)
+            n += 1
+            dt = time.perf_counter() - t0
+            if dt > budget_s / 2 or n >= 200:
+                break
+        out[B] = {"value": B * n / dt, "ms_per_learn": dt / n * 1e3, "steps": n}
+    return {"value": out[batch]["value"], "unit": "transitions/s", "cores": threads, "kind": "port",
+            "sample": f"torch {torch.__version__} fp32 restatement of DQNAgent.learn() (oracle/qnet_oracle.py) on {threads} host threads: "
+                      f"B={batch}: {out[batch]['steps']} learn steps, {out[batch]['ms_per_learn']:.0f} ms each; "
+                      f"B=32: {out[32]['steps']} steps, {out[32]['ms_per_learn']:.1f} ms each",
+            "b32": {"value": out[32]["value"], "ms_per_learn": out[32]["ms_per_learn"]},
+            "batch": batch, "ms_per_learn": out[batch]["ms_per_learn"]}
+
+
 def run_reference(args, wl):
-    """`--impl reference`: the reference's CPU implementation of the path = the oracle port on all host threads
-    (the reference itself is pure Python and cannot travel to the GPU box; BASELINE.md quotes it at
-    ~1.9e4 agent-steps/s/core).  Each step = one pass over the whole batch of the workload."""
+    """`--impl reference`: the reference's CPU implementation of the path = the oracle ports on all host threads (the reference
+    itself is pure Python and cannot travel to the GPU box; BASELINE.md quotes it at ~1.9e4 agent-steps/s/core).  Each step =
+    one pass over a bounded batch of the workload.  The layout's floor field is built by the pure-Python restatement
+    (oracle/floor_field_py.py): this process never loads libmarl_b200.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    layout = make_layout(wl)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from floor_field_py import floor_field
+    layout = make_layout(wl, floor_field=floor_field)
     threads = os.cpu_count() or 1
     # bounded sample: size one step so that K+W steps take about a minute at ~2e6 agent-steps/s/thread
     budget_agent_steps = 60.0 * 2.0e6 * threads
@@ -180,33 +239,32 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "env agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "envs_per_step": n_envs, "people": wl["people"]},
+        "config": {"workload": wl["desc"], "envs_per_step": n_envs, "people": wl["people"], "grid": [layout.L, layout.W]},
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port",
                          "sample": f"{n_envs} envs x {wl['people']} people x {args.steps} steps, oracle/env_oracle.c, {threads} threads"},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_learner:
+        lb = cpu_learner_baseline(args.learner_batch or wl["learner_batch"])
+        line["learner"] = {"metric": "learner transitions/s (DQNAgent.learn on the host)", "value": lb["value"], "unit": "transitions/s",
+                           "cpu_baseline": lb, "e2e": {"value": lb["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["loaded_product_library"] = any("libmarl_b200" in ln for ln in open("/proc/self/maps")) if os.path.exists("/proc/self/maps") else None
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
-def run_ours(args, wl):
+def env_state_bytes(layout, E, N):
+    return E * (((N + 15) // 16 * 16) * 21 + ((layout.L + 2) * ((layout.W + 2 + 31) // 32) + 3) // 4 * 16 + 96 + 2904 + 13)
+
+
+def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
+    """Device-resident headline + host-buffer e2e of the env step on one workload -> dict."""
     import torch
     import torch.distributed as dist
     from dqn_marl_b200.envs import VecEvacuationEnv
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    layout = make_layout(wl)
+    from dqn_marl_b200.parallel import max_over_ranks
     E, N = wl["envs"], wl["people"]
-    state_bytes = E * (160 * 0 + ((N + 15) // 16 * 16) * 21 + ((layout.L + 2) * ((layout.W + 2 + 31) // 32) + 3) // 4 * 16 + 96 + 2904 + 13)
+    state_bytes = env_state_bytes(layout, E, N)
     n_rot = max(2, int(L2_BYTES * 1.5 / state_bytes) + 1)
     envs = [VecEvacuationEnv(layout, E, N, device=dev, seed=2026, env_id_base=(rank * n_rot + b) * E,
                              strict_reference=False, auto_reset=True) for b in range(n_rot)]
@@ -217,12 +275,9 @@ def run_ours(args, wl):
     obs = [torch.empty((E, 1, 11, 11, 6), dtype=torch.float32, device=dev) for _ in range(n_rot)]
     rew = [torch.empty((E,), dtype=torch.float64, device=dev) for _ in range(n_rot)]
     don = [torch.empty((E,), dtype=torch.uint8, device=dev) for _ in range(n_rot)]
-
-    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get('MQ_BENCH_NO_SAMPLER')) else None      # started early: nvidia-smi needs ~100 ms before its first sample
-    for b, env in enumerate(envs):
+    for env in envs:
         env.reset()
-    # prime: bring every batch to a desynchronised mid-episode mix (untimed)
-    for t in range(args.prime):
+    for t in range(args.prime):            # prime: bring every batch to a mid-episode state (untimed)
         for b, env in enumerate(envs):
             env.step_into(actions[t % n_act], obs[b], rew[b], don[b])
     torch.cuda.synchronize(dev)
@@ -240,7 +295,8 @@ def run_ours(args, wl):
         bound[step_no % n_rot](act_rows[step_no % n_act])
         step_no += 1
 
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         one_step()
     torch.cuda.synchronize(dev)
     launches0 = sum(e.launch_count for e in envs)
@@ -255,117 +311,63 @@ def run_ours(args, wl):
     torch.cuda.synchronize(dev); barrier()
     if sampler:
         sampler.mark()
-    elapsed_ms = ev0.elapsed_time(ev1)
     launches = sum(e.launch_count for e in envs) - launches0
-    clocks = sampler.stop() if sampler else None
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = world * E * N * args.steps / (elapsed_ms * 1e-3)
+    elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1), dev)
+    res = {"value": world * E * N * args.steps / (elapsed_ms * 1e-3), "ms_per_step": elapsed_ms / args.steps, "launches": int(launches),
+           "n_rot": n_rot, "state_bytes": state_bytes, "warmup": warm}
 
-    # L2-resident variant (what a production loop that steps ONE batch sees) — reported, not the headline
-    torch.cuda.synchronize(dev)
-    ev0.record()
-    for k in range(args.steps):
-        envs[0].step_into(actions[k % n_act], obs[0], rew[0], don[0])
-    ev1.record(); torch.cuda.synchronize(dev)
-    warm_ms = ev0.elapsed_time(ev1)
-
-    # ---- e2e: host buffers through the host-facing calls (VecEvacuationEnv.step_async / step_wait): every step copies
-    #      its actions from pinned host memory (H2D), runs the step kernel and reads obs / reward / done back to pinned host
-    #      memory (D2H), all inside the timed region.  Pipelined: the n_rot independent env batches are in flight on their
-    #      own streams, so the PCIe copies of one batch overlap the kernel of another (how an asynchronous vector-env
-    #      driver calls it).  e2e_sync = the same with a host synchronisation after every step. ----
-    h_act = torch.randint(0, 5, (n_act, E, 1), dtype=torch.int32).pin_memory()
-    e2e_steps = max(10 * n_rot, min(args.steps, 300) // n_rot * n_rot)
-
-    def e2e_run(steps, sync_each):
-        for k in range(steps):
-            b = k % n_rot
-            if k >= n_rot and not sync_each:
-                envs[b].step_wait()                   # the previous step of this batch has landed on the host
-            envs[b].step_async(h_act[k % n_act])
-            if sync_each:
-                envs[b].step_wait()
-        for b in range(n_rot):
-            envs[b].step_wait()
-
-    torch.cuda.synchronize(dev)
-    e2e_run(2 * n_rot, False)
-    e2e_vals = []
-    for sync_each in (False, True):
-        barrier(); torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        e2e_run(e2e_steps, sync_each)
+    res["value_l2_resident"] = None
+    if state_bytes < L2_BYTES:             # what a loop that steps ONE small batch sees — reported, not the headline
         torch.cuda.synchronize(dev)
-        e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_vals.append(world * E * N * e2e_steps / float(t.item()))
-    e2e_value, e2e_sync_value = e2e_vals
-    h2d = h_act[0].numel() * 4
-    d2h = envs[0].h_obs.numel() * 4 + envs[0].h_reward.numel() * 8 + envs[0].h_done.numel()
+        ev0.record()
+        for k in range(args.steps):
+            envs[0].step_into(actions[k % n_act], obs[0], rew[0], don[0])
+        ev1.record(); torch.cuda.synchronize(dev)
+        res["value_l2_resident"] = E * N * args.steps / (ev0.elapsed_time(ev1) * 1e-3)
 
-    replay = run_replay_leg(args, dev) if args.replay_batch > 0 else None
-    learner = learner_fp32 = None
-    if args.loop_steps > 0:
-        del envs, obs, rew, don
-        torch.cuda.empty_cache()
-        learner = run_learner_loop(args, wl, layout, dev, rank, world, "bf16")
-        torch.cuda.empty_cache()
-        learner_fp32 = run_learner_loop(args, wl, layout, dev, rank, world, "fp32") if args.fp32_loop else None
+    if e2e:
+        # host buffers through the host-facing calls: every step copies its actions from pinned host memory (H2D), runs the step
+        # kernel and reads obs / reward / done back to pinned host memory (D2H), all inside the timed region.  Pipelined: the n_rot
+        # independent env batches are in flight on their own streams, so the PCIe copies of one batch overlap the kernel of
+        # another (how an asynchronous vector-env driver calls it).  value_sync_each_step = a host synchronisation per step.
+        h_act = torch.randint(0, 5, (n_act, E, 1), dtype=torch.int32).pin_memory()
+        e2e_steps = max(10 * n_rot, min(args.steps, 300) // n_rot * n_rot)
 
-    if rank == 0:
-        peaks, peak_src = measured_peaks()
-        alg = algorithmic_bytes_per_env_step(layout.L, layout.W, N) * E
-        kernel_ms = elapsed_ms / args.steps
-        achieved = alg / (kernel_ms * 1e-3) / 1e9
-        traffic = load_traffic(args.workload)
-        line = {
-            "metric": "env agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "envs_per_gpu": E, "people": N, "grid": [layout.L, layout.W],
-                       "l2": f"inputs larger than L2: timed loop rotates over {n_rot} independent batches "
-                             f"({n_rot * state_bytes / 1e6:.0f} MB of state > 126 MB L2)",
-                       "reset_policy": "auto-reset, fresh fire per episode (strict_reference=False)",
-                       "prime_steps": args.prime},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "value_sync_each_step": e2e_sync_value,
-                    "d2h_GBs_per_gpu": e2e_value / world / (E * N) * d2h / 1e9,
-                    "note": f"VecEvacuationEnv.step_async/step_wait: pinned host actions in (H2D), obs+reward+done out (D2H) every "
-                            f"step; {n_rot} independent env batches in flight on their own streams (copies overlap kernels); "
-                            f"value_sync_each_step = one batch at a time with a host sync per step; d2h_GBs_per_gpu = the PCIe "
-                            f"device-to-host rate this e2e value corresponds to (the bound of this leg)"},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                         "note": "canonical bytes of SURVEY.md §8d (uint8 occupancy, 24 B/person); this build packs "
-                                 "occupancy to 1 bit/cell and rewrites only changed person fields, so it moves fewer bytes"},
-            "value_l2_resident": E * N * args.steps / (warm_ms * 1e-3),
-        }
-        if replay is not None:
-            line["replay"] = replay
-        if args.loop_steps > 0:
-            line["learner"] = learner
-            if learner_fp32 is not None:
-                line["learner_fp32"] = learner_fp32
-        if world == 1 and not args.no_cpu:
-            threads = os.cpu_count() or 1
-            n_cpu_envs = min(E, 1024)
-            v0, _ = cpu_port_throughput(layout, wl, n_cpu_envs, 5, 2, threads)
-            cpu_steps = int(max(20, min(5000, 12.0 * v0 / (n_cpu_envs * N))))        # ~12 s of CPU work
-            v, dt = cpu_port_throughput(layout, wl, n_cpu_envs, cpu_steps, 5, threads)
-            line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
-                                    "sample": f"{n_cpu_envs} envs x {N} people x {cpu_steps} steps of the same workload, "
-                                              f"oracle/env_oracle.c on {threads} threads ({dt:.1f} s)"}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        def e2e_run(steps, sync_each):
+            for k in range(steps):
+                b = k % n_rot
+                if k >= n_rot and not sync_each:
+                    envs[b].step_wait()                   # the previous step of this batch has landed on the host
+                envs[b].step_async(h_act[k % n_act])
+                if sync_each:
+                    envs[b].step_wait()
+            for b in range(n_rot):
+                envs[b].step_wait()
+
+        torch.cuda.synchronize(dev)
+        e2e_run(2 * n_rot, False)
+        vals = []
+        for sync_each in (False, True):
+            barrier(); torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            e2e_run(e2e_steps, sync_each)
+            torch.cuda.synchronize(dev)
+            e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
+            vals.append(world * E * N * e2e_steps / e2e_s)
+        h2d = h_act[0].numel() * 4
+        d2h = envs[0].h_obs.numel() * 4 + envs[0].h_reward.numel() * 8 + envs[0].h_done.numel()
+        res["e2e"] = {"value": vals[0], "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "steps": e2e_steps, "value_sync_each_step": vals[1],
+                      "d2h_GBs_per_gpu": vals[0] / world / (E * N) * d2h / 1e9,
+                      "note": f"VecEvacuationEnv.step_async/step_wait: pinned host actions in (H2D), obs+reward+done out (D2H) every "
+                              f"step; {n_rot} independent env batches in flight on their own streams (copies overlap kernels); "
+                              f"value_sync_each_step = one batch at a time with a host sync per step; d2h_GBs_per_gpu = the PCIe "
+                              f"device-to-host rate this e2e value corresponds to"}
+    for env in envs:
+        env.close()
+    del envs, obs, rew, don
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_replay_leg(args, dev):
@@ -403,78 +405,229 @@ def run_replay_leg(args, dev):
     return res
 
 
-def run_learner_loop(args, wl, layout, dev, rank, world, precision="bf16"):
-    """Secondary metric of BASELINE.json: learner transitions/s in the full act -> step -> push -> learn loop
-    (train_dqn.py:98-125 batched), fp32 parity path of the Q-network, gradient all-reduce over NCCL when N > 1."""
+def run_learner_loop(args, wl, layout, dev, rank, world, precision, loop_steps, overlap=False, host_fed_steps=0):
+    """BASELINE.json's second metric: learner transitions/s in the full act -> step -> push -> sample + learn loop
+    (train_dqn.py:98-125 batched), gradient all-reduce over NCCL when N > 1.  Per-segment CUDA events are recorded without
+    host synchronisation inside the loop and read afterwards."""
     import torch
     import torch.distributed as dist
+    from dqn_marl_b200.parallel import max_over_ranks
     from dqn_marl_b200.runners.train_dqn_vec import VecTrainer
-    E, N, B = wl["envs"], wl["people"], args.learner_batch
+    peaks, peak_src = measured_peaks()
+    E, N, B = wl["envs"], wl["people"], (args.learner_batch or wl["learner_batch"])
     torch.manual_seed(0)
     tr = VecTrainer(layout, E, N, dev, dict(batch_size=B, learning_rate=1e-4, gamma=0.99, epsilon=1.0, epsilon_min=0.02,
                                              epsilon_decay=0.9995, dropout="train", precision=precision),
-                    env_id_base=rank * E, seed=2026, replay_capacity=max(1 << 17, 4 * E))
-    for _ in range(3):
+                    env_id_base=rank * E, seed=2026, replay_capacity=max(1 << 17, 4 * E), overlap=overlap)
+    for _ in range(max(3, -(-B // E) + 2)):
         tr.step()
     torch.cuda.synchronize(dev)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-    seg = [0.0, 0.0, 0.0, 0.0]
+    K = loop_steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)] if not overlap else None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     l0 = tr.env.launch_count + tr.agent.net.launch_count + tr.agent.memory.launch_count
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.loop_steps):
+    if overlap:
+        for _ in range(K):
+            tr.step()
+        tr.join()
+    else:
         a, e = tr.agent, tr.env
-        o, o2 = tr.obs[tr.cur], tr.obs[tr.cur ^ 1]
-        ev[0].record()
-        actions = a.act_batch(o, training=True)
-        ev[1].record()
-        e.step_into(actions, o2, tr.reward, tr.done)
-        ev[2].record()
-        a.remember_batch(o, actions, tr.reward, o2, tr.done)
-        ev[3].record()
-        a.learn_device()
-        ev[4].record()
-        tr.cur ^= 1
-        torch.cuda.synchronize(dev)
-        for k in range(4):
-            seg[k] += ev[k].elapsed_time(ev[k + 1])
+        for k in range(K):
+            o, o2 = tr.obs[tr.cur], tr.obs[tr.cur ^ 1]
+            ev[k][0].record()
+            actions = a.act_batch(o, training=True)
+            ev[k][1].record()
+            e.step_into(actions, o2, tr.reward, tr.done)
+            ev[k][2].record()
+            a.remember_batch(o, actions, tr.reward, o2, tr.done)
+            ev[k][3].record()
+            a.learn_device()
+            ev[k][4].record()
+            tr.cur ^= 1
     t1.record(); torch.cuda.synchronize(dev)
     if world > 1:
         dist.barrier()
-    total_ms = t0.elapsed_time(t1)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    K = args.loop_steps
+    total_ms = max_over_ranks(t0.elapsed_time(t1), dev)
     launches = tr.env.launch_count + tr.agent.net.launch_count + tr.agent.memory.launch_count - l0
-    learn_ms = seg[3] / K
-    return {"metric": "learner transitions/s (full act->step->push->learn loop)", "value": world * B * K / (total_ms * 1e-3),
-            "unit": "transitions/s", "batch_per_gpu": B, "loop_steps": K, "ms_per_loop_step": total_ms / K,
-            "env_agent_steps_per_s_in_loop": world * E * N * K / (total_ms * 1e-3),
-            "segments_ms": {"act": seg[0] / K, "env_step": seg[1] / K, "replay_push": seg[2] / K, "sample+learn": learn_ms},
-            "qnet_dtype": "bf16 tcgen05 tensor cores (conv1-3, fc1, fc2), fp32 accumulate + master weights" if precision == "bf16"
-            else "f32 (parity path, CUDA-core FFMA)", "learn_tflops": 155.4e6 * B / (learn_ms * 1e-3) / 1e12,
-            "act_tflops": 38.85e6 * E / (seg[0] / K * 1e-3) / 1e12, "gpu_launches": int(launches),
-            "allreduce": "nccl all-reduce of the flat 8,157,093-float gradient per learn step" if world > 1 else None}
+    res = {"metric": "learner transitions/s (full act->step->push->sample+learn loop)", "value": world * B * K / (total_ms * 1e-3),
+           "unit": "transitions/s", "batch_per_gpu": B, "act_batch_per_gpu": E, "loop_steps": K, "ms_per_loop_step": total_ms / K,
+           "env_agent_steps_per_s_in_loop": world * E * N * K / (total_ms * 1e-3),
+           "qnet_dtype": "bf16 tcgen05 tensor cores (conv1-3, fc1, fc2), fp32 accumulate + master weights" if precision == "bf16"
+           else "f32 (parity path, CUDA-core FFMA)", "gpu_launches": int(launches),
+           "allreduce": "nccl all-reduce of the flat 8,157,093-float gradient per learn step, overlapped with the conv backward" if world > 1 else None,
+           "schedule": "env step + push on a second stream concurrently with sample + learn (learns on the ring as of the previous push)" if overlap
+           else "sequential, the reference's order (train_dqn.py:98-125)"}
+    if not overlap:
+        seg = [sum(ev[k][j].elapsed_time(ev[k][j + 1]) for k in range(K)) / K for j in range(4)]
+        learn_ms = seg[3]
+        res["segments_ms"] = {"act": seg[0], "env_step": seg[1], "replay_push": seg[2], "sample+learn": learn_ms}
+        res["act_tflops"] = ACT_FLOP * E / (seg[0] * 1e-3) / 1e12
+        peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) if precision == "bf16" else None
+        tfl = LEARN_FLOP * B / (learn_ms * 1e-3) / 1e12
+        res["roofline"] = {"bound": "tensor", "kernel": "sample + learn step (2 forwards, backward, clip + Adam; tcgen05 convs / GEMMs)",
+                           "achieved": tfl, "peak": peak, "unit": "TFLOP/s", "frac": (tfl / peak) if peak else None, "traffic": None,
+                           "algorithmic_flop_per_step": LEARN_FLOP * B, "ms": learn_ms,
+                           "peak_source": peak_src + " bf16_tflops_sustained (kernels timed inside a long step)" if peak else
+                           "fp32 CUDA-core path: no tensor-pipe peak applies (B200 fp32 FFMA peak ~74 TFLOP/s)"}
+    # data-parallel replicas must hold the same weights after the loop
+    chk = tr.agent.net.flat_p.double().sum().reshape(1)
+    res["param_checksum"] = float(chk.item())
+    if world > 1:
+        gathered = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(gathered, chk)
+        res["replicas_identical"] = bool(all(torch.equal(gathered[0], x) for x in gathered))
+    if host_fed_steps > 0:
+        res["e2e"] = run_host_fed_learner(tr, B, host_fed_steps, dev, world)
+    tr.close()
+    del tr
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_host_fed_learner(tr, B, steps, dev, world):
+    """e2e of the learner metric: the learn step fed from HOST memory through the agent's public call — every step copies a
+    batch of B transitions (states, actions, rewards, next_states, dones) from pinned host memory (H2D), runs the learn step
+    and reads the loss back to the host (D2H), inside the timed region (VecDQNAgent.learn_host: two device slots, the copy of
+    batch k+1 overlaps the learn step of batch k)."""
+    import torch
+    import torch.distributed as dist
+    from dqn_marl_b200.parallel import max_over_ranks
+    a = tr.agent
+    n_host = 4
+    g = torch.Generator().manual_seed(5)
+    host = [dict(states=torch.rand((B, 11, 11, 6), generator=g).pin_memory(), actions=torch.randint(0, 5, (B,), generator=g).pin_memory(),
+                 rewards=torch.rand((B,), generator=g).pin_memory(), next_states=torch.rand((B, 11, 11, 6), generator=g).pin_memory(),
+                 dones=(torch.rand((B,), generator=g) < 0.05).to(torch.uint8).pin_memory()) for _ in range(n_host)]
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values())
+    for k in range(3):
+        a.learn_host(host[k % n_host])
+    a.learn_host_wait()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        a.learn_host(host[k % n_host])
+    loss = a.learn_host_wait()
+    torch.cuda.synchronize(dev)
+    dt = max_over_ranks(time.perf_counter() - t0, dev)
+    return {"value": world * B * steps / dt, "unit": "transitions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "steps": steps,
+            "ms_per_step": dt / steps * 1e3, "last_loss": float(loss),
+            "note": "VecDQNAgent.learn_host(batch in pinned host memory): H2D of the batch, learn step, loss read back every step"}
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    layout = make_layout(wl)
+    E, N = wl["envs"], wl["people"]
+    sampler = ClockSampler(local) if (rank == 0 and not os.environ.get('MQ_BENCH_NO_SAMPLER')) else None      # started early: nvidia-smi needs ~100 ms before its first sample
+    envr = run_env_legs(args, wl, layout, dev, rank, world, sampler)
+    clocks = sampler.stop() if sampler else None
+
+    replay = run_replay_leg(args, dev) if args.replay_batch > 0 else None
+    learner = learner_fp32 = learner_ovl = None
+    if not args.no_learner and args.loop_steps > 0:
+        learner = run_learner_loop(args, wl, layout, dev, rank, world, "bf16", args.loop_steps, host_fed_steps=args.host_fed_steps)
+        if args.overlap_loop:
+            learner_ovl = run_learner_loop(args, wl, layout, dev, rank, world, "bf16", args.loop_steps, overlap=True)
+        if args.fp32_loop_steps > 0:
+            learner_fp32 = run_learner_loop(args, wl, layout, dev, rank, world, "fp32", args.fp32_loop_steps)
+    secondary = None
+    if args.workload != "c2" and args.c2_steps > 0 and world == 1:
+        wl2 = WORKLOADS["c2"]
+        lay2 = make_layout(wl2)
+        a2 = argparse.Namespace(**vars(args)); a2.steps = args.c2_steps; a2.warmup = 50
+        r2 = run_env_legs(a2, wl2, lay2, dev, rank, world, None, e2e=False)
+        peaks, _ = measured_peaks()
+        alg2 = algorithmic_bytes_per_env_step(lay2.L, lay2.W, wl2["people"]) * wl2["envs"]
+        ach2 = alg2 / (r2["ms_per_step"] * 1e-3) / 1e9
+        secondary = {"workload": wl2["desc"], "value": r2["value"], "unit": "agent-steps/s", "ms_per_step": r2["ms_per_step"], "steps": args.c2_steps,
+                     "value_l2_resident": r2["value_l2_resident"],
+                     "roofline": {"bound": "hbm", "kernel": "env_step_kernel<1,28,false>", "achieved": ach2, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                  "frac": ach2 / peaks["hbm_gbs"], "traffic": load_traffic("c2"), "algorithmic_bytes_per_launch": alg2}}
+
+    if rank == 0:
+        peaks, peak_src = measured_peaks()
+        alg = algorithmic_bytes_per_env_step(layout.L, layout.W, N) * E
+        kernel_ms = envr["ms_per_step"]
+        achieved = alg / (kernel_ms * 1e-3) / 1e9
+        n_rot, state_bytes = envr["n_rot"], envr["state_bytes"]
+        line = {
+            "metric": "env agent-steps/s", "value": envr["value"], "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": envr["warmup"], "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl["desc"], "envs_per_gpu": E, "people": N, "grid": [layout.L, layout.W],
+                       "l2": f"inputs larger than L2: timed loop rotates over {n_rot} independent batches "
+                             f"({n_rot * state_bytes / 1e6:.0f} MB of state > 126 MB L2)",
+                       "reset_policy": "auto-reset, fresh fire per episode (strict_reference=False)",
+                       "prime_steps": args.prime, "learner_batch_per_gpu": args.learner_batch or wl["learner_batch"]},
+            "clocks": clocks,
+            "e2e": envr["e2e"],
+            "gpu_launches": envr["launches"],
+            "roofline": {"bound": "hbm", "kernel": "env_step_kernel", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": load_traffic(args.workload),
+                         "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                         "note": "canonical bytes of SURVEY.md §8d (uint8 occupancy, 24 B/person); this build packs "
+                                 "occupancy to 1 bit/cell and rewrites only changed person fields, so it moves fewer bytes"},
+            "value_l2_resident": envr["value_l2_resident"],
+        }
+        if replay is not None:
+            line["replay"] = replay
+        if learner is not None:
+            line["learner"] = learner
+        if learner_ovl is not None:
+            line["learner_overlapped"] = learner_ovl
+        if learner_fp32 is not None:
+            line["learner_fp32"] = learner_fp32
+        if secondary is not None:
+            line["secondary_c2"] = secondary
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            line["cpu_baseline"] = cpu_env_baseline(layout, wl, threads)
+            if learner is not None:
+                lb = cpu_learner_baseline(args.learner_batch or wl["learner_batch"])
+                learner["cpu_baseline"] = lb
+                if learner_fp32 is not None:
+                    learner_fp32["cpu_baseline"] = lb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=600)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--prime", type=int, default=150, help="untimed steps per batch before warm-up")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--loop-steps", type=int, default=8, help="steps of the full act/step/push/learn loop (0 = skip)")
-    ap.add_argument("--learner-batch", type=int, default=4096)
-    ap.add_argument("--fp32-loop", type=int, default=1, help="also run the loop with the fp32 parity path")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-learner", action="store_true", help="skip the learner legs")
+    ap.add_argument("--loop-steps", type=int, default=200, help="steps of the full act/step/push/learn loop, bf16 path (0 = skip)")
+    ap.add_argument("--fp32-loop-steps", type=int, default=10, help="steps of the same loop on the fp32 parity path (0 = skip)")
+    ap.add_argument("--overlap-loop", type=int, default=1, help="also run the loop with env step + push overlapped with sample + learn")
+    ap.add_argument("--host-fed-steps", type=int, default=60, help="learn steps fed from pinned host batches (learner e2e; 0 = skip)")
+    ap.add_argument("--learner-batch", type=int, default=0, help="learn batch per GPU (0 = the workload's: 4096, C5: 8192)")
     ap.add_argument("--replay-batch", type=int, default=65536, help="replay sample batch of the bandwidth leg (0 = skip)")
+    ap.add_argument("--c2-steps", type=int, default=3000, help="steps of the secondary C2 env-only run (0 = skip)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

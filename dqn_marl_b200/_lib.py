@@ -68,6 +68,8 @@ SIGNATURES = {
     "mq_floor_field_device": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mq_env_state_sizes": (C.c_int, [C.POINTER(MqEnvCfg), C.POINTER(MqLayout), C.POINTER(_i64), C.POINTER(_i64)]),
     "mq_env_create": (C.c_int, [C.POINTER(_vp), C.POINTER(MqEnvCfg), C.POINTER(MqLayout), C.POINTER(MqEnvState)]),
+    "mq_env_create_layouts": (C.c_int, [C.POINTER(_vp), C.POINTER(MqEnvCfg), C.POINTER(MqLayout), _i32, _vp, _i32, C.POINTER(MqEnvState)]),
+    "mq_layout_tables_device": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "mq_env_destroy": (C.c_int, [_vp]),
     "mq_env_set_reward_coefs": (C.c_int, [_vp, _f64, _f64, _f64, _f64]),
     "mq_env_reset": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -79,6 +81,7 @@ SIGNATURES = {
     "mq_replay_size": (_i64, [_vp]),
     "mq_replay_cursor": (_i64, [_vp]),
     "mq_replay_launch_count": (_i64, [_vp]),
+    "mq_replay_restore": (C.c_int, [_vp, _i64, _i64]),
     "mq_replay_push": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "mq_replay_sample": (C.c_int, [_vp, _i64, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mq_qnet_create": (C.c_int, [C.POINTER(_vp), _i32, _i64, C.POINTER(MqQnetBind)]),
@@ -147,6 +150,25 @@ def floor_field(L, W, wall, exits, add_term):
     out = np.empty((L + 2, W + 2), dtype=np.float64)
     check(lib.mq_floor_field(L, W, ptr(wall), ptr(exits), len(exits), ptr(add), ptr(out)), "mq_floor_field")
     return out
+
+
+def layout_tables_device(L, W, space, barrier, exits, n_exits, obs_exit, stream=None):
+    """mq_layout_tables_device: (dp5 (n, L+2, W+2, 8) float64, cellinfo (n, L+2, W+2) uint8) CUDA tensors from the floor fields of
+    a batch of layouts (what Layout.build derives on the host for one)."""
+    import torch
+    lib = load()
+    n = space.shape[0]
+    space = space.to(torch.float64).contiguous()
+    barrier = barrier.to(torch.uint8).contiguous()
+    exits = exits.to(torch.int32).contiguous()
+    n_exits = n_exits.to(torch.int32).contiguous()
+    obs_exit = obs_exit.to(torch.int32).contiguous()
+    dp5 = torch.empty((n, L + 2, W + 2, 8), dtype=torch.float64, device=space.device)
+    info = torch.empty((n, L + 2, W + 2), dtype=torch.uint8, device=space.device)
+    st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(space.device).cuda_stream)
+    check(lib.mq_layout_tables_device(L, W, n, ptr(space), ptr(barrier), ptr(exits), exits.shape[1], ptr(n_exits), ptr(obs_exit), ptr(dp5),
+                                      ptr(info), st), "mq_layout_tables_device")
+    return dp5, info
 
 
 def floor_field_device(L, W, wall, exits, n_exits, add_term=None, stream=None):

@@ -20,7 +20,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from .. import _lib
+from .. import _lib, parallel
 from ..replay import ReplayRing
 from . import qnet_params as qp
 from .qnet import QNet
@@ -261,6 +261,31 @@ class DQNAgent:
             "steps": self.steps,
         }, filepath)
 
+    # -- full training state (the reference's checkpoint + what it leaves out) -------------------------
+    _COUNTERS = ("steps", "_adam_t", "_act_calls", "_mask_calls", "epsilon", "seed")
+
+    def training_state_dict(self) -> dict:
+        """Everything needed to continue training bit-identically: the reference-format checkpoint (networks + Adam state +
+        epsilon + steps, dqn_agent.py:176-182) plus the replay ring and the keyed-draw counters the reference does not save."""
+        sd = {"checkpoint": {"q_network": OrderedDict((k, v.cpu()) for k, v in self.q_network.state_dict().items()),
+                             "target_network": OrderedDict((k, v.cpu()) for k, v in self.target_network.state_dict().items()),
+                             "optimizer": self.optimizer.state_dict(), "epsilon": self.epsilon, "steps": self.steps},
+              "replay": self.memory.state_dict(),
+              "counters": {k: getattr(self, k) for k in self._COUNTERS}}
+        for k in ("_tick", "_pushes"):
+            if hasattr(self, k):
+                sd["counters"][k] = getattr(self, k)
+        return sd
+
+    def load_training_state_dict(self, sd: dict):
+        ck = sd["checkpoint"]
+        self.q_network.load_state_dict(ck["q_network"])
+        self.target_network.load_state_dict(ck["target_network"])
+        self.optimizer.load_state_dict(ck["optimizer"])
+        for k, v in sd["counters"].items():
+            setattr(self, k, v)
+        self.memory.load_state_dict(sd["replay"])
+
     def load(self, filepath, allow_pickle: bool = False):
         """dqn_agent.py:184-191.  Reference-format checkpoints hold only tensors, dicts and primitives, so they load with
         `weights_only=True`; `allow_pickle=True` is the explicit opt-in for files that need the unsafe unpickler."""
@@ -292,11 +317,7 @@ class VecDQNAgent(DQNAgent):
             self.update_target_network()
         # transitions every rank is guaranteed to have pushed per remember_batch(): env shards may differ by one env
         # (parallel.env_shard), and the learn gate must open on the SAME step everywhere because learn_device() is a collective
-        self.min_push = n_envs * n_robots
-        if self.world > 1:
-            t = torch.tensor([self.min_push], dtype=torch.int64, device=self.net.device)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.pg)
-            self.min_push = int(t.item())
+        self.min_push = parallel.min_over_ranks(n_envs * n_robots, self.net.device, self.pg)
         self._pushes = 0
         self._actions = torch.zeros((n_envs * n_robots,), dtype=torch.int32, device=self.net.device)
         self._tick = 0
@@ -325,8 +346,7 @@ class VecDQNAgent(DQNAgent):
         every rank agrees on — the number of remember_batch() calls times the smallest shard's push size and the replicated
         step counter — so that all ranks enter the collective learn step together (a rank-local len(memory) opens one step
         apart when n_envs % world != 0 and the run hangs in NCCL)."""
-        filled = min(self._pushes * self.min_push, self.memory.capacity)
-        return filled > self.batch_size and self.steps >= self.warmup_steps
+        return parallel.learn_gate_open(self._pushes, self.min_push, self.memory.capacity, self.batch_size, self.steps, self.warmup_steps)
 
     def _allreduce_grads(self):
         if self.world > 1:
@@ -340,26 +360,71 @@ class VecDQNAgent(DQNAgent):
         gate of ready_to_learn() is closed."""
         if not self.ready_to_learn():
             return None
-        B = self.batch_size
-        batch = self.memory.sample(B, out=getattr(self, "_batch", None))
-        self._batch = batch
+        return self.learn_on(self.sample_batch())
+
+    def sample_batch(self) -> dict:
+        """random.sample + stacking (dqn_agent.py:132-140) into this agent's resident batch tensors."""
+        self._batch = self.memory.sample(self.batch_size, out=getattr(self, "_batch", None))
+        return self._batch
+
+    def learn_on(self, batch: dict) -> torch.Tensor:
+        """dqn_agent.py:143-166 on a batch that is already on the device (sampled, or copied from the host by learn_host)."""
+        B = batch["actions"].shape[0]
         train = self.dropout_mode == "train"
         self._adam_t += 1
         hp = self._hparams()
         m_on, m_tg = (self._mask(B) if train else None), (self._mask(B) if train else None)
-        if self.world > 1:
-            # the one exchange step (SURVEY.md §8e), overlapped: the all-reduce of the fc gradients (99 % of the bytes) runs on
-            # NCCL's stream while the convolution backward is still computing; the small conv slice follows
-            head = qp.OFFSETS[6]
-            loss = self.net.td_backward(batch, hp, m_on, m_tg, part=1)
-            w1 = torch.distributed.all_reduce(self.net.flat_g[head:], group=self.pg, async_op=True)
-            self.net.td_backward(batch, hp, m_on, m_tg, part=2)
-            w2 = torch.distributed.all_reduce(self.net.flat_g[:head], group=self.pg, async_op=True)
-            w1.wait(); w2.wait()
-        else:
-            loss = self.net.td_backward(batch, hp, m_on, m_tg)
+        loss = self.grad_step(batch, hp, m_on, m_tg)
         self.net.clip_adam(hp, self._grad_scale())
         if self.epsilon > self.epsilon_min:
             self.epsilon *= self.epsilon_decay
         self.steps += 1
         return loss
+
+    def grad_step(self, batch: dict, hp, m_on=None, m_tg=None) -> torch.Tensor:
+        """Loss + backward of this rank's batch into flat_g and, when data-parallel, the SUM over ranks of flat_g (the one exchange
+        step); `_grad_scale()` = 1/world turns it into the gradient of the global batch mean inside clip_adam."""
+        if self.world > 1:
+            # the all-reduce of the fc gradients (99 % of the bytes) runs on NCCL's stream while the convolution backward is
+            # still computing; the small conv slice follows (parallel.allreduce_overlapped)
+            loss = parallel.allreduce_overlapped(self.net.flat_g, qp.OFFSETS[6],
+                                                 lambda: self.net.td_backward(batch, hp, m_on, m_tg, part=1),
+                                                 lambda: self.net.td_backward(batch, hp, m_on, m_tg, part=2), self.pg)
+        else:
+            loss = self.net.td_backward(batch, hp, m_on, m_tg)
+        return loss
+
+    # -- host-fed learner (bench.py's learner e2e; a learner process that receives batches from remote actors) --------------
+    def learn_host(self, host_batch: dict) -> None:
+        """One learn step on a batch that lives in (pinned) HOST memory: states / next_states f32 (B,11,11,6), actions i64 (B,),
+        rewards f32 (B,), dones u8 (B,).  The H2D copy runs on a private copy stream into one of two device slots, so the copy
+        of the next batch overlaps this batch's learn step; the loss is copied back to pinned host memory every step
+        (`learn_host_wait()` returns the latest)."""
+        dev = self.net.device
+        main = torch.cuda.current_stream(dev)
+        B = host_batch["actions"].shape[0]
+        hf = getattr(self, "_hf", None)
+        if hf is None or hf["B"] != B:
+            def slot():
+                return dict(states=torch.empty((B, 11, 11, 6), dtype=torch.float32, device=dev), actions=torch.empty((B,), dtype=torch.int64, device=dev),
+                            rewards=torch.empty((B,), dtype=torch.float32, device=dev), next_states=torch.empty((B, 11, 11, 6), dtype=torch.float32, device=dev),
+                            dones=torch.empty((B,), dtype=torch.uint8, device=dev))
+            hf = self._hf = dict(B=B, k=0, cs=torch.cuda.Stream(device=dev), slots=[slot(), slot()],
+                                 free=[torch.cuda.Event(), torch.cuda.Event()], ready=[torch.cuda.Event(), torch.cuda.Event()],
+                                 loss=torch.zeros(1, dtype=torch.float32).pin_memory())
+        s = hf["k"] % 2
+        if hf["k"] >= 2:
+            hf["cs"].wait_event(hf["free"][s])            # the learn step that last read this slot has finished
+        with torch.cuda.stream(hf["cs"]):
+            for key, t in hf["slots"][s].items():
+                t.copy_(host_batch[key], non_blocking=True)
+            hf["ready"][s].record(hf["cs"])
+        main.wait_event(hf["ready"][s])
+        loss = self.learn_on(hf["slots"][s])
+        hf["free"][s].record(main)
+        hf["loss"].copy_(loss, non_blocking=True)
+        hf["k"] += 1
+
+    def learn_host_wait(self) -> float:
+        torch.cuda.current_stream(self.net.device).synchronize()
+        return float(self._hf["loss"][0])

@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 #include "common.h"
 #include "philox.cuh"
 
@@ -45,7 +46,38 @@ struct DevLayout {
     const uint8_t* cellinfo;
     const double* danger_ctr;
     const double* danger_int;
+    // several layouts in one batch (mq_env_create_layouts): tables of layout k start at dp5 + k*G*8, cellinfo + k*G and at the
+    // danger-table offsets of its LMETA row; env_layout[env] = k.  All layouts share L x W and the number of fire steps.
+    const int* env_layout;
+    const int* meta;
 };
+
+// per-layout ints (row of DevLayout::meta)
+enum { LM_CTR_BOX = 0, LM_INT_BOX = 4, LM_ROBOT_RANGE = 8, LM_ROBOT_START = 10, LM_RESET_CENTER = 18, LM_OBS_EXIT = 20,
+       LM_CTR_OFF = 22 /* long long, in doubles */, LM_INT_OFF = 24, LMETA = 32 };
+
+// The kernels take the layout of a single-layout batch straight from the kernel parameters (constant bank).  MULTI variants
+// overwrite their private copy with the tables of this env's layout.
+template <bool MULTI>
+__device__ __forceinline__ void select_layout(DevLayout& lay, int env) {
+    if (!MULTI) return;
+    const int li = __ldg(lay.env_layout + env);
+    const int* m = lay.meta + (size_t)li * LMETA;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { lay.ctr_box[k] = __ldg(m + LM_CTR_BOX + k); lay.int_box[k] = __ldg(m + LM_INT_BOX + k); }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        lay.robot_range[k] = __ldg(m + LM_ROBOT_RANGE + k);
+        lay.reset_center[k] = __ldg(m + LM_RESET_CENTER + k);
+        lay.obs_exit[k] = __ldg(m + LM_OBS_EXIT + k);
+    }
+#pragma unroll
+    for (int k = 0; k < MAXR * 2; ++k) lay.robot_start[k >> 1][k & 1] = __ldg(m + LM_ROBOT_START + k);
+    lay.dp5 += (size_t)li * lay.G * 8;
+    lay.cellinfo += (size_t)li * lay.G;
+    lay.danger_ctr += *reinterpret_cast<const long long*>(m + LM_CTR_OFF);
+    lay.danger_int += *reinterpret_cast<const long long*>(m + LM_INT_OFF);
+}
 
 struct DevCfg {
     int n_envs, N, n_pad, R;
@@ -257,9 +289,9 @@ __device__ void reset_env(const Group<WPE, CW>& g, const DevLayout& lay, const D
     gather_obs(tid, T, lay, cfg, sm, rob, sc[MQ_S_ROBOT_POS_X], sc[MQ_S_ROBOT_POS_Y], sc[MQ_S_FIRE_STEP], obs, obs64, env);
 }
 
-template <int WPE, int CW, bool BIG>
+template <int WPE, int CW, bool BIG, bool MULTI>
 __global__ void __launch_bounds__(32 * CW)
-env_reset_kernel(DevLayout lay, DevCfg cfg, DevState st, const uint8_t* env_mask, const int16_t* inject, float* obs,
+env_reset_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const uint8_t* env_mask, const int16_t* inject, float* obs,
                  double* obs64) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GROUPS = CW / WPE;
@@ -269,6 +301,8 @@ env_reset_kernel(DevLayout lay, DevCfg cfg, DevState st, const uint8_t* env_mask
     const int env = blockIdx.x * GROUPS + g.gid;
     if (env >= cfg.n_envs) return;
     if (env_mask && !env_mask[env]) return;
+    DevLayout lay = lay_in;
+    select_layout<MULTI>(lay, env);
     Smem sm;
     carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
           cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE);
@@ -425,9 +459,9 @@ __device__ long long g_env_trace[16];
 #endif
 constexpr int SCORE_UNROLL = 2;     // movers scored per lane and iteration of phase 2 (independent chains)
 
-template <int WPE, int CW, bool BIG>
+template <int WPE, int CW, bool BIG, bool MULTI>
 __global__ void __launch_bounds__(32 * CW, WPE < 8 ? 28 / CW : (BIG ? 1 : 3))      // 28 env-warps / 3 env-CTAs resident per SM (BIG: one)
-env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ actions, float* obs, double* obs64,
+env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict__ actions, float* obs, double* obs64,
                 double* reward_out, uint8_t* done_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using G = Group<WPE, CW>;
@@ -441,10 +475,14 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
     __shared__ double s_sum_all[GROUPS][2];     // sum of distances, total health
     __shared__ int s_pre[GROUPS + 1];           // COOP: exclusive prefix of the envs' scoring chunks
     __shared__ int s_lvl_all[WPE >= 8 ? GROUPS : 1][20];   // wide groups: first node of every level of the np.mean tree, [19] = levels
+    __shared__ const double* s_dp5[MULTI ? GROUPS : 1];    // MULTI + COOP: the dp5 table of every env of the CTA
 
     const G g;
     const int env = blockIdx.x * GROUPS + g.gid;
     if (env >= cfg.n_envs) return;              // whole group leaves together (GROUPS == 1 when WPE == CW)
+    DevLayout lay = lay_in;
+    select_layout<MULTI>(lay, env);
+    if (MULTI && g.gtid == 0) s_dp5[g.gid] = lay.dp5;
 #ifdef MQ_ENV_TRACE
     long long _tprev = clock64();
 #endif
@@ -656,7 +694,8 @@ env_step_kernel(DevLayout lay, DevCfg cfg, DevState st, const int* __restrict__ 
                     x[u] = (int)(p & 0xFFFFu); y[u] = (int)(p >> 16);
                     dpv[u][0] = -INFINITY; dpv[u][1] = -INFINITY;
                     if (act[u]) {
-                        const double2 v = __ldg(reinterpret_cast<const double2*>(lay.dp5 + (size_t)(x[u] * stride + y[u]) * 8) + q);
+                        const double* dp5e = MULTI ? s_dp5[e] : lay.dp5;
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(dp5e + (size_t)(x[u] * stride + y[u]) * 8) + q);
                         dpv[u][0] = v.x; dpv[u][1] = v.y;
                     }
                 }
@@ -1088,6 +1127,8 @@ struct mq_env {
     mq::DevCfg cfg;
     mq::DevState st;
     void* d_dp5 = nullptr; void* d_cellinfo = nullptr; void* d_ctr = nullptr; void* d_int = nullptr;
+    void* d_meta = nullptr; void* d_env_layout = nullptr;
+    int n_layouts = 1;
     int device = 0;
     int wpe = 8;            // warps per env: 1 (4 envs per 128-thread CTA), 8 (one 256-thread CTA per env), 16 / 32 (BIG)
     bool big = false;       // per-person arrays + proposal table in global scratch (envs too large for shared memory)
@@ -1116,23 +1157,38 @@ extern "C" int mq_env_state_sizes(const mq_env_cfg* cfg, const mq_layout* layout
 // kernel variants: (warps per env, warps per CTA, BIG)
 typedef void (*StepFn)(mq::DevLayout, mq::DevCfg, mq::DevState, const int*, float*, double*, double*, uint8_t*);
 typedef void (*ResetFn)(mq::DevLayout, mq::DevCfg, mq::DevState, const uint8_t*, const int16_t*, float*, double*);
-struct Variant { int wpe, cw; bool big; StepFn step; ResetFn reset; };
-#define MQ_VARIANT(WPE, CW, BIG) {WPE, CW, BIG, mq::env_step_kernel<WPE, CW, BIG>, mq::env_reset_kernel<WPE, CW, BIG>}
+struct Variant { int wpe, cw; bool big, multi; StepFn step; ResetFn reset; };
+#define MQ_VARIANT(WPE, CW, BIG, MULTI) {WPE, CW, BIG, MULTI, mq::env_step_kernel<WPE, CW, BIG, MULTI>, mq::env_reset_kernel<WPE, CW, BIG, MULTI>}
 static const Variant k_variants[] = {
-    MQ_VARIANT(1, SMALL_CW, false), MQ_VARIANT(1, 14, false), MQ_VARIANT(1, 28, false), MQ_VARIANT(2, SMALL_CW, false), MQ_VARIANT(4, SMALL_CW, false), MQ_VARIANT(8, 8, false), MQ_VARIANT(8, 8, true), MQ_VARIANT(16, 16, true), MQ_VARIANT(32, 32, true),
+    MQ_VARIANT(1, SMALL_CW, false, false), MQ_VARIANT(1, 14, false, false), MQ_VARIANT(1, 28, false, false), MQ_VARIANT(2, SMALL_CW, false, false),
+    MQ_VARIANT(4, SMALL_CW, false, false), MQ_VARIANT(8, 8, false, false), MQ_VARIANT(8, 8, true, false), MQ_VARIANT(16, 16, true, false),
+    MQ_VARIANT(32, 32, true, false),
+    // several layouts per batch: the shapes mq_env_create picks by default
+    MQ_VARIANT(1, SMALL_CW, false, true), MQ_VARIANT(1, 14, false, true), MQ_VARIANT(1, 28, false, true), MQ_VARIANT(8, 8, false, true),
+    MQ_VARIANT(32, 32, true, true),
 };
-static int find_variant(int wpe, bool big, int cw = 0) {
+static int find_variant(int wpe, bool big, bool multi, int cw = 0) {
     for (int i = 0; i < (int)(sizeof(k_variants) / sizeof(k_variants[0])); ++i)
-        if (k_variants[i].wpe == wpe && k_variants[i].big == big && (cw == 0 || k_variants[i].cw == cw)) return i;
+        if (k_variants[i].wpe == wpe && k_variants[i].big == big && k_variants[i].multi == multi && (cw == 0 || k_variants[i].cw == cw)) return i;
     return -1;
 }
 
-extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layout* layout, const mq_env_state* state) {
-    MQ_REQUIRE(out && cfg && layout && state, "mq_env_create: null argument");
+extern "C" int mq_env_create_layouts(mq_env** out, const mq_env_cfg* cfg, const mq_layout* layouts, int32_t n_layouts,
+                                     const int32_t* env_layout, int32_t tables_on_device, const mq_env_state* state) {
+    MQ_REQUIRE(out && cfg && layouts && state && n_layouts >= 1, "mq_env_create: null argument");
+    MQ_REQUIRE(n_layouts == 1 || env_layout, "mq_env_create_layouts: env_layout is required when there are several layouts");
+    const mq_layout* layout = &layouts[0];
     MQ_REQUIRE(cfg->n_envs > 0 && cfg->n_people > 0, "mq_env_create: n_envs and n_people must be positive");
     MQ_REQUIRE(cfg->n_robots >= 1 && cfg->n_robots <= MQ_MAX_ROBOTS, "mq_env_create: n_robots must be in 1..%d", MQ_MAX_ROBOTS);
     MQ_REQUIRE(layout->L >= 3 && layout->W >= 3 && layout->L <= 32000 && layout->W <= 32000, "mq_env_create: bad grid size");
-    MQ_REQUIRE(layout->dp5 && layout->cellinfo && layout->danger_ctr && layout->danger_int, "mq_env_create: layout tables missing");
+    for (int k = 0; k < n_layouts; ++k) {
+        MQ_REQUIRE(layouts[k].dp5 && layouts[k].cellinfo && layouts[k].danger_ctr && layouts[k].danger_int, "mq_env_create: tables of layout %d missing", k);
+        MQ_REQUIRE(layouts[k].L == layout->L && layouts[k].W == layout->W && layouts[k].n_fire_steps == layout->n_fire_steps,
+                   "mq_env_create_layouts: layout %d differs in L x W or fire steps from layout 0", k);
+    }
+    if (n_layouts > 1)
+        for (int e = 0; e < cfg->n_envs; ++e)
+            MQ_REQUIRE(env_layout[e] >= 0 && env_layout[e] < n_layouts, "mq_env_create_layouts: env_layout[%d] = %d outside 0..%d", e, env_layout[e], n_layouts - 1);
     MQ_REQUIRE(state->pos && state->health && state->acc && state->flags && state->rmap && state->robots && state->scalars,
                "mq_env_create: state buffers missing");
     MQ_REQUIRE(cfg->n_people <= 65000, "mq_env_create: at most 65000 people per env (16-bit list indices)");
@@ -1156,17 +1212,54 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     memcpy(l.robot_start, layout->robot_start, sizeof(l.robot_start));
     memcpy(l.reset_center, layout->reset_obs_center, sizeof(l.reset_center));
     memcpy(l.obs_exit, layout->obs_exit, sizeof(l.obs_exit));
+    l.env_layout = nullptr; l.meta = nullptr;
 
+    // Tables of all layouts, contiguous per kind.  Danger tables that several layouts share (same source pointer and size: the
+    // usual case of random walls around one fire) are stored once.
     const size_t n_dp5 = (size_t)l.G * 8 * sizeof(double);
-    const size_t n_ctr = (size_t)l.n_fire_steps * l.ctr_box[2] * l.ctr_box[3] * sizeof(double);
-    const size_t n_int = (size_t)l.n_fire_steps * l.int_box[2] * l.int_box[3] * sizeof(double);
+    std::vector<int> meta((size_t)n_layouts * mq::LMETA, 0);
+    std::vector<size_t> ctr_off(n_layouts), int_off(n_layouts), ctr_n(n_layouts), int_n(n_layouts);
+    size_t ctr_total = 0, int_total = 0;
+    for (int k = 0; k < n_layouts; ++k) {
+        const mq_layout& lk = layouts[k];
+        ctr_n[k] = (size_t)lk.n_fire_steps * lk.ctr_box[2] * lk.ctr_box[3];
+        int_n[k] = (size_t)lk.n_fire_steps * lk.int_box[2] * lk.int_box[3];
+        int dup_c = -1, dup_i = -1;
+        for (int q = 0; q < k && (dup_c < 0 || dup_i < 0); ++q) {
+            if (dup_c < 0 && layouts[q].danger_ctr == lk.danger_ctr && ctr_n[q] == ctr_n[k]) dup_c = q;
+            if (dup_i < 0 && layouts[q].danger_int == lk.danger_int && int_n[q] == int_n[k]) dup_i = q;
+        }
+        if (dup_c >= 0) ctr_off[k] = ctr_off[dup_c]; else { ctr_off[k] = ctr_total; ctr_total += ctr_n[k]; }
+        if (dup_i >= 0) int_off[k] = int_off[dup_i]; else { int_off[k] = int_total; int_total += int_n[k]; }
+        int* m = &meta[(size_t)k * mq::LMETA];
+        memcpy(m + mq::LM_CTR_BOX, lk.ctr_box, 4 * sizeof(int)); memcpy(m + mq::LM_INT_BOX, lk.int_box, 4 * sizeof(int));
+        memcpy(m + mq::LM_ROBOT_RANGE, lk.robot_range, 2 * sizeof(int)); memcpy(m + mq::LM_ROBOT_START, lk.robot_start, 8 * sizeof(int));
+        memcpy(m + mq::LM_RESET_CENTER, lk.reset_obs_center, 2 * sizeof(int)); memcpy(m + mq::LM_OBS_EXIT, lk.obs_exit, 2 * sizeof(int));
+        const long long co = (long long)ctr_off[k], io = (long long)int_off[k];
+        memcpy(m + mq::LM_CTR_OFF, &co, sizeof(co)); memcpy(m + mq::LM_INT_OFF, &io, sizeof(io));
+    }
     cudaError_t ce = cudaSuccess;
-    if ((ce = cudaMalloc(&e->d_dp5, n_dp5)) == cudaSuccess && (ce = cudaMalloc(&e->d_cellinfo, l.G)) == cudaSuccess &&
-        (ce = cudaMalloc(&e->d_ctr, n_ctr)) == cudaSuccess && (ce = cudaMalloc(&e->d_int, n_int)) == cudaSuccess &&
-        (ce = cudaMemcpy(e->d_dp5, layout->dp5, n_dp5, cudaMemcpyHostToDevice)) == cudaSuccess &&
-        (ce = cudaMemcpy(e->d_cellinfo, layout->cellinfo, l.G, cudaMemcpyHostToDevice)) == cudaSuccess &&
-        (ce = cudaMemcpy(e->d_ctr, layout->danger_ctr, n_ctr, cudaMemcpyHostToDevice)) == cudaSuccess &&
-        (ce = cudaMemcpy(e->d_int, layout->danger_int, n_int, cudaMemcpyHostToDevice)) == cudaSuccess) {
+    auto step = [&](cudaError_t r) { if (ce == cudaSuccess) ce = r; };
+    step(cudaMalloc(&e->d_dp5, n_dp5 * n_layouts));
+    step(cudaMalloc(&e->d_cellinfo, (size_t)l.G * n_layouts));
+    step(cudaMalloc(&e->d_ctr, ctr_total * sizeof(double)));
+    step(cudaMalloc(&e->d_int, int_total * sizeof(double)));
+    const cudaMemcpyKind kind = tables_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    for (int k = 0; k < n_layouts && ce == cudaSuccess; ++k) {
+        const mq_layout& lk = layouts[k];
+        step(cudaMemcpy((char*)e->d_dp5 + n_dp5 * k, lk.dp5, n_dp5, kind));
+        step(cudaMemcpy((char*)e->d_cellinfo + (size_t)l.G * k, lk.cellinfo, l.G, kind));
+        bool first_c = true, first_i = true;
+        for (int q = 0; q < k; ++q) { if (ctr_off[q] == ctr_off[k]) first_c = false; if (int_off[q] == int_off[k]) first_i = false; }
+        if (first_c) step(cudaMemcpy((double*)e->d_ctr + ctr_off[k], lk.danger_ctr, ctr_n[k] * sizeof(double), kind));
+        if (first_i) step(cudaMemcpy((double*)e->d_int + int_off[k], lk.danger_int, int_n[k] * sizeof(double), kind));
+    }
+    if (n_layouts > 1) {
+        step(cudaMalloc(&e->d_meta, meta.size() * sizeof(int)));
+        step(cudaMalloc(&e->d_env_layout, (size_t)cfg->n_envs * sizeof(int)));
+        if (ce == cudaSuccess) step(cudaMemcpy(e->d_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice));
+        if (ce == cudaSuccess) step(cudaMemcpy(e->d_env_layout, env_layout, (size_t)cfg->n_envs * sizeof(int), cudaMemcpyHostToDevice));
+        l.meta = (const int*)e->d_meta; l.env_layout = (const int*)e->d_env_layout;
     }
     if (ce != cudaSuccess) {
         mq_env_destroy(e);
@@ -1174,6 +1267,7 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     }
     l.dp5 = (const double*)e->d_dp5; l.cellinfo = (const uint8_t*)e->d_cellinfo;
     l.danger_ctr = (const double*)e->d_ctr; l.danger_int = (const double*)e->d_int;
+    e->n_layouts = n_layouts;
 
     double repel[25];
     for (int d2 = 0; d2 < 25; ++d2) repel[d2] = -20.0 / (std::sqrt((double)d2) + 0.1);    // people.py:94,284
@@ -1229,7 +1323,11 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
         else if (((size_t)c.smem_per_env * 14 + fixed) * 2 <= (size_t)max_smem + 4096) small_cw = 14;
         if (const char* v = getenv("MQ_SMALL_CW")) { int w = atoi(v); if (w == 4 || w == 14 || w == 28) small_cw = w; }
     }
-    e->variant = find_variant(e->wpe, e->big, e->wpe == 1 ? small_cw : 0);
+    e->variant = find_variant(e->wpe, e->big, n_layouts > 1, e->wpe == 1 ? small_cw : 0);
+    if (e->variant < 0) {
+        mq_env_destroy(e);
+        return mq::fail(MQ_ERR_UNSUPPORTED, "mq_env_create_layouts: no multi-layout kernel for %d warps per env (MQ_*_WPE / MQ_SMALL_CW overrides are single-layout only)", e->wpe);
+    }
     const int groups = e->wpe < 8 ? small_cw / e->wpe : 1;
     e->threads = 32 * k_variants[e->variant].cw;
     e->smem = (size_t)c.smem_per_env * groups;
@@ -1258,10 +1356,15 @@ extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layou
     return MQ_OK;
 }
 
+extern "C" int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layout* layout, const mq_env_state* state) {
+    return mq_env_create_layouts(out, cfg, layout, 1, nullptr, 0, state);
+}
+
 extern "C" int mq_env_destroy(mq_env* e) {
     if (!e) return MQ_OK;
     MQ_ON_DEVICE(e->device);
     cudaFree(e->d_dp5); cudaFree(e->d_cellinfo); cudaFree(e->d_ctr); cudaFree(e->d_int); cudaFree(e->d_scratch);
+    cudaFree(e->d_meta); cudaFree(e->d_env_layout);
     delete e;
     return MQ_OK;
 }

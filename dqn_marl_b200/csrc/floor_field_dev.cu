@@ -56,7 +56,62 @@ __global__ void ff_add_kernel(long long total, const double* __restrict__ add_te
     if (v != __longlong_as_double(0x7FF0000000000000LL)) d[idx] = v + add_term[idx];      // map.py:145-147
 }
 
+// dp5 / cellinfo of every layout from its floor field (what dqn_marl_b200/layout.py Layout.build derives on the host):
+//   cellinfo bit0 Check_Valid (map.py:85-92), bit1 obs channel 3 = invalid or in barrier_list (evacuation_env.py:109),
+//   bit2 obs channel 4 = the exit cell (:113), bit3 checkSavefy = Chebyshev distance <= 1 of any exit (map.py:109-112);
+//   dp5[c][d] = (space[c] - space[c + MoveTO[d]]) * 5.0 for valid pairs (people.py:270,288), -inf otherwise.
+__global__ void layout_tables_kernel(int L, int W, int G, long long total, const double* __restrict__ space, const uint8_t* __restrict__ barrier,
+                                     const int32_t* __restrict__ exits, int max_exits, const int32_t* __restrict__ n_exits,
+                                     const int32_t* __restrict__ obs_exit, double* __restrict__ dp5, uint8_t* __restrict__ cellinfo) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int stride = W + 2;
+    const int lay = (int)(idx / G);
+    const long long lay0 = (long long)lay * G;
+    const int c = (int)(idx - lay0);
+    const int x = c / stride, y = c - x * stride;
+    const double INF = __longlong_as_double(0x7FF0000000000000LL);
+    const bool interior = x >= 1 && x <= L && y >= 1 && y <= W;
+    const double sc = space[idx];
+    const bool valid = interior && sc != INF;
+    unsigned info = valid ? 1u : 0u;
+    if (!valid || barrier[idx]) info |= 2u;
+    if (x == obs_exit[lay * 2] && y == obs_exit[lay * 2 + 1]) info |= 4u;
+    const int ne = n_exits[lay];
+    for (int k = 0; k < ne; ++k) {
+        const int ex = exits[((size_t)lay * max_exits + k) * 2], ey = exits[((size_t)lay * max_exits + k) * 2 + 1];
+        if (abs(x - ex) <= 1 && abs(y - ey) <= 1) info |= 8u;
+    }
+    cellinfo[idx] = (uint8_t)info;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int dx = (i == 0 || i == 4 || i == 7) ? 1 : ((i == 2 || i == 5 || i == 6) ? -1 : 0);
+        const int dy = (i == 3 || i == 6 || i == 7) ? 1 : ((i == 1 || i == 4 || i == 5) ? -1 : 0);
+        double v = -INF;
+        if (valid) {
+            const int nx = x + dx, ny = y + dy;
+            const double sn = space[lay0 + nx * stride + ny];
+            if (nx >= 1 && nx <= L && ny >= 1 && ny <= W && sn != INF) v = (sc - sn) * 5.0;
+        }
+        dp5[idx * 8 + i] = v;
+    }
+}
+
 }  // namespace mq
+
+extern "C" int mq_layout_tables_device(int32_t L, int32_t W, int32_t n_layouts, const double* space, const uint8_t* barrier, const int32_t* exits,
+                                       int32_t max_exits, const int32_t* n_exits, const int32_t* obs_exit, double* dp5_out, uint8_t* cellinfo_out,
+                                       void* stream) {
+    MQ_REQUIRE(L > 0 && W > 0 && n_layouts > 0 && space && barrier && exits && max_exits > 0 && n_exits && obs_exit && dp5_out && cellinfo_out,
+               "mq_layout_tables_device: bad argument");
+    MQ_ON_DEVICE_OF(space);
+    const int G = (L + 2) * (W + 2);
+    const long long total = (long long)G * n_layouts;
+    mq::layout_tables_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(L, W, G, total, space, barrier, exits, max_exits, n_exits,
+                                                                                              obs_exit, dp5_out, cellinfo_out);
+    MQ_CUDA(cudaGetLastError());
+    return MQ_OK;
+}
 
 extern "C" int mq_floor_field_device(int32_t L, int32_t W, int32_t n_layouts, const uint8_t* wall, const int32_t* exits, int32_t max_exits,
                                      const int32_t* n_exits, const double* add_term, double* space_out, int32_t* sweeps_out, void* stream) {

@@ -119,6 +119,16 @@ extern "C" int64_t mq_replay_size(const mq_replay* rb) { return rb ? rb->size : 
 extern "C" int64_t mq_replay_cursor(const mq_replay* rb) { return rb ? rb->cursor : 0; }
 extern "C" int64_t mq_replay_launch_count(const mq_replay* rb) { return rb ? rb->launches : 0; }
 
+extern "C" int mq_replay_restore(mq_replay* rb, int64_t size, int64_t cursor) {
+    MQ_REQUIRE(rb, "mq_replay_restore: null handle");
+    MQ_REQUIRE(size >= 0 && size <= rb->ring.capacity && cursor >= 0 && cursor < rb->ring.capacity,
+               "mq_replay_restore: size %lld / cursor %lld outside a ring of %lld", (long long)size, (long long)cursor, rb->ring.capacity);
+    MQ_REQUIRE(size == rb->ring.capacity || cursor == size % rb->ring.capacity,
+               "mq_replay_restore: a ring that is not full writes at slot size (size %lld, cursor %lld)", (long long)size, (long long)cursor);
+    rb->size = size; rb->cursor = cursor;
+    return MQ_OK;
+}
+
 extern "C" int mq_replay_push(mq_replay* rb, const float* state, const int32_t* action, const double* reward,
                               const float* next_state, const uint8_t* done, int64_t n, void* stream) {
     MQ_REQUIRE(rb && state && action && reward && next_state && done, "mq_replay_push: null argument");

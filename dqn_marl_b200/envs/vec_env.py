@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..layout import MAX_ROBOTS, Layout
+from ..layout import MAX_ROBOTS, DeviceLayoutBatch, Layout
 
 # scalars layout (include/marl_b200.h)
 S_FIRE_STEP, S_CUR_STEP, S_PREV_EVAC, S_PREV_DEAD, S_EPISODE, S_TICK, S_EVAC, S_DEAD, S_RPX, S_RPY = range(10)
@@ -29,7 +29,9 @@ def _require_cuda(device) -> torch.device:
 
 
 class VecEvacuationEnv:
-    """Batch of environments sharing one ``Layout``.
+    """Batch of environments sharing one ``Layout`` — or, with `layout` a list of Layouts (host tables) / a
+    ``DeviceLayoutBatch`` (tables built on the device) and `env_layout` giving every env's layout index, a batch over several
+    layouts of one grid size (the reference builds one Map per env instance, evacuation_env.py:42-43).
 
     strict_reference=True keeps the reference's reset quirks (fire step survives reset — Q6; the
     single-robot env keeps its robot cell and only centres the reset observation at (15,15) — Q7).
@@ -38,30 +40,63 @@ class VecEvacuationEnv:
 
     def __init__(self, layout: Layout, n_envs: int, num_people: int = 150, device="cuda", seed: int = 0,
                  env_id_base: int = 0, strict_reference: bool = True, auto_reset: bool = True,
-                 max_steps: int = 1200, reward_coefs=(50.0, 200.0, 0.5, 1.0)):
+                 max_steps: int = 1200, reward_coefs=(50.0, 200.0, 0.5, 1.0), env_layout=None):
         self.lib = _lib.load()
         self.device = _require_cuda(device)
+        on_device = isinstance(layout, DeviceLayoutBatch)
+        layouts = None if on_device else (list(layout) if isinstance(layout, (list, tuple)) else [layout])
+        n_layouts = layout.n if on_device else len(layouts)
+        if n_layouts > 1:
+            if env_layout is None:
+                raise ValueError("several layouts need env_layout: the layout index of every env")
+            env_layout = np.ascontiguousarray(np.asarray(env_layout).reshape(-1), dtype=np.int32)
+            if env_layout.shape[0] != int(n_envs) or env_layout.min() < 0 or env_layout.max() >= n_layouts:
+                raise ValueError("env_layout must hold one index in 0..n_layouts-1 per env")
+        self.layouts, self.env_layout = layouts, env_layout
+        if not on_device:
+            layout = layouts[0]
+            if any((l.L, l.W, l.n_robots, l.danger_ctr.shape[0]) != (layout.L, layout.W, layout.n_robots, layout.danger_ctr.shape[0]) for l in layouts):
+                raise ValueError("the layouts of one batch must share L x W, the number of robots and of fire steps")
         self.layout = layout
         self.n_envs, self.num_people, self.n_robots = int(n_envs), int(num_people), layout.n_robots
         self.seed = int(seed)
+        self.env_id_base = int(env_id_base)
         self.strict_reference = bool(strict_reference)
+        self._hs = None
         L, W = layout.L, layout.W
 
-        lay = _lib.MqLayout()
-        lay.L, lay.W, lay.n_fire_steps = L, W, layout.danger_ctr.shape[0]
-        lay.ctr_box[:] = layout.ctr_box
-        lay.int_box[:] = layout.int_box
-        lay.robot_range[:] = layout.robot_range
-        for r in range(MAX_ROBOTS):
-            s = layout.robot_starts[min(r, len(layout.robot_starts) - 1)]
-            lay.robot_start[r][0], lay.robot_start[r][1] = int(s[0]), int(s[1])
-        lay.reset_obs_center[:] = layout.reset_obs_center
-        lay.obs_exit[:] = layout.obs_exit
-        self._keep = [np.ascontiguousarray(layout.dp5, dtype=np.float64),
-                      np.ascontiguousarray(layout.cellinfo, dtype=np.uint8),
-                      np.ascontiguousarray(layout.danger_ctr, dtype=np.float64),
-                      np.ascontiguousarray(layout.danger_int, dtype=np.float64)]
-        lay.dp5, lay.cellinfo, lay.danger_ctr, lay.danger_int = [a.ctypes.data for a in self._keep]
+        self._keep = []
+
+        def fill(lay, src, obs_exit, tables):
+            lay.L, lay.W, lay.n_fire_steps = L, W, src.danger_ctr.shape[0]
+            lay.ctr_box[:] = src.ctr_box
+            lay.int_box[:] = src.int_box
+            lay.robot_range[:] = src.robot_range
+            for r in range(MAX_ROBOTS):
+                s = src.robot_starts[min(r, len(src.robot_starts) - 1)]
+                lay.robot_start[r][0], lay.robot_start[r][1] = int(s[0]), int(s[1])
+            lay.reset_obs_center[:] = src.reset_obs_center
+            lay.obs_exit[:] = [int(v) for v in obs_exit]
+            lay.dp5, lay.cellinfo, lay.danger_ctr, lay.danger_int = tables
+
+        lays = (_lib.MqLayout * n_layouts)()
+        if on_device:
+            with torch.cuda.device(self.device):
+                if layout.device != self.device:
+                    raise ValueError(f"the DeviceLayoutBatch lives on {layout.device}, the env batch on {self.device}")
+                obs_exits = layout.obs_exit.cpu().numpy()
+            G = (L + 2) * (W + 2)
+            for k in range(n_layouts):
+                fill(lays[k], layout, obs_exits[k], (layout.dp5.data_ptr() + k * G * 64, layout.cellinfo.data_ptr() + k * G,
+                                                     layout.danger_ctr.data_ptr(), layout.danger_int.data_ptr()))
+            self._keep.append(layout)
+        else:
+            for k, src in enumerate(layouts):
+                arrs = [np.ascontiguousarray(src.dp5, dtype=np.float64), np.ascontiguousarray(src.cellinfo, dtype=np.uint8),
+                        np.ascontiguousarray(src.danger_ctr, dtype=np.float64), np.ascontiguousarray(src.danger_int, dtype=np.float64)]
+                self._keep.append(arrs)
+                fill(lays[k], src, src.obs_exit, [a.ctypes.data for a in arrs])
+        lay = lays[0]
 
         cfg = _lib.MqEnvCfg()
         cfg.n_envs, cfg.n_people, cfg.n_robots = self.n_envs, self.num_people, self.n_robots
@@ -87,11 +122,16 @@ class VecEvacuationEnv:
             self.rmap = torch.zeros((E, self.rmap_words), dtype=torch.int32, device=dev)
             self.robots = torch.zeros((E, MAX_ROBOTS, 2), dtype=torch.int32, device=dev)
             self.scalars = torch.zeros((E, _lib.MQ_ENV_SCALARS), dtype=torch.int32, device=dev)
-            starts = torch.tensor([[int(v) for v in layout.robot_starts[min(r, self.n_robots - 1)]] for r in range(MAX_ROBOTS)],
-                                  dtype=torch.int32, device=dev)
+            def starts_of(src):
+                return [[int(v) for v in src.robot_starts[min(r, self.n_robots - 1)]] for r in range(MAX_ROBOTS)]
+            if layouts is not None and n_layouts > 1:              # every env starts at its own layout's robot cells
+                per_layout = torch.tensor([starts_of(src) for src in layouts], dtype=torch.int32, device=dev)
+                starts = per_layout[torch.from_numpy(env_layout).to(dev).long()]
+            else:
+                starts = torch.tensor(starts_of(layout), dtype=torch.int32, device=dev).expand(E, MAX_ROBOTS, 2)
             self.robots[:] = starts                                   # map.py:76-78
-            self.scalars[:, S_RPX] = int(layout.robot_starts[0][0])
-            self.scalars[:, S_RPY] = int(layout.robot_starts[0][1])
+            self.scalars[:, S_RPX] = starts[:, 0, 0]
+            self.scalars[:, S_RPY] = starts[:, 0, 1]
             self.obs = torch.zeros((E, self.n_robots, 11, 11, 6), dtype=torch.float32, device=dev)
             self.reward = torch.zeros((E,), dtype=torch.float64, device=dev)
             self.done = torch.zeros((E,), dtype=torch.uint8, device=dev)
@@ -99,7 +139,12 @@ class VecEvacuationEnv:
         st = _lib.MqEnvState(*[_lib.ptr(t) for t in (self.pos, self.health, self.acc, self.flags, self.rmap,
                                                     self.robots, self.scalars)])
         h = C.c_void_p()
-        _lib.check(self.lib.mq_env_create(C.byref(h), C.byref(cfg), C.byref(lay), C.byref(st)), "mq_env_create")
+        if n_layouts == 1 and not on_device:
+            _lib.check(self.lib.mq_env_create(C.byref(h), C.byref(cfg), C.byref(lay), C.byref(st)), "mq_env_create")
+        else:
+            torch.cuda.synchronize(self.device)            # the device tables must be complete before they are copied
+            _lib.check(self.lib.mq_env_create_layouts(C.byref(h), C.byref(cfg), lays, n_layouts, _lib.ptr(env_layout) if n_layouts > 1 else None,
+                                                      int(on_device), C.byref(st)), "mq_env_create_layouts")
         self._h = h
 
     # ------------------------------------------------------------------
@@ -126,17 +171,21 @@ class VecEvacuationEnv:
                    "mq_env_set_reward_coefs")
 
     def reset(self, env_mask: Optional[torch.Tensor] = None, inject_spawn: Optional[torch.Tensor] = None,
-              obs64: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """EvacuationEnv.reset (evacuation_env.py:61-82) for all (or masked) envs -> obs (E, R, 11, 11, 6) f32."""
+              obs64: Optional[torch.Tensor] = None, obs_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """EvacuationEnv.reset (evacuation_env.py:61-82) for all (or masked) envs -> obs (E, R, 11, 11, 6) f32.
+        obs_out: caller-owned f32 tensor of that shape to receive the observations (rows of envs outside the mask are left
+        untouched) instead of the internal buffer."""
         if env_mask is not None:
             env_mask = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
         if inject_spawn is not None:
             inject_spawn = inject_spawn.to(device=self.device, dtype=torch.int16).contiguous()
             assert inject_spawn.shape == (self.n_envs, self.num_people, 2)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.mq_env_reset(self._h, _lib.ptr(env_mask), _lib.ptr(inject_spawn), _lib.ptr(self.obs),
+            out = self.obs if obs_out is None else obs_out
+            assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() == self.obs.numel()
+            _lib.check(self.lib.mq_env_reset(self._h, _lib.ptr(env_mask), _lib.ptr(inject_spawn), _lib.ptr(out),
                                              _lib.ptr(obs64), self._stream()), "mq_env_reset")
-        return self.obs
+        return out
 
     def step(self, actions: torch.Tensor, obs64: Optional[torch.Tensor] = None):
         """EvacuationEnv.step (evacuation_env.py:122-172) for every env.  actions: int (E, R) or (E,) on device.
@@ -210,6 +259,31 @@ class VecEvacuationEnv:
     @property
     def launch_count(self) -> int:
         return int(self.lib.mq_env_launch_count(self._h))
+
+    # -- snapshot / restore of the whole batch (the reference has no env checkpoint) ----------------
+    _STATE_TENSORS = ("pos", "health", "acc", "flags", "rmap", "robots", "scalars")
+
+    def state_dict(self) -> dict:
+        """Host copy of every env's device state.  The keyed draws are functions of (seed, env id, tick / episode counters in
+        `scalars`), so these seven tensors plus the constructor arguments continue a run bit-identically."""
+        torch.cuda.current_stream(self.device).synchronize()
+        if getattr(self, "_hs", None) is not None:
+            self._hs.synchronize()
+        sd = {k: getattr(self, k).cpu() for k in self._STATE_TENSORS}
+        sd["meta"] = {"n_envs": self.n_envs, "num_people": self.num_people, "n_robots": self.n_robots, "L": self.layout.L,
+                      "W": self.layout.W, "seed": self.seed, "env_id_base": self.env_id_base, "strict_reference": self.strict_reference}
+        return sd
+
+    def load_state_dict(self, sd: dict):
+        m = sd["meta"]
+        mine = {"n_envs": self.n_envs, "num_people": self.num_people, "n_robots": self.n_robots, "L": self.layout.L, "W": self.layout.W}
+        for k, v in mine.items():
+            if int(m[k]) != v:
+                raise ValueError(f"env snapshot has {k}={m[k]}, this batch has {k}={v}")
+        if int(m["seed"]) != self.seed or int(m["env_id_base"]) != self.env_id_base:
+            raise ValueError("env snapshot was taken with another seed / env_id_base: the keyed draws would differ")
+        for k in self._STATE_TENSORS:
+            getattr(self, k).copy_(sd[k])
 
     # ------------------------------------------------------------------
     def snapshot(self, env: int = 0) -> dict:

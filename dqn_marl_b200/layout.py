@@ -47,6 +47,38 @@ def init_barrier(A, B):
     return ((x1, y2), (x2, y1))
 
 
+def fire_add_term(fire: FireSchedule, L: int, W: int) -> np.ndarray:
+    """map.py:143-147 — 200 * danger(i,j)^2 at fire step 0, integer coordinates.  The reference squares an np.float64 scalar
+    (``danger ** 2`` -> libm pow), so do exactly that per cell."""
+    xs, ys = np.meshgrid(np.arange(L + 2), np.arange(W + 2), indexing="ij")
+    d0 = fire.danger_field(0, xs, ys)
+    add = np.zeros((L + 2, W + 2), dtype=np.float64)
+    for (i, j) in zip(*np.nonzero(d0)):
+        add[i, j] = 200 * (np.float64(d0[i, j]) ** 2)
+    return add
+
+
+def danger_tables(fire: FireSchedule, obs_fire: FireSchedule, L: int, W: int):
+    """Danger at cell centres (people.py:205, the map's fire model) and at integer coordinates (evacuation_env.py:106, the
+    env's own model) for every fire step, on their bounding boxes -> (ctr_box, danger_ctr, int_box, danger_int)."""
+    S = fire.max_steps + 1
+    bx0, by0, bx1, by1 = fire.bounding_box()
+    cx0, cy0 = max(bx0, 0), max(by0, 0)
+    cx1, cy1 = min(bx1, L + 2), min(by1, W + 2)
+    cw, ch = max(cx1 - cx0, 1), max(cy1 - cy0, 1)
+    gx, gy = np.meshgrid(np.arange(cx0, cx0 + cw), np.arange(cy0, cy0 + ch), indexing="ij")
+    danger_ctr = np.stack([fire.danger_field(s, gx + 0.5, gy + 0.5) for s in range(S)])
+    ox0, oy0, ox1, oy1 = obs_fire.bounding_box()
+    ix0 = max(ox0, -6)
+    ix1 = min(ox1, L + 8)
+    iy0 = max(oy0, -6)
+    iy1 = min(oy1, W + 8)
+    iw, ih = max(ix1 - ix0, 1), max(iy1 - iy0, 1)
+    gx, gy = np.meshgrid(np.arange(ix0, ix0 + iw), np.arange(iy0, iy0 + ih), indexing="ij")
+    danger_int = np.stack([obs_fire.danger_field(s, gx, gy) for s in range(S)])
+    return (cx0, cy0, cw, ch), danger_ctr, (ix0, iy0, iw, ih), danger_int
+
+
 @dataclass
 class Layout:
     L: int
@@ -156,13 +188,7 @@ class Layout:
         barrier[ex, ey] = 0                    # map.py:72-73
         self.barrier_mask = barrier
 
-        # map.py:143-147 — 200 * danger(i,j)^2 at fire step 0, integer coordinates.  The reference
-        # squares an np.float64 scalar (``danger ** 2`` -> libm pow), so do exactly that per cell.
-        xs, ys = np.meshgrid(np.arange(L + 2), np.arange(W + 2), indexing="ij")
-        d0 = self.fire.danger_field(0, xs, ys)
-        add = np.zeros((L + 2, W + 2), dtype=np.float64)
-        for (i, j) in zip(*np.nonzero(d0)):
-            add[i, j] = 200 * (np.float64(d0[i, j]) ** 2)
+        add = fire_add_term(self.fire, L, W)
 
         if floor_field is None:
             from . import _lib
@@ -194,24 +220,7 @@ class Layout:
         self.dp5 = dp5
 
         # danger tables on bounding boxes
-        S = self.fire.max_steps + 1
-        bx0, by0, bx1, by1 = self.fire.bounding_box()
-        cx0, cy0 = max(bx0, 0), max(by0, 0)
-        cx1, cy1 = min(bx1, L + 2), min(by1, W + 2)
-        cw, ch = max(cx1 - cx0, 1), max(cy1 - cy0, 1)
-        self.ctr_box = (cx0, cy0, cw, ch)
-        gx, gy = np.meshgrid(np.arange(cx0, cx0 + cw), np.arange(cy0, cy0 + ch), indexing="ij")
-        self.danger_ctr = np.stack([self.fire.danger_field(s, gx + 0.5, gy + 0.5) for s in range(S)])
-
-        ox0, oy0, ox1, oy1 = self.obs_fire.bounding_box()
-        ix0 = max(ox0, -6)
-        ix1 = min(ox1, L + 8)
-        iy0 = max(oy0, -6)
-        iy1 = min(oy1, W + 8)
-        iw, ih = max(ix1 - ix0, 1), max(iy1 - iy0, 1)
-        self.int_box = (ix0, iy0, iw, ih)
-        gx, gy = np.meshgrid(np.arange(ix0, ix0 + iw), np.arange(iy0, iy0 + ih), indexing="ij")
-        self.danger_int = np.stack([self.obs_fire.danger_field(s, gx, gy) for s in range(S)])
+        self.ctr_box, self.danger_ctr, self.int_box, self.danger_int = danger_tables(self.fire, self.obs_fire, L, W)
         return self
 
     # convenience lookups used by the single-env facade and tests --------------------
@@ -228,3 +237,49 @@ class Layout:
         if x0 <= x < x0 + w and y0 <= y < y0 + h:
             return float(self.danger_int[step, x - x0, y - y0])
         return 0.0
+
+
+class DeviceLayoutBatch:
+    """n layouts of one size whose floor fields and kernel tables are built ON THE DEVICE (per-env random
+    layouts): `mq_floor_field_device` (the reference's Map.Init_Potential, map.py:127-148, as a relaxation to the same fixed
+    point) -> `mq_layout_tables_device` (dp5 / cellinfo) -> `VecEvacuationEnv(DeviceLayoutBatch, ..., env_layout=...)`, which
+    hands the device tables to `mq_env_create_layouts`.  Walls and exits differ per layout; the fire (one schedule, default:
+    the reference room's source at (19, 15)), robot band and robot starts are shared, so the danger tables exist once.
+
+        barrier  (n, L+2, W+2) uint8: Map.barrier_list membership — outer ring + barrier rectangles (map.py:43-57)
+        exits    (n, max_exits, 2) int32, n_exits (n,) int32: exit cells inside 1..L x 1..W; exits[k, 0] is the env's
+                 exit_location (forced open, observation channel 4, reward: map.py:66-73, evacuation_env.py:113,194)
+    """
+
+    def __init__(self, L: int, W: int, barrier, exits, n_exits, device="cuda", fire: Optional[FireSchedule] = None,
+                 obs_fire: Optional[FireSchedule] = None, robot_range=(15, 30), robot_starts=((15, 15),), reset_obs_center=(15, 15)):
+        import torch
+        from . import _lib
+        self.L, self.W = int(L), int(W)
+        dev = torch.device(device)
+        self.device = dev
+        bar = torch.as_tensor(barrier).to(device=dev, dtype=torch.uint8).clone()
+        exits = torch.as_tensor(exits).to(device=dev, dtype=torch.int32).contiguous()
+        n_exits = torch.as_tensor(n_exits).to(device=dev, dtype=torch.int32).contiguous()
+        n = bar.shape[0]
+        assert bar.shape == (n, L + 2, W + 2) and exits.shape[0] == n and exits.shape[2] == 2
+        self.n = n
+        idx = torch.arange(n, device=dev)
+        ex0, ey0 = exits[:, 0, 0].long(), exits[:, 0, 1].long()
+        bar[idx, ex0, ey0] = 0                                   # map.py:67,72-73: Exit[0] is opened and leaves barrier_list
+        self.barrier = bar
+        self.exits, self.n_exits = exits, n_exits
+        self.fire = fire or FireSchedule([((19.0, 15.0), (2, 2), 0.4)])
+        self.obs_fire = obs_fire or FireSchedule([((19, 15), (2, 2), 0.4)])
+        self.robot_range, self.robot_starts, self.reset_obs_center = tuple(robot_range), tuple(robot_starts), tuple(reset_obs_center)
+        add = torch.from_numpy(fire_add_term(self.fire, L, W)).to(dev)
+        self.space, self.sweeps = _lib.floor_field_device(L, W, bar, exits, n_exits, add.expand(n, L + 2, W + 2).contiguous())
+        self.obs_exit = exits[:, 0, :].contiguous()
+        self.dp5, self.cellinfo = _lib.layout_tables_device(L, W, self.space, bar, exits, n_exits, self.obs_exit)
+        self.ctr_box, ctr, self.int_box, integ = danger_tables(self.fire, self.obs_fire, L, W)
+        self.danger_ctr = torch.from_numpy(np.ascontiguousarray(ctr)).to(dev)
+        self.danger_int = torch.from_numpy(np.ascontiguousarray(integ)).to(dev)
+
+    @property
+    def n_robots(self) -> int:
+        return len(self.robot_starts)

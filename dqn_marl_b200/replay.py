@@ -60,6 +60,25 @@ class ReplayRing:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    # -- snapshot / restore (the reference checkpoints only the networks, dqn_agent.py:174-182) ------------------------
+    def state_dict(self) -> dict:
+        """Host copy of the ring: the stored transitions in PHYSICAL slot order (only the filled part), len, write position
+        and the sample-draw counter — enough to continue pushing and sampling bit-identically."""
+        n = len(self)
+        torch.cuda.current_stream(self.device).synchronize()
+        return {"capacity": self.capacity, "size": n, "cursor": self.cursor, "draws": self.draws, "seed": self.seed,
+                "state": self.state[:n].cpu(), "next_state": self.next_state[:n].cpu(), "action": self.action[:n].cpu(),
+                "reward": self.reward[:n].cpu(), "done": self.done[:n].cpu()}
+
+    def load_state_dict(self, sd: dict):
+        if int(sd["capacity"]) != self.capacity:
+            raise ValueError(f"replay snapshot of capacity {sd['capacity']} does not fit a ring of capacity {self.capacity}")
+        n = int(sd["size"])
+        for name in ("state", "next_state", "action", "reward", "done"):
+            getattr(self, name)[:n].copy_(sd[name])
+        _lib.check(self.lib.mq_replay_restore(self._h, n, int(sd["cursor"])), "mq_replay_restore")
+        self.draws, self.seed = int(sd["draws"]), int(sd["seed"])
+
     def push(self, state, action, reward, next_state, done):
         """Append n transitions (device tensors): state/next_state f32 (n, 726)-viewable, action i32 (n,),
         reward f64 (n,) (the env's dtype; cast to f32 on store like dqn_agent.py:138), done u8 (n,)."""

@@ -71,6 +71,16 @@ int mq_floor_field(int32_t L, int32_t W, const uint8_t* wall, const int32_t* exi
 int mq_floor_field_device(int32_t L, int32_t W, int32_t n_layouts, const uint8_t* wall, const int32_t* exits, int32_t max_exits,
                           const int32_t* n_exits, const double* add_term, double* space_out, int32_t* sweeps_out, void* stream);
 
+/* dp5 / cellinfo (see mq_layout below) of a batch of layouts from their floor fields, on the device: what lets the output of
+ * mq_floor_field_device feed mq_env_create_layouts without a round trip through the host.
+ *   space     dev f64 [n_layouts][(L+2)*(W+2)]   (mq_floor_field_device)
+ *   barrier   dev u8  [n_layouts][(L+2)*(W+2)]   Map.barrier_list membership (map.py:43-57,72-73): observation channel 3
+ *   exits / n_exits as above;  obs_exit dev i32 [n_layouts][2]  (evacuation_env.py:113 exit_location)
+ *   dp5_out   dev f64 [n_layouts][(L+2)*(W+2)][8];  cellinfo_out dev u8 [n_layouts][(L+2)*(W+2)] */
+int mq_layout_tables_device(int32_t L, int32_t W, int32_t n_layouts, const double* space, const uint8_t* barrier, const int32_t* exits,
+                            int32_t max_exits, const int32_t* n_exits, const int32_t* obs_exit, double* dp5_out, uint8_t* cellinfo_out,
+                            void* stream);
+
 /* ------------------------------------------------------------------------
  * Layout tables (host pointers; copied to the device by mq_env_create).
  * Cell index = x*(W+2)+y, the reference indexes space[x][y] (map.py:44).
@@ -144,6 +154,13 @@ typedef struct mq_env mq_env;
 
 int mq_env_state_sizes(const mq_env_cfg* cfg, const mq_layout* layout, int64_t* n_pad, int64_t* rmap_words);
 int mq_env_create(mq_env** out, const mq_env_cfg* cfg, const mq_layout* layout, const mq_env_state* state);
+/* Several layouts in one batch (per-env layouts; the reference builds one Map per env instance,
+ * evacuation_env.py:42-43).  All layouts share L x W and n_fire_steps; walls, exits, floor fields, fire sources, robot starts
+ * may differ.  env_layout host i32 [n_envs]: the layout index of every env (NULL when n_layouts == 1).
+ * tables_on_device != 0: dp5 / cellinfo / danger_ctr / danger_int of every mq_layout are DEVICE pointers (e.g. written by
+ * mq_layout_tables_device); they are copied, the caller keeps ownership.  Danger tables given by the same pointer are stored once. */
+int mq_env_create_layouts(mq_env** out, const mq_env_cfg* cfg, const mq_layout* layouts, int32_t n_layouts,
+                          const int32_t* env_layout, int32_t tables_on_device, const mq_env_state* state);
 int mq_env_destroy(mq_env* env);
 /* EvacuationEnv.EVAC_REWARD etc. are mutated at runtime by overnight_experiments.py:69-70 */
 int mq_env_set_reward_coefs(mq_env* env, double evac_reward, double death_penalty, double death_acc_penalty,
@@ -190,6 +207,10 @@ int mq_replay_destroy(mq_replay* rb);
 int64_t mq_replay_size(const mq_replay* rb);      /* len(agent.memory) */
 int64_t mq_replay_cursor(const mq_replay* rb);
 int64_t mq_replay_launch_count(const mq_replay* rb);
+/* Checkpoint resume (the reference saves only the networks, dqn_agent.py:174-182; a deque has no other state than its
+ * contents): after the caller has copied the saved transitions back into the storage tensors, restore len(memory) and the
+ * write position.  0 <= size <= capacity, 0 <= cursor < capacity, cursor == size % capacity unless the ring is full. */
+int mq_replay_restore(mq_replay* rb, int64_t size, int64_t cursor);
 /* n transitions appended FIFO (oldest overwritten once full).  reward is the env's f64 reward,
  * cast to f32 exactly as torch.FloatTensor(rewards) does at dqn_agent.py:138. */
 int mq_replay_push(mq_replay* rb, const float* state, const int32_t* action, const double* reward,

@@ -202,7 +202,7 @@ def test_dqn_agent_facade_reference_surface(tmp_path):
         assert agent.q_network(x).shape == (4, 5)
     path = tmp_path / "ck.pth"
     agent.save(str(path))
-    ck = torch.load(str(path), map_location="cpu", weights_only=False)
+    ck = torch.load(str(path), map_location="cpu", weights_only=True)
     assert set(ck) == {"q_network", "target_network", "optimizer", "epsilon", "steps"}
     assert ck["q_network"]["fc1.weight"].shape == (512, 15488) and ck["q_network"]["conv1.weight"].shape == (32, 6, 3, 3)
     ref_q.load_state_dict(ck["q_network"])                              # a reference-side module accepts it
@@ -252,6 +252,86 @@ def test_bf16_tensor_core_path_tracks_fp32(B):
         assert cos > 0.995, (k, cos)
         assert abs(float(b.norm() / a.norm()) - 1.0) < 5e-2, (k, float(b.norm() / a.norm()))
     assert (p32 - p16).abs().max() <= 2.1e-4          # one Adam step moves a weight by at most lr = 1e-4 in either path
+
+
+def _bench_batch(B, gen, d="cuda:0"):
+    """Observations shaped like the env's: channels 1, 3, 4, 5 in {0, 1}, channel 2 (danger) in [0, 1], channel 0 == 0."""
+    def obs():
+        x = (torch.rand((B, 11, 11, 6), generator=gen) < 0.25).float()
+        x[..., 2] = torch.rand((B, 11, 11), generator=gen) * (torch.rand((B, 11, 11), generator=gen) < 0.4)
+        x[..., 0] = 0
+        return x
+    return dict(states=obs().to(d), actions=torch.randint(0, 5, (B,), generator=gen).to(d), rewards=(torch.randn(B, generator=gen) * 0.5).to(d),
+                next_states=obs().to(d), dones=(torch.rand(B, generator=gen) < 0.05).to(torch.uint8).to(d))
+
+
+def test_bf16_path_tracks_fp32_at_the_bench_batch_sizes():
+    """The sizes bench.py runs: learn B = 4096, act B = 16384 (C3: one observation per env).  Same bars as the small-batch test;
+    greedy actions of the two paths agree except where the top-two Q gap is inside the bf16 error."""
+    from dqn_marl_b200.agents import qnet_params as qp
+    q, t = torch_ref.build_nets(31, 32)
+    gen = torch.Generator().manual_seed(6)
+    B, BA = 4096, 16384
+    batch = _bench_batch(B, gen)
+    act_obs = _bench_batch(BA, gen)["states"]
+    mask = (torch.rand((B, 512), generator=gen) >= 0.2).to(torch.uint8).to("cuda:0")
+    res = {}
+    for prec in ("fp32", "bf16"):
+        net = _qnet(q, t, max_batch=BA)
+        net.set_precision(prec)
+        qa = torch.empty((BA, 5), dtype=torch.float32, device="cuda:0")
+        acts = net.act(act_obs, 0.0, 1, 0, 0, 1, None, q_out=qa).cpu()
+        loss = net.td_backward(batch, _hp(1), mask, mask).item()
+        grads = {k: v.cpu() for k, v in qp.unpack(net.flat_g).items()}
+        gnorm = net.clip_adam(_hp(1)).item()
+        res[prec] = (qa.cpu(), acts, loss, grads, gnorm)
+        net.close()
+    q32, a32, l32, g32, n32 = res["fp32"]
+    q16, a16, l16, g16, n16 = res["bf16"]
+    scale = q32.abs().max()
+    assert (q32 - q16).abs().max() <= 2e-2 * scale
+    top2 = q32.topk(2, dim=1).values
+    gap = top2[:, 0] - top2[:, 1]
+    differ = a32 != a16
+    assert float(differ.float().mean()) < 0.05
+    assert bool((gap[differ] <= 4e-2 * scale).all())          # only near-ties flip
+    assert abs(l32 - l16) <= 1e-2 * abs(l32) and abs(n32 - n16) <= 3e-2 * n32
+    for k in g32:
+        a, b = g32[k].flatten().double(), g16[k].flatten().double()
+        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+        assert cos > 0.995, (k, cos)
+        assert abs(float(b.norm() / a.norm()) - 1.0) < 5e-2, (k, float(b.norm() / a.norm()))
+
+
+def test_bf16_path_does_not_drift_over_50_learn_steps():
+    """50 consecutive learn steps (target sync every 10) on the same stream of batches and dropout masks, fp32 parity path vs bf16
+    tensor-core path from the same initial weights.  Band: every loss within 3 % (+ 1e-4 absolute), the parameter displacement of
+    the two runs aligned (cosine > 0.98) and of equal length within 5 %."""
+    q, t = torch_ref.build_nets(41, 42)
+    B, STEPS = 512, 50
+    curves, disp = {}, {}
+    for prec in ("fp32", "bf16"):
+        gen = torch.Generator().manual_seed(9)
+        net = _qnet(q, t, max_batch=B)
+        net.set_precision(prec)
+        p0 = net.flat_p.clone()
+        losses = []
+        for s in range(STEPS):
+            batch = _bench_batch(B, gen)
+            m1 = (torch.rand((B, 512), generator=gen) >= 0.2).to(torch.uint8).to("cuda:0")
+            m2 = (torch.rand((B, 512), generator=gen) >= 0.2).to(torch.uint8).to("cuda:0")
+            losses.append(net.td_backward(batch, _hp(s + 1, lr=3e-4), m1, m2).item())
+            net.clip_adam(_hp(s + 1, lr=3e-4))
+            if s % 10 == 9:
+                net.sync_target(1.0)
+        curves[prec] = np.array(losses)
+        disp[prec] = (net.flat_p - p0).double().cpu()
+        net.close()
+    a, b = curves["fp32"], curves["bf16"]
+    assert np.all(np.abs(a - b) <= 3e-2 * np.abs(a) + 1e-4), np.abs(a - b) / np.abs(a)
+    da, db = disp["fp32"], disp["bf16"]
+    cos = float((da @ db) / (da.norm() * db.norm()))
+    assert cos > 0.98 and abs(float(db.norm() / da.norm()) - 1.0) < 5e-2, (cos, float(db.norm() / da.norm()))
 
 
 def test_q_network_autograd_qmix_step_matches_torch():

@@ -96,6 +96,18 @@ def test_multi_fire_hall_tables_match_reference_map():
     _check_synth("layout_synth_hall.npz", "traj_synth_hall.npz", boxed=False)
 
 
+def test_cpp_floor_field_equals_python_restatement():
+    """The product's host builder (csrc/floor_field.cpp via mq_floor_field) against the heapq restatement of map.py:127-148
+    in oracle/floor_field_py.py, on layouts the goldens do not cover (many exits, 20 % walls, unreachable pockets)."""
+    from floor_field_py import floor_field
+    from dqn_marl_b200.layout import Layout
+    for (L, W, ne, fill, seed) in [(128, 96, 5, 0.20, 3), (64, 200, 8, 0.15, 9), (256, 256, 1, 0.10, 2024)]:
+        a = Layout.synthetic(L, W, n_exits=ne, wall_fill=fill, seed=seed)
+        b = Layout.synthetic(L, W, n_exits=ne, wall_fill=fill, seed=seed, floor_field=floor_field)
+        assert np.array_equal(a.space.view(np.uint64), b.space.view(np.uint64)), (L, W)
+        assert np.array_equal(a.dp5.view(np.uint64), b.dp5.view(np.uint64)) and np.array_equal(a.cellinfo, b.cellinfo)
+
+
 def test_dp5_and_cellinfo_semantics():
     """dp5 = (space[c]-space[n])*5.0 for valid pairs, -inf otherwise; exit neighbourhood evacuates."""
     from dqn_marl_b200.layout import CELL_EVACUATES, CELL_OBS_EXIT, MOVE_TO, Layout
