@@ -333,12 +333,12 @@ def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
         h_act = torch.randint(0, 5, (n_act, E, 1), dtype=torch.int32).pin_memory()
         e2e_steps = max(10 * n_rot, min(args.steps, 300) // n_rot * n_rot)
 
-        def e2e_run(steps, sync_each):
+        def e2e_run(steps, sync_each, wire=False):
             for k in range(steps):
                 b = k % n_rot
                 if k >= n_rot and not sync_each:
                     envs[b].step_wait()                   # the previous step of this batch has landed on the host
-                envs[b].step_async(h_act[k % n_act])
+                envs[b].step_async(h_act[k % n_act], wire=wire)
                 if sync_each:
                     envs[b].step_wait()
             for b in range(n_rot):
@@ -346,11 +346,12 @@ def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
 
         torch.cuda.synchronize(dev)
         e2e_run(2 * n_rot, False)
+        e2e_run(2 * n_rot, False, True)
         vals = []
-        for sync_each in (False, True):
+        for sync_each, wire in ((False, False), (True, False), (False, True)):
             barrier(); torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
-            e2e_run(e2e_steps, sync_each)
+            e2e_run(e2e_steps, sync_each, wire)
             torch.cuda.synchronize(dev)
             e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
             vals.append(world * E * N * e2e_steps / e2e_s)
@@ -359,6 +360,10 @@ def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
         res["e2e"] = {"value": vals[0], "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                       "steps": e2e_steps, "value_sync_each_step": vals[1],
                       "d2h_GBs_per_gpu": vals[0] / world / (E * N) * d2h / 1e9,
+                      "wire": {"value": vals[2], "d2h_bytes_per_step": envs[0].h_wire.numel() * 4 + envs[0].h_reward.numel() * 8 + envs[0].h_done.numel(),
+                               "note": "step_async(wire=True): observations cross PCIe in the compact wire form (544 B per window: channel 2 as "
+                                       "f32 + bit planes of channels 1 / 3 / 4) and are expanded to the same dense f32 host buffer by "
+                                       "mq_obs_wire_expand inside step_wait(), i.e. inside the timed region"},
                       "note": f"VecEvacuationEnv.step_async/step_wait: pinned host actions in (H2D), obs+reward+done out (D2H) every "
                               f"step; {n_rot} independent env batches in flight on their own streams (copies overlap kernels); "
                               f"value_sync_each_step = one batch at a time with a host sync per step; d2h_GBs_per_gpu = the PCIe "

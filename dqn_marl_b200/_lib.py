@@ -15,6 +15,7 @@ SO_PATH = os.environ.get("MARL_B200_SO") or os.path.join(HERE, "libmarl_b200.so"
 
 MQ_MAX_ROBOTS = 4
 MQ_OBS_SIZE = 726
+MQ_OBS_WIRE_WORDS = 136
 MQ_ENV_SCALARS = 16
 MQ_QNET_TENSORS = 12
 
@@ -74,6 +75,8 @@ SIGNATURES = {
     "mq_env_set_reward_coefs": (C.c_int, [_vp, _f64, _f64, _f64, _f64]),
     "mq_env_reset": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "mq_env_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mq_env_set_obs_wire": (C.c_int, [_vp, _vp]),
+    "mq_obs_wire_expand": (C.c_int, [_vp, _i64, _vp, _i32]),
     "mq_env_unpack_rmap": (C.c_int, [_vp, _vp, _vp]),
     "mq_env_launch_count": (_i64, [_vp]),
     "mq_replay_create": (C.c_int, [C.POINTER(_vp), _i64, _i32, C.POINTER(MqReplayStore)]),

@@ -89,6 +89,7 @@ struct DevCfg {
     unsigned char* scratch;            // BIG envs: per-env global scratch for everything but the occupancy bitmap
     long long scratch_per_env;
     double evac_reward, death_penalty, death_acc_penalty, alive_bonus;
+    uint32_t* obs_wire;                // optional compact form of the observation windows (mq_env_set_obs_wire), or nullptr
 };
 
 struct DevState {
@@ -199,11 +200,15 @@ __device__ __forceinline__ double box_lookup(const int* box, const double* tab, 
 // written as three 8-byte stores.  Centre of robot 0 = Map.robot_position (cx0, cy0); robots r >= 1 use
 // Map.robot_positions[r] (evacuation_env_multi.py:44-53).  Executed by `nthr` threads with ids `tid`.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gather_obs_wire(int tid, int nthr, const DevLayout& lay, const DevCfg& cfg, const Smem& sm,
+                                                const int (*rob)[2], int cx0, int cy0, int fire_step, int env);
 __device__ __forceinline__ void gather_obs(int tid, int nthr, const DevLayout& lay, const DevCfg& cfg, const Smem& sm,
                                            const int (*rob)[2], int cx0, int cy0, int fire_step, float* obs, double* obs64,
                                            int env) {
     const int cells = cfg.R * MQ_OBS_WIN * MQ_OBS_WIN;
     const int fs = min(fire_step, lay.n_fire_steps - 1);
+    if (cfg.obs_wire) gather_obs_wire(tid, nthr, lay, cfg, sm, rob, cx0, cy0, fire_step, env);
+    if (!obs && !obs64) return;
     for (int idx = tid; idx < cells; idx += nthr) {
         const int r = idx / (MQ_OBS_WIN * MQ_OBS_WIN), cell = idx - r * (MQ_OBS_WIN * MQ_OBS_WIN);
         const int i = cell / MQ_OBS_WIN, j = cell - i * MQ_OBS_WIN;
@@ -226,6 +231,38 @@ __device__ __forceinline__ void gather_obs(int tid, int nthr, const DevLayout& l
             double* d = obs64 + o;
             d[0] = 0.0; d[1] = v1; d[2] = v2; d[3] = v3; d[4] = v4; d[5] = v5;
         }
+    }
+}
+
+// Compact wire form of the observation windows for the host-buffer interface (mq_env_set_obs_wire): MQ_OBS_WIRE_WORDS = 136
+// words (544 B) per (env, robot) window instead of 2904 B.  Words 0..120 = channel 2 (danger, f32 bits) of cell c = i*11+j;
+// 121..124 / 125..128 / 129..132 = channels 1 / 3 / 4 as bit planes (bit c); 133..135 = 0.  Channel 0 is identically 0
+// (quirk Q1) and channel 5 marks the centre cell (evacuation_env.py:116-117): neither travels.  One lane per cell of a window
+// padded to 128 cells, so a warp's ballots ARE the plane words.  nthr and tid's warp must be whole warps.
+__device__ __forceinline__ void gather_obs_wire(int tid, int nthr, const DevLayout& lay, const DevCfg& cfg, const Smem& sm,
+                                                const int (*rob)[2], int cx0, int cy0, int fire_step, int env) {
+    const int fs = min(fire_step, lay.n_fire_steps - 1);
+    for (int idx = tid; idx < cfg.R * 128; idx += nthr) {
+        const int r = idx >> 7, cell = idx & 127;
+        const bool in_win = cell < MQ_OBS_WIN * MQ_OBS_WIN;
+        uint32_t ci = 0u, b1 = 0u;
+        float v2 = 0.f;
+        if (in_win) {
+            const int i = cell / MQ_OBS_WIN, j = cell - i * MQ_OBS_WIN;
+            const int cx = r == 0 ? cx0 : rob[r][0], cy = r == 0 ? cy0 : rob[r][1];
+            const int mx = cx + i - 5, my = cy + j - 5;
+            const bool in_grid = mx >= 0 && mx <= lay.L + 1 && my >= 0 && my <= lay.W + 1;
+            ci = in_grid ? (uint32_t)__ldg(lay.cellinfo + mx * lay.stride + my) : 2u;
+            b1 = (ci & 1u) ? bm_get(sm.bm, lay.wpr, mx, my) : 0u;
+            v2 = (float)box_lookup(lay.int_box, lay.danger_int, fs, mx, my);
+        }
+        const uint32_t p1 = __ballot_sync(0xFFFFFFFFu, b1 != 0u);
+        const uint32_t p3 = __ballot_sync(0xFFFFFFFFu, (ci & 2u) != 0u);
+        const uint32_t p4 = __ballot_sync(0xFFFFFFFFu, (ci & 4u) != 0u);
+        uint32_t* dst = cfg.obs_wire + ((size_t)env * cfg.R + r) * MQ_OBS_WIRE_WORDS;
+        if (in_win) dst[cell] = __float_as_uint(v2);
+        else if (cell >= 125) dst[133 + (cell - 125)] = 0u;
+        if ((cell & 31) == 0) { const int w = cell >> 5; dst[121 + w] = p1; dst[125 + w] = p3; dst[129 + w] = p4; }
     }
 }
 
@@ -1285,6 +1322,7 @@ extern "C" int mq_env_create_layouts(mq_env** out, const mq_env_cfg* cfg, const 
     c.n_leaf_max = c.N / 64 + 4;
     c.evac_reward = cfg->evac_reward; c.death_penalty = cfg->death_penalty;
     c.death_acc_penalty = cfg->death_acc_penalty; c.alive_bonus = cfg->alive_bonus;
+    c.obs_wire = nullptr;
     e->st = {state->pos, state->health, state->acc, state->flags, state->rmap, state->robots, state->scalars};
 
     mq::Smem tmp;
@@ -1374,6 +1412,12 @@ extern "C" int mq_env_set_reward_coefs(mq_env* e, double evac_reward, double dea
     MQ_REQUIRE(e, "mq_env_set_reward_coefs: null handle");
     e->cfg.evac_reward = evac_reward; e->cfg.death_penalty = death_penalty;
     e->cfg.death_acc_penalty = death_acc_penalty; e->cfg.alive_bonus = alive_bonus;
+    return MQ_OK;
+}
+
+extern "C" int mq_env_set_obs_wire(mq_env* e, uint32_t* wire_out) {
+    MQ_REQUIRE(e, "mq_env_set_obs_wire: null handle");
+    e->cfg.obs_wire = wire_out;
     return MQ_OK;
 }
 

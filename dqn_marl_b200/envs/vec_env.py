@@ -218,11 +218,15 @@ class VecEvacuationEnv:
         return step
 
     # ---- host-buffer interface (gym-style step_async / step_wait) ------------------------------------------------
-    def step_async(self, actions_host: torch.Tensor):
+    def step_async(self, actions_host: torch.Tensor, wire: bool = False):
         """Enqueue one step driven from HOST memory on this env batch's own stream: H2D of the (pinned) int32 actions,
         the fused step kernel, D2H of obs / reward / done into pinned host buffers.  Returns immediately; several env
         batches can be in flight so that the PCIe copies of one overlap the kernel of another.  `step_wait()` returns the
-        host tensors.  (The reference's step() is synchronous and host-side: evacuation_env.py:122-172.)"""
+        host tensors.  (The reference's step() is synchronous and host-side: evacuation_env.py:122-172.)
+
+        wire=True: the observations travel in the compact wire form (mq_env_set_obs_wire: 544 B per window instead of
+        2904 B — channel 2 as f32, channels 1 / 3 / 4 as bit planes) and `step_wait()` expands them on the host
+        (mq_obs_wire_expand) into the same pinned f32 buffer, bit-identical to the dense copy."""
         if getattr(self, "_hs", None) is None:
             self._hs = torch.cuda.Stream(device=self.device)
             self._hev = torch.cuda.Event()
@@ -230,6 +234,14 @@ class VecEvacuationEnv:
             self.h_obs = torch.empty(self.obs.shape, dtype=torch.float32).pin_memory()
             self.h_reward = torch.empty((self.n_envs,), dtype=torch.float64).pin_memory()
             self.h_done = torch.empty((self.n_envs,), dtype=torch.uint8).pin_memory()
+            self._wire_mode = False
+        if wire and getattr(self, "d_wire", None) is None:
+            self.d_wire = torch.zeros((self.n_envs, self.n_robots, _lib.MQ_OBS_WIRE_WORDS), dtype=torch.int32, device=self.device)
+            self.h_wire = torch.zeros(self.d_wire.shape, dtype=torch.int32).pin_memory()
+        if wire != self._wire_mode:
+            _lib.check(self.lib.mq_env_set_obs_wire(self._h, _lib.ptr(self.d_wire) if wire else None), "mq_env_set_obs_wire")
+            self._wire_mode = wire
+        self._wire_pending = wire
         # everything the caller has enqueued so far on its own stream (reset(), step(), writes to the state tensors such as the
         # facade's robot_position setter) happens before this step
         self._hs.wait_stream(torch.cuda.current_stream(self.device))
@@ -237,9 +249,12 @@ class VecEvacuationEnv:
         assert a.dtype == torch.int32 and a.device.type == "cpu"
         with torch.cuda.stream(self._hs):
             self._d_act.copy_(a, non_blocking=True)
-            _lib.check(self.lib.mq_env_step(self._h, _lib.ptr(self._d_act), _lib.ptr(self.obs), None, _lib.ptr(self.reward),
+            _lib.check(self.lib.mq_env_step(self._h, _lib.ptr(self._d_act), None if wire else _lib.ptr(self.obs), None, _lib.ptr(self.reward),
                                             _lib.ptr(self.done), C.c_void_p(self._hs.cuda_stream)), "mq_env_step")
-            self.h_obs.copy_(self.obs, non_blocking=True)
+            if wire:
+                self.h_wire.copy_(self.d_wire, non_blocking=True)
+            else:
+                self.h_obs.copy_(self.obs, non_blocking=True)
             self.h_reward.copy_(self.reward, non_blocking=True)
             self.h_done.copy_(self.done, non_blocking=True)
             self._hev.record(self._hs)
@@ -247,6 +262,10 @@ class VecEvacuationEnv:
     def step_wait(self):
         """Block until the step enqueued by step_async() has landed in host memory -> (obs, reward, done) pinned host tensors."""
         self._hev.synchronize()
+        if getattr(self, "_wire_pending", False):
+            _lib.check(self.lib.mq_obs_wire_expand(_lib.ptr(self.h_wire), self.n_envs * self.n_robots, _lib.ptr(self.h_obs),
+                                                   int(getattr(self, "wire_threads", 0))), "mq_obs_wire_expand")
+            self._wire_pending = False
         return self.h_obs, self.h_reward, self.h_done
 
     def rmap_bytes(self) -> torch.Tensor:

@@ -38,6 +38,7 @@ extern "C" {
 #define MQ_OBS_CH 6
 #define MQ_OBS_SIZE (MQ_OBS_WIN * MQ_OBS_WIN * MQ_OBS_CH)   /* 726 */
 #define MQ_N_ACTIONS 5                         /* evacuation_env.py:57 */
+#define MQ_OBS_WIRE_WORDS 136                  /* compact wire form of one observation window: 544 B (mq_env_set_obs_wire) */
 
 typedef enum mq_status {
     MQ_OK = 0,
@@ -181,6 +182,18 @@ int mq_env_reset(mq_env* env, const uint8_t* env_mask, const int16_t* inject_spa
  *   done_out    dev u8  [n_envs] */
 int mq_env_step(mq_env* env, const int32_t* actions, float* obs_out, double* obs64_out, double* reward_out,
                 uint8_t* done_out, void* stream);
+
+/* Compact wire form of the observations for callers that take them to the HOST every step (the reference's agent lives on the
+ * host: dqn_agent.py:101-110).  Of the 6 channels of _get_state (evacuation_env.py:84-120) channel 0 is identically 0,
+ * channels 1 / 3 / 4 hold 0 or 1 and channel 5 only marks the centre cell, so a window travels as MQ_OBS_WIRE_WORDS u32:
+ *   words 0..120    channel 2 (danger) of cell c = i*11 + j as f32 bits
+ *   words 121..124  channel 1 (People.rmap) bit plane, bit c        125..128  channel 3      129..132  channel 4      133..135  0
+ * 544 B instead of 2904 B per window over PCIe.  wire_out dev u32 [n_envs][n_robots][MQ_OBS_WIRE_WORDS], written by every
+ * following mq_env_step / mq_env_reset (in addition to obs_out / obs64_out, which may then be NULL); NULL switches it off. */
+int mq_env_set_obs_wire(mq_env* env, uint32_t* wire_out);
+/* Host routine (no GPU work): expand n_windows wire records (host memory) into dense f32 windows [n_windows][11][11][6],
+ * bit-identical to what obs_out would have held.  n_threads host threads (<= 0: one per 2048 windows, at most 16). */
+int mq_obs_wire_expand(const uint32_t* wire, int64_t n_windows, float* obs_out, int32_t n_threads);
 
 /* People.rmap as bytes: dev u8 [n_envs][(L+2)*(W+2)] */
 int mq_env_unpack_rmap(mq_env* env, uint8_t* rmap_out, void* stream);

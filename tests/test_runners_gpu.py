@@ -82,7 +82,11 @@ def test_train_dqn_c1_config_then_evaluate_and_main(project):
     res = root / "dqn_results"
     ck = _check_checkpoint(res / "dqn_model.pth")
     _check_checkpoint(res / "best_model.pth")
-    assert ck["steps"] > 100 and ck["epsilon"] < 1.0            # learn() ran every step once len(memory) > 32 (warmup_steps: 0)
+    # learn() ran every step once len(memory) > 32 (warmup_steps: 0).  Episodes are short: the fire never resets between episodes
+    # (quirk Q6), the reference's own second episode ends after ~45 steps (tests/golden/traj_room_single.npz).
+    with open(res / "reward_logs" / "reward_data.json", encoding="utf-8") as f:
+        n_steps = sum(json.load(f)["episode_steps"])
+    assert ck["steps"] == n_steps - 32 and ck["epsilon"] < 1.0
     with open(res / "reward_logs" / "reward_data.json", encoding="utf-8") as f:
         data = json.load(f)                                       # reward_visualizer.py:97-122
     assert len(data["episode_rewards"]) == 2 and len(data["step_rewards"]) == sum(data["episode_steps"])

@@ -1,0 +1,28 @@
+"""Host half of the compact observation wire format (mq_obs_wire_expand, include/marl_b200.h) without a GPU: records packed
+with numpy expand to the dense 11x11x6 windows bit for bit, for any thread count."""
+import numpy as np
+
+
+def test_wire_expand_matches_numpy_packing():
+    from dqn_marl_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    n = 5000
+    obs = np.zeros((n, 121, 6), np.float32)
+    obs[:, :, 1] = rng.random((n, 121)) < 0.3
+    obs[:, :, 2] = rng.random((n, 121)).astype(np.float32) * (rng.random((n, 121)) < 0.5)
+    obs[:, :, 3] = rng.random((n, 121)) < 0.2
+    obs[:, :, 4] = rng.random((n, 121)) < 0.01
+    obs[:, 60, 5] = 1                                               # evacuation_env.py:116-117
+    wire = np.zeros((n, _lib.MQ_OBS_WIRE_WORDS), np.uint32)
+    wire[:, :121] = obs[:, :, 2].view(np.uint32)
+    for ch, base in ((1, 121), (3, 125), (4, 129)):
+        bits = obs[:, :, ch].astype(np.uint32)
+        for c in range(121):
+            wire[:, base + (c >> 5)] |= bits[:, c] << np.uint32(c & 31)
+    out = np.empty((n, 121, 6), np.float32)
+    for threads in (1, 0, 4, 64):
+        out[:] = 7
+        _lib.check(lib.mq_obs_wire_expand(_lib.ptr(wire), n, _lib.ptr(out), threads), "mq_obs_wire_expand")
+        assert np.array_equal(out.view(np.uint32), obs.view(np.uint32)), threads
+    _lib.check(lib.mq_obs_wire_expand(_lib.ptr(wire), 0, _lib.ptr(out), 1), "empty input")
