@@ -89,5 +89,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_env_trace() -> str:
+    """libmarl_b200_envtrace.so: the same library with env.cu compiled -DMQ_ENV_TRACE (clock64 marks at the phase boundaries of
+    env_step_kernel, read by scripts/env_phase_trace.py through MARL_B200_SO).  A profiling aid, never loaded by default."""
+    build()
+    nvcc = _nvcc()
+    out = os.path.join(HERE, "libmarl_b200_envtrace.so")
+    obj = os.path.join(OBJ, "env.cu.trace.o")
+    cmd = [nvcc, *ARCH, *COMMON, "-fmad=false", "-DMQ_ENV_TRACE", "-c", os.path.join(CSRC, "env.cu"), "-o", obj]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    objs = [os.path.join(OBJ, src + ".o") for src in sources() if src != "env.cu"] + [obj]
+    subprocess.run([nvcc, *ARCH, "-shared", "-o", out, *objs], check=True, capture_output=True, text=True)
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--env-trace" in sys.argv:
+        print(build_env_trace())
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

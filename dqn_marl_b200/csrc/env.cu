@@ -125,8 +125,11 @@ __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a -
 // Small envs: everything in shared memory (returns the shared bytes).  BIG envs (gbase != nullptr): only the
 // occupancy bitmap and the pairwise-sum leaf tables stay in shared memory, the per-person arrays and the proposal
 // table live in a per-env global scratch area (returns the shared bytes; *gbytes receives the scratch bytes).
+// health_smem = false (one CTA per env, per-person arrays in shared memory): no shared copy of the health values — the chain warp
+// and the guidance term read them from the env's own global rows (L2-hot: phase 1 has just touched them), which brings the CTA
+// under a quarter of the SM's shared memory (4 resident CTAs instead of 3 at 1000 people).
 __host__ __device__ inline size_t carve(Smem& s, unsigned char* base, unsigned char* gbase, int N, int cap, int words, int nleaf,
-                                        int T, size_t* gbytes = nullptr) {
+                                        int T, size_t* gbytes = nullptr, bool health_smem = true) {
     size_t o = 0, go = 0;
     unsigned char* pb = gbase ? gbase : base;          // where the per-person arrays go
     size_t& po = gbase ? go : o;
@@ -136,7 +139,8 @@ __host__ __device__ inline size_t carve(Smem& s, unsigned char* base, unsigned c
     s.dist = (double*)(pb + po);
     if (gbase) { po += align_up(table, 16); s.dist = (double*)(pb + po); po += align_up(distb, 16); }
     else po += align_up(table > distb ? table : distb, 16);
-    s.health = (double*)(pb + po); po += align_up(sizeof(double) * N, 16);
+    s.health = nullptr;
+    if (health_smem) { s.health = (double*)(pb + po); po += align_up(sizeof(double) * N, 16); }
     s.pos = (uint32_t*)(pb + po); po += align_up(sizeof(uint32_t) * N, 16);
     s.mv = (uint32_t*)(pb + po); po += align_up(sizeof(uint32_t) * N, 16);
     s.mov = (uint16_t*)(pb + po); po += align_up(sizeof(uint16_t) * N, 16);
@@ -342,7 +346,7 @@ env_reset_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const uint8_t* env_m
     select_layout<MULTI>(lay, env);
     Smem sm;
     carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
-          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE);
+          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE, nullptr, !(Group<WPE, CW>::CHAIN && !BIG));
     int* sc = s_sc[g.gid];
     int(*rob)[2] = s_rob[g.gid];
     if (g.gtid < MQ_ENV_SCALARS) sc[g.gtid] = st.scalars[(size_t)env * MQ_ENV_SCALARS + g.gtid];
@@ -436,14 +440,20 @@ __device__ __forceinline__ double health_chain_literal(const double* h, int N) {
     return tot;
 }
 // run-based chain, executed by a whole warp; every lane returns the sum
-template <int DEPTH>      // batches of 32 fetched before any is consumed: 8 when the list lives in global scratch (BIG), else 1
-__device__ __noinline__ double health_chain_runs(const double* h, int N, int lane) {
+// FLAGS: h is the env's global health row and dead people (flags bit 1, read from fl) count as + 0.0; otherwise h already holds
+// the summands.
+template <int DEPTH, bool FLAGS = false>      // batches of 32 fetched before any is consumed: 8 when the list lives in global memory, else 1
+__device__ __noinline__ double health_chain_runs(const double* h, int N, int lane, const uint8_t* fl = nullptr) {
     double S = 0.0;
     int pend = 0;                                   // 100.0's seen since the last hurt person
     for (int b0 = 0; b0 < N; b0 += 32 * DEPTH) {
         double vv[DEPTH];
 #pragma unroll
-        for (int u = 0; u < DEPTH; ++u) { const int i = b0 + 32 * u + lane; vv[u] = i < N ? h[i] : 0.0; }
+        for (int u = 0; u < DEPTH; ++u) {
+            const int i = b0 + 32 * u + lane;
+            if (FLAGS) vv[u] = (i < N && !(fl[i] & 2u)) ? __ldcg(h + i) : 0.0;
+            else vv[u] = i < N ? h[i] : 0.0;
+        }
         uint32_t m100_[DEPTH], hard_[DEPTH], any_hard = 0;
         int n100 = 0;
 #pragma unroll
@@ -497,7 +507,7 @@ __device__ long long g_env_trace[16];
 constexpr int SCORE_UNROLL = 2;     // movers scored per lane and iteration of phase 2 (independent chains)
 
 template <int WPE, int CW, bool BIG, bool MULTI>
-__global__ void __launch_bounds__(32 * CW, WPE < 8 ? 28 / CW : (BIG ? 1 : 3))      // 28 env-warps / 3 env-CTAs resident per SM (BIG: one)
+__global__ void __launch_bounds__(32 * CW, WPE < 8 ? 28 / CW : (BIG ? 1 : 4))      // 28 env-warps / 4 env-CTAs resident per SM (BIG: one)
 env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict__ actions, float* obs, double* obs64,
                 double* reward_out, uint8_t* done_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -523,9 +533,10 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
 #ifdef MQ_ENV_TRACE
     long long _tprev = clock64();
 #endif
+    constexpr bool HSM = !(G::CHAIN && !BIG);     // shared copy of the health values (see carve)
     Smem sm;
     carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
-          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE);
+          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE, nullptr, HSM);
     int* sc = s_sc[g.gid];
     int(*rob)[2] = s_rob[g.gid];
     int* s_cnt = s_cnt_all[g.gid];
@@ -591,7 +602,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
             st.acc[base + i] = a;
         }
         sm.fl[i] = (uint8_t)fl;
-        sm.health[i] = (fl & 2u) ? 0.0 : h;          // summand of evacuation_env.py:245 (dead -> +0.0)
+        if (HSM) sm.health[i] = (fl & 2u) ? 0.0 : h;          // summand of evacuation_env.py:245 (dead -> +0.0)
         return mover;
     };
     auto push_movers = [&](bool mover, int i) {
@@ -628,7 +639,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
             if (i < N) {
                 const uint32_t fl = fl_[k];
                 sm.pos[i] = p_[k];
-                if (fl & 3u) { sm.fl[i] = (uint8_t)fl; sm.health[i] = (fl & 2u) ? 0.0 : h_[k]; }
+                if (fl & 3u) { sm.fl[i] = (uint8_t)fl; if (HSM) sm.health[i] = (fl & 2u) ? 0.0 : h_[k]; }
                 else if (dg_[k] > 0.0) hurt = true;
                 else mover = advance(i, fl, h_[k], a_[k]);
             }
@@ -674,7 +685,8 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
     ENV_MARK(1);      // phase 1
     if (G::CHAIN && !g.worker()) {
         // chain warp: the left-to-right health sum only needs phase 1; it overlaps with everything the workers do
-        const double th = health_chain_runs<BIG ? 8 : 1>(sm.health, N, lane);
+        const double th = HSM ? health_chain_runs<BIG ? 8 : 1>(sm.health, N, lane)
+                              : health_chain_runs<4, true>(st.health + base, N, lane, sm.fl);
         if (lane == 0) s_sum[1] = th;
     } else {
         const int wt = tid;                 // worker thread id (workers are the first TW threads of the group)
@@ -967,7 +979,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
                     const long long EX = 2LL * x + 1 - 2LL * lay.obs_exit[0], EY = 2LL * y + 1 - 2LL * lay.obs_exit[1];
                     const long long e4 = EX * EX + EY * EY;
                     guid += e4 > 1600 ? 4 : (e4 > 400 ? 3 : 2);                 // 2.0 / 1.5 / 1.0 (:207-212)
-                    if (sm.health[i] < 80.0) guid += 2;                         // +1.0 (:215-216)
+                    if ((HSM ? sm.health[i] : __ldcg(st.health + base + i)) < 80.0) guid += 2;      // +1.0 (:215-216)
                 }
                 const double dx = ((double)x + 0.5) - (double)rpx, dy = ((double)y + 0.5) - (double)rpy;
                 sm.dist[off++] = sqrt(dx * dx + dy * dy);                       // np.linalg.norm (:228)
@@ -1337,7 +1349,7 @@ extern "C" int mq_env_create_layouts(mq_env** out, const mq_env_cfg* cfg, const 
         if (const char* v = getenv("MQ_SMALL_WPE")) { int w = atoi(v); if (w == 1 || w == 2 || w == 4) e->wpe = w; }
         c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 32 * e->wpe);
     }
-    if (e->wpe == 8) c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 256);
+    if (e->wpe == 8) c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 256, nullptr, false);
     e->big = e->wpe == 8 && (size_t)c.smem_per_env + 2048 > (size_t)max_smem;
     if (e->big) {
         e->wpe = BIG_WPE;                              // one CTA per SM (shared-memory bound): make it a wide one

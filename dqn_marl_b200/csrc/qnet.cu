@@ -344,6 +344,9 @@ struct mq_qnet {
     int64_t launches = 0;
     // ---- bf16 tensor-core path (precision = 1) ----
     int precision = 0;                         // 0 = fp32 FFMA parity path, 1 = bf16 tcgen05 path
+    // persistent convolutions that run with TWO sets of epilogue warps (bit 0 conv2 forward, 1 conv3 forward, 2 conv3 data
+    // gradient, 3 conv2 data gradient); MQ_CONV_EPI8 overrides the default for A/B timing
+    int conv_epi8 = 0;
     bool w_dirty[2] = {true, true};            // bf16 weight copies of [online, target] are stale
     mq::bf::bf16 *w2f[2] = {nullptr, nullptr}, *w3f[2] = {nullptr, nullptr}, *w1f[2] = {nullptr, nullptr};   // forward operands
     mq::bf::bf16 *w2d = nullptr, *w3d = nullptr, *w1t = nullptr;                                              // dgrad operands (online)
@@ -447,11 +450,13 @@ static cudaError_t forward_net_bf16(mq_qnet* n, int which, const float* obs, lon
     // of the NHWC activation (no im2col buffer)
     ep = tc::Epilogue{};
     ep.out_bf16 = n->a2b; ep.ldc = C2; ep.bias = W[P_C2B]; ep.relu = 1;
-    e = tc::launch_conv_persistent<64, 32, 6>(n->a1b, n->w2f[which], B, C1, C2, 0, ep, n->n_sms, s);
+    e = (n->conv_epi8 & 1) ? tc::launch_conv_persistent<64, 32, 6, 8>(n->a1b, n->w2f[which], B, C1, C2, 0, ep, n->n_sms, s)
+                           : tc::launch_conv_persistent<64, 32, 6>(n->a1b, n->w2f[which], B, C1, C2, 0, ep, n->n_sms, s);
     if (e != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->a3b; ep.ldc = C3; ep.bias = W[P_C3B]; ep.relu = 1;
-    e = tc::launch_conv_persistent<128, 64, 3>(n->a2b, n->w3f[which], B, C2, C3, 0, ep, n->n_sms, s);
+    e = (n->conv_epi8 & 2) ? tc::launch_conv_persistent<128, 64, 3, 8>(n->a2b, n->w3f[which], B, C2, C3, 0, ep, n->n_sms, s)
+                           : tc::launch_conv_persistent<128, 64, 3>(n->a2b, n->w3f[which], B, C2, C3, 0, ep, n->n_sms, s);
     if (e != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_f32 = n->h1; ep.out_bf16 = n->h1b; ep.ldc = H1; ep.bias = W[P_F1B]; ep.relu = 1; ep.drop = drop_mask; ep.drop_scale = 1.f / (1.f - 0.2f);
@@ -607,12 +612,16 @@ static cudaError_t backward_bf16(mq_qnet* n, const float* state, long long B, co
     if ((e = conv_wgrad<128, 3, 64>(n, n->a2b, n->da3b, B, C2, C3, G[P_C3W], G[P_C3B], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da2b; ep.ldc = C2; ep.mask_bf16 = n->a2b;
-    if ((e = tc::launch_conv_persistent<64, 64, 3>(n->da3b, n->w3d, B, C3, C2, 1, ep, n->n_sms, s)) != cudaSuccess) return e;
+    e = (n->conv_epi8 & 4) ? tc::launch_conv_persistent<64, 64, 3, 8>(n->da3b, n->w3d, B, C3, C2, 1, ep, n->n_sms, s)
+                           : tc::launch_conv_persistent<64, 64, 3>(n->da3b, n->w3d, B, C3, C2, 1, ep, n->n_sms, s);
+    if (e != cudaSuccess) return e;
     // conv2
     if ((e = conv_wgrad<64, 4, 32>(n, n->a1b, n->da2b, B, C1, C2, G[P_C2W], G[P_C2B], s)) != cudaSuccess) return e;
     ep = tc::Epilogue{};
     ep.out_bf16 = n->da1b; ep.ldc = C1; ep.mask_bf16 = n->a1b;
-    if ((e = tc::launch_conv_persistent<32, 64, 4>(n->da2b, n->w2d, B, C2, C1, 1, ep, n->n_sms, s)) != cudaSuccess) return e;
+    e = (n->conv_epi8 & 8) ? tc::launch_conv_persistent<32, 64, 4, 8>(n->da2b, n->w2d, B, C2, C1, 1, ep, n->n_sms, s)
+                           : tc::launch_conv_persistent<32, 64, 4>(n->da2b, n->w2d, B, C2, C1, 1, ep, n->n_sms, s);
+    if (e != cudaSuccess) return e;
     n->launches += 2;
     // conv1: dWc1^T [32][64] = dY^T A1 (MN-major operands, 32-wide A slabs, split over the rows), reduced and transposed into
     // the [(tap, c)][32] layout; column 54 of A1 is all ones, so row 54 of the product is db = the column sums of dY.
@@ -642,6 +651,7 @@ extern "C" int mq_qnet_create(mq_qnet** out, int32_t device, int64_t max_batch, 
     mq_qnet* n = new (std::nothrow) mq_qnet();
     if (!n) return mq::fail(MQ_ERR_ALLOC, "mq_qnet_create: out of host memory");
     n->device = device; n->max_batch = max_batch;
+    if (const char* v = getenv("MQ_CONV_EPI8")) n->conv_epi8 = atoi(v);
     cudaDeviceGetAttribute(&n->n_sms, cudaDevAttrMultiProcessorCount, device);
     long long chunk = 0;
     for (int k = 0; k < MQ_QNET_TENSORS; ++k) {
