@@ -84,7 +84,8 @@ struct DevCfg {
     unsigned long long seed;
     PhiloxKeys pk;                     // round keys of `seed`
     int env_id_base, max_steps, reset_robots, reset_fire, auto_reset;
-    int hash_cap, hash_shift, n_leaf_max;
+    int hash_cap, n_leaf_max;          // proposal-table slots (a power of two or 1.5 x one: any size works with hash_cell)
+    int health_smem;                   // CTA-per-env variants: shared copy of the health values (see carve)
     int smem_per_env;
     unsigned char* scratch;            // BIG envs: per-env global scratch for everything but the occupancy bitmap
     long long scratch_per_env;
@@ -191,7 +192,8 @@ __device__ __forceinline__ void bm_set(uint32_t* bm, int wpr, int x, int y) {
 __device__ __forceinline__ void bm_clear(uint32_t* bm, int wpr, int x, int y) {
     atomicAnd(&bm[x * wpr + (y >> 5)], ~(1u << (y & 31)));
 }
-__device__ __forceinline__ uint32_t hash_cell(uint32_t c, int shift) { return (c * 0x9E3779B1u) >> shift; }
+// slot of a cell in a table of `cap` slots: multiplicative hash, then the multiply-high range reduction (no power of two needed)
+__device__ __forceinline__ uint32_t hash_cell(uint32_t c, uint32_t cap) { return __umulhi(c * 0x9E3779B1u, cap); }
 
 __device__ __forceinline__ double box_lookup(const int* box, const double* tab, int step, int x, int y) {
     int rx = x - box[0], ry = y - box[1];
@@ -346,7 +348,7 @@ env_reset_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const uint8_t* env_m
     select_layout<MULTI>(lay, env);
     Smem sm;
     carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
-          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE, nullptr, !(Group<WPE, CW>::CHAIN && !BIG));
+          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE, nullptr, !(Group<WPE, CW>::CHAIN && !BIG) || cfg.health_smem);
     int* sc = s_sc[g.gid];
     int(*rob)[2] = s_rob[g.gid];
     if (g.gtid < MQ_ENV_SCALARS) sc[g.gtid] = st.scalars[(size_t)env * MQ_ENV_SCALARS + g.gtid];
@@ -533,7 +535,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
 #ifdef MQ_ENV_TRACE
     long long _tprev = clock64();
 #endif
-    constexpr bool HSM = !(G::CHAIN && !BIG);     // shared copy of the health values (see carve)
+    const bool HSM = !(G::CHAIN && !BIG) || cfg.health_smem;     // shared copy of the health values (see carve)
     Smem sm;
     carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
           cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE, nullptr, HSM);
@@ -547,7 +549,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
     const int lane = tid & 31, warp = tid >> 5;
     const int N = cfg.N, stride = lay.stride, wpr = lay.wpr;
     const size_t base = (size_t)env * cfg.n_pad;
-    const uint32_t hmask = (uint32_t)cfg.hash_cap - 1u;
+    const uint32_t hcap = (uint32_t)cfg.hash_cap;
 
     // ---- stage: scalars, robots, occupancy bitmap; clear the proposal table ------------------------
     if (tid < MQ_ENV_SCALARS) sc[tid] = st.scalars[(size_t)env * MQ_ENV_SCALARS + tid];
@@ -886,11 +888,11 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
                 const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
                 const uint4 w4 = philox4x32(env_id, tick, (uint32_t)i, STREAM_HEALTH, cfg.pk);
                 const uint32_t t = (uint32_t)((x + move_dx(best_dir)) * stride + (y + move_dy(best_dir)));
-                uint32_t hh = hash_cell(t, cfg.hash_shift);
+                uint32_t hh = hash_cell(t, hcap);
                 for (;;) {
                     const uint32_t prev = atomicCAS(&sm.tab[hh].key, HEMPTY, t);
                     if (prev == HEMPTY || prev == t) break;
-                    hh = (hh + 1) & hmask;
+                    hh = hh + 1 == hcap ? 0u : hh + 1;
                 }
                 atomicMin(&sm.tab[hh].ml, (uint32_t)i);                      // leave half is still 0
                 atomicMin(&sm.tab[hh].best, ((unsigned long long)w4.z << 32) | (unsigned long long)i);
@@ -912,13 +914,13 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
             const uint32_t p = sm.pos[i];
             const int x = (int)(p & 0xFFFFu), y = (int)(p >> 16);
             const uint32_t c_old = (uint32_t)(x * stride + y);
-            uint32_t hh = hash_cell(c_old, cfg.hash_shift);
+            uint32_t hh = hash_cell(c_old, hcap);
             bool found = false;
             for (;;) {
                 const uint32_t k = tab_ld<BIG>(&sm.tab[hh].key);
                 if (k == HEMPTY) break;
                 if (k == c_old) { found = true; break; }
-                hh = (hh + 1) & hmask;
+                hh = hh + 1 == hcap ? 0u : hh + 1;
             }
             // old cell is somebody's target: order decides (the low half of ml is final since the barrier)
             if (found) atomicMax(&sm.tab[hh].ml, ((key + 1u) << 16) | (tab_ld<BIG>(&sm.tab[hh].ml) & 0xFFFFu));
@@ -1329,8 +1331,10 @@ extern "C" int mq_env_create_layouts(mq_env** out, const mq_env_cfg* cfg, const 
     c.reset_robots = cfg->reset_robots; c.reset_fire = cfg->reset_fire; c.auto_reset = cfg->auto_reset;
     int want = c.N + c.N / 3 + 8;                      // load factor <= 0.75 even if everybody proposes a distinct cell
     c.hash_cap = round_pow2(want < 64 ? 64 : want);    // < 2^20 (20-bit slot ids in Smem::mv)
-    int lg = 0; while ((1 << lg) < c.hash_cap) ++lg;
-    c.hash_shift = 32 - lg;
+    if (c.hash_cap >= 128 && c.hash_cap / 4 * 3 >= want) c.hash_cap = c.hash_cap / 4 * 3;      // 1.5 x 2^k is enough: 1536 slots (24 KB) at 1000 people
+    c.health_smem = 1;
+    if (const char* v = getenv("MQ_ENV_HSM")) c.health_smem = atoi(v) != 0;                    // A/B timing knobs
+    if (const char* v = getenv("MQ_ENV_HASH_POW2")) { if (atoi(v)) c.hash_cap = round_pow2(want < 64 ? 64 : want); }
     c.n_leaf_max = c.N / 64 + 4;
     c.evac_reward = cfg->evac_reward; c.death_penalty = cfg->death_penalty;
     c.death_acc_penalty = cfg->death_acc_penalty; c.alive_bonus = cfg->alive_bonus;
@@ -1349,7 +1353,7 @@ extern "C" int mq_env_create_layouts(mq_env** out, const mq_env_cfg* cfg, const 
         if (const char* v = getenv("MQ_SMALL_WPE")) { int w = atoi(v); if (w == 1 || w == 2 || w == 4) e->wpe = w; }
         c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 32 * e->wpe);
     }
-    if (e->wpe == 8) c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 256, nullptr, false);
+    if (e->wpe == 8) c.smem_per_env = (int)mq::carve(tmp, nullptr, nullptr, c.N, c.hash_cap, l.rmap_words, c.n_leaf_max, 256, nullptr, c.health_smem != 0);
     e->big = e->wpe == 8 && (size_t)c.smem_per_env + 2048 > (size_t)max_smem;
     if (e->big) {
         e->wpe = BIG_WPE;                              // one CTA per SM (shared-memory bound): make it a wide one
@@ -1381,6 +1385,7 @@ extern "C" int mq_env_create_layouts(mq_env** out, const mq_env_cfg* cfg, const 
     const int groups = e->wpe < 8 ? small_cw / e->wpe : 1;
     e->threads = 32 * k_variants[e->variant].cw;
     e->smem = (size_t)c.smem_per_env * groups;
+    if (const char* v = getenv("MQ_ENV_SMEM_PAD")) { if (e->wpe == 8 && !e->big) e->smem += (size_t)atoi(v); }     // A/B: fewer resident CTAs
     if ((int)e->smem + 2048 > max_smem) {
         size_t need = e->smem;
         mq_env_destroy(e);
