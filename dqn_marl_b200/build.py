@@ -103,8 +103,24 @@ def build_env_trace() -> str:
     return out
 
 
+def build_variant(name: str, defs) -> str:
+    """libmarl_b200_<name>.so: the library with env.cu compiled with extra -D definitions (A/B timing of tuning knobs through
+    MARL_B200_SO, e.g. build_variant("u1", ["-DMQ_SCORE_U8=1"]))."""
+    build()
+    nvcc = _nvcc()
+    out = os.path.join(HERE, f"libmarl_b200_{name}.so")
+    obj = os.path.join(OBJ, f"env.cu.{name}.o")
+    subprocess.run([nvcc, *ARCH, *COMMON, "-fmad=false", *defs, "-c", os.path.join(CSRC, "env.cu"), "-o", obj], check=True, capture_output=True, text=True)
+    objs = [os.path.join(OBJ, src + ".o") for src in sources() if src != "env.cu"] + [obj]
+    subprocess.run([nvcc, *ARCH, "-shared", "-o", out, *objs], check=True, capture_output=True, text=True)
+    return out
+
+
 if __name__ == "__main__":
-    if "--env-trace" in sys.argv:
+    if "--variant" in sys.argv:
+        k = sys.argv.index("--variant")
+        print(build_variant(sys.argv[k + 1], sys.argv[k + 2:]))
+    elif "--env-trace" in sys.argv:
         print(build_env_trace())
     else:
         print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

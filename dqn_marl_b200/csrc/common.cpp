@@ -30,27 +30,43 @@ extern "C" int mq_abi_version(void) { return MQ_ABI_VERSION; }
 #include <vector>
 
 static void expand_range(const uint32_t* wire, int64_t w0, int64_t w1, float* obs) {
+    // (b1, b3, b4) as floats for the 8 combinations of the three plane bits of a cell
+    static const float lut[8][3] = {{0.f, 0.f, 0.f}, {1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {1.f, 1.f, 0.f},
+                                    {0.f, 0.f, 1.f}, {1.f, 0.f, 1.f}, {0.f, 1.f, 1.f}, {1.f, 1.f, 1.f}};
+    constexpr int CELLS = MQ_OBS_WIN * MQ_OBS_WIN;
     for (int64_t w = w0; w < w1; ++w) {
         const uint32_t* rec = wire + w * MQ_OBS_WIRE_WORDS;
         float* o = obs + w * MQ_OBS_SIZE;
-        for (int c = 0; c < MQ_OBS_WIN * MQ_OBS_WIN; ++c) {
-            const int word = c >> 5, bit = c & 31;
-            float v2;
-            std::memcpy(&v2, rec + c, sizeof(float));
-            o[0] = 0.f;                                                   // channel 0 == space / inf (quirk Q1)
-            o[1] = (float)((rec[121 + word] >> bit) & 1u);
-            o[2] = v2;
-            o[3] = (float)((rec[125 + word] >> bit) & 1u);
-            o[4] = (float)((rec[129 + word] >> bit) & 1u);
-            o[5] = c == 60 ? 1.f : 0.f;                                   // evacuation_env.py:116-117 (i == 5 and j == 5)
-            o += MQ_OBS_CH;
+        float v2[CELLS];
+        std::memcpy(v2, rec, sizeof(v2));
+        int c = 0;
+        for (int word = 0; word < 4; ++word) {
+            uint32_t p1 = rec[121 + word], p3 = rec[125 + word], p4 = rec[129 + word];
+            const int end = word == 3 ? CELLS : 32 * (word + 1);
+            for (; c + 1 < end; c += 2) {                                   // two cells = 12 floats = three 16-byte stores
+                const float* a = lut[(p1 & 1u) | ((p3 & 1u) << 1) | ((p4 & 1u) << 2)];
+                const float* b = lut[((p1 >> 1) & 1u) | (((p3 >> 1) & 1u) << 1) | (((p4 >> 1) & 1u) << 2)];
+                const float t[12] = {0.f, a[0], v2[c], a[1], a[2], 0.f, 0.f, b[0], v2[c + 1], b[1], b[2], 0.f};
+                std::memcpy(o + 6 * c, t, sizeof(t));
+                p1 >>= 2; p3 >>= 2; p4 >>= 2;
+            }
+            if (c < end) {                                                   // cell 120, the odd one out
+                const float* a = lut[(p1 & 1u) | ((p3 & 1u) << 1) | ((p4 & 1u) << 2)];
+                const float t[6] = {0.f, a[0], v2[c], a[1], a[2], 0.f};
+                std::memcpy(o + 6 * c, t, sizeof(t));
+                ++c;
+            }
         }
+        o[60 * MQ_OBS_CH + 5] = 1.f;                                         // evacuation_env.py:116-117 (i == 5 and j == 5)
     }
 }
 
 extern "C" int mq_obs_wire_expand(const uint32_t* wire, int64_t n_windows, float* obs_out, int32_t n_threads) {
     MQ_REQUIRE(wire && obs_out && n_windows >= 0, "mq_obs_wire_expand: bad argument");
-    if (n_threads <= 0) n_threads = (int32_t)std::min<int64_t>(16, std::max<int64_t>(1, n_windows / 2048));
+    if (n_threads <= 0) {
+        const int64_t hw = std::max<int64_t>(1, (int64_t)std::thread::hardware_concurrency());
+        n_threads = (int32_t)std::min<int64_t>(hw, std::max<int64_t>(1, n_windows / 1024));
+    }
     if (n_threads == 1 || n_windows < 2 * n_threads) { expand_range(wire, 0, n_windows, obs_out); return MQ_OK; }
     std::vector<std::thread> pool;
     const int64_t per = (n_windows + n_threads - 1) / n_threads;

@@ -507,9 +507,17 @@ __device__ long long g_env_trace[16];
 #define ENV_MARK(k) do { } while (0)
 #endif
 constexpr int SCORE_UNROLL = 2;     // movers scored per lane and iteration of phase 2 (independent chains)
+// build-time tuning knobs of the CTA-per-env variant (dqn_marl_b200/build.py build_variant): resident CTAs per SM the register
+// allocation aims at, and the scoring unroll
+#ifndef MQ_CTA8_PER_SM
+#define MQ_CTA8_PER_SM 4
+#endif
+#ifndef MQ_SCORE_U8
+#define MQ_SCORE_U8 SCORE_UNROLL
+#endif
 
 template <int WPE, int CW, bool BIG, bool MULTI>
-__global__ void __launch_bounds__(32 * CW, WPE < 8 ? 28 / CW : (BIG ? 1 : 4))      // 28 env-warps / 4 env-CTAs resident per SM (BIG: one)
+__global__ void __launch_bounds__(32 * CW, WPE < 8 ? 28 / CW : (BIG ? 1 : MQ_CTA8_PER_SM))      // 28 env-warps / 4 env-CTAs resident per SM (BIG: one)
 env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict__ actions, float* obs, double* obs64,
                 double* reward_out, uint8_t* done_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -803,7 +811,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
             const int n_items = (n_mov * 4 + 31) & ~31;          // whole warps take part in the shuffles
             // U items per lane and iteration, written stage by stage and branch-free so that the U independent Philox /
             // scoring chains interleave: the loop is bound by the latency of one chain, not by issue slots
-            constexpr int U = SCORE_UNROLL;
+            constexpr int U = (WPE >= 8 && !BIG) ? MQ_SCORE_U8 : SCORE_UNROLL;
             for (int it0 = wt; it0 < n_items; it0 += U * TW) {
                 int mi[U], i[U], x[U], y[U];
                 bool act[U];
