@@ -727,7 +727,6 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
                 int mi[U], i[U], x[U], y[U], rx0[U], ry0[U], eo[U];
                 bool act[U];
                 double dpv[U][2];
-                uint4 w[U];
                 const uint16_t* movp[U]; const uint32_t* posp[U]; const uint32_t* bmp[U]; uint32_t* mvp[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -758,20 +757,17 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
                         dpv[u][0] = v.x; dpv[u][1] = v.y;
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < U; ++u)
-                    w[u] = philox4x32((uint32_t)(cfg.env_id_base + blockIdx.x * GROUPS + eo[u]), (uint32_t)s_sc[eo[u]][MQ_S_TICK], (uint32_t)i[u],
-                                      (uint32_t)q, cfg.pk);
-                double best_score[U];
-                int best_dir[U];
+                // deterministic scores first; the keyed noise is drawn only when some mover of the chunk has two or more
+                // directions within 0.2 of its best one (see LAZY NOISE below); warp-uniform decision per chunk
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    best_score[u] = -INFINITY; best_dir[u] = 8;
+                    bool adm[2];
+                    double det[2];
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         const int d = q * 2 + k;
                         const int nx = x[u] + move_dx(d), ny = y[u] + move_dy(d);
-                        const bool adm = (dpv[u][k] > -INFINITY) && !bm_get(bmp[u], wpr, nx, ny);
+                        adm[k] = (dpv[u][k] > -INFINITY) && !bm_get(bmp[u], wpr, nx, ny);
                         int d2;
                         {
                             const int ax = min(abs(nx - rx0[u]), 30000), ay = min(abs(ny - ry0[u]), 30000);
@@ -784,21 +780,37 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
                             }
                         }
                         const double eff = d2 < 25 ? c_repel[d2] : 0.0;
-                        const double un = k ? u53(w[u].z, w[u].w) : u53(w[u].x, w[u].y);
-                        const double noise = -0.1 + (0.1 - -0.1) * un;       // random.uniform(-0.1, 0.1)
-                        const double score = (dpv[u][k] + eff) + noise;        // people.py:287-291
-                        if (adm && score > best_score[u]) { best_score[u] = score; best_dir[u] = d; }
+                        det[k] = dpv[u][k] + eff;
                     }
-                }
+                    double gmax = fmax(adm[0] ? det[0] : -INFINITY, adm[1] ? det[1] : -INFINITY);
+                    gmax = fmax(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, 1));
+                    gmax = fmax(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, 2));
+                    const bool c0 = adm[0] && det[0] >= gmax - 0.25, c1 = adm[1] && det[1] >= gmax - 0.25;
+                    const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, c0), b1 = __ballot_sync(0xFFFFFFFFu, c1);
+                    const int sh = lane & 28;
+                    const int cnt = __popc((b0 >> sh) & 0xFu) + __popc((b1 >> sh) & 0xFu);
+                    if (!__any_sync(0xFFFFFFFFu, act[u] && cnt >= 2)) {
+                        if (act[u] && cnt == 1 && (c0 || c1)) mvp[u][mi[u]] = (uint32_t)(q * 2 + (c1 ? 1 : 0)) << 20;
+                        continue;
+                    }
+                    const uint4 w = philox4x32((uint32_t)(cfg.env_id_base + blockIdx.x * GROUPS + eo[u]), (uint32_t)s_sc[eo[u]][MQ_S_TICK],
+                                               (uint32_t)i[u], (uint32_t)q, cfg.pk);
+                    double best_score = -INFINITY;
+                    int best_dir = 8;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
+                    for (int k = 0; k < 2; ++k) {
+                        const double un = k ? u53(w.z, w.w) : u53(w.x, w.y);
+                        const double noise = -0.1 + (0.1 - -0.1) * un;       // random.uniform(-0.1, 0.1)
+                        const double score = det[k] + noise;                   // people.py:287-291
+                        if (adm[k] && score > best_score) { best_score = score; best_dir = q * 2 + k; }
+                    }
 #pragma unroll
                     for (int o = 1; o <= 2; o <<= 1) {
-                        const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score[u], o);
-                        const int od = __shfl_xor_sync(0xFFFFFFFFu, best_dir[u], o);
-                        if (os > best_score[u] || (os == best_score[u] && od < best_dir[u])) { best_score[u] = os; best_dir[u] = od; }
+                        const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score, o);
+                        const int od = __shfl_xor_sync(0xFFFFFFFFu, best_dir, o);
+                        if (os > best_score || (os == best_score && od < best_dir)) { best_score = os; best_dir = od; }
                     }
-                    if (act[u] && q == 0 && best_dir[u] < 8) mvp[u][mi[u]] = (uint32_t)best_dir[u] << 20;
+                    if (act[u] && q == 0 && best_dir < 8) mvp[u][mi[u]] = (uint32_t)best_dir << 20;
                 }
             }
             __syncthreads();
@@ -809,21 +821,95 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
             for (int r = 0; r < MAXR; ++r) { rbx[r] = rob[r < cfg.R ? r : 0][0]; rby[r] = rob[r < cfg.R ? r : 0][1]; }
             const int q = lane & 3, R = cfg.R;
             const int n_items = (n_mov * 4 + 31) & ~31;          // whole warps take part in the shuffles
-            // U items per lane and iteration, written stage by stage and branch-free so that the U independent Philox /
-            // scoring chains interleave: the loop is bound by the latency of one chain, not by issue slots
+            // admissibility (Check_Valid through dp5 = -inf, rmap == 0) and the deterministic part of the score of direction
+            // d = 2q + k: delta_p * 5.0 + robot_effect (people.py:268-288)
+            auto det_score = [&](int xx, int yy, double dp, int d, bool& adm) -> double {
+                const int nx = xx + move_dx(d), ny = yy + move_dy(d);
+                adm = (dp > -INFINITY) && !bm_get(sm.bm, wpr, nx, ny);
+                // squared distance to the nearest robot, coordinates saturated at 30000 (robots may sit far off-map:
+                // evaluate_strategies.py:83 sets [1000,1000]; anything >= 25 means "out of range")
+                int d2;
+                {
+                    const int ax = min(abs(nx - rbx[0]), 30000), ay = min(abs(ny - rby[0]), 30000);
+                    d2 = ax * ax + ay * ay;
+                }
+                if (R > 1) {                         // warp-uniform
+#pragma unroll
+                    for (int r = 1; r < MAXR; ++r) {
+                        const int ax = min(abs(nx - rbx[r]), 30000), ay = min(abs(ny - rby[r]), 30000);
+                        d2 = min(d2, ax * ax + ay * ay);       // r >= R repeats robot 0: harmless for the minimum
+                    }
+                }
+                const double eff = d2 < 25 ? c_repel[d2] : 0.0;
+                return dp + eff;
+            };
+            // LAZY NOISE.  random.uniform(-0.1, 0.1) (people.py:290) can only decide between directions whose deterministic
+            // scores lie within 0.2 of the best one.  Pass A evaluates the deterministic scores of every mover; a mover with a
+            // single such contender has its direction without any draw (the noise of direction d is keyed by d, so not
+            // drawing the others changes nothing).  Movers with two or more contenders (ties of the floor field, neighbours
+            // of the best cell taken) are listed per warp and get the full keyed evaluation in pass B.  The list reuses the
+            // hurt lists of phase 1 (dead since the barrier): (N + T) / worker-warps entries per warp >= its movers.
+            constexpr double NOISE_MARGIN = 0.25;                  // > 0.1 - (-0.1) plus any rounding of (det + noise)
+            constexpr int WW = TW / 32;
+            uint16_t* const my_amb = sm.hurt + (size_t)(wt >> 5) * (size_t)(((N + T) / WW) & ~7);
+            int n_amb = 0;                                          // warp-uniform
+            // U items per lane and iteration, written stage by stage and branch-free so that the U independent chains interleave
             constexpr int U = (WPE >= 8 && !BIG) ? MQ_SCORE_U8 : SCORE_UNROLL;
             for (int it0 = wt; it0 < n_items; it0 += U * TW) {
+                int mi[U], x[U], y[U];
+                bool act[U];
+                double dpv[U][2];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int it = it0 + u * TW;
+                    mi[u] = it >> 2;
+                    act[u] = it < n_items && mi[u] < n_mov;
+                    const int i = act[u] ? (int)sm.mov[mi[u]] : 0;
+                    const uint32_t p = act[u] ? sm.pos[i] : 0x00010001u;       // (1,1): neighbours stay inside the bitmap
+                    x[u] = (int)(p & 0xFFFFu); y[u] = (int)(p >> 16);
+                    dpv[u][0] = -INFINITY; dpv[u][1] = -INFINITY;
+                    if (act[u]) {
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(lay.dp5 + (size_t)(x[u] * stride + y[u]) * 8) + q);
+                        dpv[u][0] = v.x; dpv[u][1] = v.y;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    bool a0, a1;
+                    const double s0 = det_score(x[u], y[u], dpv[u][0], q * 2, a0), s1 = det_score(x[u], y[u], dpv[u][1], q * 2 + 1, a1);
+                    double gmax = fmax(a0 ? s0 : -INFINITY, a1 ? s1 : -INFINITY);
+                    gmax = fmax(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, 1));
+                    gmax = fmax(gmax, __shfl_xor_sync(0xFFFFFFFFu, gmax, 2));
+                    const bool c0 = a0 && s0 >= gmax - NOISE_MARGIN, c1 = a1 && s1 >= gmax - NOISE_MARGIN;
+                    const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, c0), b1 = __ballot_sync(0xFFFFFFFFu, c1);
+                    const int sh = lane & 28;
+                    const int cnt = __popc((b0 >> sh) & 0xFu) + __popc((b1 >> sh) & 0xFu);
+                    if (act[u] && cnt == 1 && (c0 || c1)) sm.mv[mi[u]] = (uint32_t)(q * 2 + (c1 ? 1 : 0)) << 20;
+                    const bool amb = act[u] && cnt >= 2 && q == 0;
+                    const uint32_t ab = __ballot_sync(0xFFFFFFFFu, amb);
+                    if (amb) my_amb[n_amb + __popc(ab & ((1u << lane) - 1u))] = (uint16_t)mi[u];
+                    n_amb += __popc(ab);
+                }
+            }
+            __syncwarp();
+#ifdef MQ_ENV_TRACE
+            if (lane == 0) { atomicAdd((unsigned long long*)&g_env_trace[12], (unsigned long long)n_amb); }
+            if (wt == 0) { atomicAdd((unsigned long long*)&g_env_trace[13], (unsigned long long)n_mov); }
+#endif
+            // pass B: the listed movers, all eight directions with their keyed draws, strict '>' in direction order
+            // (people.py:293): larger score wins, ties go to the lower direction
+            for (int e0 = 0; e0 < n_amb * 4; e0 += 32 * U) {
                 int mi[U], i[U], x[U], y[U];
                 bool act[U];
                 double dpv[U][2];
                 uint4 w[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int it = it0 + u * TW;
-                    mi[u] = it >> 2;
-                    act[u] = it < n_items && mi[u] < n_mov;
+                    const int e = (e0 + 32 * u + lane) >> 2;
+                    act[u] = e < n_amb;
+                    mi[u] = act[u] ? (int)my_amb[e] : 0;
                     i[u] = act[u] ? (int)sm.mov[mi[u]] : 0;
-                    const uint32_t p = act[u] ? sm.pos[i[u]] : 0x00010001u;       // (1,1): neighbours stay inside the bitmap
+                    const uint32_t p = act[u] ? sm.pos[i[u]] : 0x00010001u;
                     x[u] = (int)(p & 0xFFFFu); y[u] = (int)(p >> 16);
                     dpv[u][0] = -INFINITY; dpv[u][1] = -INFINITY;
                     if (act[u]) {
@@ -833,47 +919,26 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) w[u] = philox4x32(env_id, tick, (uint32_t)i[u], (uint32_t)q, cfg.pk);
-                double best_score[U];
-                int best_dir[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    best_score[u] = -INFINITY; best_dir[u] = 8;
+                    double best_score = -INFINITY;
+                    int best_dir = 8;
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
-                        const int d = q * 2 + k;
-                        const int nx = x[u] + move_dx(d), ny = y[u] + move_dy(d);
-                        const bool adm = (dpv[u][k] > -INFINITY) && !bm_get(sm.bm, wpr, nx, ny);
-                        // squared distance to the nearest robot, coordinates saturated at 30000 (robots may sit far off-map:
-                        // evaluate_strategies.py:83 sets [1000,1000]; anything >= 25 means "out of range")
-                        int d2;
-                        {
-                            const int ax = min(abs(nx - rbx[0]), 30000), ay = min(abs(ny - rby[0]), 30000);
-                            d2 = ax * ax + ay * ay;
-                        }
-                        if (R > 1) {                         // warp-uniform
-#pragma unroll
-                            for (int r = 1; r < MAXR; ++r) {
-                                const int ax = min(abs(nx - rbx[r]), 30000), ay = min(abs(ny - rby[r]), 30000);
-                                d2 = min(d2, ax * ax + ay * ay);       // r >= R repeats robot 0: harmless for the minimum
-                            }
-                        }
-                        const double eff = d2 < 25 ? c_repel[d2] : 0.0;
+                        bool adm;
+                        const double det = det_score(x[u], y[u], dpv[u][k], q * 2 + k, adm);
                         const double un = k ? u53(w[u].z, w[u].w) : u53(w[u].x, w[u].y);
                         const double noise = -0.1 + (0.1 - -0.1) * un;       // random.uniform(-0.1, 0.1)
-                        const double score = (dpv[u][k] + eff) + noise;        // people.py:287-291
-                        if (adm && score > best_score[u]) { best_score[u] = score; best_dir[u] = d; }
+                        const double score = det + noise;                      // people.py:287-291
+                        if (adm && score > best_score) { best_score = score; best_dir = q * 2 + k; }
                     }
-                }
-                // strict '>' in direction order (people.py:293): larger score wins, ties go to the lower direction
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
 #pragma unroll
                     for (int o = 1; o <= 2; o <<= 1) {
-                        const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score[u], o);
-                        const int od = __shfl_xor_sync(0xFFFFFFFFu, best_dir[u], o);
-                        if (os > best_score[u] || (os == best_score[u] && od < best_dir[u])) { best_score[u] = os; best_dir[u] = od; }
+                        const double os = __shfl_xor_sync(0xFFFFFFFFu, best_score, o);
+                        const int od = __shfl_xor_sync(0xFFFFFFFFu, best_dir, o);
+                        if (os > best_score || (os == best_score && od < best_dir)) { best_score = os; best_dir = od; }
                     }
-                    if (act[u] && q == 0 && best_dir[u] < 8) sm.mv[mi[u]] = (uint32_t)best_dir[u] << 20;
+                    if (act[u] && q == 0 && best_dir < 8) sm.mv[mi[u]] = (uint32_t)best_dir << 20;
                 }
             }
         }

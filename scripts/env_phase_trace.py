@@ -19,6 +19,7 @@ rew = torch.empty((E,), dtype=torch.float64, device=dev); don = torch.empty((E,)
 g = torch.Generator(device=dev); g.manual_seed(1234)
 actions = torch.randint(0, 5, (64, E, 1), generator=g, device=dev, dtype=torch.int32)
 env.reset()
+amb_note = True
 names = ["stage", "phase 1", "scoring", "proposals", "moves", "reward inputs", "tree+chain", "bitmap+obs", "reward"]
 def window(t0, t1, label):
     torch.cuda.synchronize(); lib.mq_debug_env_trace(None, 1)
@@ -29,7 +30,8 @@ def window(t0, t1, label):
     out = np.zeros(16, dtype=np.int64); lib.mq_debug_env_trace(ctypes.c_void_p(out.ctypes.data), 0)
     per = out[:9] / (E * (t1 - t0))
     print(f"{label}: {e0.elapsed_time(e1) / (t1 - t0) * 1e3:.1f} us per launch; cycles per env-step by phase: " +
-          ", ".join(f"{n} {c:.0f}" for n, c in zip(names, per)) + f"; total {per.sum():.0f}")
+          ", ".join(f"{n} {c:.0f}" for n, c in zip(names, per)) + f"; total {per.sum():.0f}" +
+          (f"; movers needing noise draws {out[12]} of {out[13]} ({100.0 * out[12] / max(out[13], 1):.1f} %)" if out[13] else ""))
 window(0, 1, "step 0 (nobody moves)"); window(1, 2, "step 1 (everybody moves)"); window(2, 3, "step 2"); window(3, 4, "step 3")
 window(4, min(150, steps), "steps 4-149")
 if steps > 150: window(150, steps, f"steps 150-{steps - 1}")
