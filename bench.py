@@ -357,17 +357,23 @@ def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
             vals.append(world * E * N * e2e_steps / e2e_s)
         h2d = h_act[0].numel() * 4
         d2h = envs[0].h_obs.numel() * 4 + envs[0].h_reward.numel() * 8 + envs[0].h_done.numel()
-        res["e2e"] = {"value": vals[0], "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        d2h_wire = envs[0].h_wire.numel() * 4 + envs[0].h_reward.numel() * 8 + envs[0].h_done.numel()
+        mode = "wire" if vals[2] > vals[0] else "dense"
+        best, d2h_best = (vals[2], d2h_wire) if mode == "wire" else (vals[0], d2h)
+        res["e2e"] = {"value": best, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_best, "mode": mode,
                       "steps": e2e_steps, "value_sync_each_step": vals[1],
-                      "d2h_GBs_per_gpu": vals[0] / world / (E * N) * d2h / 1e9,
-                      "wire": {"value": vals[2], "d2h_bytes_per_step": envs[0].h_wire.numel() * 4 + envs[0].h_reward.numel() * 8 + envs[0].h_done.numel(),
+                      "d2h_GBs_per_gpu": best / world / (E * N) * d2h_best / 1e9,
+                      "dense": {"value": vals[0], "d2h_bytes_per_step": d2h,
+                                "note": "step_async(): the dense f32 observation windows cross PCIe (2904 B per window)"},
+                      "wire": {"value": vals[2], "d2h_bytes_per_step": d2h_wire, "host_threads": getattr(envs[0], "wire_threads", None),
                                "note": "step_async(wire=True): observations cross PCIe in the compact wire form (544 B per window: channel 2 as "
                                        "f32 + bit planes of channels 1 / 3 / 4) and are expanded to the same dense f32 host buffer by "
                                        "mq_obs_wire_expand inside step_wait(), i.e. inside the timed region"},
                       "note": f"VecEvacuationEnv.step_async/step_wait: pinned host actions in (H2D), obs+reward+done out (D2H) every "
-                              f"step; {n_rot} independent env batches in flight on their own streams (copies overlap kernels); "
-                              f"value_sync_each_step = one batch at a time with a host sync per step; d2h_GBs_per_gpu = the PCIe "
-                              f"device-to-host rate this e2e value corresponds to"}
+                              f"step, the same dense f32 host buffers in both modes; value = the faster of the two transfer modes (named in "
+                              f"`mode`), both measured and listed; {n_rot} independent env batches in flight on their own streams (copies "
+                              f"overlap kernels); value_sync_each_step = dense mode, one batch at a time with a host sync per step; "
+                              f"d2h_GBs_per_gpu = the PCIe device-to-host rate the value corresponds to"}
     for env in envs:
         env.close()
     del envs, obs, rew, don

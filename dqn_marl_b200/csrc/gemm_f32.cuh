@@ -80,7 +80,9 @@ __device__ __forceinline__ float epilogue_value(const GemmParams& p, float v, in
 }
 
 template <int AMODE, int BMODE, int BN, int CDIM>
-__global__ void __launch_bounds__(GEMM_THREADS)
+// resident CTAs per SM the register allocation must allow: 2 at BN = 128 (<= 128 registers; two loader modes needed 130 / 139
+// and ran ONE CTA per SM), 3 at BN = 64, 4 at BN = 32
+__global__ void __launch_bounds__(GEMM_THREADS, BN >= 128 ? 2 : (BN >= 64 ? 3 : 4))
 gemm_f32_kernel(GemmParams p) {
     constexpr int TN = BN / 16;                       // micro-tile columns per thread
     constexpr int B_PER_THREAD = GEMM_BK * BN / GEMM_THREADS;   // 8 / 4 / 2

@@ -7,6 +7,8 @@ Host-side mirror of the reference's env surface (reference Louvre_Evacuation/env
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Optional
 
@@ -263,8 +265,13 @@ class VecEvacuationEnv:
         """Block until the step enqueued by step_async() has landed in host memory -> (obs, reward, done) pinned host tensors."""
         self._hev.synchronize()
         if getattr(self, "_wire_pending", False):
-            _lib.check(self.lib.mq_obs_wire_expand(_lib.ptr(self.h_wire), self.n_envs * self.n_robots, _lib.ptr(self.h_obs),
-                                                   int(getattr(self, "wire_threads", 0))), "mq_obs_wire_expand")
+            # host threads of the expansion: this process's share of the cores (torchrun starts LOCAL_WORLD_SIZE of us)
+            nthr = getattr(self, "wire_threads", None)
+            if nthr is None:
+                cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+                nthr = self.wire_threads = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+            _lib.check(self.lib.mq_obs_wire_expand(_lib.ptr(self.h_wire), self.n_envs * self.n_robots, _lib.ptr(self.h_obs), int(nthr)),
+                       "mq_obs_wire_expand")
             self._wire_pending = False
         return self.h_obs, self.h_reward, self.h_done
 

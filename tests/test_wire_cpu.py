@@ -25,4 +25,15 @@ def test_wire_expand_matches_numpy_packing():
         out[:] = 7
         _lib.check(lib.mq_obs_wire_expand(_lib.ptr(wire), n, _lib.ptr(out), threads), "mq_obs_wire_expand")
         assert np.array_equal(out.view(np.uint32), obs.view(np.uint32)), threads
+    # ragged counts and a destination that starts 8 bytes off a 16-byte boundary (the streaming-store path has a head and a
+    # tail), repeated calls on the persistent worker pool; the floats around the destination stay untouched
+    buf = np.full((n * 726 + 8,), 7, np.float32)
+    for off in (0, 2):
+        for m in (1, 7, 8, 9, 129, 1031, n):
+            for threads in (1, 3, 16):
+                buf[:] = 7
+                dst = buf[off:off + m * 726]
+                _lib.check(lib.mq_obs_wire_expand(_lib.ptr(wire), m, dst.ctypes.data, threads), "mq_obs_wire_expand")
+                assert np.array_equal(dst.view(np.uint32), obs[:m].reshape(-1).view(np.uint32)), (off, m, threads)
+                assert (buf[:off] == 7).all() and (buf[off + m * 726:] == 7).all(), (off, m, threads)
     _lib.check(lib.mq_obs_wire_expand(_lib.ptr(wire), 0, _lib.ptr(out), 1), "empty input")
