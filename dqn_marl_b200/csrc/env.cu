@@ -119,6 +119,9 @@ struct Smem {
     uint16_t* mov; uint32_t* mv;
     uint16_t* hurt;      // per-warp lists of the people standing in danger this step (T + N entries, T = threads of the group)
     uint8_t* fl;
+    uint32_t* tfilt;     // target filter of the move phases: one bit per hashed target cell, 10 * nleaf words ALIASING the four leaf
+                         // arrays (which the np.mean tree initialises itself, after the moves)
+    int tfilt_bits;
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -147,12 +150,13 @@ __host__ __device__ inline size_t carve(Smem& s, unsigned char* base, unsigned c
     s.mov = (uint16_t*)(pb + po); po += align_up(sizeof(uint16_t) * N, 16);
     s.hurt = (uint16_t*)(pb + po); po += align_up(sizeof(uint16_t) * (N + T), 16);
     s.fl = (uint8_t*)(pb + po); po += align_up(N, 16);
+    s.tfilt = (uint32_t*)(base + o); s.tfilt_bits = 32 * 10 * nleaf;
     s.leaf_sum = (double*)(base + o); o += sizeof(double) * 2 * nleaf;
-    o = align_up(o, 16);
-    s.bm = (uint32_t*)(base + o); o += sizeof(uint32_t) * align_up(words, 4);
     s.leaf_off = (int*)(base + o); o += sizeof(int) * 2 * nleaf;
     s.leaf_len = (int*)(base + o); o += sizeof(int) * 2 * nleaf;
     s.nchild = (int*)(base + o); o += sizeof(int) * 2 * nleaf;
+    o = align_up(o, 16);
+    s.bm = (uint32_t*)(base + o); o += sizeof(uint32_t) * align_up(words, 4);
     if (gbytes) *gbytes = align_up(go, 256);
     return align_up(o, 16);
 }
@@ -194,6 +198,9 @@ __device__ __forceinline__ void bm_clear(uint32_t* bm, int wpr, int x, int y) {
 }
 // slot of a cell in a table of `cap` slots: multiplicative hash, then the multiply-high range reduction (no power of two needed)
 __device__ __forceinline__ uint32_t hash_cell(uint32_t c, uint32_t cap) { return __umulhi(c * 0x9E3779B1u, cap); }
+
+// bit of a cell in the target filter (a hash independent of hash_cell's slot)
+__device__ __forceinline__ uint32_t filt_bit(uint32_t c, int bits) { return __umulhi((c ^ (c >> 7)) * 0x85EBCA6Bu, (uint32_t)bits); }
 
 __device__ __forceinline__ double box_lookup(const int* box, const double* tab, int step, int x, int y) {
     int rx = x - box[0], ry = y - box[1];
@@ -570,6 +577,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
         const uint4 empty = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, HEMPTY, 0x0000FFFFu);   // best = ~0, key, ml = (min 0xFFFF, leave 0)
         uint4* tab = reinterpret_cast<uint4*>(sm.tab);
         for (int h = tid; h < cfg.hash_cap; h += T) tab[h] = empty;
+        for (int w = tid; w < sm.tfilt_bits / 32; w += T) sm.tfilt[w] = 0u;
     }
     g.sync();
 
@@ -969,6 +977,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
                 }
                 atomicMin(&sm.tab[hh].ml, (uint32_t)i);                      // leave half is still 0
                 atomicMin(&sm.tab[hh].best, ((unsigned long long)w4.z << 32) | (unsigned long long)i);
+                { const uint32_t fb = filt_bit(t, sm.tfilt_bits); atomicOr(&sm.tfilt[fb >> 5], 1u << (fb & 31)); }
                 sm.mv[mi] = hh | ((uint32_t)best_dir << 20);
             }
         }
@@ -989,11 +998,15 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
             const uint32_t c_old = (uint32_t)(x * stride + y);
             uint32_t hh = hash_cell(c_old, hcap);
             bool found = false;
-            for (;;) {
-                const uint32_t k = tab_ld<BIG>(&sm.tab[hh].key);
-                if (k == HEMPTY) break;
-                if (k == c_old) { found = true; break; }
-                hh = hh + 1 == hcap ? 0u : hh + 1;
+            // most old cells are nobody's target: the filter answers that without walking a probe chain of the 2/3-full table
+            const uint32_t fb = filt_bit(c_old, sm.tfilt_bits);
+            if ((sm.tfilt[fb >> 5] >> (fb & 31)) & 1u) {
+                for (;;) {
+                    const uint32_t k = tab_ld<BIG>(&sm.tab[hh].key);
+                    if (k == HEMPTY) break;
+                    if (k == c_old) { found = true; break; }
+                    hh = hh + 1 == hcap ? 0u : hh + 1;
+                }
             }
             // old cell is somebody's target: order decides (the low half of ml is final since the barrier)
             if (found) atomicMax(&sm.tab[hh].ml, ((key + 1u) << 16) | (tab_ld<BIG>(&sm.tab[hh].ml) & 0xFFFFu));
