@@ -218,6 +218,57 @@ def cpu_learner_baseline(batch, budget_s=10.0, seed=0):
             "batch": batch, "ms_per_learn": out[batch]["ms_per_learn"]}
 
 
+def python_reference_timing(budget_s=4.0):
+    """The UNMODIFIED Python reference (staged under baseline/_ref by scripts/stage_reference.py; git-ignored, travels with the
+    snapshot), one process = one core: EvacuationEnv.step at the configs/dqn.yaml room (C1/C2 shape) and at the 256 x 256 / 1000
+    people shape, and DQNAgent.learn() at B = 32.  Reported beside the port so that the port's speed-up over the real thing is
+    on record; absent tree -> None."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "Louvre_Evacuation", "envs")):
+        return None
+    import random
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, ref_root)
+    try:
+        import numpy as np
+        import torch
+        from Louvre_Evacuation.envs.evacuation_env import EvacuationEnv
+        from Louvre_Evacuation.agents.dqn_agent import DQNAgent
+    except Exception as e:                                             # noqa: BLE001 — a missing optional import of the reference
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    finally:
+        sys.path.remove(ref_root)
+    out = {"kind": "reference", "cores": 1, "source": "baseline/_ref (unmodified Louvre_Evacuation tree)"}
+    for key, ctor, people in (("room_36x30_150", lambda: EvacuationEnv(36, 30, None, None, 150), 150),
+                              ("grid_256x256_1000", lambda: EvacuationEnv(256, 256, None, [256, 128], 1000), 1000)):
+        random.seed(1); np.random.seed(1)
+        env = ctor()
+        env.reset()
+        for _ in range(2):
+            env.step(random.randrange(5))
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget_s / 2 and n < 400:
+            _, _, done, _ = env.step(random.randrange(5))
+            n += 1
+            if done:
+                env.reset()
+        dt = time.perf_counter() - t0
+        out[key] = {"agent_steps_per_s": people * n / dt, "ms_per_env_step": dt / n * 1e3, "steps": n}
+    torch.manual_seed(0)
+    agent = DQNAgent((11, 11, 6), 5, torch.device("cpu"), {"batch_size": 32, "warmup_steps": 0, "memory_size": 2000})
+    rng = np.random.default_rng(0)
+    for _ in range(64):
+        agent.remember(rng.random((11, 11, 6)), int(rng.integers(5)), float(rng.random()), rng.random((11, 11, 6)), False)
+    agent.learn()
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s / 2 and n < 200:
+        agent.learn()
+        n += 1
+    dt = time.perf_counter() - t0
+    out["learn_b32"] = {"transitions_per_s": 32 * n / dt, "ms_per_learn": dt / n * 1e3, "steps": n, "torch_threads": torch.get_num_threads()}
+    return out
+
+
 def run_reference(args, wl):
     """`--impl reference`: the reference's CPU implementation of the path = the oracle ports on all host threads (the reference
     itself is pure Python and cannot travel to the GPU box; BASELINE.md quotes it at ~1.9e4 agent-steps/s/core).  Each step =
@@ -248,6 +299,7 @@ def run_reference(args, wl):
         lb = cpu_learner_baseline(args.learner_batch or wl["learner_batch"])
         line["learner"] = {"metric": "learner transitions/s (DQNAgent.learn on the host)", "value": lb["value"], "unit": "transitions/s",
                            "cpu_baseline": lb, "e2e": {"value": lb["value"], "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["python_reference"] = python_reference_timing()
     line["loaded_product_library"] = any("libmarl_b200" in ln for ln in open("/proc/self/maps")) if os.path.exists("/proc/self/maps") else None
     print(json.dumps(line), flush=True)
 
