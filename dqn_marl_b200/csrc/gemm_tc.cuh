@@ -303,6 +303,66 @@ __device__ __forceinline__ void epilogue_tile_tma(const Epilogue& ep, const CUte
     }
 }
 
+// ---- 32-column bf16 output whose rows are contiguous in memory (ldc == 32: conv1's activation, conv2's data gradient) ----
+// A warp's 32 rows x 64 bytes are ONE contiguous 2 KB block of the output.  Stored straight from the TMEM register layout
+// (one row per thread) every instruction writes 16 bytes into each of 32 different sectors: four partial-sector writes per
+// sector, and the L2 write path bounds the kernel (conv1 forward: 92 us for 127 MB at B = 16384).  Here the warp transposes
+// through a 2 KB shared-memory tile (XOR-swizzled 16-byte chunks: conflict-free both ways) and writes 512 contiguous bytes
+// per instruction.  rows_ok = number of valid rows of this warp (clipped at the end of the matrix); mask_row as above.
+__host__ __device__ inline bool rows32_eligible(const Epilogue& ep) {
+    return ep.out_bf16 && !ep.out_f32 && !ep.mask_f32 && !ep.drop && !ep.partial && ep.ldc == 32;
+}
+__device__ __forceinline__ void epilogue_rows32_bf16(const Epilogue& ep, uint32_t tmem_acc, int q, int lane, const __nv_bfloat16* mask_row,
+                                                     long long row0, int rows_ok, unsigned char* stage) {
+    uint32_t r[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16), r);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+    }
+    if (ep.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (mask_row) {
+        const uint4* mk = reinterpret_cast<const uint4*>(mask_row);
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const uint4 w = __ldg(mk + j / 8);
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ws[k]);
+                if (!(__low2float(b2) > 0.f)) v[j + 2 * k] = 0.f;
+                if (!(__high2float(b2) > 0.f)) v[j + 2 * k + 1] = 0.f;
+            }
+        }
+    }
+    __syncwarp();                                          // the previous tile's reads of the staging block are done
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * c], v[8 * c + 1]), p1 = __floats2bfloat162_rn(v[8 * c + 2], v[8 * c + 3]);
+        const __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * c + 4], v[8 * c + 5]), p3 = __floats2bfloat162_rn(v[8 * c + 6], v[8 * c + 7]);
+        *reinterpret_cast<uint4*>(stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+            make_uint4(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1),
+                       *reinterpret_cast<const uint32_t*>(&p2), *reinterpret_cast<const uint32_t*>(&p3));
+    }
+    __syncwarp();
+    unsigned char* dst = reinterpret_cast<unsigned char*>(ep.out_bf16 + row0 * 32);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int lin = k * 32 + lane, row = lin >> 2, chunk = lin & 3;
+        if (row < rows_ok)
+            *reinterpret_cast<uint4*>(dst + lin * 16) = *reinterpret_cast<const uint4*>(stage + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+    }
+}
+
 // common prologue: barriers, tensor-map prefetch, TMEM allocation
 struct Pipe {
     uint64_t *full_bar, *empty_bar, *tmem_full_bar;
@@ -611,8 +671,9 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
     const int n_base = blockIdx.y * BN;             // output-channel slice of this CTA (gridDim.y = Cout / BN)
     unsigned char* wtile = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = wtile + (size_t)nkb * W_BYTES;
-    unsigned char* stage = ring + STAGES * A_BYTES;            // EPI x 4 KB epilogue staging tiles (tma_store only)
-    uint64_t* full_bar = (uint64_t*)(stage + (tma_store ? EPI * 4096 : 0));
+    unsigned char* stage = ring + STAGES * A_BYTES;            // EPI x 4 KB epilogue staging tiles (tma_store), EPI x 2 KB (32-column rows)
+    const bool rows32 = BN == 32 && n_total == 32 && rows32_eligible(ep);
+    uint64_t* full_bar = (uint64_t*)(stage + (tma_store ? EPI * 4096 : (rows32 ? EPI * 2048 : 0)));
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;       // [2]
     uint64_t* tmem_empty = tmem_full + 2;           // [2]
@@ -722,6 +783,11 @@ conv_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmap_a, const __
                     epilogue_tile_tma<HW>(ep, &tmap_out, acc, q, lane, mrow, n0, q * 32, (int)sample, stage + (warp - 2) * 4096);
                     done = true;
                 }
+            }
+            if (!done && rows32) {
+                const __nv_bfloat16* mrow = (ep.mask_bf16 && r < PIXELS) ? ep.mask_bf16 + ((size_t)sample * PIXELS + r) * 32 : nullptr;
+                epilogue_rows32_bf16(ep, acc, q, lane, mrow, sample * PIXELS + q * 32, max(0, min(32, PIXELS - q * 32)), stage + (warp - 2) * 2048);
+                done = true;
             }
             if (!done) epilogue_tile<HW>(ep, acc, q, r < PIXELS, sample * PIXELS + r, n0, batch * PIXELS, n_total, 0);
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -843,27 +909,36 @@ gemm_bf16_resident_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
 // thread per tile row, straight from the fp32 observation [B][11][11][6]: row = (sample, pixel), column k = tap * 6 + c for
 // k < 54, 1.0 at k = 54 (the ones column of qnet_bf16.cuh), zero above; 16-byte chunk c of row r goes to chunk c ^ (r & 7)
 // (the SWIZZLE_128B pattern the K-major descriptors expect).  Generic-proxy writes, then fence.proxy.async before the arrive.
+// observation staging of the conv1 builders: the whole samples a 128-row tile touches (at most three: 128 > 121), fp32
+constexpr int CONV1_STAGE_FLOATS = 3 * PIXELS * 6 + 2;       // 8720 bytes, a multiple of 16
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+constexpr int CONV1_THREADS = THREADS + 256 + 128;           // producer, MMA, 4 epilogue warps, 8 builder warps, 4 more epilogue warps
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(THREADS + 256, 1)
+__global__ void __launch_bounds__(CONV1_THREADS, 1)
 conv1_obs_resident_kernel(const float* __restrict__ obs, const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_a1,
                           int store_a1, long long M, int N, Epilogue ep) {
     constexpr int nkb = 1;
     extern __shared__ unsigned char smem_raw[];
     constexpr int BK = 64;
     constexpr int A_BYTES = BM * BK * 2, W_BYTES = BN * BK * 2;
-    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    constexpr int NACC = 4;                       // accumulator ring in TMEM (4 x BN columns)
+    constexpr uint32_t TMEM_COLS = NACC * BN < 32 ? 32 : NACC * BN;
     unsigned char* wtile = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* ring = wtile + (((size_t)nkb * W_BYTES + 1023) & ~(size_t)1023);
-    uint64_t* full_bar = (uint64_t*)(ring + STAGES * A_BYTES);
+    float* obs_stage = (float*)(ring + STAGES * A_BYTES);              // [2 builder groups][2 buffers][CONV1_STAGE_FLOATS]
+    unsigned char* epi_stage = (unsigned char*)(obs_stage + 4 * CONV1_STAGE_FLOATS);     // [8 epilogue warps][2 KB]
+    uint64_t* full_bar = (uint64_t*)(epi_stage + 8 * 2048);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full = empty_bar + STAGES;       // [2]
-    uint64_t* tmem_empty = tmem_full + 2;           // [2]
-    uint64_t* w_full = tmem_empty + 2;
+    uint64_t* tmem_full = empty_bar + STAGES;       // [NACC]
+    uint64_t* tmem_empty = tmem_full + NACC;        // [NACC]
+    uint64_t* w_full = tmem_empty + NACC;
     uint32_t* tmem_ptr = (uint32_t*)(w_full + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 4); mbar_init(&empty_bar[s], 1); }      // four builder warps fill a stage
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
+        for (int b = 0; b < NACC; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 4); }
         mbar_init(w_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
@@ -892,8 +967,8 @@ conv1_obs_resident_kernel(const float* __restrict__ obs, const __grid_constant__
             long long g = 0;
             int it = 0;
             for (long long tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-                const int buf = it & 1;
-                mbar_wait(&tmem_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1));
+                const int buf = it % NACC;
+                mbar_wait(&tmem_empty[buf], (uint32_t)(((it / NACC) & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
                 for (int kb = 0; kb < nkb; ++kb, ++g) {
@@ -910,14 +985,39 @@ conv1_obs_resident_kernel(const float* __restrict__ obs, const __grid_constant__
                 umma_commit(&tmem_full[buf]);
             }
         }
-    } else if (warp >= 6) {
-        // ===== builders: warps 6..9, thread j builds row j of the tile =====
-        // two groups of four warps take alternate tiles: building a tile is a latency chain (loads, convert, swizzled stores,
-        // proxy fence), two in flight keep the MMAs and the epilogue fed
+    } else if (warp >= 6 && warp < 14) {
+        // ===== builders: warps 6..13, thread j builds row j of the tile =====
+        // two groups of four warps take alternate tiles.  The observation of the samples a tile touches is first brought to
+        // shared memory with coalesced asynchronous copies (the tile AFTER the one being built is in flight meanwhile); the 27
+        // values of a row's 3x3x6 neighbourhood are then shared-memory reads.  Reading them straight from global memory (27
+        // scattered 8-byte loads per thread) left the kernel waiting on L2 round trips: 30 % of the HBM rate.
         const int j = ((warp - 6) & 3) * 32 + lane, bgrp = (warp - 6) >> 2;
-        long long g = 0;
-        for (long long tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++g) {
-            if ((int)(g & 1) != bgrp) continue;
+        constexpr int OBS_F = PIXELS * 6;
+        float* const stg = obs_stage + bgrp * 2 * CONV1_STAGE_FLOATS;
+        const long long batch = M / PIXELS;
+        auto prefetch = [&](long long tile, int buf) {
+            const long long b_lo = tile * BM / PIXELS;
+            long long b_hi = (tile * BM + BM - 1) / PIXELS;
+            if (b_hi > batch - 1) b_hi = batch - 1;
+            const int n8 = (int)(b_hi - b_lo + 1) * (OBS_F / 2);              // 8-byte pieces (a sample = 2904 bytes, 8-byte aligned)
+            const float* src = obs + b_lo * OBS_F;
+            float* dst = stg + buf * CONV1_STAGE_FLOATS;
+            for (int c = j; c < n8; c += 128) cp_async8(dst + 2 * c, src + 2 * c);
+        };
+        {
+            const long long first = (long long)blockIdx.x + (long long)bgrp * gridDim.x;
+            if (first < m_tiles) prefetch(first, 0);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        long long g = bgrp;
+        int kown = 0;
+        for (long long tile = (long long)blockIdx.x + g * gridDim.x; tile < m_tiles; tile += 2LL * gridDim.x, g += 2, ++kown) {
+            const int buf = kown & 1;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            // every copy of this tile has landed, and every thread of the group is done reading the other buffer (previous tile)
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + bgrp) : "memory");
+            if (tile + 2LL * gridDim.x < m_tiles) prefetch(tile + 2LL * gridDim.x, buf ^ 1);
+            asm volatile("cp.async.commit_group;" ::: "memory");
             const int s = (int)(g % STAGES);
             mbar_wait(&empty_bar[s], (uint32_t)(((g / STAGES) & 1) ^ 1));
             const long long r = tile * BM + j;
@@ -927,15 +1027,14 @@ conv1_obs_resident_kernel(const float* __restrict__ obs, const __grid_constant__
             if (r < M) {
                 const long long b = r / PIXELS;
                 const int q = (int)(r - b * PIXELS), i = q / 11, jx = q - i * 11;
-                const float* src = obs + b * (PIXELS * 6);
-                // all 27 loads are issued unconditionally (clamped coordinates) so that they are in flight together; taps
-                // outside the image are zeroed afterwards — a branch per tap serialised nine round trips
+                const float* src = stg + buf * CONV1_STAGE_FLOATS + (int)(b - tile * BM / PIXELS) * OBS_F;
+                // all 27 loads are issued unconditionally (clamped coordinates); taps outside the image are zeroed afterwards
                 float2 x[9][3];
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
                     const int ii = min(max(i + t / 3 - 1, 0), 10), jj = min(max(jx + t % 3 - 1, 0), 10);
                     const float2* p2 = reinterpret_cast<const float2*>(src + (ii * 11 + jj) * 6);
-                    x[t][0] = __ldg(p2); x[t][1] = __ldg(p2 + 1); x[t][2] = __ldg(p2 + 2);
+                    x[t][0] = p2[0]; x[t][1] = p2[1]; x[t][2] = p2[2];
                 }
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
@@ -972,14 +1071,24 @@ conv1_obs_resident_kernel(const float* __restrict__ obs, const __grid_constant__
         }
         if (store_a1 && j == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     } else {
-        const int q = warp & 3;
+        // ===== epilogue: two sets of four warps (2..5 and 14..17), set e drains accumulator buffer e = every other tile.  One
+        // set (TMEM load, bias, ReLU, pack, stores: ~500 cycles per tile) was as slow as the builders. =====
+        const int q = warp & 3, eset = warp >= 14 ? 1 : 0;
         int it = 0;
         for (long long tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-            const int buf = it & 1;
-            mbar_wait(&tmem_full[buf], (uint32_t)((it >> 1) & 1));
+            const int buf = it % NACC;
+            if ((it & 1) != eset) continue;
+            mbar_wait(&tmem_full[buf], (uint32_t)((it / NACC) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const long long row = tile * BM + q * 32 + lane;
-            epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, row < M, row, 0, M, N, 0);
+            if (BN == 32 && rows32_eligible(ep)) {
+                const long long row0 = tile * BM + q * 32;
+                const int rows_ok = (int)max(0LL, min(32LL, M - row0));
+                const __nv_bfloat16* mrow = (ep.mask_bf16 && row < M) ? ep.mask_bf16 + row * 32 : nullptr;
+                epilogue_rows32_bf16(ep, tmem_base + (uint32_t)(buf * BN), q, lane, mrow, row0, rows_ok, epi_stage + ((warp >= 14 ? warp - 10 : warp - 2) << 11));
+            } else {
+                epilogue_tile<BN>(ep, tmem_base + (uint32_t)(buf * BN), q, row < M, row, 0, M, N, 0);
+            }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -1276,13 +1385,13 @@ inline cudaError_t launch_conv1_obs(const float* obs, const __nv_bfloat16* W1c, 
     if (!make_tmap(&tw, W1c, (uint64_t)BN, (uint64_t)BK, (uint64_t)BK, BN)) return cudaErrorInvalidValue;
     ta1 = tw;
     if (a1_out && !make_tmap(&ta1, a1_out, (uint64_t)batch * PIXELS, (uint64_t)BK, (uint64_t)BK, BM)) return cudaErrorInvalidValue;
-    const int smem = ((BN * BK * 2 + 1023) & ~1023) + STAGES * BM * BK * 2 + 1024 + 256;
+    const int smem = ((BN * BK * 2 + 1023) & ~1023) + STAGES * BM * BK * 2 + 4 * CONV1_STAGE_FLOATS * 4 + 8 * 2048 + 1024 + 256;
     static SmemMemo memo{};
     if (cudaError_t e = ensure_smem(memo, conv1_obs_resident_kernel<BN, STAGES>, smem); e != cudaSuccess) return e;
     ep.partial = nullptr;
     const long long M = batch * PIXELS, m_tiles = (M + BM - 1) / BM;
     const unsigned grid = (unsigned)(m_tiles < n_sms ? m_tiles : n_sms);
-    conv1_obs_resident_kernel<BN, STAGES><<<grid, THREADS + 256, smem, stream>>>(obs, tw, ta1, a1_out ? 1 : 0, M, BN, ep);
+    conv1_obs_resident_kernel<BN, STAGES><<<grid, CONV1_THREADS, smem, stream>>>(obs, tw, ta1, a1_out ? 1 : 0, M, BN, ep);
     return cudaGetLastError();
 }
 
@@ -1360,7 +1469,7 @@ inline cudaError_t launch_conv_persistent(const __nv_bfloat16* X, const __nv_bfl
     static_assert(HWE >= 32, "an epilogue warp handles at least 32 columns");
     CUtensorMap to = ta;
     const int tma_store = (HWE % 64 == 0 && tma_store_eligible(ep, Cout, BN) && ep.ldc == Cout && make_tmap_out_conv(&to, ep.out_bf16, (uint64_t)batch, (uint64_t)Cout)) ? 1 : 0;
-    const int smem = nkb * BN * BK * 2 + STAGES * 160 * BK * 2 + (tma_store ? EPI * 4096 : 0) + 1024 + 256;
+    const int smem = nkb * BN * BK * 2 + STAGES * 160 * BK * 2 + (tma_store ? EPI * 4096 : (BN == 32 ? EPI * 2048 : 0)) + 1024 + 256;
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static SmemMemo memo{};
     if (cudaError_t e = ensure_smem(memo, conv_bf16_persistent_kernel<BN, BK, STAGES, EPI>, smem); e != cudaSuccess) return e;
