@@ -224,9 +224,22 @@ inline int launch_gemm(GemmParams p, size_t partial_cap, int n_sms, cudaStream_t
     const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM, tiles_n = (p.N + BN - 1) / BN;
     const int tiles = tiles_m * tiles_n;
     const int k_tiles = (p.K + GEMM_BK - 1) / GEMM_BK;
+    // split-K so that the grid fills whole waves: `slots` CTAs are resident at once (launch bounds above), a grid of
+    // tiles x splits CTAs runs in ceil(tiles x splits / slots) waves of which the last may be nearly empty.  Small grids take
+    // the largest split that still fits ONE wave; grids of a few waves take the split (<= 4) with the fullest last wave.
     int splits = 1;
-    if (tiles < n_sms && k_tiles >= 8) {
-        splits = (2 * n_sms + tiles - 1) / tiles;
+    const int slots = n_sms * (BN >= 128 ? 2 : (BN >= 64 ? 3 : 4));
+    if (k_tiles >= 8) {
+        if (tiles <= slots / 2) {
+            splits = slots / tiles;
+        } else if (tiles < 6 * slots) {
+            double best = 0.0;
+            for (int sp = 1; sp <= 4; ++sp) {
+                const double waves = (double)tiles * sp / slots;
+                const double eff = waves / (double)(long long)(waves + 0.999999) - 0.01 * (sp - 1);      // a split costs a partial round trip
+                if (eff > best) { best = eff; splits = sp; }
+            }
+        }
         if (splits > k_tiles / 4) splits = k_tiles / 4;
         while (splits > 1 && (size_t)splits * p.M * p.N > partial_cap) --splits;
         if (splits < 1) splits = 1;
