@@ -71,6 +71,92 @@ __device__ __forceinline__ float load_b(const GemmParams& p, int k, int n) {
     return __ldg(p.B + ((size_t)(tap * p.N + n)) * CDIM + co);
 }
 
+// ---- 16-byte operand loads along the contiguous dimension of each loader mode ----------------------------------------
+// K-vector: elements (m, k .. k+3) of A / (k .. k+3, n) of B; MN-vector: (m .. m+3, k) / (k, n .. n+3).  k and m / n are
+// multiples of 4 by construction.  One address computation and bounds test per four elements instead of per element, and a
+// warp's request covers whole sectors: the scalar loaders kept the load / store unit, not the FMA pipe, busy (ncu: MIO
+// throttle and short-scoreboard stalls first, L1 at 81 %).  Anything irregular (partial vector at an edge, unaligned base)
+// falls back to the element-wise loaders, so every shape stays legal.
+template <int AMODE, int CDIM> struct AVec {
+    static constexpr bool K = AMODE == A_ROW || ((AMODE == A_IM2COL || AMODE == A_IM2COL_FLIP) && CDIM % 4 == 0);
+    static constexpr bool M = AMODE == A_COL || (AMODE == A_IM2COL_T && CDIM % 4 == 0);
+};
+template <int BMODE, int CDIM> struct BVec {
+    static constexpr bool N = BMODE == B_ROW;
+    static constexpr bool K = BMODE == B_COL || (BMODE == B_CONVW_T && CDIM % 4 == 0);
+};
+__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int AMODE, int CDIM>
+__device__ __forceinline__ float4 load_a_kvec(const GemmParams& p, int m, int k, int k_end) {
+    if (m < p.M && k + 3 < k_end) {
+        const float* ptr = nullptr;
+        bool zero = false;
+        if (AMODE == A_ROW) ptr = p.A + (size_t)m * p.lda + k;
+        else {
+            const int b = m / OBS_PIX, q = m - b * OBS_PIX, i = q / OBS_HW, j = q - i * OBS_HW;
+            const int tap = k / CDIM, c = k - tap * CDIM;                 // c .. c+3 lie in the same tap (CDIM % 4 == 0)
+            const int di = tap / 3 - 1, dj = tap - (tap / 3) * 3 - 1;
+            const int ii = (AMODE == A_IM2COL_FLIP) ? i - di : i + di, jj = (AMODE == A_IM2COL_FLIP) ? j - dj : j + dj;
+            zero = (unsigned)ii >= (unsigned)OBS_HW || (unsigned)jj >= (unsigned)OBS_HW;
+            ptr = p.A + ((size_t)(b * OBS_PIX + ii * OBS_HW + jj)) * CDIM + c;
+        }
+        if (zero) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (aligned16(ptr)) return __ldg(reinterpret_cast<const float4*>(ptr));
+    }
+    float4 v;
+    v.x = k < k_end ? load_a<AMODE, CDIM>(p, m, k) : 0.f;
+    v.y = k + 1 < k_end ? load_a<AMODE, CDIM>(p, m, k + 1) : 0.f;
+    v.z = k + 2 < k_end ? load_a<AMODE, CDIM>(p, m, k + 2) : 0.f;
+    v.w = k + 3 < k_end ? load_a<AMODE, CDIM>(p, m, k + 3) : 0.f;
+    return v;
+}
+template <int AMODE, int CDIM>
+__device__ __forceinline__ float4 load_a_mvec(const GemmParams& p, int m, int k, int k_end) {
+    if (k >= k_end) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m + 3 < p.M) {
+        const float* ptr = nullptr;
+        bool zero = false;
+        if (AMODE == A_COL) ptr = p.A + (size_t)k * p.lda + m;
+        else {                                                           // A_IM2COL_T: m = (tap, c .. c+3), k = pixel
+            const int b = k / OBS_PIX, q = k - b * OBS_PIX, i = q / OBS_HW, j = q - i * OBS_HW;
+            const int tap = m / CDIM, c = m - tap * CDIM;
+            const int ii = i + tap / 3 - 1, jj = j + (tap - (tap / 3) * 3) - 1;
+            zero = (unsigned)ii >= (unsigned)OBS_HW || (unsigned)jj >= (unsigned)OBS_HW;
+            ptr = p.A + ((size_t)(b * OBS_PIX + ii * OBS_HW + jj)) * CDIM + c;
+        }
+        if (zero) return make_float4(0.f, 0.f, 0.f, 0.f);
+        if (aligned16(ptr)) return __ldg(reinterpret_cast<const float4*>(ptr));
+    }
+    return make_float4(load_a<AMODE, CDIM>(p, m, k), load_a<AMODE, CDIM>(p, m + 1, k), load_a<AMODE, CDIM>(p, m + 2, k),
+                       load_a<AMODE, CDIM>(p, m + 3, k));
+}
+template <int BMODE, int CDIM>
+__device__ __forceinline__ float4 load_b_nvec(const GemmParams& p, int k, int n, int k_end) {
+    if (k >= k_end) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n + 3 < p.N) {
+        const float* ptr = p.B + (size_t)k * p.ldb + n;                  // B_ROW
+        if (aligned16(ptr)) return __ldg(reinterpret_cast<const float4*>(ptr));
+    }
+    return make_float4(load_b<BMODE, CDIM>(p, k, n), load_b<BMODE, CDIM>(p, k, n + 1), load_b<BMODE, CDIM>(p, k, n + 2),
+                       load_b<BMODE, CDIM>(p, k, n + 3));
+}
+template <int BMODE, int CDIM>
+__device__ __forceinline__ float4 load_b_kvec(const GemmParams& p, int k, int n, int k_end) {
+    if (n < p.N && k + 3 < k_end) {
+        const float* ptr;
+        if (BMODE == B_COL) ptr = p.B + (size_t)n * p.ldb + k;
+        else { const int tap = k / CDIM, co = k - tap * CDIM; ptr = p.B + ((size_t)(tap * p.N + n)) * CDIM + co; }
+        if (aligned16(ptr)) return __ldg(reinterpret_cast<const float4*>(ptr));
+    }
+    float4 v;
+    v.x = k < k_end ? load_b<BMODE, CDIM>(p, k, n) : 0.f;
+    v.y = k + 1 < k_end ? load_b<BMODE, CDIM>(p, k + 1, n) : 0.f;
+    v.z = k + 2 < k_end ? load_b<BMODE, CDIM>(p, k + 2, n) : 0.f;
+    v.w = k + 3 < k_end ? load_b<BMODE, CDIM>(p, k + 3, n) : 0.f;
+    return v;
+}
+
 __device__ __forceinline__ float epilogue_value(const GemmParams& p, float v, int m, int n) {
     if (p.bias) v += __ldg(p.bias + n);
     if (p.relu) v = fmaxf(v, 0.f);
@@ -100,25 +186,85 @@ gemm_f32_kernel(GemmParams p) {
     const int b_n = t % BN, b_k0 = (t / BN) * B_PER_THREAD;
     // micro-tile column j of thread tx: two interleaved groups of 4 for BN = 128 (conflict-free float4 reads)
     auto col_of = [&](int j) { return TN == 8 ? (j >> 2) * 64 + tx * 4 + (j & 3) : tx * TN + j; };
-    float ra[8], rb[B_PER_THREAD];
+    using AV = AVec<AMODE, CDIM>;
+    using BV = BVec<BMODE, CDIM>;
+    constexpr bool A_VEC = AV::K || AV::M, B_VEC = BV::K || BV::N;
+    constexpr int NB4 = BN >= 64 ? BN / 64 : 1;       // float4 of B per thread (BN = 32: the first 128 threads hold one)
+    float ra[A_VEC ? 1 : 8], rb[B_VEC ? 1 : B_PER_THREAD];
+    float4 ra4[A_VEC ? 2 : 1], rb4[B_VEC ? NB4 : 1];
     float acc[8][TN];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
+    // vector staging assignments (f = t + 256 i numbers the float4 of a tile):
+    //   A K-vectors: row = t >> 1, k-quad = (t & 1) + 2 i      (two lanes share a row: 32 contiguous bytes; the transposing
+    //                scalar stores of a warp then hit 16 rows x 2 quads = 32 different banks)
+    //   A M-vectors: k = (t >> 5) + 8 i, m-quad = t & 31       (one 16-byte shared store)
+    //   B N-vectors: k = f / (BN/4), n-quad = f % (BN/4);  B K-vectors: n = (f % 2BN) >> 1, k-quad = (f & 1) + 2 (f / 2BN)
     auto fetch = [&](int k0) {
+        if constexpr (AV::K) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) ra[q] = (k0 + a_k0 + q < k_end) ? load_a<AMODE, CDIM>(p, m0 + a_m, k0 + a_k0 + q) : 0.f;
+            for (int i = 0; i < 2; ++i) ra4[i] = load_a_kvec<AMODE, CDIM>(p, m0 + (t >> 1), k0 + ((t & 1) + 2 * i) * 4, k_end);
+        } else if constexpr (AV::M) {
 #pragma unroll
-        for (int q = 0; q < B_PER_THREAD; ++q)
-            rb[q] = (k0 + b_k0 + q < k_end) ? load_b<BMODE, CDIM>(p, k0 + b_k0 + q, n0 + b_n) : 0.f;
+            for (int i = 0; i < 2; ++i) ra4[i] = load_a_mvec<AMODE, CDIM>(p, m0 + (t & 31) * 4, k0 + (t >> 5) + 8 * i, k_end);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ra[q] = (k0 + a_k0 + q < k_end) ? load_a<AMODE, CDIM>(p, m0 + a_m, k0 + a_k0 + q) : 0.f;
+        }
+        if constexpr (BV::N) {
+#pragma unroll
+            for (int i = 0; i < NB4; ++i) {
+                const int f = t + GEMM_THREADS * i;
+                if (f < 4 * BN) rb4[i] = load_b_nvec<BMODE, CDIM>(p, k0 + f / (BN / 4), n0 + (f % (BN / 4)) * 4, k_end);
+            }
+        } else if constexpr (BV::K) {
+#pragma unroll
+            for (int i = 0; i < NB4; ++i) {
+                const int f = t + GEMM_THREADS * i;
+                if (f < 4 * BN) rb4[i] = load_b_kvec<BMODE, CDIM>(p, k0 + ((f & 1) + 2 * (f / (2 * BN))) * 4, n0 + ((f % (2 * BN)) >> 1), k_end);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < B_PER_THREAD; ++q)
+                rb[q] = (k0 + b_k0 + q < k_end) ? load_b<BMODE, CDIM>(p, k0 + b_k0 + q, n0 + b_n) : 0.f;
+        }
     };
     auto stash = [&](int buf) {
+        if constexpr (AV::K) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) As[buf][a_k0 + q][a_m] = ra[q];
+            for (int i = 0; i < 2; ++i) {
+                const int kq = ((t & 1) + 2 * i) * 4, row = t >> 1;
+                As[buf][kq][row] = ra4[i].x; As[buf][kq + 1][row] = ra4[i].y; As[buf][kq + 2][row] = ra4[i].z; As[buf][kq + 3][row] = ra4[i].w;
+            }
+        } else if constexpr (AV::M) {
 #pragma unroll
-        for (int q = 0; q < B_PER_THREAD; ++q) Bs[buf][b_k0 + q][b_n] = rb[q];
+            for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(&As[buf][(t >> 5) + 8 * i][(t & 31) * 4]) = ra4[i];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) As[buf][a_k0 + q][a_m] = ra[q];
+        }
+        if constexpr (BV::N) {
+#pragma unroll
+            for (int i = 0; i < NB4; ++i) {
+                const int f = t + GEMM_THREADS * i;
+                if (f < 4 * BN) *reinterpret_cast<float4*>(&Bs[buf][f / (BN / 4)][(f % (BN / 4)) * 4]) = rb4[i];
+            }
+        } else if constexpr (BV::K) {
+#pragma unroll
+            for (int i = 0; i < NB4; ++i) {
+                const int f = t + GEMM_THREADS * i;
+                if (f < 4 * BN) {
+                    const int kq = ((f & 1) + 2 * (f / (2 * BN))) * 4, n = (f % (2 * BN)) >> 1;
+                    Bs[buf][kq][n] = rb4[i].x; Bs[buf][kq + 1][n] = rb4[i].y; Bs[buf][kq + 2][n] = rb4[i].z; Bs[buf][kq + 3][n] = rb4[i].w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < B_PER_THREAD; ++q) Bs[buf][b_k0 + q][b_n] = rb[q];
+        }
     };
 
     int buf = 0;
