@@ -192,11 +192,13 @@ gemm_f32_kernel(GemmParams p) {
     constexpr int NB4 = BN >= 64 ? BN / 64 : 1;       // float4 of B per thread (BN = 32: the first 128 threads hold one)
     float ra[A_VEC ? 1 : 8], rb[B_VEC ? 1 : B_PER_THREAD];
     float4 ra4[A_VEC ? 2 : 1], rb4[B_VEC ? NB4 : 1];
-    float acc[8][TN];
+    // accumulators as pairs of adjacent columns: the inner product issues packed FMAs (fma.rn.f32x2, two IEEE fp32 FMAs per
+    // instruction: same results, half the issue slots of the FMA stream)
+    float2 acc2[8][TN / 2];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < TN / 2; ++j) acc2[i][j] = make_float2(0.f, 0.f);
 
     // vector staging assignments (f = t + 256 i numbers the float4 of a tile):
     //   A K-vectors: row = t >> 1, k-quad = (t & 1) + 2 i      (two lanes share a row: 32 contiguous bytes; the transposing
@@ -290,9 +292,11 @@ gemm_f32_kernel(GemmParams p) {
                 for (int j = 0; j < TN; ++j) b[j] = Bs[buf][kk][tx * TN + j];
             }
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 8; ++i) {
+                const float2 a2 = make_float2(a[i], a[i]);
 #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < TN; j += 2) acc2[i][j / 2] = __ffma2_rn(a2, make_float2(b[j], b[j + 1]), acc2[i][j / 2]);
+            }
         }
         if (more) { stash(buf ^ 1); }
         __syncthreads();
@@ -308,7 +312,7 @@ gemm_f32_kernel(GemmParams p) {
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
                 const int n = n0 + col_of(j);
-                if (n < p.N) dst[(size_t)m * p.N + n] = acc[i][j];
+                if (n < p.N) dst[(size_t)m * p.N + n] = (j & 1) ? acc2[i][j / 2].y : acc2[i][j / 2].x;
             }
         }
     } else {
@@ -320,7 +324,7 @@ gemm_f32_kernel(GemmParams p) {
             for (int j = 0; j < TN; ++j) {
                 const int n = n0 + col_of(j);
                 if (n < p.N) {
-                    const float v = epilogue_value(p, acc[i][j], m, n);
+                    const float v = epilogue_value(p, (j & 1) ? acc2[i][j / 2].y : acc2[i][j / 2].x, m, n);
                     p.C[(size_t)m * p.ldc + n] = v;
                     if (p.Cb) p.Cb[(size_t)m * p.ldc + n] = __float2bfloat16(v);
                 }
