@@ -1,5 +1,6 @@
 #!/bin/bash
-# Final-evidence visit (1 GPU): full GPU test suite, both bench arms, launch lists, --set full captures of the hot kernels.
+# Final-evidence visit (1 GPU), part 1: full GPU test suite, both bench arms, launch lists, --set full captures of the env step
+# (gpurun returns at most 64 MiB per call: the learner capture is scripts/gpu_final_learn.sh).
 tag=${1:-r02}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q --maxfail=10 > gpurun_out/${tag}_pytest_full.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${tag}_pytest_full.log
@@ -20,7 +21,4 @@ echo "env capture rc=$?"
 python scripts/env_step_profile.py c2 40 > /dev/null 2>&1 && \
   $NCU --set full --import-source on -k regex:env_step_kernel -s 40 -c 2 -o gpurun_out/${tag}_env_step_c2 python scripts/env_step_profile.py c2 40 > gpurun_out/${tag}_env_c2_ncu.log 2>&1
 echo "env c2 capture rc=$?"
-python scripts/learn_step_profile.py bf16 4096 > gpurun_out/${tag}_learn_plain.log 2>&1 && \
-  $NCU --set full --import-source on -k regex:"pair|persistent|conv1_obs|gemm_bf16_tn|gemm_bf16_tc|clip_adam|replay" -s 141 -c 47 -o gpurun_out/${tag}_learn_kernels python scripts/learn_step_profile.py bf16 4096 > gpurun_out/${tag}_learn_ncu.log 2>&1
-echo "learn capture rc=$?"; cat gpurun_out/${tag}_learn_plain.log
 ls -la gpurun_out | grep ${tag}_ | tail -20

@@ -72,7 +72,7 @@ for label, M, N, K, relu_a in [("fc1 forward shape, relu'd activations", 512, 51
     # interleaved per 64-wide K block (what an in-kernel split loop would do)
     kb = K // 64
     def inter(parts):
-        return torch.stack([p.view(p.shape[0], kb, 64) for p in parts], 2).reshape(p.shape[0], -1).contiguous()
+        return torch.stack([q.view(q.shape[0], kb, 64) for q in parts], 2).reshape(parts[0].shape[0], -1).contiguous()
     A6i = inter([ah, ah, am, ah, al, am]); B6i = inter([bh, bm, bh, bl, bh, bm])
     for sp in (1, 8):
         report(f"6 products interleaved, split-K {sp}", gemm(A6i, B6i, sp), ref)
