@@ -317,20 +317,23 @@ def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
     from dqn_marl_b200.parallel import max_over_ranks
     E, N = wl["envs"], wl["people"]
     state_bytes = env_state_bytes(layout, E, N)
+    # n_rot batches rotate in the device-timed loop (enough to exceed L2); the host-buffer e2e leg keeps n_e2e >= n_rot batches in
+    # flight (default 4: with the compact wire form the host expansion of one batch has to hide behind the kernels of the others)
     n_rot = max(2, int(L2_BYTES * 1.5 / state_bytes) + 1)
-    envs = [VecEvacuationEnv(layout, E, N, device=dev, seed=2026, env_id_base=(rank * n_rot + b) * E,
-                             strict_reference=False, auto_reset=True) for b in range(n_rot)]
+    n_e2e = max(n_rot, int(getattr(args, "batches", 0) or 0) or 4) if e2e else n_rot
+    envs = [VecEvacuationEnv(layout, E, N, device=dev, seed=2026, env_id_base=(rank * n_e2e + b) * E,
+                             strict_reference=False, auto_reset=True) for b in range(n_e2e)]
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
     n_act = 64
     actions = torch.randint(0, 5, (n_act, E, 1), generator=g, device=dev, dtype=torch.int32)
-    obs = [torch.empty((E, 1, 11, 11, 6), dtype=torch.float32, device=dev) for _ in range(n_rot)]
-    rew = [torch.empty((E,), dtype=torch.float64, device=dev) for _ in range(n_rot)]
-    don = [torch.empty((E,), dtype=torch.uint8, device=dev) for _ in range(n_rot)]
-    for env in envs:
+    obs = [torch.empty((E, 1, 11, 11, 6), dtype=torch.float32, device=dev) for _ in range(n_e2e)]
+    rew = [torch.empty((E,), dtype=torch.float64, device=dev) for _ in range(n_e2e)]
+    don = [torch.empty((E,), dtype=torch.uint8, device=dev) for _ in range(n_e2e)]
+    for env in envs[:n_rot]:
         env.reset()
     for t in range(args.prime):            # prime: bring every batch to a mid-episode state (untimed)
-        for b, env in enumerate(envs):
+        for b, env in enumerate(envs[:n_rot]):
             env.step_into(actions[t % n_act], obs[b], rew[b], don[b])
     torch.cuda.synchronize(dev)
 
@@ -383,49 +386,65 @@ def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
         # independent env batches are in flight on their own streams, so the PCIe copies of one batch overlap the kernel of
         # another (how an asynchronous vector-env driver calls it).  value_sync_each_step = a host synchronisation per step.
         h_act = torch.randint(0, 5, (n_act, E, 1), dtype=torch.int32).pin_memory()
-        e2e_steps = max(10 * n_rot, min(args.steps, 300) // n_rot * n_rot)
+        # every batch covers the same episode ages as in the device-timed window (at most 300 steps each)
+        per_batch = max(10, min(args.steps // n_rot, 300))
+        e2e_steps = per_batch * n_e2e
 
         def e2e_run(steps, sync_each, wire=False):
             for k in range(steps):
-                b = k % n_rot
-                if k >= n_rot and not sync_each:
+                b = k % n_e2e
+                if k >= n_e2e and not sync_each:
                     envs[b].step_wait()                   # the previous step of this batch has landed on the host
                 envs[b].step_async(h_act[k % n_act], wire=wire)
                 if sync_each:
                     envs[b].step_wait()
-            for b in range(n_rot):
+            for b in range(n_e2e):
                 envs[b].step_wait()
 
-        torch.cuda.synchronize(dev)
-        e2e_run(2 * n_rot, False)
-        e2e_run(2 * n_rot, False, True)
-        vals = []
-        for sync_each, wire in ((False, False), (True, False), (False, True)):
+        def reprime():
+            # every e2e mode starts from the episode age at which the device-timed window started (fresh episodes, the same
+            # number of untimed device-resident steps), so that its steps cost what the headline's steps cost
+            for env in envs:
+                env.reset()
+            for t in range(args.prime + warm // n_rot):
+                for b, env in enumerate(envs):
+                    env.step_into(actions[t % n_act], obs[b], rew[b], don[b])
+            torch.cuda.synchronize(dev)
+
+        def timed(sync_each, wire):
+            reprime()
+            e2e_run(n_e2e, sync_each, wire)
             barrier(); torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             e2e_run(e2e_steps, sync_each, wire)
             torch.cuda.synchronize(dev)
             e2e_s = max_over_ranks(time.perf_counter() - t0, dev)
-            vals.append(world * E * N * e2e_steps / e2e_s)
+            return world * E * N * e2e_steps / e2e_s
+
+        e2e_run(n_e2e, False)                              # (allocations: streams, pinned buffers, wire buffers, worker threads)
+        e2e_run(n_e2e, False, True)
+        v_dense, v_sync, v_wire = timed(False, False), timed(True, False), timed(False, True)
         h2d = h_act[0].numel() * 4
-        d2h = envs[0].h_obs.numel() * 4 + envs[0].h_reward.numel() * 8 + envs[0].h_done.numel()
-        d2h_wire = envs[0].h_wire.numel() * 4 + envs[0].h_reward.numel() * 8 + envs[0].h_done.numel()
-        mode = "wire" if vals[2] > vals[0] else "dense"
-        best, d2h_best = (vals[2], d2h_wire) if mode == "wire" else (vals[0], d2h)
+        rd = envs[0].h_reward.numel() * 8 + envs[0].h_done.numel()
+        d2h = envs[0].h_obs.numel() * 4 + rd
+        d2h_wire = envs[0].h_wire.numel() * 4 + rd
+        mode, best, d2h_best = max((("dense", v_dense, d2h), ("wire", v_wire, d2h_wire)), key=lambda m: m[1])
         res["e2e"] = {"value": best, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_best, "mode": mode,
-                      "steps": e2e_steps, "value_sync_each_step": vals[1],
+                      "steps": e2e_steps, "value_sync_each_step": v_sync,
                       "d2h_GBs_per_gpu": best / world / (E * N) * d2h_best / 1e9,
-                      "dense": {"value": vals[0], "d2h_bytes_per_step": d2h,
+                      "dense": {"value": v_dense, "d2h_bytes_per_step": d2h,
                                 "note": "step_async(): the dense f32 observation windows cross PCIe (2904 B per window)"},
-                      "wire": {"value": vals[2], "d2h_bytes_per_step": d2h_wire, "host_threads": getattr(envs[0], "wire_threads", None),
+                      "wire": {"value": v_wire, "d2h_bytes_per_step": d2h_wire, "host_threads": getattr(envs[0], "wire_threads", None),
                                "note": "step_async(wire=True): observations cross PCIe in the compact wire form (544 B per window: channel 2 as "
                                        "f32 + bit planes of channels 1 / 3 / 4) and are expanded to the same dense f32 host buffer by "
                                        "mq_obs_wire_expand inside step_wait(), i.e. inside the timed region"},
                       "note": f"VecEvacuationEnv.step_async/step_wait: pinned host actions in (H2D), obs+reward+done out (D2H) every "
-                              f"step, the same dense f32 host buffers in both modes; value = the faster of the two transfer modes (named in "
-                              f"`mode`), both measured and listed; {n_rot} independent env batches in flight on their own streams (copies "
-                              f"overlap kernels); value_sync_each_step = dense mode, one batch at a time with a host sync per step; "
-                              f"d2h_GBs_per_gpu = the PCIe device-to-host rate the value corresponds to"}
+                              f"step, the same dense f32 host buffers in both modes; value = the faster of the two transfer modes (named "
+                              f"in `mode`), both measured and listed; {n_e2e} independent env batches in flight on their own streams "
+                              f"(copies and the host expansion of one overlap the kernels of the others); every mode starts from fresh "
+                              f"episodes primed to the age at which the device-timed window started; value_sync_each_step = dense mode, "
+                              f"one batch at a time with a host sync per step; d2h_GBs_per_gpu = the PCIe device-to-host rate the value "
+                              f"corresponds to"}
     for env in envs:
         env.close()
     del envs, obs, rew, don
@@ -682,6 +701,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--prime", type=int, default=150, help="untimed steps per batch before warm-up")
+    ap.add_argument("--batches", type=int, default=0, help="independent env batches rotated / in flight (0 = 4, or more if it takes more to exceed L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-learner", action="store_true", help="skip the learner legs")
     ap.add_argument("--loop-steps", type=int, default=200, help="steps of the full act/step/push/learn loop, bf16 path (0 = skip)")

@@ -220,7 +220,7 @@ class VecEvacuationEnv:
         return step
 
     # ---- host-buffer interface (gym-style step_async / step_wait) ------------------------------------------------
-    def step_async(self, actions_host: torch.Tensor, wire: bool = False):
+    def step_async(self, actions_host: torch.Tensor, wire=False):
         """Enqueue one step driven from HOST memory on this env batch's own stream: H2D of the (pinned) int32 actions,
         the fused step kernel, D2H of obs / reward / done into pinned host buffers.  Returns immediately; several env
         batches can be in flight so that the PCIe copies of one overlap the kernel of another.  `step_wait()` returns the
@@ -228,7 +228,9 @@ class VecEvacuationEnv:
 
         wire=True: the observations travel in the compact wire form (mq_env_set_obs_wire: 544 B per window instead of
         2904 B — channel 2 as f32, channels 1 / 3 / 4 as bit planes) and `step_wait()` expands them on the host
-        (mq_obs_wire_expand) into the same pinned f32 buffer, bit-identical to the dense copy."""
+        (mq_obs_wire_expand) into the same pinned f32 buffer, bit-identical to the dense copy.
+        wire=f (0 < f < 1): HYBRID — the last round(f * n_envs) envs travel in wire form, the others dense, so that the PCIe
+        link (dense part) and the host cores (expansion of the wire part) work side by side; same host buffers."""
         if getattr(self, "_hs", None) is None:
             self._hs = torch.cuda.Stream(device=self.device)
             self._hev = torch.cuda.Event()
@@ -237,13 +239,16 @@ class VecEvacuationEnv:
             self.h_reward = torch.empty((self.n_envs,), dtype=torch.float64).pin_memory()
             self.h_done = torch.empty((self.n_envs,), dtype=torch.uint8).pin_memory()
             self._wire_mode = False
-        if wire and getattr(self, "d_wire", None) is None:
+        frac = 1.0 if wire is True else (0.0 if wire is False or wire is None else float(wire))
+        n_wire = max(0, min(self.n_envs, int(round(frac * self.n_envs))))
+        n_dense = self.n_envs - n_wire
+        if n_wire and getattr(self, "d_wire", None) is None:
             self.d_wire = torch.zeros((self.n_envs, self.n_robots, _lib.MQ_OBS_WIRE_WORDS), dtype=torch.int32, device=self.device)
             self.h_wire = torch.zeros(self.d_wire.shape, dtype=torch.int32).pin_memory()
-        if wire != self._wire_mode:
-            _lib.check(self.lib.mq_env_set_obs_wire(self._h, _lib.ptr(self.d_wire) if wire else None), "mq_env_set_obs_wire")
-            self._wire_mode = wire
-        self._wire_pending = wire
+        if bool(n_wire) != self._wire_mode:
+            _lib.check(self.lib.mq_env_set_obs_wire(self._h, _lib.ptr(self.d_wire) if n_wire else None), "mq_env_set_obs_wire")
+            self._wire_mode = bool(n_wire)
+        self._wire_pending = n_wire
         # everything the caller has enqueued so far on its own stream (reset(), step(), writes to the state tensors such as the
         # facade's robot_position setter) happens before this step
         self._hs.wait_stream(torch.cuda.current_stream(self.device))
@@ -251,12 +256,12 @@ class VecEvacuationEnv:
         assert a.dtype == torch.int32 and a.device.type == "cpu"
         with torch.cuda.stream(self._hs):
             self._d_act.copy_(a, non_blocking=True)
-            _lib.check(self.lib.mq_env_step(self._h, _lib.ptr(self._d_act), None if wire else _lib.ptr(self.obs), None, _lib.ptr(self.reward),
+            _lib.check(self.lib.mq_env_step(self._h, _lib.ptr(self._d_act), _lib.ptr(self.obs) if n_dense else None, None, _lib.ptr(self.reward),
                                             _lib.ptr(self.done), C.c_void_p(self._hs.cuda_stream)), "mq_env_step")
-            if wire:
-                self.h_wire.copy_(self.d_wire, non_blocking=True)
-            else:
-                self.h_obs.copy_(self.obs, non_blocking=True)
+            if n_dense:
+                self.h_obs[:n_dense].copy_(self.obs[:n_dense], non_blocking=True)
+            if n_wire:
+                self.h_wire[n_dense:].copy_(self.d_wire[n_dense:], non_blocking=True)
             self.h_reward.copy_(self.reward, non_blocking=True)
             self.h_done.copy_(self.done, non_blocking=True)
             self._hev.record(self._hs)
@@ -264,15 +269,17 @@ class VecEvacuationEnv:
     def step_wait(self):
         """Block until the step enqueued by step_async() has landed in host memory -> (obs, reward, done) pinned host tensors."""
         self._hev.synchronize()
-        if getattr(self, "_wire_pending", False):
+        n_wire = int(getattr(self, "_wire_pending", 0) or 0)
+        if n_wire:
             # host threads of the expansion: this process's share of the cores (torchrun starts LOCAL_WORLD_SIZE of us)
             nthr = getattr(self, "wire_threads", None)
             if nthr is None:
                 cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
                 nthr = self.wire_threads = max(1, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
-            _lib.check(self.lib.mq_obs_wire_expand(_lib.ptr(self.h_wire), self.n_envs * self.n_robots, _lib.ptr(self.h_obs), int(nthr)),
-                       "mq_obs_wire_expand")
-            self._wire_pending = False
+            n_dense = self.n_envs - n_wire
+            _lib.check(self.lib.mq_obs_wire_expand(C.c_void_p(self.h_wire[n_dense:].data_ptr()), n_wire * self.n_robots,
+                                                   C.c_void_p(self.h_obs[n_dense:].data_ptr()), int(nthr)), "mq_obs_wire_expand")
+            self._wire_pending = 0
         return self.h_obs, self.h_reward, self.h_done
 
     def rmap_bytes(self) -> torch.Tensor:

@@ -33,10 +33,15 @@ def test_wire_observations_expand_to_the_dense_ones(n_robots, N, E):
         assert torch.equal(oa.view(torch.int32), ob.view(torch.int32)), f"step {t}"
         assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(da, db)
     assert b.h_wire.numel() * 4 == E * n_robots * 544
-    # switching back to the dense form keeps working
-    act = torch.zeros((E, n_robots), dtype=torch.int32).pin_memory()
-    a.step_async(act); b.step_async(act)
-    assert torch.equal(a.step_wait()[0], b.step_wait()[0])
+    # hybrid transfer: part of the envs dense, the rest in wire form, same host buffers; then back to the dense form
+    for frac in (0.4, 0.02, 0.97, False):
+        act = torch.tensor(rng.integers(0, 5, size=(E, n_robots)).astype(np.int32)).pin_memory()
+        a.h_obs.fill_(-3.0); b.h_obs.fill_(-5.0)
+        a.step_async(act); b.step_async(act, wire=frac)
+        oa, ra, da = a.step_wait()
+        ob, rb, db = b.step_wait()
+        assert torch.equal(oa.view(torch.int32), ob.view(torch.int32)), frac
+        assert torch.equal(ra.view(torch.int64), rb.view(torch.int64)) and torch.equal(da, db)
 
 
 def test_wire_from_reset_and_explicit_threads():
