@@ -281,18 +281,22 @@ def run_reference(args, wl):
     from floor_field_py import floor_field
     layout = make_layout(wl, floor_field=floor_field)
     threads = os.cpu_count() or 1
-    # bounded sample: size one step so that K+W steps take about a minute at ~2e6 agent-steps/s/thread
+    # bounded sample: size one step so that prime + W + K steps take about a minute at ~2e6 agent-steps/s/thread.  Like the GPU
+    # arm, the batch is first run into the steady state of auto-reset (args.prime untimed steps: a step of a fresh, lock-stepped
+    # episode costs more than the average step of a long run, on the CPU too), then W warm-up and K timed steps.
     budget_agent_steps = 60.0 * 2.0e6 * threads
-    n_envs = int(budget_agent_steps / max(1, args.steps + args.warmup) / wl["people"])
+    n_envs = int(budget_agent_steps / max(1, args.prime + args.steps + args.warmup) / wl["people"])
     n_envs = max(threads * 4, min(wl["envs"], n_envs))
-    value, dt = cpu_port_throughput(layout, wl, n_envs, args.steps, args.warmup, threads)
+    value, dt = cpu_port_throughput(layout, wl, n_envs, args.steps, args.prime + args.warmup, threads)
     line = {
         "impl": "reference", "metric": "env agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "envs_per_step": n_envs, "people": wl["people"], "grid": [layout.L, layout.W]},
+        "config": {"workload": wl["desc"], "envs_per_step": n_envs, "people": wl["people"], "grid": [layout.L, layout.W],
+                   "prime_steps": args.prime},
         "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{n_envs} envs x {wl['people']} people x {args.steps} steps, oracle/env_oracle.c, {threads} threads"},
+                         "sample": f"{n_envs} envs x {wl['people']} people x {args.steps} steps after {args.prime} untimed priming steps "
+                                   f"(steady state of auto-reset, as in the GPU arm), oracle/env_oracle.c, {threads} threads"},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if not args.no_learner:
@@ -330,10 +334,15 @@ def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
     obs = [torch.empty((E, 1, 11, 11, 6), dtype=torch.float32, device=dev) for _ in range(n_e2e)]
     rew = [torch.empty((E,), dtype=torch.float64, device=dev) for _ in range(n_e2e)]
     don = [torch.empty((E,), dtype=torch.uint8, device=dev) for _ in range(n_e2e)]
-    for env in envs[:n_rot]:
+    for env in envs:
         env.reset()
-    for t in range(args.prime):            # prime: bring every batch to a mid-episode state (untimed)
-        for b, env in enumerate(envs[:n_rot]):
+    # prime (untimed): run every batch into its STEADY STATE.  All envs start their first episode together and in lock step
+    # (everybody has speed 1.0: steps alternate between "everybody moves" and "nobody moves"), and a step gets cheaper as an
+    # episode empties (C3: 0.98 ms at step 0, 0.55 ms at step 600, `scripts/step_time_trace.py`).  After a few episodes of
+    # auto-reset the ages are mixed and the step time settles (C3: ~0.80 ms from step ~1500 on): that is what a long-running
+    # vector env costs, and it makes the number independent of which K steps are timed.
+    for t in range(args.prime):
+        for b, env in enumerate(envs):
             env.step_into(actions[t % n_act], obs[b], rew[b], don[b])
     torch.cuda.synchronize(dev)
 
@@ -386,7 +395,6 @@ def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
         # independent env batches are in flight on their own streams, so the PCIe copies of one batch overlap the kernel of
         # another (how an asynchronous vector-env driver calls it).  value_sync_each_step = a host synchronisation per step.
         h_act = torch.randint(0, 5, (n_act, E, 1), dtype=torch.int32).pin_memory()
-        # every batch covers the same episode ages as in the device-timed window (at most 300 steps each)
         per_batch = max(10, min(args.steps // n_rot, 300))
         e2e_steps = per_batch * n_e2e
 
@@ -401,18 +409,7 @@ def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
             for b in range(n_e2e):
                 envs[b].step_wait()
 
-        def reprime():
-            # every e2e mode starts from the episode age at which the device-timed window started (fresh episodes, the same
-            # number of untimed device-resident steps), so that its steps cost what the headline's steps cost
-            for env in envs:
-                env.reset()
-            for t in range(args.prime + warm // n_rot):
-                for b, env in enumerate(envs):
-                    env.step_into(actions[t % n_act], obs[b], rew[b], don[b])
-            torch.cuda.synchronize(dev)
-
         def timed(sync_each, wire):
-            reprime()
             e2e_run(n_e2e, sync_each, wire)
             barrier(); torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
@@ -441,8 +438,8 @@ def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
                       "note": f"VecEvacuationEnv.step_async/step_wait: pinned host actions in (H2D), obs+reward+done out (D2H) every "
                               f"step, the same dense f32 host buffers in both modes; value = the faster of the two transfer modes (named "
                               f"in `mode`), both measured and listed; {n_e2e} independent env batches in flight on their own streams "
-                              f"(copies and the host expansion of one overlap the kernels of the others); every mode starts from fresh "
-                              f"episodes primed to the age at which the device-timed window started; value_sync_each_step = dense mode, "
+                              f"(copies and the host expansion of one overlap the kernels of the others); like the device-timed window, "
+                              f"every mode runs on batches in their steady state (see prime_steps); value_sync_each_step = dense mode, "
                               f"one batch at a time with a host sync per step; d2h_GBs_per_gpu = the PCIe device-to-host rate the value "
                               f"corresponds to"}
     for env in envs:
@@ -501,6 +498,13 @@ def run_learner_loop(args, wl, layout, dev, rank, world, precision, loop_steps, 
     tr = VecTrainer(layout, E, N, dev, dict(batch_size=B, learning_rate=1e-4, gamma=0.99, epsilon=1.0, epsilon_min=0.02,
                                              epsilon_decay=0.9995, dropout="train", precision=precision),
                     env_id_base=rank * E, seed=2026, replay_capacity=max(1 << 17, 4 * E), overlap=overlap)
+    # the env batch of the loop is run into its steady state first (random actions, untimed; see run_env_legs), so that the env
+    # segment of the loop costs what it costs in a long training run and not what the first, lock-stepped episode costs
+    g = torch.Generator(device=dev)
+    g.manual_seed(4321 + rank)
+    rand_act = torch.randint(0, 5, (64, E, 1), generator=g, device=dev, dtype=torch.int32)
+    for t in range(args.prime if precision == "bf16" else min(args.prime, 300)):
+        tr.env.step_into(rand_act[t % 64], tr.obs[tr.cur], tr.reward, tr.done)
     for _ in range(max(3, -(-B // E) + 2)):
         tr.step()
     torch.cuda.synchronize(dev)
@@ -700,7 +704,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--prime", type=int, default=150, help="untimed steps per batch before warm-up")
+    ap.add_argument("--prime", type=int, default=1500, help="untimed steps per batch before warm-up (default: into the steady state of auto-reset)")
     ap.add_argument("--batches", type=int, default=0, help="independent env batches rotated / in flight (0 = 4, or more if it takes more to exceed L2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-learner", action="store_true", help="skip the learner legs")

@@ -34,4 +34,5 @@ def window(t0, t1, label):
           (f"; movers needing noise draws {out[12]} of {out[13]} ({100.0 * out[12] / max(out[13], 1):.1f} %)" if out[13] else ""))
 window(0, 1, "step 0 (nobody moves)"); window(1, 2, "step 1 (everybody moves)"); window(2, 3, "step 2"); window(3, 4, "step 3")
 window(4, min(150, steps), "steps 4-149")
-if steps > 150: window(150, steps, f"steps 150-{steps - 1}")
+if steps > 150: window(150, min(steps, 1500), f"steps 150-{min(steps, 1500) - 1}")
+if steps > 1500: window(1500, steps, f"steps 1500-{steps - 1} (steady state of auto-reset)")
