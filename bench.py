@@ -281,11 +281,12 @@ def run_reference(args, wl):
     from floor_field_py import floor_field
     layout = make_layout(wl, floor_field=floor_field)
     threads = os.cpu_count() or 1
-    # bounded sample: size one step so that prime + W + K steps take about a minute at ~2e6 agent-steps/s/thread.  Like the GPU
+    # bounded sample: size one step so that prime + W + K steps take about a minute at this host's measured speed.  Like the GPU
     # arm, the batch is first run into the steady state of auto-reset (args.prime untimed steps: a step of a fresh, lock-stepped
     # episode costs more than the average step of a long run, on the CPU too), then W warm-up and K timed steps.
-    budget_agent_steps = 60.0 * 2.0e6 * threads
-    n_envs = int(budget_agent_steps / max(1, args.prime + args.steps + args.warmup) / wl["people"])
+    probe_envs = max(threads * 4, min(wl["envs"], 1024))
+    v0, _ = cpu_port_throughput(layout, wl, probe_envs, 3, 1, threads)                # agent-steps/s of this host, fresh episodes
+    n_envs = int(v0 * 50.0 / max(1, args.prime + args.steps + args.warmup) / wl["people"])      # ~50 s of work in all
     n_envs = max(threads * 4, min(wl["envs"], n_envs))
     value, dt = cpu_port_throughput(layout, wl, n_envs, args.steps, args.prime + args.warmup, threads)
     line = {
