@@ -31,6 +31,10 @@
 
 namespace mq {
 
+// smallest group (warps per env) that sets its last warp aside for the sequential health sum
+#ifndef MQ_CHAIN_MIN_WPE
+#define MQ_CHAIN_MIN_WPE 8
+#endif
 constexpr int MAXR = MQ_MAX_ROBOTS;
 constexpr uint32_t HEMPTY = 0xFFFFFFFFu;
 
@@ -170,7 +174,7 @@ template <bool BIG> __device__ __forceinline__ unsigned long long tab_ld(const u
 template <int WPE, int CW>
 struct Group {
     static constexpr int SIZE = 32 * WPE;
-    static constexpr bool CHAIN = WPE >= 8;            // a dedicated chain warp only pays for wide groups
+    static constexpr bool CHAIN = WPE >= MQ_CHAIN_MIN_WPE;   // a dedicated chain warp only pays for wide groups
     static constexpr int WORKERS = CHAIN ? SIZE - 32 : SIZE;
     int gtid, gid;
     __device__ __forceinline__ Group() : gtid(threadIdx.x % SIZE), gid(threadIdx.x / SIZE) {}
@@ -355,7 +359,7 @@ env_reset_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const uint8_t* env_m
     select_layout<MULTI>(lay, env);
     Smem sm;
     carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
-          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE, nullptr, !(Group<WPE, CW>::CHAIN && !BIG) || cfg.health_smem);
+          cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE, nullptr, !(WPE >= 8 && !BIG) || cfg.health_smem);
     int* sc = s_sc[g.gid];
     int(*rob)[2] = s_rob[g.gid];
     if (g.gtid < MQ_ENV_SCALARS) sc[g.gtid] = st.scalars[(size_t)env * MQ_ENV_SCALARS + g.gtid];
@@ -550,7 +554,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
 #ifdef MQ_ENV_TRACE
     long long _tprev = clock64();
 #endif
-    const bool HSM = !(G::CHAIN && !BIG) || cfg.health_smem;     // shared copy of the health values (see carve)
+    const bool HSM = !(WPE >= 8 && !BIG) || cfg.health_smem;     // shared copy of the health values (see carve)
     Smem sm;
     carve(sm, smem_raw + (size_t)g.gid * cfg.smem_per_env, BIG ? cfg.scratch + (size_t)env * cfg.scratch_per_env : nullptr, cfg.N,
           cfg.hash_cap, lay.rmap_words, cfg.n_leaf_max, Group<WPE, CW>::SIZE, nullptr, HSM);
@@ -1158,7 +1162,11 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
                     __syncwarp();
                 }
                 if (lane == 0) s_sum[0] = sm.leaf_sum[0];
-                if (!G::CHAIN) { const double th = health_chain_runs<BIG ? 8 : 1>(sm.health, N, lane); if (lane == 0) s_sum[1] = th; }
+                if (!G::CHAIN) {
+                    const double th = HSM ? health_chain_runs<BIG ? 8 : 1>(sm.health, N, lane)
+                                          : health_chain_runs<4, true>(st.health + base, N, lane, sm.fl);
+                    if (lane == 0) s_sum[1] = th;
+                }
             }
         } else {
         if (warp == 0) {
