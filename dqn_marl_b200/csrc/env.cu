@@ -517,14 +517,17 @@ __device__ long long g_env_trace[16];
 #else
 #define ENV_MARK(k) do { } while (0)
 #endif
-constexpr int SCORE_UNROLL = 2;     // movers scored per lane and iteration of phase 2 (independent chains)
+#ifndef MQ_SCORE_U_SMALL
+#define MQ_SCORE_U_SMALL 2
+#endif
+constexpr int SCORE_UNROLL = MQ_SCORE_U_SMALL;     // movers scored per lane and iteration of phase 2 (warp-per-env and BIG variants)
 // build-time tuning knobs of the CTA-per-env variant (dqn_marl_b200/build.py build_variant): resident CTAs per SM the register
 // allocation aims at, and the scoring unroll
 #ifndef MQ_CTA8_PER_SM
 #define MQ_CTA8_PER_SM 4
 #endif
 #ifndef MQ_SCORE_U8
-#define MQ_SCORE_U8 SCORE_UNROLL
+#define MQ_SCORE_U8 1      // CTA-per-env variant: with the lazy noise one mover per lane is fastest (fewer live registers: 0.759 vs 0.794 ms at C3)
 #endif
 
 template <int WPE, int CW, bool BIG, bool MULTI>
