@@ -839,9 +839,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
             __syncthreads();
         }
         if (!coop) {
-            int rbx[MAXR], rby[MAXR];
-#pragma unroll
-            for (int r = 0; r < MAXR; ++r) { rbx[r] = rob[r < cfg.R ? r : 0][0]; rby[r] = rob[r < cfg.R ? r : 0][1]; }
+            const int rbx0 = rob[0][0], rby0 = rob[0][1];        // robot 0 in registers; further robots (R > 1) are read from shared memory
             const int q = lane & 3, R = cfg.R;
             const int n_items = (n_mov * 4 + 31) & ~31;          // whole warps take part in the shuffles
             // admissibility (Check_Valid through dp5 = -inf, rmap == 0) and the deterministic part of the score of direction
@@ -853,14 +851,13 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
                 // evaluate_strategies.py:83 sets [1000,1000]; anything >= 25 means "out of range")
                 int d2;
                 {
-                    const int ax = min(abs(nx - rbx[0]), 30000), ay = min(abs(ny - rby[0]), 30000);
+                    const int ax = min(abs(nx - rbx0), 30000), ay = min(abs(ny - rby0), 30000);
                     d2 = ax * ax + ay * ay;
                 }
                 if (R > 1) {                         // warp-uniform
-#pragma unroll
-                    for (int r = 1; r < MAXR; ++r) {
-                        const int ax = min(abs(nx - rbx[r]), 30000), ay = min(abs(ny - rby[r]), 30000);
-                        d2 = min(d2, ax * ax + ay * ay);       // r >= R repeats robot 0: harmless for the minimum
+                    for (int r = 1; r < R; ++r) {
+                        const int ax = min(abs(nx - rob[r][0]), 30000), ay = min(abs(ny - rob[r][1]), 30000);
+                        d2 = min(d2, ax * ax + ay * ay);
                     }
                 }
                 const double eff = d2 < 25 ? c_repel[d2] : 0.0;
