@@ -510,7 +510,10 @@ __device__ __noinline__ double health_chain_runs(const double* h, int N, int lan
 // ---------------------------------------------------------------------------------------------
 // The fused step.
 // ---------------------------------------------------------------------------------------------
-constexpr int PF_MAX = 5;  // persons per thread whose state is fetched before any of them is processed (5 x 32 >= 150: one pass at C2)
+#ifndef MQ_PF_MAX
+#define MQ_PF_MAX 5
+#endif
+constexpr int PF_MAX = MQ_PF_MAX;  // persons per thread whose state is fetched before any of them is processed (5 x 32 >= 150: one pass at C2)
 #ifdef MQ_ENV_TRACE
 __device__ long long g_env_trace[16];
 #define ENV_MARK(k) do { if (tid == 0) { const long long _t = clock64(); atomicAdd((unsigned long long*)&g_env_trace[k], (unsigned long long)(_t - _tprev)); _tprev = _t; } } while (0)
