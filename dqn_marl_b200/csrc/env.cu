@@ -513,6 +513,9 @@ __device__ __noinline__ double health_chain_runs(const double* h, int N, int lan
 #ifndef MQ_PF_MAX
 #define MQ_PF_MAX 5
 #endif
+#ifndef MQ_PF_WIDE
+#define MQ_PF_WIDE 2      // persons per thread prefetched in phase 1 of the CTA-per-env variants (4: 0.752 ms at C3, 2: 0.718, 1: 0.722 — registers)
+#endif
 constexpr int PF_MAX = MQ_PF_MAX;  // persons per thread whose state is fetched before any of them is processed (5 x 32 >= 150: one pass at C2)
 #ifdef MQ_ENV_TRACE
 __device__ long long g_env_trace[16];
@@ -653,7 +656,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
             }
         }
     };
-    constexpr int PF = WPE == 1 ? PF_MAX : 4;
+    constexpr int PF = WPE == 1 ? PF_MAX : MQ_PF_WIDE;
     for (int i0 = 0; i0 < N; i0 += T * PF) {
         uint32_t p_[PF], fl_[PF];
         double h_[PF], a_[PF], dg_[PF];
