@@ -1142,7 +1142,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
                 }
                 if (lane == 0) { lvl[nlev] = hi; lvl[19] = nlev; }
             } else {
-                store_bitmap(wt - 32, TW - 32, lay, sm, st.rmap, env);
+                if (n_mov > 0) store_bitmap(wt - 32, TW - 32, lay, sm, st.rmap, env);      // nobody moved: the global copy is current
                 gather_obs(wt - 32, TW - 32, lay, cfg, sm, rob, rpx, rpy, fs_new, obs, obs64, env);
             }
             g.wsync();
@@ -1199,7 +1199,7 @@ env_step_kernel(DevLayout lay_in, DevCfg cfg, DevState st, const int* __restrict
         }
         ENV_MARK(6);      // tree + chain
         // fire models step (evacuation_env.py:138-142; fire_model.py:63-67) — the observation uses the new step
-        store_bitmap(wt, TW, lay, sm, st.rmap, env);
+        if (n_mov > 0) store_bitmap(wt, TW, lay, sm, st.rmap, env);      // nobody moved: the global copy is current
         gather_obs(wt, TW, lay, cfg, sm, rob, rpx, rpy, min(sc[MQ_S_FIRE_STEP] + 1, lay.n_fire_steps - 1), obs, obs64, env);
         }
     }
