@@ -204,8 +204,49 @@ class DQNAgent:
         return state.to(device=self.net.device, dtype=torch.float32)
 
     # ------------------------------------------------------------------
+    # -- single-transition fast path (the reference's loop, train_dqn.py:98-125: one env, numpy states) ----------------------
+    _RM_SLOTS = 8
+    _RM_BYTES = 2 * 726 * 4 + 8 + 4 + 4          # state f32 | next_state f32 | reward f64 | action i32 | done u8 (+ pad)
+
+    def _staging(self):
+        st = getattr(self, "_stage", None)
+        if st is None:
+            d, nb, ob = self.net.device, self._RM_BYTES, 726 * 4
+            hs = torch.zeros((self._RM_SLOTS, nb), dtype=torch.uint8).pin_memory()
+            ds = torch.zeros((self._RM_SLOTS, nb), dtype=torch.uint8, device=d)
+
+            def views(buf):
+                return [dict(s=b[0:ob].view(torch.float32).view(1, 726), ns=b[ob:2 * ob].view(torch.float32).view(1, 726),
+                             r=b[2 * ob:2 * ob + 8].view(torch.float64), a=b[2 * ob + 8:2 * ob + 12].view(torch.int32),
+                             d=b[2 * ob + 12:2 * ob + 13]) for b in buf]
+            hv = views(hs)
+            st = self._stage = dict(hs=hs, ds=ds, hv=[{k: v.numpy() for k, v in e.items()} for e in hv], dv=views(ds), k=0,
+                                    ev=[torch.cuda.Event() for _ in range(self._RM_SLOTS)], used=[False] * self._RM_SLOTS,
+                                    hx=torch.zeros((1, 726), dtype=torch.float32).pin_memory(),
+                                    dx=torch.zeros((1, 726), dtype=torch.float32, device=d),
+                                    da=torch.zeros((1,), dtype=torch.int32, device=d), ha=torch.zeros((1,), dtype=torch.int32).pin_memory())
+            st["hx_np"], st["ha_np"] = st["hx"].numpy(), st["ha"].numpy()
+        return st
+
     def remember(self, state, action, reward, next_state, done):
-        """dqn_agent.py:97-99"""
+        """dqn_agent.py:97-99.  numpy states (what the reference's runners pass) travel as ONE asynchronous copy of a pinned
+        staging slot — state, next_state, reward, action, done — followed by the push kernel; nothing waits for the device."""
+        if isinstance(state, np.ndarray) and isinstance(next_state, np.ndarray) and state.size == 726 and next_state.size == 726:
+            st = self._staging()
+            k = st["k"] % self._RM_SLOTS
+            st["k"] += 1
+            if st["used"][k]:
+                st["ev"][k].synchronize()             # the copy that last read this pinned slot (8 remember() calls ago)
+            h, dv = st["hv"][k], st["dv"][k]
+            np.copyto(h["s"], state.reshape(1, 726), casting="same_kind")           # float64 -> float32 like dqn_agent.py:136-139
+            np.copyto(h["ns"], next_state.reshape(1, 726), casting="same_kind")
+            h["r"][0], h["a"][0], h["d"][0] = float(reward), int(action), 1 if done else 0
+            with torch.cuda.device(self.net.device):
+                st["ds"][k].copy_(st["hs"][k], non_blocking=True)
+                st["ev"][k].record()
+                st["used"][k] = True
+                self.memory.push(dv["s"], dv["a"], dv["r"], dv["ns"], dv["d"])
+            return
         d = self.net.device
         self.memory.push(self._to_dev(state).reshape(1, 726).contiguous(), torch.tensor([int(action)], dtype=torch.int32, device=d),
                          torch.tensor([float(reward)], dtype=torch.float64, device=d),
@@ -213,6 +254,18 @@ class DQNAgent:
 
     def act(self, state, training=False):
         """dqn_agent.py:101-124 — epsilon-greedy on top of the online forward, one fused launch sequence."""
+        if isinstance(state, np.ndarray) and state.size == 726:
+            # one state from the host: pinned upload, forward + epsilon-greedy head, pinned read-back, ONE synchronisation
+            st = self._staging()
+            np.copyto(st["hx_np"], state.reshape(1, 726), casting="same_kind")      # dqn_agent.py:109
+            with torch.cuda.device(self.net.device):
+                st["dx"].copy_(st["hx"], non_blocking=True)
+                mask = self._mask(1) if self.dropout_mode == "train" else None
+                self._act_calls += 1
+                self.net.act(st["dx"], self.epsilon if training else 0.0, self.seed, 0, self._act_calls, 1, mask, out=st["da"])
+                st["ha"].copy_(st["da"], non_blocking=True)
+                torch.cuda.current_stream(self.net.device).synchronize()
+            return int(st["ha_np"][0])
         x = self._to_dev(state)
         if x.dim() == 3:
             x = x.unsqueeze(0)
@@ -228,7 +281,8 @@ class DQNAgent:
         if len(self.memory) < self.batch_size or self.steps < self.warmup_steps:
             return None
         B = self.batch_size
-        batch = self.memory.sample(B)
+        prev = getattr(self, "_learn_batch", None)
+        batch = self._learn_batch = self.memory.sample(B, out=prev if prev is not None and prev["actions"].shape[0] == B else None)
         train = self.dropout_mode == "train"
         self._adam_t += 1
         hp = self._hparams()

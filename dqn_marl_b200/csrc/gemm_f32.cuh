@@ -34,6 +34,10 @@ struct GemmParams {
     // split-K
     float* partial;              // [splits][M][N] when splits > 1
     int splits, k_chunk;
+    // Small-batch form (launch_gemm_swapped): the kernel computes C^T — its rows are the ORIGINAL columns — so that a batch of
+    // <= 32 rows becomes the narrow BN = 32 side of the tile instead of filling 1..32 of its 128 rows.  bias / mask_act / drop
+    // and the store are indexed in ORIGINAL coordinates (row = kernel column); drop_ld = row length of `drop` (original N).
+    int trans_out, drop_ld;
 };
 
 constexpr int GEMM_BM = 128, GEMM_BK = 16, GEMM_THREADS = 256;
@@ -157,11 +161,16 @@ __device__ __forceinline__ float4 load_b_kvec(const GemmParams& p, int k, int n,
     return v;
 }
 
+// (m, n) = kernel coordinates; with trans_out the output element is C[n][m]
+__device__ __forceinline__ size_t out_index(const GemmParams& p, int m, int n) {
+    return p.trans_out ? (size_t)n * p.ldc + m : (size_t)m * p.ldc + n;
+}
 __device__ __forceinline__ float epilogue_value(const GemmParams& p, float v, int m, int n) {
+    if (p.trans_out) { const int t = m; m = n; n = t; }
     if (p.bias) v += __ldg(p.bias + n);
     if (p.relu) v = fmaxf(v, 0.f);
     if (p.mask_act) v = (__ldg(p.mask_act + (size_t)m * p.ldc + n) > 0.f) ? v : 0.f;
-    if (p.drop) v = __ldg(p.drop + (size_t)m * p.N + n) ? v * p.drop_scale : 0.f;
+    if (p.drop) v = __ldg(p.drop + (size_t)m * (p.drop_ld ? p.drop_ld : p.N) + n) ? v * p.drop_scale : 0.f;      // drop_ld = 0: a caller that fills GemmParams itself
     return v;
 }
 
@@ -325,8 +334,9 @@ gemm_f32_kernel(GemmParams p) {
                 const int n = n0 + col_of(j);
                 if (n < p.N) {
                     const float v = epilogue_value(p, (j & 1) ? acc2[i][j / 2].y : acc2[i][j / 2].x, m, n);
-                    p.C[(size_t)m * p.ldc + n] = v;
-                    if (p.Cb) p.Cb[(size_t)m * p.ldc + n] = __float2bfloat16(v);
+                    const size_t o = out_index(p, m, n);
+                    p.C[o] = v;
+                    if (p.Cb) p.Cb[o] = __float2bfloat16(v);
                 }
             }
         }
@@ -335,14 +345,25 @@ gemm_f32_kernel(GemmParams p) {
 
 __global__ void __launch_bounds__(256) splitk_epilogue_kernel(GemmParams p) {
     const size_t total = (size_t)p.M * p.N;
-    if (p.N % 4 == 0 && p.ldc % 4 == 0 && (((uintptr_t)p.C | (uintptr_t)p.partial) & 15) == 0 && ((uintptr_t)p.Cb & 7) == 0) {
+    // The partials of one output element are summed in split order (deterministic); the loads of eight splits are issued
+    // together — a loop of dependent load -> add pairs made the reduce of a small-batch layer (148 splits of a 32 x 512 output)
+    // a 10 us latency chain.
+    if (!p.trans_out && p.N % 4 == 0 && p.ldc % 4 == 0 && (((uintptr_t)p.C | (uintptr_t)p.partial) & 15) == 0 && ((uintptr_t)p.Cb & 7) == 0) {
         // four columns per thread: 16-byte loads of the partials, one pass
         const size_t total4 = total / 4;
         for (size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < total4; i4 += (size_t)gridDim.x * blockDim.x) {
             const size_t idx = i4 * 4;
             const int m = (int)(idx / p.N), n = (int)(idx - (size_t)m * p.N);
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int s = 0; s < p.splits; ++s) {                                          // fixed order: deterministic
+            int s = 0;
+            for (; s + 8 <= p.splits; s += 8) {                                           // fixed order: deterministic
+                float4 w[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const float4*>(p.partial + (size_t)(s + u) * total + idx);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { a.x += w[u].x; a.y += w[u].y; a.z += w[u].z; a.w += w[u].w; }
+            }
+            for (; s < p.splits; ++s) {
                 const float4 w = *reinterpret_cast<const float4*>(p.partial + (size_t)s * total + idx);
                 a.x += w.x; a.y += w.y; a.z += w.z; a.w += w.w;
             }
@@ -361,10 +382,19 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(GemmParams p) {
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int m = (int)(idx / p.N), n = (int)(idx - (size_t)m * p.N);
         float v = 0.f;
-        for (int s = 0; s < p.splits; ++s) v += p.partial[(size_t)s * total + idx];     // fixed order: deterministic
+        int s = 0;
+        for (; s + 8 <= p.splits; s += 8) {                                               // fixed order: deterministic
+            float w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w[u] = p.partial[(size_t)(s + u) * total + idx];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += w[u];
+        }
+        for (; s < p.splits; ++s) v += p.partial[(size_t)s * total + idx];
         v = epilogue_value(p, v, m, n);
-        p.C[(size_t)m * p.ldc + n] = v;
-        if (p.Cb) p.Cb[(size_t)m * p.ldc + n] = __float2bfloat16(v);
+        const size_t o = out_index(p, m, n);
+        p.C[o] = v;
+        if (p.Cb) p.Cb[o] = __float2bfloat16(v);
     }
 }
 
@@ -396,6 +426,7 @@ inline int launch_gemm(GemmParams p, size_t partial_cap, int n_sms, cudaStream_t
     }
     int chunk_tiles = (k_tiles + splits - 1) / splits;
     splits = (k_tiles + chunk_tiles - 1) / chunk_tiles;
+    if (p.drop_ld == 0) p.drop_ld = p.trans_out ? p.M : p.N;
     p.splits = splits;
     p.k_chunk = chunk_tiles * GEMM_BK;
     dim3 grid(tiles_n, tiles_m, splits);
@@ -409,5 +440,22 @@ inline int launch_gemm(GemmParams p, size_t partial_cap, int n_sms, cudaStream_t
     }
     return 1;
 }
+
+// Small-batch fully connected layers.  C[m][n] (m < M <= 32 batch rows) is computed as C^T = B^T A^T: the kernel's 128-row side
+// runs over the layer's output features and the batch is the narrow BN = 32 side, so no FFMA is spent on padding rows (the
+// 128 x BN tile on a 1- or 32-row batch spent 75-99 % of its FMAs there: fc1 forward 47 us at B = 1 and at B = 32).
+//   wt_mode = A_ROW: the layer's weight is W[n][k] (forward, PyTorch Linear layout), x[m][k] row-major
+//   wt_mode = A_COL: the weight is W[k][n] (data gradient: dX = dY W), x[m][k] row-major
+// `p` is filled in ORIGINAL coordinates (M batch rows, N features, K, A = x / lda, B = W / ldb, C / ldc, bias, mask_act, drop).
+template <int WT_MODE>
+inline int launch_gemm_swapped(GemmParams p, size_t partial_cap, int n_sms, cudaStream_t stream) {
+    GemmParams q = p;
+    q.M = p.N; q.N = p.M;
+    q.A = p.B; q.lda = p.ldb;
+    q.B = p.A; q.ldb = p.lda;
+    q.trans_out = 1; q.drop_ld = p.N;
+    return launch_gemm<WT_MODE, B_COL, 32, 1>(q, partial_cap, n_sms, stream);
+}
+constexpr int GEMM_SWAP_MAX_M = 32;
 
 }  // namespace mq

@@ -487,10 +487,13 @@ static int forward_net(mq_qnet* n, float* const* W, const float* obs, long long 
     // fc1: [B][15488] x W1^T, ReLU, Dropout(0.2) (dqn_agent.py:56-57)
     p.M = (int)B; p.N = H1; p.K = FLAT; p.A = n->a3; p.lda = FLAT; p.B = W[P_F1W]; p.ldb = FLAT; p.C = n->h1; p.ldc = H1;
     p.bias = W[P_F1B]; p.drop = drop_mask; p.drop_scale = 1.f / (1.f - 0.2f);
-    n->launches += launch_gemm<A_ROW, B_COL, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    const bool small = B <= GEMM_SWAP_MAX_M;          // C1 (configs/dqn.yaml: B = 32) and single-env act(): transposed small-batch form
+    if (small) n->launches += launch_gemm_swapped<A_ROW>(p, n->partial_cap, n->n_sms, s);
+    else n->launches += launch_gemm<A_ROW, B_COL, 128, 1>(p, n->partial_cap, n->n_sms, s);
     // fc2
     p.N = H2; p.K = H1; p.A = n->h1; p.lda = H1; p.B = W[P_F2W]; p.ldb = H1; p.C = n->h2; p.ldc = H2; p.bias = W[P_F2B]; p.drop = nullptr;
-    n->launches += launch_gemm<A_ROW, B_COL, 64, 1>(p, n->partial_cap, n->n_sms, s);
+    if (small) n->launches += launch_gemm_swapped<A_ROW>(p, n->partial_cap, n->n_sms, s);
+    else n->launches += launch_gemm<A_ROW, B_COL, 64, 1>(p, n->partial_cap, n->n_sms, s);
     return 0;
 }
 
@@ -758,7 +761,9 @@ static void backward_fp32(mq_qnet* n, const float* state, long long B, const uin
     p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
     p.M = (int)B; p.N = H1; p.K = H2; p.A = n->dh2; p.lda = H2; p.B = W[P_F2W]; p.ldb = H1; p.C = n->dh1; p.ldc = H1;
     p.mask_act = n->h1; p.drop = drop_online; p.drop_scale = 1.f / (1.f - 0.2f);
-    n->launches += launch_gemm<A_ROW, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    const bool small = B <= GEMM_SWAP_MAX_M;          // as in forward_net
+    if (small) n->launches += launch_gemm_swapped<A_COL>(p, n->partial_cap, n->n_sms, s);
+    else n->launches += launch_gemm<A_ROW, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
     // fc1: dW1[512][15488] = dh1^T a3 ; db1 ; da3 = dh1 W1 masked by a3 > 0
     p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
     p.M = H1; p.N = FLAT; p.K = (int)B; p.A = n->dh1; p.lda = H1; p.B = n->a3; p.ldb = FLAT; p.C = G[P_F1W]; p.ldc = FLAT;
@@ -766,7 +771,8 @@ static void backward_fp32(mq_qnet* n, const float* state, long long B, const uin
     launch_colsum(n, n->dh1, B, H1, G[P_F1B], s);
     p = GemmParams{}; p.batch = (int)B; p.partial = n->partial;
     p.M = (int)B; p.N = FLAT; p.K = H1; p.A = n->dh1; p.lda = H1; p.B = W[P_F1W]; p.ldb = FLAT; p.C = n->da3; p.ldc = FLAT; p.mask_act = n->a3;
-    n->launches += launch_gemm<A_ROW, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
+    if (small) n->launches += launch_gemm_swapped<A_COL>(p, n->partial_cap, n->n_sms, s);
+    else n->launches += launch_gemm<A_ROW, B_ROW, 128, 1>(p, n->partial_cap, n->n_sms, s);
     }
     if (part == 1) return;
     // conv3: dWc3[(tap,c)][n] = im2col(a2)^T da3 ; db ; da2 = dgrad masked by a2 > 0

@@ -24,18 +24,56 @@ from .vec_env import S_CUR_STEP, S_DEAD, S_EVAC, S_FIRE_STEP, S_RPX, S_RPY, VecE
 
 
 class _Person:
-    """Read-only view with the attribute names of the reference's Person (people.py:8-23)."""
-    __slots__ = ("id", "pos", "health", "savety", "dead", "trajectory", "move_accumulator", "speed")
+    """Read-only view with the attribute names of the reference's Person (people.py:8-23).  The values are read on access
+    from the env's host mirror of the device state (one pinned copy per step, `EvacuationEnv._pull`), so a step costs no
+    per-person Python work; `trajectory` (people.py:21, evacuation_env.py:80,135: one {'pos', 'step'} entry per step) is
+    materialised from the per-step position records when somebody reads it."""
+    __slots__ = ("id", "_i", "_env", "_traj", "_traj_upto")
 
-    def __init__(self, pid):
+    def __init__(self, pid, env=None):
         self.id = pid
-        self.pos = (0.5, 0.5)
-        self.health = 100.0
-        self.savety = False
-        self.dead = False
-        self.trajectory = []
-        self.move_accumulator = 0.0
-        self.speed = 1.0
+        self._i = pid - 1
+        self._env = env
+        self._traj = []
+        self._traj_upto = 0
+
+    @property
+    def pos(self):
+        v = int(self._env._h_pos_np[self._i])
+        return ((v & 0xFFFF) + 0.5, ((v >> 16) & 0xFFFF) + 0.5)
+
+    @property
+    def health(self):
+        return float(self._env._h_health_np[self._i])
+
+    @property
+    def move_accumulator(self):
+        return float(self._env._h_acc_np[self._i])
+
+    @property
+    def savety(self):
+        return bool(self._env._h_flags_np[self._i] & 1)
+
+    @property
+    def dead(self):
+        return bool(self._env._h_flags_np[self._i] & 2)
+
+    @property
+    def speed(self):
+        """people.py:38-44"""
+        h = self.health
+        return 0.4 if h < 20 else 0.3 + 0.7 * h / 100
+
+    @property
+    def trajectory(self):
+        rec = self._env._traj_rec
+        if self._traj_upto > len(rec):            # the env was reset since the last read
+            self._traj, self._traj_upto = [], 0
+        for pos, label in rec[self._traj_upto:]:
+            v = int(pos[self._i])
+            self._traj.append({"pos": ((v & 0xFFFF) + 0.5, ((v >> 16) & 0xFFFF) + 0.5), "step": label})
+        self._traj_upto = len(rec)
+        return self._traj
 
 
 class _FireModelView:
@@ -48,9 +86,10 @@ class _FireModelView:
     def update(self):
         sc = self._env._vec.scalars
         sc[0, S_FIRE_STEP] = torch.clamp(sc[0, S_FIRE_STEP] + 1, max=self._sched.max_steps)
+        self._env._h_sc_np[S_FIRE_STEP] = min(int(self._env._h_sc_np[S_FIRE_STEP]) + 1, self._sched.max_steps)
 
     def get_max_danger(self, position):
-        step = int(self._env._vec.scalars[0, S_FIRE_STEP].item())
+        step = int(self._env._h_sc_np[S_FIRE_STEP])
         return float(self._sched.danger_field(step, np.float64(position[0]), np.float64(position[1])))
 
 
@@ -83,24 +122,27 @@ class _MapView:
     # robot at [1000, 1000]); writes go to the device state.
     @property
     def robot_positions(self):
-        r = self._env._vec.robots[0, :self._env._vec.n_robots].cpu().numpy()
-        return [[int(a), int(b)] for a, b in r]
+        e = self._env
+        return [[int(a), int(b)] for a, b in e._h_robots_np[:e._vec.n_robots]]
 
     @robot_positions.setter
     def robot_positions(self, value):
-        v = self._env._vec
+        e = self._env
+        v = e._vec
         for r, p in enumerate(value[:v.n_robots]):
             v.robots[0, r, 0], v.robots[0, r, 1] = int(p[0]), int(p[1])
+            e._h_robots_np[r, 0], e._h_robots_np[r, 1] = int(p[0]), int(p[1])
 
     @property
     def robot_position(self):
-        sc = self._env._vec.scalars[0].cpu().numpy()
+        sc = self._env._h_sc_np
         return [int(sc[S_RPX]), int(sc[S_RPY])]
 
     @robot_position.setter
     def robot_position(self, value):
         sc = self._env._vec.scalars
         sc[0, S_RPX], sc[0, S_RPY] = int(value[0]), int(value[1])
+        self._env._h_sc_np[S_RPX], self._env._h_sc_np[S_RPY] = int(value[0]), int(value[1])
 
 
 class _PeopleView:
@@ -108,7 +150,7 @@ class _PeopleView:
 
     def __init__(self, env, n):
         self._env = env
-        self.list = [_Person(i + 1) for i in range(n)]
+        self.list = [_Person(i + 1, env) for i in range(n)]
         self.tot = n
 
     @property
@@ -170,6 +212,22 @@ class EvacuationEnv:
         dev = self._vec.device
         self._obs64 = torch.zeros((1, self._N_ROBOTS, 11, 11, 6), dtype=torch.float64, device=dev)
         self._act = torch.zeros((1, self._N_ROBOTS), dtype=torch.int32, device=dev)
+        # Host mirror of everything a step hands back (pinned): the step enqueues the action upload, the kernel and these
+        # copies on one stream and synchronises ONCE; person / map views read the mirror.
+        v, N = self._vec, num_people
+
+        def pinned(t):
+            return torch.empty(t.shape, dtype=t.dtype).pin_memory()
+        self._mirror = [(pinned(v.pos[0, :N]), v.pos[0, :N]), (pinned(v.health[0, :N]), v.health[0, :N]),
+                        (pinned(v.acc[0, :N]), v.acc[0, :N]), (pinned(v.flags[0, :N]), v.flags[0, :N]),
+                        (pinned(v.robots[0]), v.robots[0]), (pinned(v.scalars[0]), v.scalars[0]),
+                        (pinned(self._obs64[0]), self._obs64[0]), (pinned(v.reward), v.reward), (pinned(v.done), v.done)]
+        (self._h_pos_np, self._h_health_np, self._h_acc_np, self._h_flags_np, self._h_robots_np, self._h_sc_np, self._h_obs_np,
+         self._h_rew_np, self._h_done_np) = [h.numpy() for h, _ in self._mirror]
+        self._h_pos_np = self._h_pos_np.view(np.uint32)
+        self._h_act = torch.zeros((1, self._N_ROBOTS), dtype=torch.int32).pin_memory()
+        self._h_act_np = self._h_act.numpy()
+        self._traj_rec = []
         self.map = _MapView(self, self._layout)
         self.fire_model = _FireModelView(self, self._layout.obs_fire)
         self.people = _PeopleView(self, num_people)
@@ -187,25 +245,22 @@ class EvacuationEnv:
             self._coefs_sent = c
 
     def _pull(self, step_label=None, reset=False):
-        s = self._vec.snapshot(0)
-        sc = s["scalars"]
+        """Device -> host mirror: nine small asynchronous copies into pinned memory and ONE synchronisation (the reference API
+        hands back Python scalars and numpy arrays, so a step has to wait for the device exactly once)."""
+        for h, d in self._mirror:
+            h.copy_(d, non_blocking=True)
+        torch.cuda.current_stream(self._vec.device).synchronize()
+        sc = self._h_sc_np
         self.current_step = int(sc[S_CUR_STEP])
         self.time = self.current_step * self.time_per_step
         self._evac, self._dead = int(sc[S_EVAC]), int(sc[S_DEAD])
-        for i, p in enumerate(self.people.list):
-            p.pos = (float(s["px"][i]) + 0.5, float(s["py"][i]) + 0.5)
-            p.health = float(s["health"][i])
-            p.move_accumulator = float(s["acc"][i])
-            p.savety = bool(s["flags"][i] & 1)
-            p.dead = bool(s["flags"][i] & 2)
-            if reset:
-                p.trajectory = [{"pos": p.pos, "step": 0}]
-            else:
-                p.trajectory.append({"pos": p.pos, "step": step_label})
-        return s
+        if reset:
+            self._traj_rec = [(self._h_pos_np.copy(), 0)]              # evacuation_env.py:80
+        else:
+            self._traj_rec.append((self._h_pos_np.copy(), step_label))     # evacuation_env.py:135
 
     def _state(self):
-        o = self._obs64[0].cpu().numpy()
+        o = self._h_obs_np.copy()
         return o[0] if self._N_ROBOTS == 1 else [o[r] for r in range(self._N_ROBOTS)]
 
     def reset(self):
@@ -227,12 +282,12 @@ class EvacuationEnv:
         step_label = self.current_step
         acts = action if self._N_ROBOTS > 1 else [action]
         for r, a in enumerate(acts):
-            a = int(a) if isinstance(a, (int, np.integer)) or hasattr(a, "__int__") else -1
-            self._act[0, r] = a
-        _, rew, done = self._vec.step(self._act, obs64=self._obs64)
-        reward = float(rew[0].item())
-        done = bool(done[0].item())
+            self._h_act_np[0, r] = int(a) if isinstance(a, (int, np.integer)) or hasattr(a, "__int__") else -1
+        self._act.copy_(self._h_act, non_blocking=True)
+        self._vec.step(self._act, obs64=self._obs64)
         self._pull(step_label=step_label)
+        reward = float(self._h_rew_np[0])
+        done = bool(self._h_done_np[0])
         if self._N_ROBOTS == 1:
             self.robot_trajectory.append((tuple(self.map.robot_position), step_label))
         else:
@@ -252,8 +307,7 @@ class EvacuationEnv:
 
     def get_performance_metrics(self):
         """evacuation_env.py:290-309"""
-        pl = self.people.list
-        alive = [p.health for p in pl if not p.dead]
+        alive = [float(h) for h in self._h_health_np[(self._h_flags_np & 2) == 0]]
         return {
             "evacuated": self._evac, "dead": self._dead, "remaining": self.num_people - self._evac - self._dead,
             "evacuation_rate": self._evac / self.num_people, "death_rate": self._dead / self.num_people,
