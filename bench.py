@@ -25,6 +25,9 @@ the stress shape of configs[4].  One env "step" = one fused env-step launch over
             fp32 restatement of DQNAgent.learn(), oracle/qnet_oracle.py, on the host cores at B = 32 and B = batch),
             param_checksum / replicas_identical (data-parallel replicas hold the same weights after the loop)}.
   learner_fp32  the same loop on the 1e-5 parity path (CUDA-core FFMA), fewer steps.
+  c1_dropin  BASELINE.json configs[0] (configs/dqn.yaml: one env, 150 people, B = 32) through the drop-in classes, wall clock per
+            act / step / remember / learn call; the reference arm reports the same loop on the unmodified reference
+            (python_reference.c1_loop).
 
 `--impl reference` times the reference's CPU implementation of the path (the oracle ports; the reference itself is pure
 Python and cannot travel to the GPU box) on all host threads, without loading libmarl_b200.so.
@@ -266,7 +269,47 @@ def python_reference_timing(budget_s=4.0):
         n += 1
     dt = time.perf_counter() - t0
     out["learn_b32"] = {"transitions_per_s": 32 * n / dt, "ms_per_learn": dt / n * 1e3, "steps": n, "torch_threads": torch.get_num_threads()}
+    try:
+        out["c1_loop"] = c1_loop_timing(EvacuationEnv, DQNAgent, torch.device("cpu"), iters=240, budget_s=max(6.0, budget_s))
+    except Exception as e:                                             # noqa: BLE001
+        out["c1_loop"] = {"unavailable": f"{type(e).__name__}: {e}"}
     return out
+
+
+def c1_loop_timing(EvacuationEnv, DQNAgent, device, iters, budget_s, extra_cfg=None):
+    """BASELINE.json configs[0] = configs/dqn.yaml: ONE 36x30 env with 150 people, B = 32, replay 50 000, the loop of
+    runners/train_dqn.py:98-125 (act -> step -> remember -> learn, reset on done) through the reference's class surface;
+    wall clock per call, every call synchronous as the reference API demands.  The same function times the drop-in classes
+    (ours arm) and the unmodified reference classes (reference arm, CPU)."""
+    import random
+    import numpy as np
+    random.seed(1); np.random.seed(1)
+    cfg = dict(gamma=0.99, epsilon=1.0, epsilon_min=0.02, epsilon_decay=0.9995, learning_rate=1e-4, batch_size=32,
+               target_update_freq=200, warmup_steps=0, memory_size=50000)
+    cfg.update(extra_cfg or {})
+    env = EvacuationEnv(width=36, height=30, num_people=150)
+    agent = DQNAgent(env.state_size, env.action_size, device, cfg)
+    state = env.reset()
+    T = dict(act=0.0, step=0.0, remember=0.0, learn=0.0)
+    n, warm, t_start = 0, 40, time.perf_counter()
+    for it in range(iters):
+        t0 = time.perf_counter(); a = agent.act(state, training=True)
+        t1 = time.perf_counter(); nstate, r, done, _info = env.step(a)
+        t2 = time.perf_counter(); agent.remember(state, a, r, nstate, done)
+        t3 = time.perf_counter(); loss = agent.learn() if len(agent.memory) > agent.batch_size else None
+        t4 = time.perf_counter()
+        state = env.reset() if done else nstate
+        if it >= warm and loss is not None:
+            T["act"] += t1 - t0; T["step"] += t2 - t1; T["remember"] += t3 - t2; T["learn"] += t4 - t3; n += 1
+        if time.perf_counter() - t_start > budget_s and n >= 20:
+            break
+    if n == 0:
+        return None
+    ms = {k: v / n * 1e3 for k, v in T.items()}
+    it_ms = sum(ms.values())
+    return {"workload": "configs/dqn.yaml (BASELINE.json configs[0]): one 36x30 env, 150 people, B = 32, act -> step -> remember -> learn per iteration",
+            "ms_per_call": ms, "ms_per_iteration": it_ms, "iterations": n, "agent_steps_per_s": 150 / (it_ms * 1e-3),
+            "learned_transitions_per_s": 32 / (it_ms * 1e-3)}
 
 
 def run_reference(args, wl):
@@ -685,6 +728,14 @@ def run_ours(args, wl):
             line["learner_fp32"] = learner_fp32
         if secondary is not None:
             line["secondary_c2"] = secondary
+        if world == 1 and args.c1_iters > 0:
+            from dqn_marl_b200.envs.evacuation_env import EvacuationEnv
+            from dqn_marl_b200.agents.dqn_agent import DQNAgent
+            c1 = c1_loop_timing(EvacuationEnv, DQNAgent, dev, iters=args.c1_iters, budget_s=20.0, extra_cfg={"seed": 2})
+            if c1 is not None:
+                c1["note"] = ("the drop-in classes (dqn_marl_b200.envs.EvacuationEnv / agents.DQNAgent, fp32 parity path) driven exactly like the "
+                              "reference's classes; the reference arm's python_reference.c1_loop is the same loop on the unmodified reference (CPU)")
+                line["c1_dropin"] = c1
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             line["cpu_baseline"] = cpu_env_baseline(layout, wl, threads)
@@ -716,6 +767,7 @@ def main():
     ap.add_argument("--learner-batch", type=int, default=0, help="learn batch per GPU (0 = the workload's: 4096, C5: 8192)")
     ap.add_argument("--replay-batch", type=int, default=65536, help="replay sample batch of the bandwidth leg (0 = skip)")
     ap.add_argument("--c2-steps", type=int, default=3000, help="steps of the secondary C2 env-only run (0 = skip)")
+    ap.add_argument("--c1-iters", type=int, default=400, help="iterations of the C1 (configs/dqn.yaml) loop through the drop-in classes (0 = skip)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

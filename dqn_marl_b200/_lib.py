@@ -91,6 +91,7 @@ SIGNATURES = {
     "mq_qnet_destroy": (C.c_int, [_vp]),
     "mq_qnet_forward": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _vp, _vp]),
     "mq_qnet_act": (C.c_int, [_vp, _vp, _i64, _f32, _u64, _u32, _u32, _i32, _vp, _vp, _vp, _vp]),
+    "mq_qnet_explore_draw": (C.c_int, [_f32, _u64, _u32, _u32, _u32, C.POINTER(_i32)]),
     "mq_qnet_td_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(MqHparams), _vp, _vp, _vp, _vp]),
     "mq_qnet_td_backward_part": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(MqHparams), _vp, _vp, _vp, _i32, _vp]),
     "mq_qnet_backward": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp]),

@@ -226,6 +226,8 @@ class DQNAgent:
                                     dx=torch.zeros((1, 726), dtype=torch.float32, device=d),
                                     da=torch.zeros((1,), dtype=torch.int32, device=d), ha=torch.zeros((1,), dtype=torch.int32).pin_memory())
             st["hx_np"], st["ha_np"] = st["hx"].numpy(), st["ha"].numpy()
+            import ctypes
+            st["explore"] = ctypes.pointer(ctypes.c_int32(0))
         return st
 
     def remember(self, state, action, reward, next_state, done):
@@ -257,6 +259,16 @@ class DQNAgent:
         if isinstance(state, np.ndarray) and state.size == 726:
             # one state from the host: pinned upload, forward + epsilon-greedy head, pinned read-back, ONE synchronisation
             st = self._staging()
+            if training and self.epsilon > 0.0:
+                # the exploration draw of this call, evaluated on the host (the same keyed draw the kernel makes): when it says
+                # "explore" the reference returns the random action without a forward (dqn_agent.py:103-104) — so do we.  The
+                # call and dropout-mask counters advance exactly as on the forward path, so later draws do not depend on it.
+                if self.net.lib.mq_qnet_explore_draw(float(self.epsilon), int(self.seed), 0, (self._act_calls + 1) & 0xFFFFFFFF, 0,
+                                                     st["explore"]):
+                    if self.dropout_mode == "train":
+                        self._mask_calls += 1
+                    self._act_calls += 1
+                    return int(st["explore"].contents.value)
             np.copyto(st["hx_np"], state.reshape(1, 726), casting="same_kind")      # dqn_agent.py:109
             with torch.cuda.device(self.net.device):
                 st["dx"].copy_(st["hx"], non_blocking=True)

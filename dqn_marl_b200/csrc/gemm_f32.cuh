@@ -312,12 +312,27 @@ gemm_f32_kernel(GemmParams p) {
         buf ^= 1;
     }
 
+    // Stores: four adjacent columns of the micro-tile per 16-byte store where the row length and the base allow it (the scalar
+    // form issued 64 four-byte stores per thread, each touching a quarter of a sector).
     if (p.splits > 1) {
         float* dst = p.partial + (size_t)blockIdx.z * p.M * p.N;
+        const bool vec = TN >= 4 && p.N % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int m = m0 + ty * 8 + i;
             if (m >= p.M) continue;
+            if (TN >= 4 && vec) {
+#pragma unroll
+                for (int j = 0; j + 3 < TN; j += 4) {
+                    const int n = n0 + col_of(j);
+                    if (n + 3 < p.N) *reinterpret_cast<float4*>(dst + (size_t)m * p.N + n) = make_float4(acc2[i][j / 2].x, acc2[i][j / 2].y, acc2[i][j / 2 + 1].x, acc2[i][j / 2 + 1].y);
+                    else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (n + q < p.N) dst[(size_t)m * p.N + n + q] = (q & 1) ? acc2[i][(j + q) / 2].y : acc2[i][(j + q) / 2].x;
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
                 const int n = n0 + col_of(j);
@@ -325,10 +340,32 @@ gemm_f32_kernel(GemmParams p) {
             }
         }
     } else {
+        const bool vec = TN >= 4 && !p.trans_out && p.ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.Cb) & 7) == 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int m = m0 + ty * 8 + i;
             if (m >= p.M) continue;
+            if (TN >= 4 && vec) {
+#pragma unroll
+                for (int j = 0; j + 3 < TN; j += 4) {
+                    const int n = n0 + col_of(j);
+                    float v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = (n + q < p.N) ? epilogue_value(p, (q & 1) ? acc2[i][(j + q) / 2].y : acc2[i][(j + q) / 2].x, m, n + q) : 0.f;
+                    const size_t o = (size_t)m * p.ldc + n;
+                    if (n + 3 < p.N) {
+                        *reinterpret_cast<float4*>(p.C + o) = make_float4(v[0], v[1], v[2], v[3]);
+                        if (p.Cb) {
+                            const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+                            *reinterpret_cast<uint2*>(p.Cb + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (n + q < p.N) { p.C[o + q] = v[q]; if (p.Cb) p.Cb[o + q] = __float2bfloat16(v[q]); }
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
                 const int n = n0 + col_of(j);
@@ -346,7 +383,7 @@ gemm_f32_kernel(GemmParams p) {
 __global__ void __launch_bounds__(256) splitk_epilogue_kernel(GemmParams p) {
     const size_t total = (size_t)p.M * p.N;
     // The partials of one output element are summed in split order (deterministic); the loads of eight splits are issued
-    // together — a loop of dependent load -> add pairs made the reduce of a small-batch layer (148 splits of a 32 x 512 output)
+    // together (16 / 32 at a time) — a loop of dependent load -> add pairs made the reduce of a small-batch layer (148 splits of a 32 x 512 output)
     // a 10 us latency chain.
     if (!p.trans_out && p.N % 4 == 0 && p.ldc % 4 == 0 && (((uintptr_t)p.C | (uintptr_t)p.partial) & 15) == 0 && ((uintptr_t)p.Cb & 7) == 0) {
         // four columns per thread: 16-byte loads of the partials, one pass
@@ -356,12 +393,12 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(GemmParams p) {
             const int m = (int)(idx / p.N), n = (int)(idx - (size_t)m * p.N);
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
             int s = 0;
-            for (; s + 8 <= p.splits; s += 8) {                                           // fixed order: deterministic
-                float4 w[8];
+            for (; s + 16 <= p.splits; s += 16) {                                         // fixed order: deterministic
+                float4 w[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const float4*>(p.partial + (size_t)(s + u) * total + idx);
+                for (int u = 0; u < 16; ++u) w[u] = *reinterpret_cast<const float4*>(p.partial + (size_t)(s + u) * total + idx);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { a.x += w[u].x; a.y += w[u].y; a.z += w[u].z; a.w += w[u].w; }
+                for (int u = 0; u < 16; ++u) { a.x += w[u].x; a.y += w[u].y; a.z += w[u].z; a.w += w[u].w; }
             }
             for (; s < p.splits; ++s) {
                 const float4 w = *reinterpret_cast<const float4*>(p.partial + (size_t)s * total + idx);
@@ -383,7 +420,14 @@ __global__ void __launch_bounds__(256) splitk_epilogue_kernel(GemmParams p) {
         const int m = (int)(idx / p.N), n = (int)(idx - (size_t)m * p.N);
         float v = 0.f;
         int s = 0;
-        for (; s + 8 <= p.splits; s += 8) {                                               // fixed order: deterministic
+        for (; s + 32 <= p.splits; s += 32) {                                             // fixed order: deterministic
+            float w[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) w[u] = p.partial[(size_t)(s + u) * total + idx];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v += w[u];
+        }
+        for (; s + 8 <= p.splits; s += 8) {
             float w[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) w[u] = p.partial[(size_t)(s + u) * total + idx];

@@ -737,6 +737,17 @@ extern "C" int mq_qnet_act(mq_qnet* n, const float* obs, int64_t B, float eps, u
     return MQ_OK;
 }
 
+extern "C" int mq_qnet_explore_draw(float eps, uint64_t seed, uint32_t env, uint32_t tick, uint32_t robot, int32_t* action_out) {
+    // the same words and comparison as qhead_kernel's mode 1, evaluated on the host
+    const uint4 w = mq::philox4x32(env, tick, robot, mq::STREAM_AGENT, seed);
+    const double u = mq::u53(w.x, w.y);
+    if (eps > 0.f && u <= (double)eps) {
+        if (action_out) *action_out = (int32_t)(((uint64_t)w.z * (uint64_t)mq::NA) >> 32);
+        return 1;
+    }
+    return 0;
+}
+
 // backward of the fp32 parity path from n->dq (loss.backward(), dqn_agent.py:154-155); the online activations are in the workspace
 static void backward_fp32(mq_qnet* n, const float* state, long long B, const uint8_t* drop_online, cudaStream_t s, int part = 0) {
     using namespace mq;

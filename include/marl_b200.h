@@ -277,6 +277,11 @@ int mq_qnet_forward(mq_qnet* net, int32_t which, const float* obs, int64_t B, co
 int mq_qnet_act(mq_qnet* net, const float* obs, int64_t B, float eps, uint64_t seed, uint32_t env_id_base,
                 uint32_t tick, int32_t n_robots, const uint8_t* drop_mask, int32_t* action_out, float* q_out,
                 void* stream);
+/* HOST function, no device work: the keyed exploration draw mq_qnet_act makes for sample (env, robot) at `tick` —
+ * returns 1 and sets *action_out to the random action when u <= eps (`np.random.random() <= self.epsilon` ->
+ * `random.randrange(action_size)`, dqn_agent.py:103-104), else 0.  The single-env drop-in agent asks this first and,
+ * like the reference, skips the network forward when it explores; the draw is the one the kernel would make. */
+int mq_qnet_explore_draw(float eps, uint64_t seed, uint32_t env, uint32_t tick, uint32_t robot, int32_t* action_out);
 /* The differentiable half of DQNAgent.learn() (dqn_agent.py:143-155) on a sampled batch: target forward, online
  * forward, TD target, loss, full backward into the bound gradient tensors.  drop_online / drop_target: u8 [B][512]
  * keep-masks of the two forward passes or NULL (= .eval()).  loss_out dev f32 [1].  The caller may all-reduce the

@@ -218,6 +218,36 @@ def test_dqn_agent_facade_reference_surface(tmp_path):
     assert agent3.learn() is None
 
 
+def test_single_state_fast_paths_equal_the_device_paths():
+    """The numpy-state paths of the drop-in agent (pinned staging for act / remember, exploration decided on the host by
+    mq_qnet_explore_draw so that an exploring act() launches nothing — dqn_agent.py:103-104 returns before the forward too) make
+    the same decisions and store the same transitions as the tensor paths that run everything on the device."""
+    from dqn_marl_b200.agents.dqn_agent import DQNAgent
+    cfg = dict(epsilon=0.5, batch_size=32, warmup_steps=0, memory_size=300, seed=77)
+    torch.manual_seed(9); fast = DQNAgent((11, 11, 6), 5, torch.device("cuda:0"), cfg)
+    torch.manual_seed(9); slow = DQNAgent((11, 11, 6), 5, torch.device("cuda:0"), cfg)
+    rng = np.random.default_rng(3)
+    n_explore, launches0 = 0, fast.net.launch_count
+    for i in range(120):
+        s, ns = rng.random((11, 11, 6)), rng.random((11, 11, 6))
+        before = fast.net.launch_count
+        a = fast.act(s, training=True)
+        n_explore += fast.net.launch_count == before
+        b = slow.act(torch.from_numpy(s.astype(np.float32)), training=True)          # tensor input: forward + in-kernel draw
+        assert isinstance(a, int) and a == b, i
+        r, d = float(rng.normal()), bool(i % 11 == 0)
+        fast.remember(s, a, r, ns, d)
+        slow.remember(torch.from_numpy(s.astype(np.float32)), a, r, torch.from_numpy(ns.astype(np.float32)), d)
+    assert 35 < n_explore < 85 and fast._act_calls == slow._act_calls == 120 and fast._mask_calls == slow._mask_calls
+    for name in ("state", "next_state", "action", "reward", "done"):
+        assert torch.equal(getattr(fast.memory, name)[:120], getattr(slow.memory, name)[:120]), name
+    assert fast.act(rng.random((11, 11, 6)), training=False) in range(5)
+    la, lb = fast.learn(), slow.learn()
+    assert la == lb and torch.equal(fast.net.flat_p, slow.net.flat_p)
+    la, lb = fast.learn(), slow.learn()                                              # second call reuses the resident batch tensors
+    assert la == lb and torch.equal(fast.net.flat_p, slow.net.flat_p)
+
+
 @pytest.mark.parametrize("B", [256, 200])
 def test_bf16_tensor_core_path_tracks_fp32(B):
     """The tcgen05 bf16 path (every layer but the 5-output head on tensor cores, fp32 accumulate / master weights) against the fp32

@@ -35,7 +35,7 @@ def test_reference_arm_line():
 @pytest.mark.gpu
 def test_gpu_arm_line():
     d = _run(["--steps", "6", "--warmup", "3", "--prime", "30", "--loop-steps", "3", "--fp32-loop-steps", "1", "--host-fed-steps", "2",
-              "--c2-steps", "30", "--replay-batch", "4096"], 900)
+              "--c2-steps", "30", "--replay-batch", "4096", "--c1-iters", "120"], 900)
     assert BASE | {"clocks", "gpu_launches", "roofline"} <= set(d)
     assert d["metric"] == "env agent-steps/s" and d["n_gpus"] == 1 and d["steps"] == 6 and d["scaling"] == "weak" and d["data"] == "synthetic"
     assert d["gpu_launches"] == 6 and d["value"] > 1e9 and d["dtype"] == "f64" and "workload" in d["config"]
@@ -51,3 +51,6 @@ def test_gpu_arm_line():
     assert set(ln["segments_ms"]) == {"act", "env_step", "replay_push", "sample+learn"}
     assert d["secondary_c2"]["value"] > 0 and d["replay"]["sample"]["frac_of_hbm_peak"] > 0 and d["learner_fp32"]["value"] > 0
     assert "hw_slowdown" not in d["clocks"]["reasons"]
+    c1 = d["c1_dropin"]                                   # BASELINE.json configs[0] through the drop-in classes
+    assert set(c1["ms_per_call"]) == {"act", "step", "remember", "learn"} and c1["iterations"] >= 20
+    assert abs(c1["ms_per_iteration"] - sum(c1["ms_per_call"].values())) < 1e-9 and 0 < c1["ms_per_iteration"] < 50

@@ -256,6 +256,12 @@ def test_reference_facade_replays_golden(name):
         assert [q.savety for q in p] == [(b & 1) == 1 for b in g["flags"][f]]
     pm = env.get_performance_metrics()
     assert pm["evacuated"] + pm["dead"] + pm["remaining"] == m["n_people"]
+    # trajectories are materialised on access: one {'pos', 'step'} entry per step since the last reset (evacuation_env.py:80,135)
+    last_reset = max(f for f in range(F) if g["op"][f] != OP_STEP)
+    tr = env.people.list[3].trajectory
+    assert len(tr) == F - last_reset and tr[0]["step"] == 0 and tr[-1]["pos"] == env.people.list[3].pos
+    assert [int(e["pos"][0]) for e in tr] == [int(g["px"][f][3]) for f in range(last_reset, F)]
+    assert env.people.list[3].trajectory is tr and len(env.robot_trajectory) >= len(tr)
     assert np.array_equal(env.people.rmap != 0, np.unpackbits(g["rmap"][F - 1])[:(m["width"] + 2) * (m["height"] + 2)].reshape(m["width"] + 2, -1) != 0)
     assert env.map.Check_Valid(5, 5) and not env.map.Check_Valid(19, 15) and not env.map.Check_Valid(0, 3)
 
