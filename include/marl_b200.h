@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MQ_ABI_VERSION 2      /* 2: mq_env_create_layouts, mq_layout_tables_device, mq_replay_restore */
+#define MQ_ABI_VERSION 3      /* 2: mq_env_create_layouts, mq_layout_tables_device, mq_replay_restore; 3: mq_qnet_explore_draw */
 #define MQ_MAX_ROBOTS 4
 #define MQ_OBS_WIN 11                          /* evacuation_env.py:56  state_size = (11, 11, 6) */
 #define MQ_OBS_CH 6

@@ -21,7 +21,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in marl_b200.h but not exported by libmarl_b200.so"
     assert sorted(_lib.SIGNATURES) == names, "python binding and header disagree"
-    assert _lib.load().mq_abi_version() == 2
+    assert _lib.load().mq_abi_version() == 3
 
 
 def test_floor_field_errors_are_reported():
