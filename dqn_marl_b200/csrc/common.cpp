@@ -90,11 +90,96 @@ static inline void expand_window(const uint32_t* rec, float* o) {
 }
 #endif
 
+// ---- AVX-512 form (runtime-dispatched; the translation unit itself is compiled for baseline x86-64) -----------------------
+// Eight cells = 48 output floats = three 64-byte vectors.  The channel-2 values of the eight cells are spread to their slots
+// (6 i + 2) by one permute per vector; the bits of the three planes are deposited to their slots (6 i + 1 / + 3 / + 4) with PDEP
+// into a 48-bit mask whose three 16-bit pieces blend 1.0f into the vectors.  About 20 instructions per eight cells against
+// about 60 for the pair-LUT form: the expansion was compute-bound (5 GB/s of output per host thread, linear in the threads),
+// which is what capped the host-buffer rate of an 8-GPU box (4 threads per rank).
+#if defined(__x86_64__) && defined(__GNUC__)
+#define MQ_WIRE_AVX512 1
+#include <immintrin.h>
+namespace {
+struct Avx512Tables {
+    alignas(64) int32_t idx[3][16];
+    uint16_t ch2[3];
+    uint64_t m1 = 0, m3 = 0, m4 = 0;
+    Avx512Tables() {
+        for (int k = 0; k < 3; ++k) {
+            ch2[k] = 0;
+            for (int j = 0; j < 16; ++j) {
+                const int f = 16 * k + j, cell = f / 6, ch = f % 6;
+                idx[k][j] = ch == 2 ? cell : 0;
+                if (ch == 2) ch2[k] |= (uint16_t)(1u << j);
+            }
+        }
+        for (int i = 0; i < 8; ++i) { m1 |= 1ull << (6 * i + 1); m3 |= 1ull << (6 * i + 3); m4 |= 1ull << (6 * i + 4); }
+    }
+};
+const Avx512Tables g_t512;
+}  // namespace
+
+__attribute__((target("avx512f,avx512vl,bmi2")))
+static inline void expand_window_avx512(const uint32_t* rec, float* o) {
+    const uint8_t* b1 = reinterpret_cast<const uint8_t*>(rec + 121);
+    const uint8_t* b3 = reinterpret_cast<const uint8_t*>(rec + 125);
+    const uint8_t* b4 = reinterpret_cast<const uint8_t*>(rec + 129);
+    const __m512i i0 = _mm512_load_si512(g_t512.idx[0]), i1 = _mm512_load_si512(g_t512.idx[1]), i2 = _mm512_load_si512(g_t512.idx[2]);
+    const __mmask16 c0 = g_t512.ch2[0], c1 = g_t512.ch2[1], c2 = g_t512.ch2[2];
+    const __m512 ones = _mm512_set1_ps(1.f);
+    for (int g = 0; g < 15; ++g) {                                       // cells 8 g .. 8 g + 7
+        const __m512 v = _mm512_castps256_ps512(_mm256_loadu_ps(reinterpret_cast<const float*>(rec + 8 * g)));
+        const uint64_t m = _pdep_u64(b1[g], g_t512.m1) | _pdep_u64(b3[g], g_t512.m3) | _pdep_u64(b4[g], g_t512.m4);
+        float* q = o + 48 * g;
+        _mm512_storeu_ps(q, _mm512_mask_mov_ps(_mm512_maskz_permutexvar_ps(c0, i0, v), (__mmask16)m, ones));
+        _mm512_storeu_ps(q + 16, _mm512_mask_mov_ps(_mm512_maskz_permutexvar_ps(c1, i1, v), (__mmask16)(m >> 16), ones));
+        _mm512_storeu_ps(q + 32, _mm512_mask_mov_ps(_mm512_maskz_permutexvar_ps(c2, i2, v), (__mmask16)(m >> 32), ones));
+    }
+    float v;                                                             // cell 120: bit 0 of byte 15 of every plane
+    std::memcpy(&v, rec + 120, 4);
+    const float t[6] = {0.f, (float)(b1[15] & 1u), v, (float)(b3[15] & 1u), (float)(b4[15] & 1u), 0.f};
+    std::memcpy(o + 6 * 120, t, sizeof(t));
+    o[60 * MQ_OBS_CH + 5] = 1.f;                                         // evacuation_env.py:116-117 (i == 5 and j == 5)
+}
+
+// as expand_range below, with 64-byte streaming stores
+__attribute__((target("avx512f,avx512vl,bmi2")))
+static void expand_range_avx512(const uint32_t* wire, int64_t w0, int64_t w1, float* obs) {
+    constexpr int BLOCK = 8;
+    alignas(64) float stage[BLOCK * MQ_OBS_SIZE + 16];
+    for (int64_t w = w0; w < w1; w += BLOCK) {
+        const int n = (int)std::min<int64_t>(BLOCK, w1 - w);
+        float* dst = obs + w * MQ_OBS_SIZE;
+        const size_t total = (size_t)n * MQ_OBS_SIZE;                    // floats
+        const size_t mis = ((uintptr_t)dst & 63u) / 4;                   // stage + mis has the 64-byte alignment of dst
+        for (int k = 0; k < n; ++k) expand_window_avx512(wire + (w + k) * MQ_OBS_WIRE_WORDS, stage + mis + (size_t)k * MQ_OBS_SIZE);
+        size_t k = 0;
+        const size_t head = mis ? 16 - mis : 0;
+        for (; k < head && k < total; ++k) dst[k] = stage[mis + k];
+        for (; k + 16 <= total; k += 16) _mm512_stream_ps(dst + k, _mm512_load_ps(stage + mis + k));
+        for (; k < total; ++k) dst[k] = stage[mis + k];
+    }
+    _mm_sfence();
+}
+
+static bool wire_use_avx512() {
+    static const bool use = [] {
+        const char* v = getenv("MQ_WIRE_ISA");                           // A/B knob: "sse2" forces the baseline form
+        if (v && std::strcmp(v, "sse2") == 0) return false;
+        return __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("bmi2");
+    }();
+    return use;
+}
+#endif
+
 // Windows [w0, w1): expanded eight at a time into a cache-resident staging block, which then leaves for the (pinned, never
 // re-read by this thread) destination with 16-byte streaming stores — no read-for-ownership of 2.9 KB per window, i.e. half
 // the memory traffic of plain stores.  The destination range is only 8-byte aligned (726 floats per window): the first and
 // last partial 16 bytes of the range go out as plain stores.
 static void expand_range(const uint32_t* wire, int64_t w0, int64_t w1, float* obs) {
+#ifdef MQ_WIRE_AVX512
+    if (((uintptr_t)obs & 3u) == 0 && wire_use_avx512()) { expand_range_avx512(wire, w0, w1, obs); return; }
+#endif
     constexpr int BLOCK = 8;
     alignas(64) float stage[BLOCK * MQ_OBS_SIZE + 4];
     for (int64_t w = w0; w < w1; w += BLOCK) {

@@ -35,15 +35,16 @@ def test_reference_arm_line():
 @pytest.mark.gpu
 def test_gpu_arm_line():
     d = _run(["--steps", "6", "--warmup", "3", "--prime", "30", "--loop-steps", "3", "--fp32-loop-steps", "1", "--host-fed-steps", "2",
-              "--c2-steps", "30", "--replay-batch", "4096", "--c1-iters", "120"], 900)
+              "--c2-steps", "30", "--replay-batch", "4096", "--c1-iters", "120", "--e2e-hybrid", "1"], 900)
     assert BASE | {"clocks", "gpu_launches", "roofline"} <= set(d)
     assert d["metric"] == "env agent-steps/s" and d["n_gpus"] == 1 and d["steps"] == 6 and d["scaling"] == "weak" and d["data"] == "synthetic"
     assert d["gpu_launches"] == 6 and d["value"] > 1e9 and d["dtype"] == "f64" and "workload" in d["config"]
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"]
     e = d["e2e"]
-    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["mode"] in ("dense", "wire")
-    assert e["dense"]["value"] > 0 and e["wire"]["value"] > 0 and e["value"] == max(e["dense"]["value"], e["wire"]["value"])
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["dense"]["value"] > 0 and e["wire"]["value"] > 0 and 0 < e["hybrid"]["wire_fraction"] < 1
+    assert e["value"] == max(e["dense"]["value"], e["wire"]["value"], e["hybrid"]["value"]) and e["mode"] in ("dense", "wire", "hybrid")
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["value"] > 0 and cb["cores"] >= 1
     ln = d["learner"]
