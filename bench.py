@@ -784,7 +784,7 @@ def main():
     ap.add_argument("--learner-batch", type=int, default=0, help="learn batch per GPU (0 = the workload's: 4096, C5: 8192)")
     ap.add_argument("--replay-batch", type=int, default=65536, help="replay sample batch of the bandwidth leg (0 = skip)")
     ap.add_argument("--c2-steps", type=int, default=3000, help="steps of the secondary C2 env-only run (0 = skip)")
-    ap.add_argument("--e2e-hybrid", type=int, default=-1, help="also time the hybrid dense + wire transfer mode of the e2e leg (-1 = only when N > 1, where the host bounds both pure modes)")
+    ap.add_argument("--e2e-hybrid", type=int, default=0, help="1 = also time the hybrid dense + wire transfer mode of the e2e leg (measured on 2 GPUs: slower than either pure mode, so off by default)")
     ap.add_argument("--c1-iters", type=int, default=400, help="iterations of the C1 (configs/dqn.yaml) loop through the drop-in classes (0 = skip)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
