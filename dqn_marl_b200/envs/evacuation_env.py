@@ -159,25 +159,29 @@ class _PeopleView:
 
 
 class LazyInfo(dict):
-    """step() info dict; the O(N) lists of evacuation_env.py:160-170 are materialised on first access."""
+    """step() info dict; the O(N) lists of evacuation_env.py:160-170 are built on first access — from copies of THIS step's
+    person arrays, so an info dict that is read later still describes the step that returned it."""
 
     _LAZY = ("people_positions", "health_values", "evacuation_status")
 
     def __init__(self, env, eager):
         super().__init__(eager)
-        self._env = env
+        self._snap = (env._traj_rec[-1][0], env._h_health_np.copy(), env._h_flags_np.copy())
 
     def __missing__(self, key):
         if key in self._LAZY:
-            pl = self._env.people.list
-            self["people_positions"] = [p.pos for p in pl]
-            self["health_values"] = [p.health for p in pl]
-            self["evacuation_status"] = [p.savety for p in pl]
+            pos, health, flags = self._snap
+            self["people_positions"] = [((int(v) & 0xFFFF) + 0.5, ((int(v) >> 16) & 0xFFFF) + 0.5) for v in pos]
+            self["health_values"] = [float(h) for h in health]
+            self["evacuation_status"] = [bool(f & 1) for f in flags]
             return dict.__getitem__(self, key)
         raise KeyError(key)
 
     def __contains__(self, key):
         return key in self._LAZY or dict.__contains__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
 
 
 class EvacuationEnv:

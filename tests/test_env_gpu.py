@@ -237,10 +237,13 @@ def test_reference_facade_replays_golden(name):
     env = cls(m["width"], m["height"], None, m["exit"], m["n_people"], device="cuda:0", seed=m["seed"])
     assert env.state_size == (11, 11, 6) and env.action_size == 5 and env.max_steps == 1200
     F = min(len(g["op"]), 80)
+    kept = None
     for f in range(1, F):
         if g["op"][f] == OP_STEP:
             a = g["actions"][f]
             state, reward, done, info = env.step([int(x) for x in a] if m["kind"] == "multi" else int(a[0]))
+            if kept is None and m["kind"] == "single":
+                kept = (f, info)                      # read only at the end: must still describe frame f
             assert isinstance(reward, float) and isinstance(done, bool)
             assert reward == g["reward"][f] and done == bool(g["done"][f])
             assert info["current_step"] == int(g["cur_step"][f]) and info["simulation_time"] == 0.5 * int(g["cur_step"][f])
@@ -254,6 +257,10 @@ def test_reference_facade_replays_golden(name):
         p = env.people.list
         assert [int(q.pos[0]) for q in p] == g["px"][f].tolist() and [q.health for q in p] == g["health"][f].tolist()
         assert [q.savety for q in p] == [(b & 1) == 1 for b in g["flags"][f]]
+    if kept is not None:
+        f0, info0 = kept
+        assert [int(p[0]) for p in info0["people_positions"]] == g["px"][f0].tolist() and info0["health_values"] == g["health"][f0].tolist()
+        assert info0["evacuation_status"] == [(b & 1) == 1 for b in g["flags"][f0]]
     pm = env.get_performance_metrics()
     assert pm["evacuated"] + pm["dead"] + pm["remaining"] == m["n_people"]
     # trajectories are materialised on access: one {'pos', 'step'} entry per step since the last reset (evacuation_env.py:80,135)
