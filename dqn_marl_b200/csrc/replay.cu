@@ -6,8 +6,8 @@
 // pickled float64), never leaves the GPU, and is sampled by a keyed permutation so every index of a batch
 // is computed independently by its own warp (no host RNG, no host gather, no H2D copy).
 //
-// Both kernels are pure HBM copies: one warp moves one 2904 B observation row with 64-bit accesses (rows
-// are 8-byte, not 16-byte, aligned: 726 floats), all loads of a row issued before the stores.
+// Both kernels are pure HBM copies: one warp moves one 2904 B observation row, 128-bit loads and (phase permitting)
+// 128-bit stores, all loads of a row issued before the stores (copy_row).
 #include <cstdint>
 #include <new>
 #include "common.h"
@@ -15,21 +15,44 @@
 
 namespace mq {
 
-constexpr int ROW_F2 = MQ_OBS_SIZE / 2;                 // 363 float2 per observation row
-constexpr int ROW_ITERS = (ROW_F2 + 31) / 32;           // 12 accesses per lane
+// One warp moves one 2904-byte observation row.  Rows are 726 floats: 8-byte, not 16-byte aligned — a row starts either on a
+// 16-byte boundary or 8 bytes after one.  Its 724-float body is read with 128-bit loads from the first 16-byte boundary of the
+// SOURCE (181 uint4, all issued before the first store) and the odd 8 bytes — the head of a row that starts off a boundary, the
+// tail of one that starts on it — by lane 0.  When source and destination have the same phase the body is stored with 128-bit
+// stores too; otherwise (a sampled slot and its batch row differ in parity) each 16 bytes leave as two 64-bit stores.
+constexpr int ROW_BODY4 = (MQ_OBS_SIZE - 2) / 4;        // 181 uint4
+constexpr int ROW_ITERS = (ROW_BODY4 + 31) / 32;        // 6 loads per lane
+static_assert(MQ_OBS_SIZE % 4 == 2, "row = 16-byte body + one float2");
 
-__device__ __forceinline__ void copy_row(const float2* __restrict__ src, float2* __restrict__ dst, int lane) {
-    float2 v[ROW_ITERS];
+__device__ __forceinline__ void copy_row(const float* __restrict__ src, float* __restrict__ dst, int lane) {
+    const bool s8 = (reinterpret_cast<uintptr_t>(src) & 8u) != 0, d8 = (reinterpret_cast<uintptr_t>(dst) & 8u) != 0;
+    const int off = s8 ? 2 : 0;                          // floats in front of the 16-byte aligned body (source side)
+    const int odd = s8 ? 0 : MQ_OBS_SIZE - 2;            // float offset of the odd float2
+    const uint4* sb = reinterpret_cast<const uint4*>(src + off);
+    uint4 v[ROW_ITERS];
+    float2 e = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < ROW_ITERS; ++k) {
-        int i = lane + 32 * k;
-        if (i < ROW_F2) v[k] = __ldg(src + i);
+        const int i = lane + 32 * k;
+        if (i < ROW_BODY4) v[k] = __ldg(sb + i);
     }
+    if (lane == 0) e = __ldg(reinterpret_cast<const float2*>(src + odd));
+    if (s8 == d8) {
+        uint4* db = reinterpret_cast<uint4*>(dst + off);
 #pragma unroll
-    for (int k = 0; k < ROW_ITERS; ++k) {
-        int i = lane + 32 * k;
-        if (i < ROW_F2) dst[i] = v[k];
+        for (int k = 0; k < ROW_ITERS; ++k) {
+            const int i = lane + 32 * k;
+            if (i < ROW_BODY4) db[i] = v[k];
+        }
+    } else {
+        uint2* db = reinterpret_cast<uint2*>(dst + off);
+#pragma unroll
+        for (int k = 0; k < ROW_ITERS; ++k) {
+            const int i = lane + 32 * k;
+            if (i < ROW_BODY4) { db[2 * i] = make_uint2(v[k].x, v[k].y); db[2 * i + 1] = make_uint2(v[k].z, v[k].w); }
+        }
     }
+    if (lane == 0) *reinterpret_cast<float2*>(dst + odd) = e;
 }
 
 struct RingView {
@@ -48,11 +71,9 @@ replay_push_kernel(RingView ring, long long cursor, const float* __restrict__ st
     const long long k = w >> 1;
     const long long slot = (cursor + k) % ring.capacity;
     if (w & 1) {
-        copy_row(reinterpret_cast<const float2*>(next_state + k * MQ_OBS_SIZE),
-                 reinterpret_cast<float2*>(ring.next_state + slot * MQ_OBS_SIZE), lane);
+        copy_row(next_state + k * MQ_OBS_SIZE, ring.next_state + slot * MQ_OBS_SIZE, lane);
     } else {
-        copy_row(reinterpret_cast<const float2*>(state + k * MQ_OBS_SIZE),
-                 reinterpret_cast<float2*>(ring.state + slot * MQ_OBS_SIZE), lane);
+        copy_row(state + k * MQ_OBS_SIZE, ring.state + slot * MQ_OBS_SIZE, lane);
         if (lane == 0) {
             ring.action[slot] = action[k];
             ring.reward[slot] = (float)reward[k];     // torch.FloatTensor(rewards) (dqn_agent.py:138)
@@ -74,11 +95,9 @@ replay_sample_kernel(RingView ring, long long size, long long oldest, uint4 roun
     const long long logical = inject ? inject[k] : (long long)feistel_index((uint64_t)k, (uint64_t)size, round_keys);
     const long long slot = (oldest + logical) % ring.capacity;
     if (w & 1) {
-        copy_row(reinterpret_cast<const float2*>(ring.next_state + slot * MQ_OBS_SIZE),
-                 reinterpret_cast<float2*>(next_state + k * MQ_OBS_SIZE), lane);
+        copy_row(ring.next_state + slot * MQ_OBS_SIZE, next_state + k * MQ_OBS_SIZE, lane);
     } else {
-        copy_row(reinterpret_cast<const float2*>(ring.state + slot * MQ_OBS_SIZE),
-                 reinterpret_cast<float2*>(state + k * MQ_OBS_SIZE), lane);
+        copy_row(ring.state + slot * MQ_OBS_SIZE, state + k * MQ_OBS_SIZE, lane);
         if (lane == 0) {
             action[k] = (long long)ring.action[slot];       // torch.LongTensor(actions) (dqn_agent.py:137)
             reward[k] = ring.reward[slot];
