@@ -336,11 +336,11 @@ def run_reference(args, wl):
         "impl": "reference", "metric": "env agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["desc"], "envs_per_step": n_envs, "people": wl["people"], "grid": [layout.L, layout.W],
-                   "prime_steps": args.prime},
-        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{n_envs} envs x {wl['people']} people x {args.steps} steps after {args.prime} untimed priming steps "
-                                   f"(steady state of auto-reset, as in the GPU arm), oracle/env_oracle.c, {threads} threads"},
+        "config": bench_config(args, wl, layout),
+        "cpu_baseline": {"value": value, "unit": "agent-steps/s", "cores": threads, "kind": "port", "envs_per_step": n_envs,
+                         "sample": f"bounded sample of the workload: {n_envs} of its {wl['envs']} envs x {wl['people']} people x {args.steps} steps "
+                                   f"after {args.prime} untimed priming steps (steady state of auto-reset, as in the GPU arm), "
+                                   f"oracle/env_oracle.c, {threads} threads"},
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     if not args.no_learner:
@@ -357,6 +357,23 @@ def env_state_bytes(layout, E, N):
     return E * (((N + 15) // 16 * 16) * 21 + ((layout.L + 2) * ((layout.W + 2 + 31) // 32) + 3) // 4 * 16 + 96 + 2904 + 13)
 
 
+def rotating_batches(layout, E, N):
+    """Independent env batches the device-timed loop rotates over so that their state together exceeds L2."""
+    return max(2, int(L2_BYTES * 1.5 / env_state_bytes(layout, E, N)) + 1)
+
+
+def bench_config(args, wl, layout):
+    """`config` of the JSON line — the SAME dict in both arms (the reference arm runs a bounded sample of this workload and says
+    so in cpu_baseline.sample)."""
+    E, N = wl["envs"], wl["people"]
+    n_rot, state_bytes = rotating_batches(layout, E, N), env_state_bytes(layout, E, N)
+    return {"workload": wl["desc"], "envs_per_gpu": E, "people": N, "grid": [layout.L, layout.W],
+            "l2": f"inputs larger than L2: timed loop rotates over {n_rot} independent batches "
+                  f"({n_rot * state_bytes / 1e6:.0f} MB of state > 126 MB L2)",
+            "reset_policy": "auto-reset, fresh fire per episode (strict_reference=False)",
+            "prime_steps": args.prime, "learner_batch_per_gpu": args.learner_batch or wl["learner_batch"]}
+
+
 def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
     """Device-resident headline + host-buffer e2e of the env step on one workload -> dict."""
     import torch
@@ -367,7 +384,7 @@ def run_env_legs(args, wl, layout, dev, rank, world, sampler=None, e2e=True):
     state_bytes = env_state_bytes(layout, E, N)
     # n_rot batches rotate in the device-timed loop (enough to exceed L2); the host-buffer e2e leg keeps n_e2e >= n_rot batches in
     # flight (default 4: with the compact wire form the host expansion of one batch has to hide behind the kernels of the others)
-    n_rot = max(2, int(L2_BYTES * 1.5 / state_bytes) + 1)
+    n_rot = rotating_batches(layout, E, N)
     n_e2e = max(n_rot, int(getattr(args, "batches", 0) or 0) or 4) if e2e else n_rot
     envs = [VecEvacuationEnv(layout, E, N, device=dev, seed=2026, env_id_base=(rank * n_e2e + b) * E,
                              strict_reference=False, auto_reset=True) for b in range(n_e2e)]
@@ -720,11 +737,7 @@ def run_ours(args, wl):
             "metric": "env agent-steps/s", "value": envr["value"], "unit": "agent-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": envr["warmup"], "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["desc"], "envs_per_gpu": E, "people": N, "grid": [layout.L, layout.W],
-                       "l2": f"inputs larger than L2: timed loop rotates over {n_rot} independent batches "
-                             f"({n_rot * state_bytes / 1e6:.0f} MB of state > 126 MB L2)",
-                       "reset_policy": "auto-reset, fresh fire per episode (strict_reference=False)",
-                       "prime_steps": args.prime, "learner_batch_per_gpu": args.learner_batch or wl["learner_batch"]},
+            "config": bench_config(args, wl, layout),
             "clocks": clocks,
             "e2e": envr["e2e"],
             "gpu_launches": envr["launches"],
