@@ -124,3 +124,49 @@ def test_two_robot_runners(project, runner, prefix):
         rows = list(csv.DictReader(f))
     assert len(rows) == 200
     assert all(abs(float(r["evac_rate"]) + float(r["death_rate"]) - 1.0) < 1e-9 or float(r["evac_rate"]) + float(r["death_rate"]) < 1.0 for r in rows)
+
+
+def test_evaluate_all_strategies_runner(project):
+    """runners/evaluate_all_strategies.py (five policies: no robot = robots parked at [1000, 1000] through the writable
+    `env.map.robot_position(s)`, static robot, single DQN, double DQN, QMIX), unmodified: it loads five reference-format
+    checkpoints — written here by this package's own `DQNAgent.save()` — into `DQNAgent(state_size, action_size, device, {})`
+    (empty config: the defaults of dqn_agent.py:73-80) and plays whole episodes on `EvacuationEnv` / `EvacuationEnvMulti`."""
+    import torch
+    from dqn_marl_b200.agents.dqn_agent import DQNAgent
+    root, cfg = project
+    cfg["env"]["num_people"] = 6
+    _write_cfg(root, cfg)
+    res = root / "dqn_results"
+    res.mkdir()
+    for k, name in enumerate(("best_model.pth", "double_dqn_agent1.pth", "double_dqn_agent2.pth", "qmix_agent1.pth", "qmix_agent2.pth")):
+        torch.manual_seed(100 + k)
+        agent = DQNAgent((11, 11, 6), 5, torch.device("cuda:0"), {"memory_size": 64, "seed": k})
+        agent.save(str(res / name))
+        del agent
+    out = _run(root, root / "Louvre_Evacuation" / "runners" / "evaluate_all_strategies.py", "--episodes", "1")
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "五策略比较" in out.stdout, out.stdout[-2000:]
+    rows = [ln.split("\t") for ln in out.stdout.splitlines() if ln.count("\t") == 3 and ln.rstrip().endswith(tuple("0123456789"))]
+    assert [r[0] for r in rows] == ["无机器人", "静态机器人", "单机器人DQN", "双机器人DoubleDQN", "双机器人QMIX"], out.stdout[-2000:]
+    for r in rows:
+        assert 0.0 <= float(r[2].rstrip("%")) <= 100.0 and 0.0 < float(r[3]) <= 600.0          # death rate, simulated seconds
+
+
+def test_overnight_experiments_runner(project):
+    """runners/overnight_experiments.py, unmodified, on a 2 x 2 grid of reward coefficients with one episode each: the runner
+    mutates the CLASS attributes `EvacuationEnv.DEATH_PENALTY / ALIVE_BONUS` between runs (:69-70; the facade forwards them to
+    the kernel's reward coefficients), builds `EvacuationEnv(**cfg['env'])` and samples with `agent.act(state, training=True)`."""
+    root, cfg = project
+    cfg["env"]["num_people"] = 6
+    _write_cfg(root, cfg)
+    out = _run(root, root / "Louvre_Evacuation" / "runners" / "overnight_experiments.py", "--episodes", "1", "--death_min", "100",
+               "--death_max", "150", "--death_step", "50", "--alive_min", "0.2", "--alive_max", "0.3", "--alive_step", "0.1")
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    res = root / "dqn_results"
+    with open(res / "experiment_summary.csv", encoding="utf-8") as f:
+        rows = list(csv.DictReader(f))
+    assert len(rows) == 4 and {(int(float(r["death_penalty"])), round(float(r["alive_bonus"]), 1)) for r in rows} == {(100, 0.2), (100, 0.3), (150, 0.2), (150, 0.3)}
+    assert all(0.0 <= float(r["death_rate"]) <= 1.0 and 0.0 <= float(r["evac_rate"]) <= 1.0 for r in rows)
+    with open(res / "best_reward_cfg.json", encoding="utf-8") as f:
+        best = json.load(f)
+    assert set(best) == {"death_penalty", "alive_bonus"}
