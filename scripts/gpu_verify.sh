@@ -1,10 +1,11 @@
 #!/bin/bash
-# Verification visit (1 GPU): full GPU test suite, smoke, both bench arms at their defaults, the C5 stress shape.
+# Verification visit (1 GPU): full GPU test suite, smoke, both bench arms at their defaults, the C1 wall clock, the C5 stress shape.
 tag=${1:-r02v}
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q --maxfail=10 > gpurun_out/${tag}_pytest_full.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/${tag}_pytest_full.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"
 python bench.py > gpurun_out/${tag}_bench_n1.json 2> gpurun_out/${tag}_bench_n1.err; echo "bench rc=$?"
+python scripts/c1_profile.py 600 > gpurun_out/${tag}_c1_wall.txt 2>&1; head -1 gpurun_out/${tag}_c1_wall.txt
 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/${tag}_bench_reference_arm.json 2> gpurun_out/${tag}_bench_reference_arm.err; echo "reference arm rc=$?"
 python bench.py --workload c5 --steps 200 --warmup 10 --no-cpu --loop-steps 20 --fp32-loop-steps 0 --overlap-loop 0 --host-fed-steps 0 --c2-steps 0 --c1-iters 0 > gpurun_out/${tag}_bench_c5.json 2> gpurun_out/${tag}_bench_c5.err; echo "c5 rc=$?"
 python - <<PY
