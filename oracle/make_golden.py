@@ -39,9 +39,14 @@ def actions_for(seed, t, R, n_act=6):
     return [int((w[r] * n_act) >> 32) for r in range(R)]
 
 
-def record(kind, W, H, exit_loc, N, seed, n_steps, name, extra_resets=(), layout=None):
+def record(kind, W, H, exit_loc, N, seed, n_steps, name, extra_resets=(), layout=None, max_time=None):
     R = 2 if kind == "multi" else 1
     ref = RefEnv(kind, W, H, exit_loc, N, seed=seed, layout=layout)
+    if max_time is not None:
+        # shorter episodes through the reference's own instance attribute: `time_is_up = self.time >= self.max_simulation_time`
+        # (evacuation_env.py:27,153) — the time-limit branch of `done`, which no full-length episode of 150 people reaches
+        ref.env.max_simulation_time = max_time
+        ref.env.max_steps = int(max_time / ref.env.time_per_step)
     frames = []
 
     def grab(op, act, obs, reward, done):
@@ -64,6 +69,8 @@ def record(kind, W, H, exit_loc, N, seed, n_steps, name, extra_resets=(), layout
     extra = {} if layout is None else dict(layout=dict(exits=[list(map(int, e)) for e in layout["exits"]],
                                                        barriers=[[list(map(int, A)), list(map(int, B))] for (A, B) in layout["barriers"]],
                                                        fire_first_only=bool(layout.get("fire_first_only", False))))
+    if max_time is not None:
+        extra["max_steps"] = int(max_time / 0.5)
     out["meta"] = meta(kind=kind, width=W, height=H, exit=list(exit_loc) if exit_loc else [36, 15], n_people=N,
                        seed=seed, n_robots=R, **extra)
     path = os.path.join(OUT, name)
@@ -114,10 +121,17 @@ def main_synthetic():
     layout_file(ref, "layout_synth_hall.npz", steps=range(0, 101))        # every fire step the trajectory visits
 
 
+def main_timelimit():
+    # 150 people, episodes cut at 12.5 simulated seconds = 25 steps: `done` by time with people still inside, reset, again
+    record("single", 36, 30, None, 150, 4321, 60, "traj_room_timelimit.npz", max_time=12.5)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "--synthetic-only" in sys.argv:
         return main_synthetic()
+    if "--timelimit-only" in sys.argv:
+        return main_timelimit()
     ref = record("single", 36, 30, None, 150, 1234, 260, "traj_room_single.npz", extra_resets=(7,))
     layout_file(ref, "layout_room.npz", steps=range(0, 181))
     record("multi", 36, 30, None, 150, 99, 120, "traj_room_multi.npz")
@@ -129,6 +143,7 @@ def main():
     ref = record("single", 256, 256, [256, 128], 1000, 2024, 24, "traj_big256.npz")
     layout_file(ref, "layout_big256.npz", steps=[0, 5, 24, 90, 180], box=(-6, -6, 50, 46))
     main_synthetic()
+    main_timelimit()
 
 
 if __name__ == "__main__":

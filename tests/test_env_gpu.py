@@ -11,7 +11,7 @@ from util import OP_RESET, OP_STEP, assert_frame_equal, layout_for, load_golden
 pytestmark = pytest.mark.gpu
 
 TRAJS = ["traj_room_single.npz", "traj_room_multi.npz", "traj_room_small.npz", "traj_room_westexit.npz",
-         "traj_big256.npz", "traj_room_allevac.npz", "traj_synth_gallery.npz", "traj_synth_hall.npz"]
+         "traj_big256.npz", "traj_room_allevac.npz", "traj_synth_gallery.npz", "traj_synth_hall.npz", "traj_room_timelimit.npz"]
 
 
 def _vec(lay, n_envs, N, seed, **kw):
@@ -24,7 +24,7 @@ def test_gpu_replays_reference_golden(name):
     g = load_golden(name)
     m = g["meta"]
     lay = layout_for(m)
-    env = _vec(lay, 1, m["n_people"], m["seed"])
+    env = _vec(lay, 1, m["n_people"], m["seed"], max_steps=m.get("max_steps", 1200))     # traj_room_timelimit: done by time
     obs64 = torch.zeros((1, m["n_robots"], 11, 11, 6), dtype=torch.float64, device="cuda:0")
     F = len(g["op"])
     obs = env.reset(obs64=obs64)

@@ -7,7 +7,7 @@ import pytest
 from util import OP_RESET, OP_STEP, assert_frame_equal, layout_for, load_golden
 
 TRAJS = ["traj_room_single.npz", "traj_room_multi.npz", "traj_room_small.npz", "traj_room_westexit.npz",
-         "traj_big256.npz", "traj_room_allevac.npz", "traj_synth_gallery.npz", "traj_synth_hall.npz"]
+         "traj_big256.npz", "traj_room_allevac.npz", "traj_synth_gallery.npz", "traj_synth_hall.npz", "traj_room_timelimit.npz"]
 
 
 @pytest.mark.parametrize("name", TRAJS)
@@ -16,7 +16,8 @@ def test_oracle_replays_reference(name):
     g = load_golden(name)
     m = g["meta"]
     lay = layout_for(m)
-    env = OracleEnv(LayoutTables.from_layout(lay), m["n_people"], m["n_robots"], seed=m["seed"])
+    # traj_room_timelimit: episodes cut by the reference's `time >= max_simulation_time` (evacuation_env.py:153)
+    env = OracleEnv(LayoutTables.from_layout(lay), m["n_people"], m["n_robots"], seed=m["seed"], max_steps=m.get("max_steps", 1200))
     F = len(g["op"])
     obs = env.reset()
     assert_frame_equal(g, 0, env.snapshot(), obs, None, None, lay.L, lay.W, name)
