@@ -39,7 +39,7 @@ def actions_for(seed, t, R, n_act=6):
     return [int((w[r] * n_act) >> 32) for r in range(R)]
 
 
-def record(kind, W, H, exit_loc, N, seed, n_steps, name, extra_resets=(), layout=None, max_time=None):
+def record(kind, W, H, exit_loc, N, seed, n_steps, name, extra_resets=(), layout=None, max_time=None, forced_actions=None):
     R = 2 if kind == "multi" else 1
     ref = RefEnv(kind, W, H, exit_loc, N, seed=seed, layout=layout)
     if max_time is not None:
@@ -59,6 +59,8 @@ def record(kind, W, H, exit_loc, N, seed, n_steps, name, extra_resets=(), layout
     t = 0
     while t < n_steps:
         act = actions_for(seed, t, R)
+        if forced_actions and t in forced_actions:            # steer the robot (the actions are stored per frame anyway)
+            act = list(forced_actions[t])
         obs, rew, done, _ = ref.step(act if kind == "multi" else act[0])
         grab(OP_STEP, act, obs, rew, done)
         t += 1
@@ -121,6 +123,21 @@ def main_synthetic():
     layout_file(ref, "layout_synth_hall.npz", steps=range(0, 101))        # every fire step the trajectory visits
 
 
+def main_branches():
+    """Two trajectories aimed at branches of the reference the other goldens leave cold (found by tracing the reference while
+    this script runs: evacuation_env.py:114 and map.py:70-73 were never executed; what stays cold after this is unreachable
+    code — evacuation_env.py:218, people.py:79 — or off the path):
+    * traj_topexit — 40 x 20 room whose exit (17, 20) lies on the TOP edge, inside the robot's observation window from the
+      first frame (observation channel 4 = 1, evacuation_env.py:113-114), opened through a barrier rectangle that covers it
+      (`space[ex][ey+1] = 1` for an exit on the top edge and `barrier_list.remove((ex, ey))`, map.py:70-73);
+    * traj_westexit_far — west exit, the robot STEERED (+y past the fire barrier, then +x) to the east end of its range, where
+      further +x moves are refused (`15 <= x <= 30`, map.py:194) and everybody it influences is more than 20 cells from the
+      exit (guidance tier 2.0, evacuation_env.py:207-208)."""
+    top = dict(exits=[(17, 20)], barriers=[((18, 12), (20, 14)), ((17, 20), (18, 20))], fire_first_only=True)
+    record("single", 40, 20, [17, 20], 80, 811, 60, "traj_topexit.npz", extra_resets=(35,), layout=top)
+    record("single", 40, 24, [1, 12], 150, 812, 50, "traj_westexit_far.npz", forced_actions={**{t: [3] for t in range(3)}, **{t: [0] for t in range(3, 18)}})       # +y past the fire barrier, then +x
+
+
 def main_timelimit():
     # 150 people, episodes cut at 12.5 simulated seconds = 25 steps: `done` by time with people still inside, reset, again
     record("single", 36, 30, None, 150, 4321, 60, "traj_room_timelimit.npz", max_time=12.5)
@@ -132,6 +149,8 @@ def main():
         return main_synthetic()
     if "--timelimit-only" in sys.argv:
         return main_timelimit()
+    if "--branches-only" in sys.argv:
+        return main_branches()
     ref = record("single", 36, 30, None, 150, 1234, 260, "traj_room_single.npz", extra_resets=(7,))
     layout_file(ref, "layout_room.npz", steps=range(0, 181))
     record("multi", 36, 30, None, 150, 99, 120, "traj_room_multi.npz")
@@ -144,6 +163,7 @@ def main():
     layout_file(ref, "layout_big256.npz", steps=[0, 5, 24, 90, 180], box=(-6, -6, 50, 46))
     main_synthetic()
     main_timelimit()
+    main_branches()
 
 
 if __name__ == "__main__":

@@ -7,7 +7,8 @@ import pytest
 from util import OP_RESET, OP_STEP, assert_frame_equal, layout_for, load_golden
 
 TRAJS = ["traj_room_single.npz", "traj_room_multi.npz", "traj_room_small.npz", "traj_room_westexit.npz",
-         "traj_big256.npz", "traj_room_allevac.npz", "traj_synth_gallery.npz", "traj_synth_hall.npz", "traj_room_timelimit.npz"]
+         "traj_big256.npz", "traj_room_allevac.npz", "traj_synth_gallery.npz", "traj_synth_hall.npz", "traj_room_timelimit.npz",
+         "traj_topexit.npz", "traj_westexit_far.npz"]
 
 
 @pytest.mark.parametrize("name", TRAJS)
